@@ -1,0 +1,317 @@
+/*
+ * lcr_contract.h — the numerical contract of the longcallR-b200 boundary.
+ *
+ * Header-only, usable from C++ host code and from CUDA device code.  Everything
+ * here is part of the *specification* of the C ABI in longcallr_b200.h:
+ *
+ *   - how the (unseedable, thread_rng) random draws of the reference are
+ *     replaced by a counter-based generator the caller seeds
+ *     (reference draws: src/phase.rs:444,611,674,1198-1224, src/snpfrags.rs:256,349);
+ *   - the deterministic log10 / 10^x used for QUAL/GQ/phase-score so that the
+ *     GPU path and the CPU oracle agree bit-for-bit (reference uses Rust std
+ *     f64::log10 / f64::powf: src/candidate.rs:268-335, src/snpfrags.rs:245,483);
+ *   - the fixed-point scale of the per-read / per-SNP log-likelihood sums of the
+ *     phasing sweeps (reference: f64 sums in list order, src/phase.rs:77-176).
+ *
+ * The oracle's "reference-order" mode uses libm and sequential f64 sums instead
+ * and is compared with this contract at 1e-9 on every fixture.
+ */
+#ifndef LCR_CONTRACT_H
+#define LCR_CONTRACT_H
+
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define LCR_HD __host__ __device__ __forceinline__
+#else
+#define LCR_HD static inline
+#endif
+
+/* ------------------------------------------------------------------ RNG --- */
+
+/* splitmix64 finaliser */
+LCR_HD uint64_t lcr_mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+/* Random streams.  `call` and `idx` are documented per stream. */
+enum {
+    LCR_RNG_INIT_DELTA = 0,    /* phase.rs:611-614   call=0,            idx=candidate index in region   */
+    LCR_RNG_INIT_SIGMA = 1,    /* phase.rs:673-680   call=enum config c (0 on the LD path), idx=read index in region */
+    LCR_RNG_PERTURB_DELTA = 2, /* phase.rs:1202-1209 call=tidx,         idx=candidate index             */
+    LCR_RNG_PERTURB_SIGMA = 3, /* phase.rs:1218-1225 call=tidx,         idx=read index                  */
+    LCR_RNG_RESCUE_SIGMA = 4   /* snpfrags.rs:256-262,349-355 call=candidate index, idx=read index      */
+};
+
+/* region key: independent of how regions are batched */
+LCR_HD uint64_t lcr_region_key(int32_t tid, uint32_t start) {
+    return lcr_mix64(((uint64_t)(uint32_t)tid << 32) | (uint64_t)start);
+}
+
+/* uniform in [0,1) with 53 random bits, like rand 0.8 `gen::<f64>()` */
+LCR_HD double lcr_uniform(uint64_t seed, uint64_t region_key, uint32_t stream, uint32_t call, uint32_t idx) {
+    uint64_t h = lcr_mix64(seed ^ region_key);
+    h = lcr_mix64(h ^ (((uint64_t)stream << 32) | (uint64_t)call));
+    h = lcr_mix64(h ^ (uint64_t)idx);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* ------------------------------------------------- deterministic math --- */
+
+LCR_HD uint64_t lcr_d2u(double x) {
+    uint64_t u;
+#if defined(__CUDA_ARCH__)
+    u = (uint64_t)__double_as_longlong(x);
+#else
+    memcpy(&u, &x, 8);
+#endif
+    return u;
+}
+LCR_HD double lcr_u2d(uint64_t u) {
+    double x;
+#if defined(__CUDA_ARCH__)
+    x = __longlong_as_double((long long)u);
+#else
+    memcpy(&x, &u, 8);
+#endif
+    return x;
+}
+
+/* natural log, ~1 ulp; only +,-,*,/ and fma, so host and device agree bit-for-bit
+   (compile host with -ffp-contract=off and device with -fmad=false). */
+LCR_HD double lcr_log(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return lcr_u2d(0x7ff8000000000000ULL);
+    if (x == 0.0) return lcr_u2d(0xfff0000000000000ULL);
+    uint64_t b = lcr_d2u(x);
+    if ((b >> 52) == 0x7ffULL) return x; /* +inf */
+    int e = (int)(b >> 52);
+    if (e == 0) { /* subnormal */
+        x = x * 18014398509481984.0; /* 2^54 */
+        b = lcr_d2u(x);
+        e = (int)(b >> 52) - 54;
+    }
+    e -= 1023;
+    double m = lcr_u2d((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double z = s * s;
+    /* atanh series: log m = 2 s (1 + z/3 + z^2/5 + ...), |s| <= 0.1716 */
+    double p = 1.0 / 27.0;
+    p = fma(p, z, 1.0 / 25.0);
+    p = fma(p, z, 1.0 / 23.0);
+    p = fma(p, z, 1.0 / 21.0);
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    p = p * z;                 /* series minus its leading 1 */
+    double lnm = fma(2.0 * s, p, 2.0 * s);
+    const double LN2_HI = 6.93147180369123816490e-01; /* top 33 bits of ln 2 */
+    const double LN2_LO = 1.90821492927058770002e-10;
+    double de = (double)e;
+    return fma(de, LN2_HI, fma(de, LN2_LO, lnm));
+}
+
+LCR_HD double lcr_log10(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return lcr_u2d(0x7ff8000000000000ULL);
+    if (x == 0.0) return lcr_u2d(0xfff0000000000000ULL);
+    uint64_t b = lcr_d2u(x);
+    if ((b >> 52) == 0x7ffULL) return x;
+    int e = (int)(b >> 52);
+    if (e == 0) {
+        x = x * 18014398509481984.0;
+        b = lcr_d2u(x);
+        e = (int)(b >> 52) - 54;
+    }
+    e -= 1023;
+    double m = lcr_u2d((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double z = s * s;
+    double p = 1.0 / 27.0;
+    p = fma(p, z, 1.0 / 25.0);
+    p = fma(p, z, 1.0 / 23.0);
+    p = fma(p, z, 1.0 / 21.0);
+    p = fma(p, z, 1.0 / 19.0);
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, 1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, 1.0 / 3.0);
+    p = p * z;
+    double lnm = fma(2.0 * s, p, 2.0 * s);
+    const double LOG10_2_HI = 3.01029995663611771306e-01; /* top bits of log10(2) */
+    const double LOG10_2_LO = 3.69423907715893078616e-13;
+    const double LOG10_E = 4.34294481903251827651e-01;
+    double de = (double)e;
+    return fma(de, LOG10_2_HI, fma(de, LOG10_2_LO, lnm * LOG10_E));
+}
+
+/* 10^x, ~1-2 ulp in the normal range; exact 0 below 10^-324, +inf above 10^308.26 */
+LCR_HD double lcr_exp10(double x) {
+    if (x != x) return x;
+    if (x > 308.2547155599167) return lcr_u2d(0x7ff0000000000000ULL);
+    if (x < -323.6072453387798) return 0.0; /* below half the smallest subnormal */
+    const double LOG2_10_HI = 3.32192809484989240445e+00; /* log2(10) split */
+    const double LOG2_10_LO = 1.21204317033709228939e-14;
+    double t = x * 3.32192809488736218171e+00;
+    double k = floor(t + 0.5);
+    double r = fma(x, LOG2_10_HI, -k);
+    r = fma(x, LOG2_10_LO, r);
+    const double LN2 = 6.93147180559945286227e-01;
+    double y = r * LN2;
+    double p = 1.0 / 6227020800.0;             /* 1/13! */
+    p = fma(p, y, 1.0 / 479001600.0);
+    p = fma(p, y, 1.0 / 39916800.0);
+    p = fma(p, y, 1.0 / 3628800.0);
+    p = fma(p, y, 1.0 / 362880.0);
+    p = fma(p, y, 1.0 / 40320.0);
+    p = fma(p, y, 1.0 / 5040.0);
+    p = fma(p, y, 1.0 / 720.0);
+    p = fma(p, y, 1.0 / 120.0);
+    p = fma(p, y, 1.0 / 24.0);
+    p = fma(p, y, 1.0 / 6.0);
+    p = fma(p, y, 0.5);
+    p = fma(p, y, 1.0);
+    p = fma(p, y, 1.0);
+    int ki = (int)k;
+    if (ki >= -1022) {
+        if (ki > 1023) { /* p < 1 here or we returned inf above; split the scale */
+            return (p * lcr_u2d((uint64_t)(ki - 1 + 1023) << 52)) * 2.0;
+        }
+        return p * lcr_u2d((uint64_t)(ki + 1023) << 52);
+    }
+    /* subnormal result: two-step scale, one extra (deterministic) rounding */
+    return (p * lcr_u2d((uint64_t)(ki + 128 + 1023) << 52)) * lcr_u2d((uint64_t)(1023 - 128) << 52);
+}
+
+/* f32 natural log as the reference's f32::ln (candidate.rs:33): correctly rounded
+   from the f64 value. */
+LCR_HD float lcr_logf(float x) { return (float)lcr_log((double)x); }
+
+/* Rust `f64 as i32`: saturating, NaN -> 0  (vcf.rs:51,67,72) */
+LCR_HD int32_t lcr_f64_as_i32(double v) {
+    if (v != v) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return (int32_t)(-2147483647 - 1);
+    return (int32_t)v;
+}
+
+/* ------------------------------------------ fixed point for the sweeps --- */
+
+/* log10 terms of the sweeps are carried as int64 with LCR_FX_FRAC fractional bits:
+   order-independent (hence parallel-reducible) and exactly reproducible.
+   Capacity: |log10 term| <= 3.0004 (q capped at 30) -> 2^63 / 2^36 / 3 ~ 4.4e7 terms per sum. */
+#define LCR_FX_FRAC 36
+#define LCR_FX_ONE ((double)(1ULL << LCR_FX_FRAC))
+#define LCR_FX_INVALID INT64_MIN /* log10(0): base quality 0 at a phase site (reference panics: phase.rs:307) */
+
+LCR_HD double lcr_fx_to_f64(int64_t v) { return (double)v * (1.0 / LCR_FX_ONE); }
+
+#define LCR_MAX_BASE_QUALITY 30 /* main.rs:19-21 */
+
+/* Host-side LUT builder (libm; both the product and the oracle call this on the
+   same machine, so both see identical table bits). */
+typedef struct lcr_luts {
+    /* genotype likelihood, eps = 0.1^(q/10)  (candidate.rs:268,275) */
+    double gl_log_err[LCR_MAX_BASE_QUALITY + 1];  /* log10(eps)     */
+    double gl_log_ok[LCR_MAX_BASE_QUALITY + 1];   /* log10(1 - eps) */
+    /* fragment elements, eps = 10^(-q/10)  (fragment.rs:133) */
+    double fr_prob[LCR_MAX_BASE_QUALITY + 1];
+    double fr_log_err[LCR_MAX_BASE_QUALITY + 1];
+    double fr_log_ok[LCR_MAX_BASE_QUALITY + 1];
+    int64_t fx_err[LCR_MAX_BASE_QUALITY + 1];     /* round(log10(eps)   * 2^36) */
+    int64_t fx_ok[LCR_MAX_BASE_QUALITY + 1];      /* round(log10(1-eps) * 2^36), LCR_FX_INVALID at q=0 */
+    /* genotype likelihood in fixed point (same scale); gl_fx_ok[0] is unused: a base of
+       quality 0 makes the term log10(0) = -inf and is carried as a flag (candidate.rs:267-279) */
+    int64_t gl_fx_err[LCR_MAX_BASE_QUALITY + 1];
+    int64_t gl_fx_ok[LCR_MAX_BASE_QUALITY + 1];
+    int64_t fx_prior_homref, fx_prior_homvar, fx_prior_het, fx_log10_2;
+    /* priors of the SNP sweep (phase.rs:136-144) and of genotyping (candidate.rs:239-240) */
+    double prior_homref_log, prior_homvar_log, prior_het_log, log10_2;
+    double gl_prior_log[3]; /* log10 of [theta/2, theta, 1-1.5 theta] */
+    float sor_threshold;    /* cal_strand_odds_ratio(5,5,9,1), candidate.rs:49-51 */
+} lcr_luts;
+
+#if !defined(__CUDA_ARCH__)
+static inline float lcr_strand_odds_ratio(int32_t ref_fw, int32_t ref_rv, int32_t alt_fw, int32_t alt_rv);
+static inline void lcr_build_luts(lcr_luts *t) {
+    for (int q = 0; q <= LCR_MAX_BASE_QUALITY; ++q) {
+        double e1 = pow(0.1, (double)q / 10.0);
+        t->gl_log_err[q] = log10(e1);
+        t->gl_log_ok[q] = log10(1.0 - e1);
+        double e2 = pow(10.0, -((double)q) / 10.0);
+        t->fr_prob[q] = e2;
+        t->fr_log_err[q] = log10(e2);
+        t->fr_log_ok[q] = log10(1.0 - e2);
+        t->fx_err[q] = (int64_t)llrint(t->fr_log_err[q] * LCR_FX_ONE);
+        t->fx_ok[q] = (e2 >= 1.0) ? LCR_FX_INVALID : (int64_t)llrint(t->fr_log_ok[q] * LCR_FX_ONE);
+        t->gl_fx_err[q] = (int64_t)llrint(t->gl_log_err[q] * LCR_FX_ONE);
+        t->gl_fx_ok[q] = (e1 >= 1.0) ? 0 : (int64_t)llrint(t->gl_log_ok[q] * LCR_FX_ONE);
+    }
+    t->prior_homref_log = log10(1.0 - 1.5 * 0.001);
+    t->prior_homvar_log = log10(0.5 * 0.001);
+    t->prior_het_log = log10(0.001);
+    t->log10_2 = log10(2.0);
+    t->fx_prior_homref = (int64_t)llrint(t->prior_homref_log * LCR_FX_ONE);
+    t->fx_prior_homvar = (int64_t)llrint(t->prior_homvar_log * LCR_FX_ONE);
+    t->fx_prior_het = (int64_t)llrint(t->prior_het_log * LCR_FX_ONE);
+    t->fx_log10_2 = (int64_t)llrint(t->log10_2 * LCR_FX_ONE);
+    const double theta = 0.001;
+    t->gl_prior_log[0] = log10(theta / 2.0);
+    t->gl_prior_log[1] = log10(theta);
+    t->gl_prior_log[2] = log10(1.0 - 1.5 * theta);
+    t->sor_threshold = lcr_strand_odds_ratio(5, 5, 9, 1);
+}
+#endif
+
+/* StrandOddsRatio in f32, candidate.rs:24-35 */
+LCR_HD float lcr_strand_odds_ratio(int32_t ref_fw, int32_t ref_rv, int32_t alt_fw, int32_t alt_rv) {
+    float x00 = (float)(ref_fw + 1);
+    float x01 = (float)(ref_rv + 1);
+    float x10 = (float)(alt_fw + 1);
+    float x11 = (float)(alt_rv + 1);
+    float symmetrical_ratio = (x00 * x11) / (x01 * x10) + (x01 * x10) / (x00 * x11);
+    float ref_ratio = (x00 < x01 ? x00 : x01) / (x00 > x01 ? x00 : x01);
+    float alt_ratio = (x10 < x11 ? x10 : x11) / (x10 > x11 ? x10 : x11);
+    return lcr_logf(symmetrical_ratio) + lcr_logf(ref_ratio) - lcr_logf(alt_ratio);
+}
+
+/* two-tailed binomial(p=0.5) test `p < 0.05` evaluated exactly in integers
+   (replaces statrs 0.16 Binomial::cdf at candidate.rs:37-47,222; n <= 30). */
+LCR_HD int lcr_binom_two_tailed_lt_0p05(uint32_t k, uint32_t n) {
+    /* C(n,i) by recurrence, all < 2^30 */
+    uint64_t c = 1, cdf_k = 0, cdf_km1 = 0;
+    for (uint32_t i = 0; i <= n; ++i) {
+        if (i <= k) cdf_k += c;
+        if (i + 1 <= k) cdf_km1 += c;
+        c = c * (uint64_t)(n - i) / (uint64_t)(i + 1);
+    }
+    uint64_t total = 1ULL << n;
+    uint64_t tail;
+    if (k == 0) tail = cdf_k;                /* 2*cdf(0)            */
+    else if (k == n) tail = total - cdf_km1; /* 2*(1-cdf(n-1))      */
+    else {
+        uint64_t up = total - cdf_km1;
+        tail = cdf_k < up ? cdf_k : up;
+    }
+    /* 2*tail/2^n < 0.05  <=>  40*tail < 2^n */
+    return 40ULL * tail < total;
+}
+
+#endif /* LCR_CONTRACT_H */
