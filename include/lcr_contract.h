@@ -248,9 +248,24 @@ typedef struct lcr_luts {
     float sor_threshold;    /* cal_strand_odds_ratio(5,5,9,1), candidate.rs:49-51 */
 } lcr_luts;
 
-#if !defined(__CUDA_ARCH__)
-static inline float lcr_strand_odds_ratio(int32_t ref_fw, int32_t ref_rv, int32_t alt_fw, int32_t alt_rv);
-static inline void lcr_build_luts(lcr_luts *t) {
+/* StrandOddsRatio in f32, candidate.rs:24-35 */
+LCR_HD float lcr_strand_odds_ratio(int32_t ref_fw, int32_t ref_rv, int32_t alt_fw, int32_t alt_rv) {
+    float x00 = (float)(ref_fw + 1);
+    float x01 = (float)(ref_rv + 1);
+    float x10 = (float)(alt_fw + 1);
+    float x11 = (float)(alt_rv + 1);
+    float symmetrical_ratio = (x00 * x11) / (x01 * x10) + (x01 * x10) / (x00 * x11);
+    float ref_ratio = (x00 < x01 ? x00 : x01) / (x00 > x01 ? x00 : x01);
+    float alt_ratio = (x10 < x11 ? x10 : x11) / (x10 > x11 ? x10 : x11);
+    return lcr_logf(symmetrical_ratio) + lcr_logf(ref_ratio) - lcr_logf(alt_ratio);
+}
+
+#if defined(__CUDACC__)
+#define LCR_H __host__ static inline
+#else
+#define LCR_H static inline
+#endif
+LCR_H void lcr_build_luts(lcr_luts *t) {
     for (int q = 0; q <= LCR_MAX_BASE_QUALITY; ++q) {
         double e1 = pow(0.1, (double)q / 10.0);
         t->gl_log_err[q] = log10(e1);
@@ -277,19 +292,6 @@ static inline void lcr_build_luts(lcr_luts *t) {
     t->gl_prior_log[1] = log10(theta);
     t->gl_prior_log[2] = log10(1.0 - 1.5 * theta);
     t->sor_threshold = lcr_strand_odds_ratio(5, 5, 9, 1);
-}
-#endif
-
-/* StrandOddsRatio in f32, candidate.rs:24-35 */
-LCR_HD float lcr_strand_odds_ratio(int32_t ref_fw, int32_t ref_rv, int32_t alt_fw, int32_t alt_rv) {
-    float x00 = (float)(ref_fw + 1);
-    float x01 = (float)(ref_rv + 1);
-    float x10 = (float)(alt_fw + 1);
-    float x11 = (float)(alt_rv + 1);
-    float symmetrical_ratio = (x00 * x11) / (x01 * x10) + (x01 * x10) / (x00 * x11);
-    float ref_ratio = (x00 < x01 ? x00 : x01) / (x00 > x01 ? x00 : x01);
-    float alt_ratio = (x10 < x11 ? x10 : x11) / (x10 > x11 ? x10 : x11);
-    return lcr_logf(symmetrical_ratio) + lcr_logf(ref_ratio) - lcr_logf(alt_ratio);
 }
 
 /* two-tailed binomial(p=0.5) test `p < 0.05` evaluated exactly in integers

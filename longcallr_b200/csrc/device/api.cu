@@ -1,0 +1,620 @@
+/*
+ * api.cu — the C ABI of include/longcallr_b200.h: contexts, reference upload, batch upload,
+ * the device run (pileup/genotype stage, fragment + phasing stage) and result fetch.
+ *
+ * The call sequence mirrors the reference worker (src/thread.rs:78-221): lcr_set_reference is
+ * `ref_seqs.get(chr)` (:59,:79), lcr_submit is the closure body, and the returned records are
+ * what the three queues receive (:204-221).  There is no CPU fallback: without a device every
+ * compute entry point returns LCR_ERR_NO_DEVICE.
+ */
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "lcr_frag.h"
+
+int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flags);
+
+namespace {
+
+struct ResultBox {
+    lcr_result res{};
+    std::vector<uint32_t> cand_off;
+    std::vector<lcr_candidate> cand;
+    std::vector<int32_t> region_status;
+    std::vector<int8_t> hp;
+    std::vector<uint32_t> ps;
+    std::vector<uint8_t> is_fragment;
+    std::vector<uint64_t> pos_off;
+    std::vector<uint32_t> acgt, fwd, d, n, ts;
+    std::vector<uint32_t> frag_off, frag_read, elem_snp;
+    std::vector<uint64_t> elem_off;
+    std::vector<int8_t> elem_cell;
+    std::vector<uint8_t> elem_base;
+};
+
+/* debug copy of the fragment matrix, filled by the run when LCR_FLAG_EMIT_FRAGMENTS is set */
+struct FragDebug {
+    std::vector<uint32_t> frag_slot, frag_elem_off, elem_snp;
+    std::vector<int8_t> elem_cell;
+    std::vector<uint8_t> elem_base;
+};
+
+struct DbExtra {
+    FragDebug fragdbg;
+    std::vector<lcr_region> h_regions;
+    std::vector<int32_t> h_status0;
+};
+
+template <class T>
+int dalloc(lcr_ctx *ctx, T **p, size_t n) {
+    LCR_CUDA_TRY(ctx, cudaMallocAsync((void **)p, sizeof(T) * (n ? n : 1), ctx->stream));
+    return 0;
+}
+#define DALLOC(p, n)                          \
+    do {                                      \
+        int rc__ = dalloc(ctx, &(p), (n));    \
+        if (rc__) return rc__;                \
+    } while (0)
+#define TRY(expr) LCR_CUDA_TRY(ctx, expr)
+#define DFREE(p)                                               \
+    do {                                                       \
+        if (p) { cudaFreeAsync((void *)(p), ctx->stream); (p) = nullptr; } \
+    } while (0)
+
+template <class T>
+int h2d(lcr_ctx *ctx, T **dst, const T *src, size_t n, uint64_t *bytes) {
+    int rc = dalloc(ctx, dst, n);
+    if (rc) return rc;
+    if (n) {
+        LCR_CUDA_TRY(ctx, cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+        if (bytes) *bytes += sizeof(T) * n;
+    }
+    return 0;
+}
+
+__global__ void k_init_pairs(LcrPairEntry *t, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { t[i].key = ~0ull; t[i].cis = 0; t[i].trans = 0; }
+}
+
+int exclusive_scan_u32(lcr_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream);
+    void *tmp = nullptr;
+    TRY(cudaMallocAsync(&tmp, bytes ? bytes : 16, ctx->stream));
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, ctx->stream));
+    TRY(cudaFreeAsync(tmp, ctx->stream));
+    return 0;
+}
+
+} // namespace
+
+struct lcr_device_batch_full : lcr_device_batch {
+    DbExtra extra;
+    uint8_t *slot_flags = nullptr;
+};
+
+static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_slots = db->n_slots, n_cand = db->n_cand, n_regions = db->n_regions;
+    uint32_t *frag_flag = nullptr, *elem_count = nullptr, *frag_scan = nullptr, *elem_scan = nullptr;
+    uint32_t *cover_count = nullptr, *cover_off = nullptr, *cover_cursor = nullptr, *cover_frag = nullptr;
+    int8_t *cover_cell = nullptr;
+    uint32_t *frag_slot = nullptr, *frag_elem_off = nullptr, *frag_links = nullptr, *elem_snp = nullptr;
+    int8_t *elem_cell = nullptr;
+    uint8_t *elem_base = nullptr;
+    DALLOC(frag_flag, (size_t)n_slots + 1);
+    DALLOC(elem_count, (size_t)n_slots + 1);
+    DALLOC(frag_scan, (size_t)n_slots + 1);
+    DALLOC(elem_scan, (size_t)n_slots + 1);
+    DALLOC(cover_count, (size_t)n_cand + 1);
+    DALLOC(cover_off, (size_t)n_cand + 1);
+    DALLOC(cover_cursor, (size_t)n_cand + 1);
+    TRY(cudaMemsetAsync(frag_flag, 0, sizeof(uint32_t) * ((size_t)n_slots + 1), st));
+    TRY(cudaMemsetAsync(elem_count, 0, sizeof(uint32_t) * ((size_t)n_slots + 1), st));
+    TRY(cudaMemsetAsync(cover_count, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
+    TRY(cudaMemsetAsync(cover_cursor, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
+
+    FragArgs fa{};
+    fa.P = ctx->P;
+    fa.n_slots = n_slots;
+    fa.regions = db->regions;
+    fa.slot_off = db->slot_off; fa.slot_region = db->slot_region; fa.slot_flags = db->slot_flags;
+    fa.pos = db->pos; fa.seq_off = db->seq_off; fa.cig_off = db->cig_off; fa.seq = db->seq; fa.qual = db->qual; fa.cigar = db->cigar;
+    fa.rstate = db->rstate; fa.cand = db->cand; fa.stats = db->d_stats;
+    fa.frag_flag = frag_flag; fa.elem_count = elem_count; fa.frag_scan = frag_scan; fa.elem_scan = elem_scan;
+    fa.cover_count = cover_count; fa.cover_off = cover_off; fa.cover_cursor = cover_cursor;
+    fa.is_fragment = db->is_fragment;
+    lcr_launch_frag_count(fa, st);
+    int rc;
+    if ((rc = exclusive_scan_u32(ctx, frag_flag, frag_scan, (size_t)n_slots + 1))) return rc;
+    if ((rc = exclusive_scan_u32(ctx, elem_count, elem_scan, (size_t)n_slots + 1))) return rc;
+    if ((rc = exclusive_scan_u32(ctx, cover_count, cover_off, (size_t)n_cand + 1))) return rc;
+    db->timing.kernel_launches += 4;
+    uint32_t n_frag_total = 0, n_elem_total = 0;
+    std::vector<LcrRegionState> hrs(n_regions);
+    TRY(cudaMemcpyAsync(&n_frag_total, frag_scan + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&n_elem_total, elem_scan + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(hrs.data(), db->rstate, sizeof(LcrRegionState) * n_regions, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    /* LD pair tables: one open-addressing segment per region that takes the LD path */
+    uint64_t table_size = 0;
+    for (uint32_t r = 0; r < n_regions; ++r) {
+        LcrRegionState &s = hrs[r];
+        s.pair_begin = 0; s.pair_cap = 0;
+        if (s.status != 0 || s.n_cand <= ctx->P.max_enum_snps || !s.n_ld_pairs_cap) continue;
+        uint64_t bound = std::min<uint64_t>(s.n_ld_pairs_cap, (uint64_t)s.n_cand * (s.n_cand - 1) / 2);
+        uint64_t cap = 16;
+        while (cap < 2 * bound) cap <<= 1;
+        if (table_size + cap > 0xfffffff0ull) { ctx->last_error = "LD pair table too large"; return LCR_ERR_OOM; }
+        s.pair_begin = (uint32_t)table_size;
+        s.pair_cap = (uint32_t)cap;
+        table_size += cap;
+    }
+    TRY(cudaMemcpyAsync(db->rstate, hrs.data(), sizeof(LcrRegionState) * n_regions, cudaMemcpyHostToDevice, st));
+    lcr_launch_region_frag_ranges(n_regions, db->slot_off, frag_scan, db->rstate, st);
+    db->timing.kernel_launches += 1;
+    db->n_frag = n_frag_total;
+    db->n_elem = n_elem_total;
+    DALLOC(frag_slot, (size_t)n_frag_total + 1);
+    DALLOC(frag_elem_off, (size_t)n_frag_total + 1);
+    DALLOC(frag_links, (size_t)n_frag_total + 1);
+    DALLOC(elem_snp, n_elem_total);
+    DALLOC(elem_cell, n_elem_total);
+    DALLOC(elem_base, n_elem_total);
+    DALLOC(cover_frag, n_elem_total);
+    DALLOC(cover_cell, n_elem_total);
+    if (!n_frag_total) TRY(cudaMemsetAsync(frag_elem_off, 0, sizeof(uint32_t), st));
+    fa.n_frag_total = n_frag_total; fa.n_elem_total = n_elem_total;
+    fa.frag_slot = frag_slot; fa.frag_elem_off = frag_elem_off; fa.frag_links = frag_links;
+    fa.elem_snp = elem_snp; fa.elem_cell = elem_cell; fa.elem_base = elem_base;
+    fa.cover_frag = cover_frag; fa.cover_cell = cover_cell;
+    lcr_launch_frag_fill(fa, st);
+    db->timing.kernel_launches += 1;
+
+    /* LD graph */
+    LcrPairEntry *table = nullptr;
+    uint32_t *entry_region = nullptr, *deg = nullptr, *adj_off = nullptr, *adj_cursor = nullptr, *adj = nullptr;
+    DALLOC(deg, (size_t)n_cand + 1);
+    DALLOC(adj_off, (size_t)n_cand + 1);
+    DALLOC(adj_cursor, (size_t)n_cand + 1);
+    TRY(cudaMemsetAsync(deg, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
+    TRY(cudaMemsetAsync(adj_cursor, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
+    uint32_t adj_total = 0;
+    if (table_size) {
+        DALLOC(table, table_size);
+        DALLOC(entry_region, table_size / 16);
+        k_init_pairs<<<(uint32_t)((table_size + 255) / 256), 256, 0, st>>>(table, table_size);
+        lcr_launch_fill_entry_region(n_regions, db->rstate, entry_region, st);
+        lcr_launch_pair_count(fa, table, st);
+        lcr_launch_ld_edges(false, ctx->P.ld_weight_threshold, n_regions, db->rstate, table, table_size, entry_region, deg, nullptr, nullptr, nullptr, st);
+        db->timing.kernel_launches += 4;
+    }
+    if ((rc = exclusive_scan_u32(ctx, deg, adj_off, (size_t)n_cand + 1))) return rc;
+    db->timing.kernel_launches += 1;
+    if (table_size) {
+        TRY(cudaMemcpyAsync(&adj_total, adj_off + n_cand, 4, cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st));
+    }
+    DALLOC(adj, adj_total);
+    if (table_size && adj_total) {
+        lcr_launch_ld_edges(true, ctx->P.ld_weight_threshold, n_regions, db->rstate, table, table_size, entry_region, deg, adj_off, adj_cursor, adj, st);
+        lcr_launch_adj_sort(n_cand, adj_off, adj, st);
+        db->timing.kernel_launches += 2;
+    }
+    cudaEvent_t ev_frag;
+    TRY(cudaEventCreate(&ev_frag));
+    TRY(cudaEventRecord(ev_frag, st));
+
+    /* phasing state */
+    PhaseArgs pa{};
+    pa.P = ctx->P;
+    pa.n_regions = n_regions;
+    pa.regions = db->regions; pa.slot_off = db->slot_off; pa.rstate = db->rstate; pa.cand = db->cand;
+    pa.tables = ctx->d_tables; pa.stats = db->d_stats;
+    pa.frag_slot = frag_slot; pa.frag_elem_off = frag_elem_off; pa.frag_links = frag_links;
+    pa.elem_snp = elem_snp; pa.elem_cell = elem_cell;
+    pa.cover_off = cover_off; pa.cover_frag = cover_frag; pa.cover_cell = cover_cell;
+    pa.adj_off = adj_off; pa.adj = adj;
+    DALLOC(pa.hap, n_cand); DALLOC(pa.gen, n_cand); DALLOC(pa.best_hap, n_cand); DALLOC(pa.best_gen, n_cand);
+    DALLOC(pa.phase0, n_cand); DALLOC(pa.conserved, n_cand);
+    DALLOC(pa.label, n_cand); DALLOC(pa.rank, n_cand);
+    DALLOC(pa.work, (size_t)adj_total + n_cand + 1);
+    DALLOC(pa.blk_q, n_cand); DALLOC(pa.blk_qflip, n_cand);
+    DALLOC(pa.tag, n_frag_total); DALLOC(pa.best_tag, n_frag_total); DALLOC(pa.fp, n_frag_total); DALLOC(pa.assign, n_frag_total);
+    pa.hp = db->hp; pa.ps = db->ps;
+    lcr_launch_phase(pa, st);
+    db->timing.kernel_launches += 1;
+    cudaEvent_t ev_end;
+    TRY(cudaEventCreate(&ev_end));
+    TRY(cudaEventRecord(ev_end, st));
+
+    if (ctx->P.flags & LCR_FLAG_EMIT_FRAGMENTS) {
+        FragDebug &fd = db->extra.fragdbg;
+        fd.frag_slot.resize(n_frag_total); fd.frag_elem_off.resize((size_t)n_frag_total + 1);
+        fd.elem_snp.resize(n_elem_total); fd.elem_cell.resize(n_elem_total); fd.elem_base.resize(n_elem_total);
+        if (n_frag_total) TRY(cudaMemcpyAsync(fd.frag_slot.data(), frag_slot, 4ull * n_frag_total, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(fd.frag_elem_off.data(), frag_elem_off, 4ull * ((size_t)n_frag_total + (n_frag_total ? 1 : 0)), cudaMemcpyDeviceToHost, st));
+        if (n_elem_total) {
+            TRY(cudaMemcpyAsync(fd.elem_snp.data(), elem_snp, 4ull * n_elem_total, cudaMemcpyDeviceToHost, st));
+            TRY(cudaMemcpyAsync(fd.elem_cell.data(), elem_cell, n_elem_total, cudaMemcpyDeviceToHost, st));
+            TRY(cudaMemcpyAsync(fd.elem_base.data(), elem_base, n_elem_total, cudaMemcpyDeviceToHost, st));
+        }
+        if (!n_frag_total) fd.frag_elem_off[0] = 0;
+    }
+    TRY(cudaStreamSynchronize(st));
+    TRY(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_frag, ev_end);
+    db->timing.ms_phase = ms;
+    cudaEventDestroy(ev_frag);
+    cudaEventDestroy(ev_end);
+
+    DFREE(frag_flag); DFREE(elem_count); DFREE(frag_scan); DFREE(elem_scan);
+    DFREE(cover_count); DFREE(cover_off); DFREE(cover_cursor); DFREE(cover_frag); DFREE(cover_cell);
+    DFREE(frag_slot); DFREE(frag_elem_off); DFREE(frag_links); DFREE(elem_snp); DFREE(elem_cell); DFREE(elem_base);
+    DFREE(table); DFREE(entry_region); DFREE(deg); DFREE(adj_off); DFREE(adj_cursor); DFREE(adj);
+    DFREE(pa.hap); DFREE(pa.gen); DFREE(pa.best_hap); DFREE(pa.best_gen); DFREE(pa.phase0); DFREE(pa.conserved);
+    DFREE(pa.label); DFREE(pa.rank); DFREE(pa.work); DFREE(pa.blk_q); DFREE(pa.blk_qflip);
+    DFREE(pa.tag); DFREE(pa.best_tag); DFREE(pa.fp); DFREE(pa.assign);
+    return LCR_OK;
+}
+
+extern "C" {
+
+int lcr_abi_version(void) { return LCR_ABI_VERSION; }
+
+const char *lcr_strerror(int status) {
+    switch (status) {
+        case LCR_OK: return "ok";
+        case LCR_ERR_INVALID_ARG: return "invalid argument";
+        case LCR_ERR_CUDA: return "CUDA error";
+        case LCR_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback on this path)";
+        case LCR_ERR_OOM: return "out of memory";
+        case LCR_ERR_BAD_CIGAR: return "unknown or inconsistent CIGAR operation";
+        case LCR_ERR_NO_REFERENCE: return "region on a contig without reference sequence";
+        case LCR_ERR_BASEQ_ZERO: return "base quality 0 at a fragment site";
+        default: return "unknown status";
+    }
+}
+
+const char *lcr_last_error(lcr_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
+    if (!p || !out) return LCR_ERR_INVALID_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return LCR_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return LCR_ERR_NO_DEVICE;
+    lcr_ctx *ctx = new (std::nothrow) lcr_ctx();
+    if (!ctx) return LCR_ERR_OOM;
+    ctx->P = *p;
+    ctx->device = device;
+    ctx->sticky = 0;
+    ctx->d_ref_table = nullptr;
+    ctx->d_ref_len = nullptr;
+    ctx->ref_table_cap = 0;
+    ctx->ref_dirty = true;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LCR_ERR_CUDA; }
+    /* keep freed blocks in the stream-ordered pool between runs */
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    lcr_build_luts(&ctx->luts);
+    LcrDeviceTables t{};
+    for (int q = 0; q <= LCR_MAX_BASE_QUALITY; ++q) {
+        t.gl_fx_err[q] = ctx->luts.gl_fx_err[q];
+        t.gl_fx_ok[q] = ctx->luts.gl_fx_ok[q];
+        t.fx_err[q] = ctx->luts.fx_err[q];
+        t.fx_ok[q] = ctx->luts.fx_ok[q];
+    }
+    t.fx_prior_homref = ctx->luts.fx_prior_homref; t.fx_prior_homvar = ctx->luts.fx_prior_homvar;
+    t.fx_prior_het = ctx->luts.fx_prior_het; t.fx_log10_2 = ctx->luts.fx_log10_2;
+    t.log10_2 = ctx->luts.log10_2;
+    for (int i = 0; i < 3; ++i) t.gl_prior_log[i] = ctx->luts.gl_prior_log[i];
+    t.sor_threshold = ctx->luts.sor_threshold;
+    if (cudaMalloc(&ctx->d_tables, sizeof t) != cudaSuccess || cudaMemcpy(ctx->d_tables, &t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return LCR_ERR_CUDA;
+    }
+    *out = ctx;
+    return LCR_OK;
+}
+
+void lcr_destroy(lcr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (uint8_t *p : ctx->d_ref) if (p) cudaFree(p);
+    if (ctx->d_ref_table) cudaFree(ctx->d_ref_table);
+    if (ctx->d_ref_len) cudaFree(ctx->d_ref_len);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int lcr_set_reference(lcr_ctx *ctx, int32_t tid, const uint8_t *seq, uint64_t len) {
+    if (!ctx || tid < 0 || (!seq && len)) return LCR_ERR_INVALID_ARG;
+    if (ctx->sticky) return ctx->sticky;
+    TRY(cudaSetDevice(ctx->device));
+    if ((size_t)tid >= ctx->d_ref.size()) { ctx->d_ref.resize(tid + 1, nullptr); ctx->ref_len.resize(tid + 1, 0); }
+    if (ctx->d_ref[tid]) { TRY(cudaFree(ctx->d_ref[tid])); ctx->d_ref[tid] = nullptr; }
+    TRY(cudaMalloc(&ctx->d_ref[tid], len ? len : 1));
+    if (len) TRY(cudaMemcpyAsync(ctx->d_ref[tid], seq, len, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->ref_len[tid] = len;
+    ctx->ref_dirty = true;
+    return LCR_OK;
+}
+
+int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) {
+    if (!ctx || !b || !out) return LCR_ERR_INVALID_ARG;
+    if (ctx->sticky) return ctx->sticky;
+    if (b->n_regions && !b->regions) return LCR_ERR_INVALID_ARG;
+    if (b->n_reads && (!b->pos || !b->flag || !b->mapq || !b->ts || !b->de || !b->seq_off || !b->cig_off)) return LCR_ERR_INVALID_ARG;
+    TRY(cudaSetDevice(ctx->device));
+    lcr_device_batch_full *db = new (std::nothrow) lcr_device_batch_full();
+    if (!db) return LCR_ERR_OOM;
+    db->n_regions = b->n_regions;
+    db->n_reads = b->n_reads;
+    db->ran = false;
+    memset(&db->timing, 0, sizeof db->timing);
+    /* prefix sums over region lengths and read ranges; regions that cannot run get their status here */
+    std::vector<uint32_t> slot_off(b->n_regions + 1, 0), tile_base(b->n_regions + 1, 0);
+    std::vector<uint64_t> pos_off(b->n_regions + 1, 0);
+    db->extra.h_status0.assign(b->n_regions, 0);
+    for (uint32_t r = 0; r < b->n_regions; ++r) {
+        const lcr_region &g = b->regions[r];
+        int32_t stt = 0;
+        if (g.end < g.start || g.start < 1 || g.read_end < g.read_begin || g.read_end > b->n_reads) stt = LCR_ERR_INVALID_ARG;
+        else if (g.tid < 0 || (size_t)g.tid >= ctx->d_ref.size() || !ctx->d_ref[g.tid]) stt = LCR_ERR_NO_REFERENCE;
+        else if ((uint64_t)g.end - 1 > ctx->ref_len[g.tid]) stt = LCR_ERR_INVALID_ARG;
+        db->extra.h_status0[r] = stt;
+        const uint64_t len = stt ? 0 : (uint64_t)(g.end - g.start);
+        const uint32_t nreads = stt ? 0 : g.read_end - g.read_begin;
+        slot_off[r + 1] = slot_off[r] + nreads;
+        tile_base[r + 1] = tile_base[r] + (uint32_t)((len + LCR_TILE - 1) / LCR_TILE);
+        pos_off[r + 1] = pos_off[r] + len;
+    }
+    db->n_slots = slot_off[b->n_regions];
+    db->n_tiles = tile_base[b->n_regions];
+    db->n_pos = pos_off[b->n_regions];
+    std::vector<uint32_t> slot_region(db->n_slots), tile_region(db->n_tiles);
+    for (uint32_t r = 0; r < b->n_regions; ++r) {
+        std::fill(slot_region.begin() + slot_off[r], slot_region.begin() + slot_off[r + 1], r);
+        std::fill(tile_region.begin() + tile_base[r], tile_region.begin() + tile_base[r + 1], r);
+    }
+    db->h_pos_off = pos_off;
+    db->h_slot_off = slot_off;
+    db->extra.h_regions.assign(b->regions, b->regions + b->n_regions);
+    const uint64_t n_bases = b->n_reads ? b->seq_off[b->n_reads] : 0, n_cig = b->n_reads ? b->cig_off[b->n_reads] : 0;
+    db->n_bases = n_bases;
+    db->n_cigar = n_cig;
+    uint64_t bytes = 0;
+    int rc = 0;
+#define UP(field, src, n) if (!rc) rc = h2d(ctx, &db->field, src, (size_t)(n), &bytes)
+    UP(regions, b->regions, b->n_regions);
+    UP(pos, b->pos, b->n_reads);
+    UP(flag, b->flag, b->n_reads);
+    UP(mapq, b->mapq, b->n_reads);
+    UP(ts, b->ts, b->n_reads);
+    UP(de, b->de, b->n_reads);
+    if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
+    else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
+    UP(seq, b->seq, n_bases);
+    UP(qual, b->qual, n_bases);
+    UP(cigar, b->cigar, n_cig);
+    UP(slot_off, slot_off.data(), slot_off.size());
+    UP(slot_region, slot_region.data(), slot_region.size());
+    UP(tile_base, tile_base.data(), tile_base.size());
+    UP(tile_region, tile_region.data(), tile_region.size());
+    UP(pos_off, pos_off.data(), pos_off.size());
+#undef UP
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
+    }
+    if (rc) { lcr_release(ctx, db); return rc; }
+    db->h2d_bytes = bytes;
+    *out = db;
+    return LCR_OK;
+}
+
+static void free_results(lcr_ctx *ctx, lcr_device_batch_full *db) {
+    DFREE(db->rstate); DFREE(db->cand); DFREE(db->hp); DFREE(db->ps); DFREE(db->is_fragment); DFREE(db->d_stats);
+    DFREE(db->pl_acgt); DFREE(db->pl_fwd); DFREE(db->pl_d); DFREE(db->pl_n); DFREE(db->pl_ts);
+    DFREE(db->slot_flags);
+    db->n_cand = 0;
+    db->ran = false;
+}
+
+int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
+    if (!ctx || !dbb) return LCR_ERR_INVALID_ARG;
+    if (ctx->sticky) return ctx->sticky;
+    lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
+    TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    free_results(ctx, db);
+    const uint64_t h2d_keep = db->h2d_bytes;
+    memset(&db->timing, 0, sizeof db->timing);
+    db->timing.h2d_bytes = h2d_keep;
+    if (ctx->ref_dirty) {
+        const int n = (int)ctx->d_ref.size();
+        if (ctx->d_ref_table) { TRY(cudaFree(ctx->d_ref_table)); ctx->d_ref_table = nullptr; }
+        TRY(cudaMalloc(&ctx->d_ref_table, sizeof(uint8_t *) * (n ? n : 1)));
+        if (n) TRY(cudaMemcpy(ctx->d_ref_table, ctx->d_ref.data(), sizeof(uint8_t *) * n, cudaMemcpyHostToDevice));
+        ctx->ref_dirty = false;
+    }
+    cudaEvent_t ev0, ev1, ev2;
+    TRY(cudaEventCreate(&ev0)); TRY(cudaEventCreate(&ev1)); TRY(cudaEventCreate(&ev2));
+    TRY(cudaEventRecord(ev0, st));
+    /* result buffers */
+    DALLOC(db->rstate, db->n_regions);
+    {
+        std::vector<LcrRegionState> init(db->n_regions);
+        for (uint32_t r = 0; r < db->n_regions; ++r) { memset(&init[r], 0, sizeof init[r]); init[r].status = db->extra.h_status0[r]; }
+        if (db->n_regions) TRY(cudaMemcpyAsync(db->rstate, init.data(), sizeof(LcrRegionState) * db->n_regions, cudaMemcpyHostToDevice, st));
+        TRY(cudaStreamSynchronize(st));
+    }
+    DALLOC(db->hp, db->n_reads); DALLOC(db->ps, db->n_reads); DALLOC(db->is_fragment, db->n_reads);
+    DALLOC(db->d_stats, 1);
+    DALLOC(db->slot_flags, db->n_slots);
+    TRY(cudaMemsetAsync(db->hp, 0xff, db->n_reads ? db->n_reads : 1, st));
+    TRY(cudaMemsetAsync(db->ps, 0, sizeof(uint32_t) * (db->n_reads ? db->n_reads : 1), st));
+    TRY(cudaMemsetAsync(db->is_fragment, 0, db->n_reads ? db->n_reads : 1, st));
+    TRY(cudaMemsetAsync(db->d_stats, 0, sizeof(lcr_stats), st));
+    TRY(cudaMemsetAsync(db->slot_flags, 0, db->n_slots ? db->n_slots : 1, st));
+    if (ctx->P.flags & LCR_FLAG_EMIT_PLANES) {
+        DALLOC(db->pl_acgt, db->n_pos * 4); DALLOC(db->pl_fwd, db->n_pos * 4); DALLOC(db->pl_d, db->n_pos); DALLOC(db->pl_n, db->n_pos); DALLOC(db->pl_ts, db->n_pos * 2);
+    }
+    int rc = lcr_stage_pileup_impl(ctx, db, db->slot_flags);
+    if (rc) return rc;
+    TRY(cudaEventRecord(ev1, st));
+    if (!(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) {
+        rc = stage_fragments_phase(ctx, db);
+        if (rc) return rc;
+    }
+    TRY(cudaEventRecord(ev2, st));
+    TRY(cudaStreamSynchronize(st));
+    TRY(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1); db->timing.ms_pileup = ms;
+    cudaEventElapsedTime(&ms, ev1, ev2); db->timing.ms_fragments = ms - db->timing.ms_phase;
+    cudaEventElapsedTime(&ms, ev0, ev2); db->timing.ms_total = ms;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    db->ran = true;
+    return LCR_OK;
+}
+
+int lcr_fetch(lcr_ctx *ctx, lcr_device_batch *dbb, lcr_result **out) {
+    if (!ctx || !dbb || !out) return LCR_ERR_INVALID_ARG;
+    if (ctx->sticky) return ctx->sticky;
+    lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
+    if (!db->ran) return LCR_ERR_INVALID_ARG;
+    TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ResultBox *box = new (std::nothrow) ResultBox();
+    if (!box) return LCR_ERR_OOM;
+    const uint32_t nr = db->n_regions, nreads = db->n_reads, nc = db->n_cand;
+    std::vector<LcrRegionState> hrs(nr);
+    box->cand.resize(nc);
+    box->hp.resize(nreads); box->ps.resize(nreads); box->is_fragment.resize(nreads);
+    uint64_t bytes = 0;
+    auto d2h = [&](void *dst, const void *src, size_t n) -> cudaError_t {
+        if (!n) return cudaSuccess;
+        bytes += n;
+        return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+    };
+    lcr_stats hs{};
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = d2h(hrs.data(), db->rstate, sizeof(LcrRegionState) * nr);
+    if (e == cudaSuccess) e = d2h(box->cand.data(), db->cand, sizeof(lcr_candidate) * nc);
+    if (e == cudaSuccess) e = d2h(box->hp.data(), db->hp, nreads);
+    if (e == cudaSuccess) e = d2h(box->ps.data(), db->ps, 4ull * nreads);
+    if (e == cudaSuccess) e = d2h(box->is_fragment.data(), db->is_fragment, nreads);
+    if (e == cudaSuccess) e = d2h(&hs, db->d_stats, sizeof hs);
+    const bool planes = db->pl_acgt != nullptr;
+    if (planes) {
+        const uint64_t np = db->n_pos;
+        box->acgt.resize(np * 4); box->fwd.resize(np * 4); box->d.resize(np); box->n.resize(np); box->ts.resize(np * 2);
+        if (e == cudaSuccess) e = d2h(box->acgt.data(), db->pl_acgt, 16 * np);
+        if (e == cudaSuccess) e = d2h(box->fwd.data(), db->pl_fwd, 16 * np);
+        if (e == cudaSuccess) e = d2h(box->d.data(), db->pl_d, 4 * np);
+        if (e == cudaSuccess) e = d2h(box->n.data(), db->pl_n, 4 * np);
+        if (e == cudaSuccess) e = d2h(box->ts.data(), db->pl_ts, 8 * np);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { delete box; ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
+    db->timing.d2h_bytes = bytes;
+    box->cand_off.assign(nr + 1, 0);
+    box->region_status.assign(nr, 0);
+    for (uint32_t r = 0; r < nr; ++r) {
+        box->region_status[r] = hrs[r].status;
+        box->cand_off[r + 1] = box->cand_off[r] + (hrs[r].status == 0 || true ? hrs[r].n_cand : 0);
+    }
+    lcr_result &res = box->res;
+    res.n_regions = nr; res.n_reads = nreads; res.n_cand = nc;
+    res.cand_off = box->cand_off.data();
+    res.cand = box->cand.data();
+    res.region_status = box->region_status.data();
+    res.hp = box->hp.data(); res.ps = box->ps.data(); res.is_fragment = box->is_fragment.data();
+    hs.n_positions = db->n_pos;
+    hs.n_candidates = nc;
+    hs.n_fragments = db->n_frag;
+    res.stats = hs;
+    if (planes) {
+        box->pos_off = db->h_pos_off;
+        res.planes.n_pos = db->n_pos;
+        res.planes.pos_off = box->pos_off.data();
+        res.planes.acgt = box->acgt.data(); res.planes.fwd = box->fwd.data(); res.planes.d = box->d.data();
+        res.planes.n = box->n.data(); res.planes.ts = box->ts.data();
+    }
+    if ((ctx->P.flags & LCR_FLAG_EMIT_FRAGMENTS) && !(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) {
+        const FragDebug &fd = db->extra.fragdbg;
+        const size_t nf = fd.frag_slot.size();
+        box->frag_off.assign(nr + 1, 0);
+        for (uint32_t r = 0; r < nr; ++r) box->frag_off[r + 1] = hrs[r].frag_begin + hrs[r].n_frag;
+        for (uint32_t r = 0; r < nr; ++r) box->frag_off[r + 1] = std::max(box->frag_off[r + 1], box->frag_off[r]);
+        box->frag_read.resize(nf);
+        for (size_t f = 0; f < nf; ++f) {
+            const uint32_t slot = fd.frag_slot[f];
+            const uint32_t r = (uint32_t)(std::upper_bound(db->h_slot_off.begin(), db->h_slot_off.end(), slot) - db->h_slot_off.begin()) - 1;
+            box->frag_read[f] = db->extra.h_regions[r].read_begin + (slot - db->h_slot_off[r]);
+        }
+        box->elem_off.assign(fd.frag_elem_off.begin(), fd.frag_elem_off.end());
+        if (box->elem_off.empty()) box->elem_off.push_back(0);
+        box->elem_snp = fd.elem_snp; box->elem_cell = fd.elem_cell; box->elem_base = fd.elem_base;
+        res.fragments.n_frag = nf;
+        res.fragments.n_elem = fd.elem_snp.size();
+        res.fragments.frag_off = box->frag_off.data();
+        res.fragments.frag_read = box->frag_read.data();
+        res.fragments.elem_off = box->elem_off.data();
+        res.fragments.elem_snp = box->elem_snp.data();
+        res.fragments.elem_cell = box->elem_cell.data();
+        res.fragments.elem_base = box->elem_base.data();
+    }
+    *out = &box->res;
+    return LCR_OK;
+}
+
+void lcr_free_result(lcr_result *res) {
+    if (res) delete reinterpret_cast<ResultBox *>(res);
+}
+
+void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
+    if (!ctx || !dbb) return;
+    lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
+    cudaSetDevice(ctx->device);
+    free_results(ctx, db);
+    DFREE(db->regions); DFREE(db->pos); DFREE(db->flag); DFREE(db->mapq); DFREE(db->ts); DFREE(db->de);
+    DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); DFREE(db->qual); DFREE(db->cigar);
+    DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
+    cudaStreamSynchronize(ctx->stream);
+    delete db;
+}
+
+int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out) {
+    if (!ctx || !db || !out) return LCR_ERR_INVALID_ARG;
+    *out = db->timing;
+    return LCR_OK;
+}
+
+int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
+    lcr_device_batch *db = nullptr;
+    int rc = lcr_upload(ctx, batch, &db);
+    if (rc) return rc;
+    rc = lcr_run_device(ctx, db);
+    if (!rc) rc = lcr_fetch(ctx, db, out);
+    lcr_release(ctx, db);
+    return rc;
+}
+
+} /* extern "C" */

@@ -1,0 +1,243 @@
+/*
+ * fragments.cu — read x SNP fragment matrix (CSR by read, CSC by SNP) and LD pair table.
+ *
+ * Replaces src/fragment.rs:10-309 (SNPFrag::get_fragments):
+ *   :28-54    read filter (shared with the pileup: slot_flags) and "pos > last candidate" skip
+ *   :63-80    first candidate at or after the read start
+ *   :93-194   CIGAR walk; one FragElem per candidate position on an M/=/X base
+ *   :207-240  allele-pair counts (only the pairs divide_snps_into_blocks can look at are kept:
+ *             both SNPs for_phasing and biallelic with the reference, candidate.rs:619-676)
+ *   :242-307  num_hete_links, for_phasing, snp_cover_fragments
+ *
+ * A cell is the int8 p * (baseq + 1) with baseq capped at 30 (fragment.rs:127-143).
+ */
+#include "lcr_frag.h"
+
+namespace {
+
+__device__ __forceinline__ bool ld_eligible(const lcr_candidate &c) {
+    /* candidate.rs:640-676: for_phasing, exactly one of the two alleles is the reference, no zero frequency */
+    if (!(c.flags & LCR_CF_FOR_PHASING)) return false;
+    const bool a0 = c.alleles[0] == c.reference, a1 = c.alleles[1] == c.reference;
+    if (a0 == a1) return false;
+    return c.allele_freqs[0] != 0.0f && c.allele_freqs[1] != 0.0f;
+}
+
+/* walk one read over the region's candidates; F is called for every kept element */
+template <class F>
+__device__ int walk_fragment(const FragArgs &a, uint32_t read, const lcr_candidate *c, uint32_t nc, F &&emit) {
+    const int64_t pos = a.pos[read];
+    const uint64_t c0 = a.cig_off[read], c1 = a.cig_off[read + 1];
+    const uint64_t s0 = a.seq_off[read];
+    const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
+    const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
+    uint32_t idx = 0;
+    if (!(pos <= c[0].pos)) {
+        uint32_t lo = 0, hi = nc;
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (c[m].pos < pos) lo = m + 1; else hi = m; }
+        idx = lo;
+    }
+    int64_t pr = pos;
+    int64_t pq = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (int64_t)(a.cigar[c0] >> 4) : 0;
+    for (uint64_t ci = c0; ci < c1; ++ci) {
+        const uint32_t op = a.cigar[ci], opc = op & 0xf;
+        const int64_t len = op >> 4;
+        if (opc == 4 || opc == 5) continue;
+        if (opc == 1) { pq += len; continue; }
+        const int64_t op_end = pr + len;
+        if (opc == 0 || opc == 7 || opc == 8) {
+            while (idx < nc && c[idx].pos < op_end) {
+                const int64_t qp = pq + (c[idx].pos - pr);
+                if (qp >= seq_len) return LCR_ERR_BAD_CIGAR;
+                const lcr_candidate &s = c[idx];
+                const uint8_t base = seq[qp];
+                const uint32_t rq = qual[qp];
+                const uint32_t q = rq < 30u ? rq : 30u;
+                int p;
+                if (base == s.reference) p = 1;
+                else if (base == s.alleles[0] || base == s.alleles[1]) p = -1;
+                else p = 0;
+                if (!(s.flags & LCR_CF_DENSE) && p != 0) {
+                    if (q == 0) return LCR_ERR_BASEQ_ZERO;
+                    emit(idx, base, (int8_t)(p * (int)(q + 1)), s);
+                }
+                ++idx;
+            }
+            pq += len;
+        } else if (opc == 2 || opc == 3) {
+            while (idx < nc && c[idx].pos < op_end) ++idx;
+        } else return LCR_ERR_BAD_CIGAR;
+        pr = op_end;
+    }
+    return 0;
+}
+
+__global__ void k_frag_count(FragArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_slots) return;
+    uint32_t isfrag = 0, nelem = 0;
+    if (a.slot_flags[slot]) {
+        const uint32_t reg = a.slot_region[slot];
+        const LcrRegionState rs = a.rstate[reg];
+        if (rs.status == 0 && rs.n_cand) {
+            const lcr_candidate *c = a.cand + rs.cand_begin;
+            const uint32_t read = a.regions[reg].read_begin + (slot - a.slot_off[reg]);
+            if (!((int64_t)a.pos[read] > c[rs.n_cand - 1].pos)) {
+                isfrag = 1;
+                uint32_t elig = 0;
+                const bool ld_region = rs.n_cand > a.P.max_enum_snps;
+                int rc = walk_fragment(a, read, c, rs.n_cand, [&](uint32_t idx, uint8_t, int8_t, const lcr_candidate &s) {
+                    nelem++;
+                    atomicAdd(&a.cover_count[rs.cand_begin + idx], 1u);
+                    if (ld_region && ld_eligible(s)) elig++;
+                });
+                if (rc) atomicMin(&a.rstate[reg].status, rc);
+                if (elig > 1) atomicAdd(&a.rstate[reg].n_ld_pairs_cap, elig * (elig - 1) / 2);
+            }
+        }
+    }
+    a.frag_flag[slot] = isfrag;
+    a.elem_count[slot] = nelem;
+}
+
+__global__ void k_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate) {
+    const uint32_t reg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (reg >= n_regions) return;
+    const uint32_t b = frag_scan[slot_off[reg]], e = frag_scan[slot_off[reg + 1]];
+    rstate[reg].frag_begin = b;
+    rstate[reg].n_frag = e - b;
+}
+
+__global__ void k_frag_fill(FragArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_slots || !a.frag_flag[slot]) return;
+    const uint32_t reg = a.slot_region[slot];
+    const LcrRegionState rs = a.rstate[reg];
+    const uint32_t read = a.regions[reg].read_begin + (slot - a.slot_off[reg]);
+    const uint32_t f = a.frag_scan[slot];
+    const uint32_t e0 = a.elem_scan[slot];
+    a.frag_slot[f] = slot;
+    a.frag_elem_off[f] = e0;
+    if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
+    a.is_fragment[read] = 1;
+    if (rs.status != 0 || !rs.n_cand) { a.frag_links[f] = 0; return; }
+    const lcr_candidate *c = a.cand + rs.cand_begin;
+    uint32_t k = 0, links = 0;
+    const uint32_t floc = f - rs.frag_begin;
+    walk_fragment(a, read, c, rs.n_cand, [&](uint32_t idx, uint8_t base, int8_t cell, const lcr_candidate &s) {
+        a.elem_snp[e0 + k] = idx;
+        a.elem_cell[e0 + k] = cell;
+        a.elem_base[e0 + k] = base;
+        ++k;
+        if (s.flags & LCR_CF_FOR_PHASING) links++;
+        const uint32_t g = rs.cand_begin + idx;
+        const uint32_t w = a.cover_off[g] + atomicAdd(&a.cover_cursor[g], 1u);
+        a.cover_frag[w] = floc;
+        a.cover_cell[w] = cell;
+    });
+    a.frag_links[f] = links;
+    if (links >= a.P.min_linkers && links) atomicAdd((unsigned long long *)&a.stats->nnz_phase, (unsigned long long)links);
+}
+
+/* fragment.rs:207-240 restricted to the pairs candidate.rs:628-692 evaluates: cis / trans counts per SNP pair */
+__global__ void k_pair_count(FragArgs a, LcrPairEntry *table) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.n_frag_total) return;
+    const uint32_t slot = a.frag_slot[f];
+    const uint32_t reg = a.slot_region[slot];
+    const LcrRegionState rs = a.rstate[reg];
+    if (rs.status != 0 || rs.n_cand <= a.P.max_enum_snps || !rs.pair_cap) return;
+    const lcr_candidate *c = a.cand + rs.cand_begin;
+    const uint32_t e0 = a.frag_elem_off[f], e1 = a.frag_elem_off[f + 1];
+    LcrPairEntry *tab = table + rs.pair_begin;
+    const uint32_t mask = rs.pair_cap - 1;
+    for (uint32_t x = e0; x < e1; ++x) {
+        const uint32_t i = a.elem_snp[x];
+        if (!ld_eligible(c[i])) continue;
+        const int pi = a.elem_cell[x] > 0 ? 1 : -1;
+        for (uint32_t y = x + 1; y < e1; ++y) {
+            const uint32_t j = a.elem_snp[y];
+            if (!ld_eligible(c[j])) continue;
+            const int pj = a.elem_cell[y] > 0 ? 1 : -1;
+            const unsigned long long key = ((unsigned long long)i << 32) | j;
+            uint32_t h = (uint32_t)lcr_mix64(key) & mask;
+            for (;;) {
+                unsigned long long prev = atomicCAS((unsigned long long *)&tab[h].key, ~0ull, key);
+                if (prev == ~0ull || prev == key) break;
+                h = (h + 1) & mask;
+            }
+            atomicAdd(pi * pj > 0 ? &tab[h].cis : &tab[h].trans, 1u);
+        }
+    }
+}
+
+/* candidate.rs:679-713 + snp.rs:158-188: perfect-LD pairs (min(cis, trans) == 0, |weight| >= threshold) become edges */
+template <bool FILL>
+__global__ void k_ld_edges(uint32_t ld_weight_threshold, uint32_t n_regions, const LcrRegionState *rstate, const LcrPairEntry *table, uint64_t table_size,
+                           const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= table_size) return;
+    const LcrPairEntry e = table[t];
+    if (e.key == ~0ull) return;
+    const uint32_t c1 = e.cis < e.trans ? e.cis : e.trans, c2 = e.cis < e.trans ? e.trans : e.cis;
+    if (c1 != 0 || c2 < ld_weight_threshold || c2 == 0) return;
+    const uint32_t reg = entry_region[t >> 4]; /* region of every 16-entry group (capacities are multiples of 16) */
+    const uint32_t cb = rstate[reg].cand_begin;
+    const uint32_t i = (uint32_t)(e.key >> 32), j = (uint32_t)e.key;
+    const uint32_t sign = e.cis > e.trans ? 0u : 0x80000000u; /* weight > 0: same haplotype */
+    if (!FILL) {
+        atomicAdd(&deg[cb + i], 1u);
+        atomicAdd(&deg[cb + j], 1u);
+    } else {
+        adj[adj_off[cb + i] + atomicAdd(&adj_cursor[cb + i], 1u)] = j | sign;
+        adj[adj_off[cb + j] + atomicAdd(&adj_cursor[cb + j], 1u)] = i | sign;
+    }
+}
+
+/* GraphMap adjacency order: edges are inserted in lexicographic (i, j) order, so every node's
+   neighbour list ends up ascending by neighbour index */
+__global__ void k_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const uint32_t b = adj_off[i], e = adj_off[i + 1];
+    for (uint32_t x = b + 1; x < e; ++x) {
+        const uint32_t v = adj[x];
+        uint32_t y = x;
+        while (y > b && (adj[y - 1] & 0x7fffffffu) > (v & 0x7fffffffu)) { adj[y] = adj[y - 1]; --y; }
+        adj[y] = v;
+    }
+}
+
+__global__ void k_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region) {
+    const uint32_t reg = blockIdx.x;
+    const LcrRegionState rs = rstate[reg];
+    for (uint32_t g = threadIdx.x; g < rs.pair_cap / 16; g += blockDim.x) entry_region[rs.pair_begin / 16 + g] = reg;
+}
+
+} // namespace
+
+void lcr_launch_frag_count(const FragArgs &a, cudaStream_t st) {
+    if (a.n_slots) k_frag_count<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
+}
+void lcr_launch_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate, cudaStream_t st) {
+    if (n_regions) k_region_frag_ranges<<<(n_regions + 127) / 128, 128, 0, st>>>(n_regions, slot_off, frag_scan, rstate);
+}
+void lcr_launch_frag_fill(const FragArgs &a, cudaStream_t st) {
+    if (a.n_slots) k_frag_fill<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
+}
+void lcr_launch_pair_count(const FragArgs &a, LcrPairEntry *table, cudaStream_t st) {
+    if (a.n_frag_total) k_pair_count<<<(a.n_frag_total + 127) / 128, 128, 0, st>>>(a, table);
+}
+void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrRegionState *rstate, const LcrPairEntry *table, uint64_t table_size,
+                         const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj, cudaStream_t st) {
+    if (!table_size) return;
+    const uint32_t g = (uint32_t)((table_size + 255) / 256);
+    if (fill) k_ld_edges<true><<<g, 256, 0, st>>>(thr, n_regions, rstate, table, table_size, entry_region, deg, adj_off, adj_cursor, adj);
+    else k_ld_edges<false><<<g, 256, 0, st>>>(thr, n_regions, rstate, table, table_size, entry_region, deg, adj_off, adj_cursor, adj);
+}
+void lcr_launch_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj, cudaStream_t st) {
+    if (n_cand) k_adj_sort<<<(n_cand + 127) / 128, 128, 0, st>>>(n_cand, adj_off, adj);
+}
+void lcr_launch_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region, cudaStream_t st) {
+    if (n_regions) k_fill_entry_region<<<n_regions, 128, 0, st>>>(n_regions, rstate, entry_region);
+}

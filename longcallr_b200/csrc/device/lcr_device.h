@@ -1,0 +1,132 @@
+/*
+ * lcr_device.h — internal layout of the device pipeline (sm_100a).
+ *
+ * One lcr_submit / lcr_run_device call = the per-region worker body of
+ * src/thread.rs:78-221 for every region of the batch:
+ *
+ *   slot prep        read filter + fetch window (util.rs:636-668), tile work items
+ *   tile pileup      util.rs:650-948 fused with the per-site filter cascade and
+ *                    genotype likelihood of candidate.rs:75-463
+ *   cand finalize    position sort + dense-cluster filters (candidate.rs:465-526)
+ *   fragment build   fragment.rs:28-308 (CSR by read, CSC by SNP, LD pair table)
+ *   phase            phase.rs:1087-1296 + snpfrags.rs:191-733, one CTA per region
+ *
+ * Vocabulary: a *slot* is one (region, read) pair; a *tile* is TILE consecutive
+ * positions of one region; an *item* is the part of one read that falls in one tile.
+ */
+#ifndef LCR_DEVICE_H
+#define LCR_DEVICE_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "longcallr_b200.h"
+#include "lcr_contract.h"
+
+#define LCR_TILE 512        /* positions per pileup tile == threads per pileup CTA */
+#define LCR_ROWS 64         /* read rows staged in shared memory per chunk          */
+#define LCR_CODE_NONE 7u    /* row byte: (q << 3) | code; code 0-3 ACGT, 4 other base, 5 deletion, 6 intron, 7 nothing */
+
+struct LcrItem {            /* part of one read inside one tile (20 B) */
+    uint32_t slot;          /* (region, read) pair                                  */
+    uint32_t cig;           /* CIGAR op index within the read where the tile is entered */
+    uint32_t opoff;         /* reference bases of that op already consumed          */
+    uint32_t rpos;          /* pos_in_read at the checkpoint                        */
+    int32_t fpos;           /* pos_in_freq_vec at the checkpoint                    */
+};
+
+/* per-region scalars produced on the device */
+struct LcrRegionState {
+    int32_t status;
+    uint32_t n_cand;
+    uint32_t cand_begin;    /* first candidate in the sorted candidate array        */
+    uint32_t n_frag;
+    uint32_t frag_begin;
+    uint32_t n_ld_pairs_cap; /* upper bound of LD pair instances (sum k(k-1)/2)     */
+    uint32_t pair_begin;    /* first slot of this region in the pair hash table     */
+    uint32_t pair_cap;
+};
+
+struct LcrDeviceTables {    /* what the kernels need from lcr_luts, in device-friendly form */
+    int64_t gl_fx_err[32], gl_fx_ok[32];
+    int64_t fx_err[32], fx_ok[32];
+    int64_t fx_prior_homref, fx_prior_homvar, fx_prior_het, fx_log10_2;
+    double log10_2;
+    double gl_prior_log[3];
+    float sor_threshold;
+};
+
+struct lcr_ctx {
+    lcr_params P;
+    int device;
+    cudaStream_t stream;
+    lcr_luts luts;
+    LcrDeviceTables *d_tables; /* device copy */
+    std::vector<uint8_t *> d_ref;
+    std::vector<uint64_t> ref_len;
+    uint8_t **d_ref_table;     /* device array of contig pointers */
+    uint64_t *d_ref_len;
+    int ref_table_cap;
+    bool ref_dirty;
+    std::string last_error;
+    int sticky;
+    int sm_count;
+};
+
+struct lcr_device_batch {
+    /* inputs, resident */
+    uint32_t n_regions, n_reads, n_slots, n_tiles;
+    uint64_t n_pos, n_bases, n_cigar;
+    lcr_region *regions;
+    int32_t *pos;
+    uint16_t *flag;
+    uint8_t *mapq;
+    int8_t *ts;
+    float *de;
+    uint64_t *seq_off, *cig_off;
+    uint8_t *seq, *qual;
+    uint32_t *cigar;
+    /* derived on the host at upload: cheap prefix sums over region lengths / read ranges */
+    uint32_t *slot_off;    /* [n_regions+1] */
+    uint32_t *slot_region; /* [n_slots]     */
+    uint32_t *tile_base;   /* [n_regions+1] */
+    uint32_t *tile_region; /* [n_tiles]     */
+    uint64_t *pos_off;     /* [n_regions+1] */
+    std::vector<uint64_t> h_pos_off;
+    std::vector<uint32_t> h_slot_off;
+    uint64_t h2d_bytes;
+    /* results, resident after lcr_run_device */
+    LcrRegionState *rstate;   /* [n_regions] */
+    lcr_candidate *cand;      /* [n_cand] sorted by (region, pos) */
+    uint32_t n_cand;
+    int8_t *hp;               /* [n_reads] */
+    uint32_t *ps;             /* [n_reads] */
+    uint8_t *is_fragment;     /* [n_reads] */
+    lcr_stats *d_stats;
+    /* optional debug outputs */
+    uint32_t *pl_acgt, *pl_fwd, *pl_d, *pl_n, *pl_ts;
+    uint32_t n_frag;
+    uint64_t n_elem;
+    uint32_t *fr_frag_off, *fr_frag_read, *fr_elem_snp;
+    uint64_t *fr_elem_off;
+    int8_t *fr_elem_cell;
+    uint8_t *fr_elem_base;
+    bool ran;
+    lcr_timing timing;
+};
+
+/* error plumbing */
+#define LCR_CUDA_TRY(ctx, expr)                                                         \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);    \
+            (ctx)->sticky = (e__ == cudaErrorMemoryAllocation) ? LCR_ERR_OOM : LCR_ERR_CUDA; \
+            return (ctx)->sticky;                                                       \
+        }                                                                               \
+    } while (0)
+
+#endif

@@ -1,0 +1,619 @@
+/*
+ * phase.cu — haplotype phasing of one region per CTA, all iterations on the device.
+ *
+ * Replaces:
+ *   src/phase.rs:32-49      aki                                  (aki_fx)
+ *   src/phase.rs:810-976    SNPFrag::cross_optimize              (cross_optimize)
+ *   src/phase.rs:257-276    cal_overall_probability              (objective)
+ *   src/phase.rs:600-691    init_haplotypes_LD2 / init_assignment / init_genotype
+ *   src/phase.rs:1087-1296  SNPFrag::phase                       (phase_enum / phase_ld)
+ *   src/phase.rs:1298-1394  cross_optimize_by_block              (cross_optimize_by_block)
+ *   src/snpfrags.rs:548-625 assign_reads_haplotype               (assign_reads)
+ *   src/snpfrags.rs:378-546 assign_snp_haplotype_genotype        (assign_snps)
+ *   src/snpfrags.rs:191-376 eval_rna_edit_var_phase / eval_low_frac_var_phase (rescue)
+ *   src/snpfrags.rs:628-733 assign_phase_set                     (phase_sets)
+ *
+ * All log10 sums are int64 fixed point (LCR_FX_FRAC fractional bits), so every sweep is an
+ * order-independent integer reduction: reads flip on the sign of sum(p * sigma * delta * W[q])
+ * over their heterozygous sites, SNPs pick the arg-max of four integer column sums.
+ */
+#include "lcr_frag.h"
+
+#define PB 256
+#define NONE32 0xffffffffu
+
+namespace {
+
+struct Ctx {
+    const PhaseArgs &a;
+    const LcrDeviceTables &T;
+    uint32_t reg, n, nf, cb, fb, tid;
+    lcr_candidate *c;
+    uint64_t region_key;
+    uint32_t slot0;
+    /* region views */
+    int8_t *hap, *gen, *best_hap, *best_gen, *tag, *best_tag;
+    uint8_t *phase0, *conserved, *fp, *assign;
+    uint32_t *label, *rank, *work;
+    long long *blk_q, *blk_qflip;
+    const uint32_t *frag_slot, *frag_elem_off, *frag_links, *cover_off, *adj_off;
+    long long *sh; /* shared scratch, PB/32 * 8 entries */
+    unsigned long long n_iters;
+};
+
+__device__ __forceinline__ int64_t aki_fx(const LcrDeviceTables &T, int sigma, int delta, int eta, int p, int q) {
+    const int x = eta == 0 ? sigma * delta : eta;
+    return p == x ? T.fx_ok[q] : T.fx_err[q];
+}
+__device__ __forceinline__ int cell_p(int8_t cell) { return cell > 0 ? 1 : -1; }
+__device__ __forceinline__ int cell_q(int8_t cell) { return (cell > 0 ? cell : -cell) - 1; }
+
+__device__ long long block_sum(Ctx &x, long long v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((x.tid & 31) == 0) x.sh[x.tid >> 5] = v;
+    __syncthreads();
+    long long r = 0;
+    for (int w = 0; w < PB / 32; ++w) r += x.sh[w];
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ double uniform(const Ctx &x, uint32_t stream, uint32_t call, uint32_t idx) {
+    return lcr_uniform(x.a.P.seed, x.region_key, stream, call, idx);
+}
+__device__ __forceinline__ uint32_t read_rel(const Ctx &x, uint32_t k) { return x.frag_slot[k] - x.slot0; }
+
+struct ColFx {
+    long long het_d = 0, het_nd = 0, homref = 0, homvar = 0;
+    uint32_t cov = 0;
+};
+__device__ __forceinline__ void col_add(const LcrDeviceTables &T, ColFx &c, int sigma, int delta, int p, int q) {
+    c.het_d += aki_fx(T, sigma, delta, 0, p, q);
+    c.het_nd += aki_fx(T, sigma, -delta, 0, p, q);
+    c.homref += aki_fx(T, sigma, delta, 1, p, q);
+    c.homvar += aki_fx(T, sigma, delta, -1, p, q);
+    c.cov++;
+}
+__device__ __forceinline__ void col_L(const LcrDeviceTables &T, const ColFx &c, long long L[4], long long &D) {
+    const long long ph = T.fx_prior_het - (long long)c.cov * T.fx_log10_2;
+    L[0] = c.het_d + ph;
+    L[1] = c.het_nd + ph;
+    L[2] = c.homref + T.fx_prior_homref;
+    L[3] = c.homvar + T.fx_prior_homvar;
+    D = L[3] + L[0] + L[2] + L[1];
+}
+
+/* cal_overall_probability (phase.rs:257-276) */
+__device__ long long objective(Ctx &x) {
+    long long s = 0;
+    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        if (!x.fp[k] || x.tag[k] == 0) continue;
+        const int sg = x.tag[k];
+        for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+            const uint32_t i = x.a.elem_snp[e];
+            if (!x.phase0[i]) continue;
+            const int8_t cell = x.a.elem_cell[e];
+            s += aki_fx(x.T, sg, x.hap[i], x.gen[i], cell_p(cell), cell_q(cell));
+        }
+    }
+    return block_sum(x, s);
+}
+
+/* cross_optimize (phase.rs:810-976) */
+__device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genotype) {
+    bool hg_increase = true, ht_increase = true;
+    int num_iters = 0;
+    while (hg_increase | ht_increase) {
+        x.n_iters++;
+        int better = 0;
+        /* sigma sweep (phase.rs:823-868) */
+        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+            if (!x.fp[k]) continue;
+            const int sg = x.tag[k];
+            if (sg == 0) continue;
+            long long diff = 0;
+            for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+                const uint32_t i = x.a.elem_snp[e];
+                if (!x.phase0[i] || x.gen[i] != 0) continue;
+                const int8_t cell = x.a.elem_cell[e];
+                const int q = cell_q(cell);
+                const long long W = x.T.fx_ok[q] - x.T.fx_err[q];
+                diff += (cell_p(cell) == sg * x.hap[i]) ? W : -W;
+            }
+            if (diff < 0) { x.tag[k] = (int8_t)(-sg); better = 1; }
+        }
+        better = __syncthreads_or(better);
+        if (!better) ht_increase = false;
+        else { ht_increase = true; hg_increase = true; }
+        /* delta / eta sweep (phase.rs:872-958) */
+        better = 0;
+        for (uint32_t i = x.tid; i < x.n; i += PB) {
+            if (!x.phase0[i]) continue;
+            if (keep_conserved && x.conserved[i]) continue;
+            const int d = x.hap[i], eta = x.gen[i];
+            ColFx col;
+            for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
+                const uint32_t k = x.a.cover_frag[w];
+                if (!x.fp[k] || x.tag[k] == 0) continue;
+                const int8_t cell = x.a.cover_cell[w];
+                col_add(x.T, col, x.tag[k], d, cell_p(cell), cell_q(cell));
+            }
+            if (!col.cov) continue;
+            long long L[4], D;
+            col_L(x.T, col, L, D);
+            const long long L_old = eta == 0 ? L[0] : (eta == 1 ? L[2] : L[3]);
+            long long L_new;
+            int nd = d, ne = eta;
+            if (with_genotype) {
+                long long mx = L[0] > L[1] ? L[0] : L[1];
+                const long long m2 = L[2] > L[3] ? L[2] : L[3];
+                mx = mx > m2 ? mx : m2;
+                if (L[0] == mx) { nd = d; ne = 0; L_new = L[0]; }
+                else if (L[1] == mx) { nd = -d; ne = 0; L_new = L[1]; }
+                else if (L[2] == mx) { nd = d; ne = 1; L_new = L[2]; }
+                else { nd = d; ne = -1; L_new = L[3]; }
+            } else if (eta == 0) {
+                if (L[0] >= L[1]) { nd = d; ne = 0; L_new = L[0]; } else { nd = -d; ne = 0; L_new = L[1]; }
+            } else {
+                if (L[2] >= L[3]) { nd = d; ne = 1; L_new = L[2]; } else { nd = d; ne = -1; L_new = L[3]; }
+            }
+            x.hap[i] = (int8_t)nd;
+            x.gen[i] = (int8_t)ne;
+            if (L_new > L_old) better = 1;
+        }
+        better = __syncthreads_or(better);
+        if (!better) hg_increase = false;
+        else { hg_increase = true; ht_increase = true; }
+        if (++num_iters > 20) break;
+    }
+    return objective(x);
+}
+
+__device__ void save_best(Ctx &x) {
+    for (uint32_t i = x.tid; i < x.n; i += PB) { x.best_hap[i] = x.hap[i]; x.best_gen[i] = x.gen[i]; }
+    for (uint32_t k = x.tid; k < x.nf; k += PB) x.best_tag[k] = x.tag[k];
+    __syncthreads();
+}
+__device__ void load_best(Ctx &x) {
+    for (uint32_t i = x.tid; i < x.n; i += PB) { x.hap[i] = x.best_hap[i]; x.gen[i] = x.best_gen[i]; }
+    for (uint32_t k = x.tid; k < x.nf; k += PB) x.tag[k] = x.best_tag[k];
+    __syncthreads();
+}
+__device__ void init_genotype(Ctx &x) { /* phase.rs:682-691 */
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        const int vt = x.c[i].variant_type;
+        x.gen[i] = (int8_t)(vt == 0 ? 1 : (vt == 1 ? 0 : ((vt == 2 || vt == 3) ? -1 : x.gen[i])));
+    }
+}
+__device__ void init_assignment(Ctx &x, uint32_t call) { /* phase.rs:673-680 */
+    for (uint32_t k = x.tid; k < x.nf; k += PB)
+        if (x.fp[k]) x.tag[k] = uniform(x, LCR_RNG_INIT_SIGMA, call, read_rel(x, k)) < 0.5 ? -1 : 1;
+}
+
+/* phase.rs:1097-1122: all 2^n starting haplotypes */
+__device__ void phase_enum(Ctx &x) {
+    long long best = 0;
+    bool have = false;
+    const uint32_t n_cfg = 1u << x.n;
+    for (uint32_t cfg = 0; cfg < n_cfg; ++cfg) {
+        for (uint32_t i = x.tid; i < x.n; i += PB) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
+        init_assignment(x, cfg);
+        init_genotype(x);
+        __syncthreads();
+        const long long prob = cross_optimize(x, false, true);
+        if (!have || prob > best) { best = prob; have = true; save_best(x); }
+    }
+    load_best(x);
+}
+
+/* does fragment k carry, before SNP idx in its row, an element outside the block rooted at `root`? (phase.rs:1334-1338) */
+__device__ __forceinline__ bool flip_read_of(const Ctx &x, uint32_t k, uint32_t idx, uint32_t root) {
+    for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+        const uint32_t s = x.a.elem_snp[e];
+        if (s >= idx) break;
+        if (x.label[s] != root) return false;
+    }
+    return true;
+}
+
+/* cross_optimize_by_block (phase.rs:1298-1394); block scores are sums of round((1 - L1/D) * 2^40) */
+__device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
+    for (uint32_t i = x.tid; i < x.n; i += PB) { x.blk_q[i] = 0; x.blk_qflip[i] = 0; }
+    __syncthreads();
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        const uint32_t root = x.label[i];
+        if (root == NONE32) continue;
+        const int d = x.hap[i], eta = x.gen[i];
+        ColFx c0, c1;
+        for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
+            const uint32_t k = x.a.cover_frag[w];
+            if (!x.fp[k] || x.tag[k] == 0) continue;
+            const int8_t cell = x.a.cover_cell[w];
+            const int sg = x.tag[k];
+            const int sf = flip_read_of(x, k, i, root) ? -sg : sg;
+            col_add(x.T, c0, sg, d, cell_p(cell), cell_q(cell));
+            col_add(x.T, c1, sf, -d, cell_p(cell), cell_q(cell));
+        }
+        long long L[4], D;
+        col_L(x.T, c0, L, D);
+        const double t0 = 1.0 - (double)(eta == 0 ? L[0] : (eta == 1 ? L[2] : L[3])) / (double)D;
+        col_L(x.T, c1, L, D);
+        const double t1 = 1.0 - (double)(eta == 0 ? L[0] : (eta == 1 ? L[2] : L[3])) / (double)D;
+        atomicAdd((unsigned long long *)&x.blk_q[root], (unsigned long long)__double2ll_rn(t0 * 1099511627776.0));
+        atomicAdd((unsigned long long *)&x.blk_qflip[root], (unsigned long long)__double2ll_rn(t1 * 1099511627776.0));
+    }
+    __syncthreads();
+    /* haplotags: only the last block of ld_blocks (the component of the lowest LD node) survives the
+       per-block rewrite of tmp_haplotag (phase.rs:1365-1378) */
+    if (root0 != NONE32 && x.blk_q[root0] < x.blk_qflip[root0]) {
+        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+            if (!x.fp[k] || x.tag[k] == 0) continue;
+            uint32_t best_idx = NONE32, best_rank = 0;
+            for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+                const uint32_t s = x.a.elem_snp[e];
+                if (x.label[s] != root0) continue;
+                if (best_idx == NONE32 || x.rank[s] > best_rank) { best_idx = s; best_rank = x.rank[s]; }
+            }
+            if (best_idx == NONE32) continue;
+            if (flip_read_of(x, k, best_idx, root0)) x.tag[k] = (int8_t)(-x.tag[k]);
+        }
+    }
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        const uint32_t root = x.label[i];
+        if (root != NONE32 && x.blk_q[root] < x.blk_qflip[root]) x.hap[i] = (int8_t)(-x.hap[i]);
+    }
+    __syncthreads();
+    return objective(x);
+}
+
+/* phase.rs:1123-1294: LD-seeded start, block flips, random perturbation restarts */
+__device__ void phase_ld(Ctx &x) {
+    const uint32_t *adj_off = x.adj_off;
+    const uint32_t adj_base = adj_off[0];
+    const uint32_t *adj = x.a.adj;
+    /* init_haplotypes_LD2 (phase.rs:600-652) */
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        x.hap[i] = uniform(x, LCR_RNG_INIT_DELTA, 0, i) < 0.5 ? 1 : -1;
+        x.label[i] = NONE32;
+        x.rank[i] = 0;
+        x.conserved[i] = adj_off[i + 1] > adj_off[i] ? 1 : 0;
+    }
+    __syncthreads();
+    __shared__ uint32_t s_root0;
+    if (x.tid == 0) {
+        /* Bfs from the first node of every block: a node takes its sign from the neighbour that was
+           dequeued first, which is the node that discovered it */
+        uint32_t root0 = NONE32;
+        uint32_t *queue = x.work;
+        for (uint32_t r = 0; r < x.n; ++r) {
+            if (adj_off[r + 1] == adj_off[r] || x.label[r] != NONE32) continue;
+            if (root0 == NONE32) root0 = r;
+            uint32_t qh = 0, qt = 0;
+            x.label[r] = r;
+            x.hap[r] = 1;
+            queue[qt++] = r;
+            while (qh < qt) {
+                const uint32_t nx = queue[qh++];
+                for (uint32_t w = adj_off[nx]; w < adj_off[nx + 1]; ++w) {
+                    const uint32_t v = adj[w] & 0x7fffffffu;
+                    if (x.label[v] != NONE32) continue;
+                    x.label[v] = r;
+                    x.hap[v] = (adj[w] & 0x80000000u) ? (int8_t)(-x.hap[nx]) : x.hap[nx];
+                    queue[qt++] = v;
+                }
+            }
+        }
+        /* order of block[0..] for the last block: petgraph Dfs from its first node */
+        if (root0 != NONE32) {
+            uint32_t *stack = x.work;
+            uint32_t sp = 0, order = 0;
+            stack[sp++] = root0;
+            while (sp) {
+                const uint32_t node = stack[--sp];
+                if (x.rank[node]) continue;
+                x.rank[node] = ++order;
+                for (uint32_t w = adj_off[node]; w < adj_off[node + 1]; ++w) {
+                    const uint32_t v = adj[w] & 0x7fffffffu;
+                    if (!x.rank[v]) stack[sp++] = v;
+                }
+            }
+        }
+        s_root0 = root0;
+        (void)adj_base;
+    }
+    __syncthreads();
+    const uint32_t root0 = s_root0;
+    init_genotype(x);
+    init_assignment(x, 0);
+    __syncthreads();
+    long long best = cross_optimize(x, true, false);
+    save_best(x);
+    load_best(x);
+    long long prob = cross_optimize_by_block(x, root0);
+    if (prob > best) { best = prob; save_best(x); }
+    load_best(x);
+    for (uint32_t t = 0; t <= x.n / 4; ++t) {
+        const bool flip = (t & 1u) == 1u;
+        for (uint32_t i = x.tid; i < x.n; i += PB) {
+            const double rg = uniform(x, LCR_RNG_PERTURB_DELTA, t, i);
+            if (rg < 0.1) x.hap[i] = flip ? 1 : -1;
+            else if (rg >= 0.9) x.hap[i] = flip ? -1 : 1;
+        }
+        __syncthreads();
+        prob = cross_optimize(x, false, false);
+        if (prob > best) { best = prob; save_best(x); }
+        load_best(x);
+        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+            if (!x.fp[k] || x.tag[k] == 0) continue;
+            if (uniform(x, LCR_RNG_PERTURB_SIGMA, t, read_rel(x, k)) < 0.1) x.tag[k] = (int8_t)(-x.tag[k]);
+        }
+        __syncthreads();
+        prob = cross_optimize(x, false, false);
+        if (prob > best) { best = prob; save_best(x); }
+        load_best(x);
+    }
+}
+
+/* assign_reads_haplotype (snpfrags.rs:548-625) */
+__device__ void assign_reads(Ctx &x, bool record) {
+    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        if (!x.fp[k]) continue;
+        const int sg = x.tag[k];
+        long long A = 0, B = 0;
+        uint32_t cnt = 0;
+        for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+            const lcr_candidate &s = x.c[x.a.elem_snp[e]];
+            if (!(s.flags & LCR_CF_FOR_PHASING) || s.haplotype == 0 || s.genotype != 0) continue;
+            const int8_t cell = x.a.elem_cell[e];
+            A += aki_fx(x.T, sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
+            B += aki_fx(x.T, -sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
+            cnt++;
+        }
+        int asg = 0;
+        if (sg == 0 || cnt == 0) { x.tag[k] = 0; }
+        else {
+            const double den = lcr_fx_to_f64(A + B);
+            const double q = 1.0 - lcr_fx_to_f64(A) / den;
+            const double qn = 1.0 - lcr_fx_to_f64(B) / den;
+            if (fabs(q - qn) >= x.a.P.read_assignment_cutoff) {
+                if (q >= qn) asg = sg == 1 ? 1 : 2;
+                else { asg = sg == 1 ? 2 : 1; x.tag[k] = (int8_t)(sg == 1 ? -1 : 1); }
+            } else x.tag[k] = 0;
+        }
+        x.assign[k] = (uint8_t)asg;
+        if (record) {
+            const uint32_t read = x.a.regions[x.reg].read_begin + read_rel(x, k);
+            x.a.hp[read] = (int8_t)asg;
+        }
+    }
+    __syncthreads();
+}
+
+/* -10 log10(1 - cal_phase_score_log) from three column sums (phase.rs:238-255, snpfrags.rs:483) */
+__device__ __forceinline__ double phase_score_from(long long L1, long long L2, long long L3) {
+    const double v = 1.0 - lcr_fx_to_f64(L1) / lcr_fx_to_f64(L2 + L3);
+    return -10.0 * lcr_log10(1.0 - v);
+}
+
+/* assign_snp_haplotype_genotype (snpfrags.rs:378-546) */
+__device__ void assign_snps(Ctx &x) {
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        lcr_candidate &s = x.c[i];
+        if (!(s.flags & LCR_CF_FOR_PHASING)) { s.flags |= LCR_CF_NON_SELECTED; continue; }
+        if (x.cover_off[i + 1] == x.cover_off[i]) { s.flags |= LCR_CF_SINGLE; continue; }
+        const int d = s.haplotype;
+        ColFx col;
+        long long Lp = 0, Lm = 0; /* het sums for delta = +1 / -1 */
+        int hap1 = 0, hap2 = 0;
+        for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
+            const uint32_t k = x.a.cover_frag[w];
+            if (!x.fp[k] || x.frag_links[k] < x.a.P.min_linkers) continue;
+            if (s.variant_type == 1 && x.assign[k] == 0) continue;
+            if (x.assign[k] == 1) hap1++; else if (x.assign[k] == 2) hap2++;
+            const int8_t cell = x.a.cover_cell[w];
+            const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
+            col_add(x.T, col, sg, d, p, q);
+            Lp += aki_fx(x.T, sg, 1, 0, p, q);
+            Lm += aki_fx(x.T, sg, -1, 0, p, q);
+        }
+        if (!col.cov) { s.flags |= LCR_CF_NON_SELECTED; continue; }
+        long long L[4], D;
+        col_L(x.T, col, L, D);
+        long long mx = L[0] > L[1] ? L[0] : L[1];
+        const long long m2 = L[2] > L[3] ? L[2] : L[3];
+        mx = mx > m2 ? mx : m2;
+        if (L[0] == mx) { s.haplotype = (int8_t)d; s.genotype = 0; s.variant_type = 1; }
+        else if (L[1] == mx) { s.haplotype = (int8_t)(-d); s.genotype = 0; s.variant_type = 1; }
+        else if (L[2] == mx) { s.haplotype = (int8_t)d; s.genotype = 1; s.variant_type = 0; }
+        else { s.haplotype = (int8_t)d; s.genotype = -1; if (s.variant_type != 2 && s.variant_type != 3) s.variant_type = 2; }
+        if (s.genotype != 0) { s.flags |= LCR_CF_NON_SELECTED; continue; }
+        if (hap1 >= 1 && hap2 >= 1) s.phase_score = phase_score_from(s.haplotype == 1 ? Lp : Lm, Lp, Lm);
+        else s.phase_score = 0.19940219;
+    }
+    __syncthreads();
+}
+
+/* eval_rna_edit_var_phase / eval_low_frac_var_phase (snpfrags.rs:191-376), candidates visited in list order */
+__device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
+    const float mps = x.a.P.min_phase_score - 3.0f;
+    __shared__ int s_decision;
+    for (uint32_t ti = 0; ti < x.n; ++ti) {
+        lcr_candidate &s = x.c[ti];
+        if (!(s.flags & list_flag)) continue;
+        if (x.cover_off[ti + 1] == x.cover_off[ti]) { if (x.tid == 0) s.flags |= LCR_CF_SINGLE; __syncthreads(); continue; }
+        if (s.variant_type != 1) { if (x.tid == 0) s.flags |= LCR_CF_NON_SELECTED; __syncthreads(); continue; }
+        long long Lp = 0, Lm = 0, h1 = 0, h2 = 0, cnt = 0;
+        for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += PB) {
+            const uint32_t k = x.a.cover_frag[w];
+            if (!x.fp[k] || x.assign[k] == 0 || x.frag_links[k] < x.a.P.min_linkers) continue;
+            if (x.assign[k] == 1) h1++; else if (x.assign[k] == 2) h2++;
+            const int8_t cell = x.a.cover_cell[w];
+            const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
+            Lp += aki_fx(x.T, sg, 1, 0, p, q);
+            Lm += aki_fx(x.T, sg, -1, 0, p, q);
+            cnt++;
+        }
+        Lp = block_sum(x, Lp); Lm = block_sum(x, Lm); h1 = block_sum(x, h1); h2 = block_sum(x, h2); cnt = block_sum(x, cnt);
+        if (x.tid == 0) {
+            int decision = 0;
+            if (cnt == 0 || h1 < 2 || h2 < 2) s.flags |= LCR_CF_SINGLE;
+            else {
+                const double s1 = phase_score_from(Lp, Lp, Lm), s2 = phase_score_from(Lm, Lp, Lm);
+                s.flags &= ~LCR_CF_SINGLE;
+                const double best = fmax(s1, s2);
+                if (best >= (double)mps) {
+                    s.flags &= ~(LCR_CF_NON_SELECTED | LCR_CF_RNA_EDITING);
+                    if (low_frac) s.flags &= ~LCR_CF_CAND_SOMATIC;
+                    s.flags |= LCR_CF_FOR_PHASING;
+                    s.haplotype = s1 >= s2 ? 1 : -1;
+                    s.genotype = 0;
+                    s.variant_type = 1;
+                    s.phase_score = best;
+                    decision = 1;
+                } else {
+                    s.flags |= LCR_CF_NON_SELECTED;
+                    if (low_frac) { s.flags |= LCR_CF_CAND_SOMATIC; s.flags &= ~LCR_CF_FOR_PHASING; }
+                    else s.flags |= LCR_CF_RNA_EDITING;
+                }
+            }
+            s_decision = decision;
+        }
+        __syncthreads();
+        if (s_decision) {
+            for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += PB) {
+                const uint32_t k = x.a.cover_frag[w];
+                x.fp[k] = 1;
+                if (x.tag[k] == 0 || x.assign[k] == 0) x.tag[k] = uniform(x, LCR_RNG_RESCUE_SIGMA, ti, read_rel(x, k)) < 0.5 ? -1 : 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* assign_phase_set (snpfrags.rs:628-733): a read links the nodes it sees with the same p * delta */
+__device__ void phase_sets(Ctx &x) {
+    const double mps = (double)x.a.P.min_phase_score;
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        const lcr_candidate &s = x.c[i];
+        const bool node = s.genotype == 0 && s.variant_type == 1 && !(s.flags & (LCR_CF_DENSE | LCR_CF_RNA_EDITING)) && !(s.phase_score < mps);
+        x.label[i] = node ? i : NONE32;
+    }
+    __syncthreads();
+    for (;;) {
+        int changed = 0;
+        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+            if (!x.fp[k] || x.assign[k] == 0) continue;
+            uint32_t mn[2] = {NONE32, NONE32};
+            for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+                const uint32_t i = x.a.elem_snp[e];
+                const uint32_t l = x.label[i];
+                if (l == NONE32) continue;
+                const int cls = (cell_p(x.a.elem_cell[e]) * x.c[i].haplotype) > 0 ? 0 : 1;
+                if (l < mn[cls]) mn[cls] = l;
+            }
+            for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+                const uint32_t i = x.a.elem_snp[e];
+                const uint32_t l = x.label[i];
+                if (l == NONE32) continue;
+                const int cls = (cell_p(x.a.elem_cell[e]) * x.c[i].haplotype) > 0 ? 0 : 1;
+                if (mn[cls] < l) { atomicMin(&x.label[i], mn[cls]); changed = 1; }
+            }
+        }
+        /* pointer jumping */
+        __syncthreads();
+        for (uint32_t i = x.tid; i < x.n; i += PB) {
+            uint32_t l = x.label[i];
+            if (l == NONE32) continue;
+            while (x.label[l] < l) l = x.label[l];
+            if (l < x.label[i]) { x.label[i] = l; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (uint32_t i = x.tid; i < x.n; i += PB)
+        if (x.label[i] != NONE32) x.c[i].phase_set = (uint32_t)(x.c[x.label[i]].pos + 1);
+    /* components are visited in descending order of their first node; a read keeps the first id it meets */
+    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        if (!x.fp[k] || x.assign[k] == 0) continue;
+        uint32_t cnt[2] = {0, 0}, root[2] = {0, 0}, nn = 0;
+        for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+            const uint32_t i = x.a.elem_snp[e];
+            const uint32_t l = x.label[i];
+            if (l == NONE32) continue;
+            const int cls = (cell_p(x.a.elem_cell[e]) * x.c[i].haplotype) > 0 ? 0 : 1;
+            cnt[cls]++; root[cls] = l; nn++;
+        }
+        uint32_t best = NONE32;
+        if (nn == 1) best = cnt[0] ? root[0] : root[1];
+        else {
+            if (cnt[0] >= 2) best = root[0];
+            if (cnt[1] >= 2 && (best == NONE32 || root[1] > best)) best = root[1];
+        }
+        if (best != NONE32) {
+            const uint32_t read = x.a.regions[x.reg].read_begin + read_rel(x, k);
+            x.a.ps[read] = (uint32_t)(x.c[best].pos + 1);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
+    __shared__ long long sh[PB / 32 * 2];
+    const uint32_t reg = blockIdx.x;
+    const LcrRegionState rs = a.rstate[reg];
+    if (rs.status != 0 || rs.n_cand == 0) return;
+    Ctx x{a, *a.tables};
+    x.reg = reg; x.n = rs.n_cand; x.nf = rs.n_frag; x.cb = rs.cand_begin; x.fb = rs.frag_begin; x.tid = threadIdx.x;
+    x.c = a.cand + x.cb;
+    x.region_key = lcr_region_key(a.regions[reg].tid, a.regions[reg].start);
+    x.slot0 = a.slot_off[reg];
+    x.hap = a.hap + x.cb; x.gen = a.gen + x.cb; x.best_hap = a.best_hap + x.cb; x.best_gen = a.best_gen + x.cb;
+    x.phase0 = a.phase0 + x.cb; x.conserved = a.conserved + x.cb;
+    x.label = a.label + x.cb; x.rank = a.rank + x.cb;
+    x.blk_q = a.blk_q + x.cb; x.blk_qflip = a.blk_qflip + x.cb;
+    x.tag = a.tag + x.fb; x.best_tag = a.best_tag + x.fb; x.fp = a.fp + x.fb; x.assign = a.assign + x.fb;
+    x.frag_slot = a.frag_slot + x.fb; x.frag_elem_off = a.frag_elem_off + x.fb; x.frag_links = a.frag_links + x.fb;
+    x.cover_off = a.cover_off + x.cb;
+    x.adj_off = a.adj_off ? a.adj_off + x.cb : nullptr;
+    x.work = (a.adj_off && a.work) ? a.work + (a.adj_off[x.cb] + x.cb) : nullptr;
+    x.sh = sh;
+    x.n_iters = 0;
+
+    for (uint32_t i = x.tid; i < x.n; i += PB) {
+        x.hap[i] = 0;
+        x.gen[i] = x.c[i].genotype;
+        x.phase0[i] = (x.c[i].flags & LCR_CF_FOR_PHASING) ? 1 : 0;
+        x.conserved[i] = 0;
+    }
+    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        x.tag[k] = 0;
+        x.assign[k] = 0;
+        x.fp[k] = x.frag_links[k] >= a.P.min_linkers ? 1 : 0;
+    }
+    __syncthreads();
+    uint64_t n_calls;
+    if (x.n <= a.P.max_enum_snps) { phase_enum(x); n_calls = 1ull << x.n; }
+    else { phase_ld(x); n_calls = 1ull + 2ull * (x.n / 4 + 1); }
+    for (uint32_t i = x.tid; i < x.n; i += PB) { x.c[i].haplotype = x.hap[i]; x.c[i].genotype = x.gen[i]; }
+    __syncthreads();
+    /* thread.rs:168-201 */
+    assign_reads(x, false);
+    assign_snps(x);
+    assign_reads(x, false);
+    assign_snps(x);
+    rescue(x, LCR_CF_EDIT_LIST, false);
+    rescue(x, LCR_CF_SOMATIC_LIST, true);
+    assign_reads(x, true);
+    assign_snps(x);
+    phase_sets(x);
+    if (x.tid == 0) {
+        atomicAdd((unsigned long long *)&a.stats->n_cross_optimize, (unsigned long long)n_calls);
+        atomicAdd((unsigned long long *)&a.stats->n_sweep_iters, x.n_iters);
+    }
+}
+
+} // namespace
+
+void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st) {
+    if (a.n_regions) k_phase<<<a.n_regions, PB, 0, st>>>(a);
+}

@@ -1142,6 +1142,7 @@ struct Worker {
             std::unordered_set<uint32_t> block_set(block.begin(), block.end());
             std::unordered_map<uint32_t, int> flip_map;
             double q = 0, q_flip = 0;
+            int64_t qfx = 0, qfx_flip = 0; /* contract: sums of round(term * 2^40), order-independent */
             for (uint32_t idx : block) {
                 const int d = cands[idx].haplotype, e = cands[idx].genotype;
                 sigma.clear(); sigma_flip.clear(); ps.clear(); qs.clear();
@@ -1171,14 +1172,14 @@ struct Worker {
                         const int64_t L1 = e == 0 ? L[0] : (e == 1 ? L[2] : L[3]);
                         return 1.0 - (double)L1 / (double)D;
                     };
-                    q += term(c0);
-                    q_flip += term(c1);
+                    qfx += (int64_t)llrint(term(c0) * 1099511627776.0);
+                    qfx_flip += (int64_t)llrint(term(c1) * 1099511627776.0);
                 } else {
                     q += cal_delta_eta_sigma_log(d, e, sigma, ps, qs);
                     q_flip += cal_delta_eta_sigma_log(-d, e, sigma_flip, ps, qs);
                 }
             }
-            if (q < q_flip) {
+            if (FX ? qfx < qfx_flip : q < q_flip) {
                 for (uint32_t idx : block) { tmp_haplotype[idx] = -cands[idx].haplotype; has_haplotype[idx] = 1; }
                 for (size_t k = 0; k < frags.size(); ++k) {
                     auto it = flip_map.find((uint32_t)k);
