@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — aligned bases piled-up + het-SNP fragment alleles phased per second (BASELINE.json metric).
+
+One step = one pass of the whole hot path (read filter, tile pileup + site genotyping, fragment
+matrix, phasing, read/SNP assignment, phase sets) over one synthetic batch.
+
+  value   device-resident: inputs already in HBM, lcr_run_device timed with CUDA events on the
+          library's own stream (lcr_get_timing), L2 flushed between steps
+  e2e     the same pass through lcr_submit with pinned HOST buffers: H2D of the decoded reads,
+          the run, D2H of candidates / HP / PS, timed by wall clock around the call
+  --impl reference   the reference's CPU algorithm (the line-faithful C++ port in oracle/, mode 1;
+          the Rust crate cannot be built here) on all host cores, same workload and metric
+
+Multi-GPU (torchrun): contigs shard across ranks (weak scaling, one synthetic contig per rank);
+rank 0 broadcasts the packed reference over NCCL and gathers the per-region candidate records.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: synthetic 1 Mb contig, 30x ONT-cDNA, ~1k het SNPs
+    "cfg2": dict(preset="ont-cdna", synth=dict(contig_len=1_000_000, n_contigs=1, platform=1, depth=30.0, n_het=1000, n_edit=200, max_intron=300, max_gap=600, both_strands=1)),
+    # configs[2]: synthetic chr20 (64 Mb), 30x HiFi MAS-Seq, ~50k candidate sites
+    "cfg3": dict(preset="hifi-masseq", synth=dict(contig_len=64_000_000, n_contigs=1, platform=0, depth=30.0, n_het=40000, n_edit=10000, max_intron=300, max_gap=600, both_strands=0)),
+    # configs[4]: phasing stress, 500 kb gene-dense block at 500x, 5k het SNPs
+    "cfg5": dict(preset="hifi-masseq", synth=dict(contig_len=500_000, n_contigs=1, platform=0, depth=500.0, n_het=5000, n_edit=0, max_intron=500, max_gap=600, both_strands=0, single_region=1)),
+    # small case for quick checks
+    "tiny": dict(preset="hifi-masseq", synth=dict(contig_len=100_000, n_contigs=1, platform=0, depth=30.0, n_het=100, n_edit=20, max_intron=300, max_gap=600, both_strands=0)),
+}
+METRIC = "aligned bases piled-up + het-SNP fragments phased /sec (synthetic 30x)"
+UNIT = "bases+alleles/s"
+SEED = 20251017
+
+
+def sample_clocks(stop, out, gpu_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": reasons}
+
+
+def make_workload(name, rank):
+    from longcallr_b200 import host
+
+    w = WORKLOADS[name]
+    syn = host.Synthetic(seed=SEED + 7919 * rank, **w["synth"])
+    p = host.params_preset(w["preset"], seed=SEED)
+    regions, _ = host.find_regions(syn.reads, p)
+    return w, syn, p, regions
+
+
+def bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s):
+    """How many leading regions the CPU port can process in about budget_s seconds (probe on 16 regions)."""
+    probe_n = max(1, min(len(regions), 16))
+    t0 = time.perf_counter()
+    r = ob.run(p, host.BatchView(syn.reads, regions[:probe_n]), refs, mode=1, threads=cores)
+    dt = max(time.perf_counter() - t0, 1e-9)
+    units = max(r.stats["n_aligned_bases"] + r.stats["nnz_phase"], 1)
+    est_total_s = dt * len(regions) / probe_n
+    if est_total_s <= budget_s:
+        return len(regions)
+    return max(probe_n, int(len(regions) * budget_s / est_total_s))
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference algorithm (oracle port, reference-order f64 mode) on all host cores."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from longcallr_b200 import host
+
+    w, syn, p, regions = make_workload(args.workload, 0)
+    batch = host.BatchView(syn.reads, regions)
+    refs = syn.reference.for_reads(syn.reads)
+    cores = os.cpu_count() or 1
+    n_sample = bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s=8.0)
+    sb = host.BatchView(syn.reads, regions[:n_sample])
+    for _ in range(args.warmup):
+        ob.run(p, sb, refs, mode=1, threads=cores)
+    t0 = time.perf_counter()
+    units = 0
+    for _ in range(args.steps):
+        r = ob.run(p, sb, refs, mode=1, threads=cores)
+        units += r.stats["n_aligned_bases"] + r.stats["nnz_phase"]
+    dt = time.perf_counter() - t0
+    value = units / dt
+    sample = f"{n_sample} of {len(regions)} regions of {args.workload} per step ({units // max(args.steps, 1)} units), C++ port of the reference loops, {cores} threads over regions"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64",
+        "data": "synthetic", "config": {"workload": args.workload, **WORKLOADS[args.workload]["synth"], "preset": w["preset"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from longcallr_b200 import abi, host
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w, syn, p, regions = make_workload(args.workload, rank)
+    refs = syn.reference.for_reads(syn.reads)
+
+    # reference slice: rank 0 packs every rank's contig and broadcasts it once over NCCL (north_star);
+    # each rank keeps its own contig.  Contig lengths are equal by construction (weak scaling).
+    ref_np = np.ascontiguousarray(refs[0])
+    if world > 1:
+        L = int(ref_np.size)
+        packed = torch.empty(world * L, dtype=torch.uint8, device="cuda")
+        mine = torch.from_numpy(ref_np).cuda()
+        parts = [torch.empty(L, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            packed.copy_(torch.cat(parts))
+        dist.broadcast(packed, src=0)
+        got = packed[rank * L:(rank + 1) * L].cpu().numpy()
+        assert np.array_equal(got, ref_np), "reference broadcast mismatch"
+        ref_np = got
+        del packed, parts
+
+    eng = host.Engine(p, device=local_rank)
+    eng.set_reference(0, ref_np)
+
+    # pinned staging buffers for the end-to-end path
+    pinned_keep = []
+
+    def alloc_pinned(nbytes):
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        pinned_keep.append(t)
+        return t.numpy()
+
+    pinned_reads = host.ArrayReadSet.like(syn.reads, alloc_pinned)
+    batch = host.BatchView(pinned_reads, regions)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        flush.add_(1)
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    handle = eng.upload(batch)
+    for _ in range(args.warmup):
+        eng.run_device(handle)
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop, samples, local_rank), daemon=True)
+    barrier()
+    th.start()
+    dev_ms, pile_ms, pile_bytes, launches = 0.0, 0.0, 0, 0
+    phase_ms, frag_ms = 0.0, 0.0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        eng.run_device(handle)
+        t = eng.timing(handle)
+        dev_ms += t["ms_total"]
+        pile_ms += t["ms_pileup_kernel"]
+        phase_ms += t["ms_phase"]
+        frag_ms += t["ms_fragments"]
+        pile_bytes += t["pileup_alg_bytes"]
+        launches += t["kernel_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    stop.set()
+    th.join()
+    res = eng.fetch(handle)
+    eng.release(handle)
+    units = res.stats["n_aligned_bases"] + res.stats["nnz_phase"]
+
+    # ---- end to end through lcr_submit with host buffers ----
+    for _ in range(2):
+        r = eng.submit_raw(batch)
+        eng.free_result(r)
+    barrier()
+    e2e_t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        flush_l2()
+        h = eng.upload(batch)
+        eng.run_device(h)
+        rr = eng.fetch(h)
+        tt = eng.timing(h)
+        h2d, d2h = tt["h2d_bytes"], tt["d2h_bytes"]
+        eng.release(h)
+    barrier()
+    e2e_ms = (time.perf_counter() - e2e_t0) * 1e3
+    n_cand_total = rr.n_cand
+    if world > 1:
+        # gather of per-region VCF records to rank 0 (fixed 88-byte candidate records, padded to the max count)
+        cnt = torch.tensor([rr.n_cand], device="cuda", dtype=torch.int64)
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        mx = int(max(int(c.item()) for c in cnts))
+        rec = torch.zeros(mx * abi.CANDIDATE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        raw = torch.from_numpy(np.frombuffer(rr.cand.tobytes(), dtype=np.uint8).copy()).cuda()
+        rec[: raw.numel()] = raw
+        outl = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
+        dist.gather(rec, outl, dst=0)
+        n_cand_total = int(sum(int(c.item()) for c in cnts))
+
+    # max over ranks
+    tvals = torch.tensor([dev_ms, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(tvals[0]), float(tvals[1])
+    uvals = torch.tensor([units], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(uvals, op=dist.ReduceOp.SUM)
+    total_units = float(uvals[0])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = (pile_bytes / 1e9) / (pile_ms / 1e3) if pile_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": total_units * args.steps / (dev_ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64 fixed-point (f64 for QUAL)",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "preset": w["preset"], **w["synth"], "regions_per_gpu": int(len(regions)), "reads_per_gpu": int(syn.reads.n_reads),
+                       "aligned_bases_per_gpu": int(res.stats["n_aligned_bases"]), "phase_alleles_per_gpu": int(res.stats["nnz_phase"]),
+                       "candidates": int(n_cand_total), "cross_optimize_calls": int(res.stats["n_cross_optimize"]), "sweep_iters": int(res.stats["n_sweep_iters"]),
+                       "l2": "flushed between steps (512 MiB write)", "sharding": "one contig per rank, no data-path collective"},
+            "e2e": {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks_summary(samples),
+            "roofline": {"kernel": "k_pileup_tile", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "alg_bytes_per_launch": int(pile_bytes / max(args.steps, 1)), "ms_per_launch": pile_ms / max(args.steps, 1)},
+            "stage_ms_per_step": {"pileup_kernel": pile_ms / args.steps, "fragments": frag_ms / args.steps, "phase": phase_ms / args.steps, "total": dev_ms / args.steps},
+        }
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_binding as ob
+
+            cores = os.cpu_count() or 1
+            n_sample = bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s=15.0)
+            cb = host.BatchView(syn.reads, regions[:n_sample])
+            t0 = time.perf_counter()
+            r1 = ob.run(p, cb, refs, mode=1, threads=cores)
+            dt = time.perf_counter() - t0
+            cu = r1.stats["n_aligned_bases"] + r1.stats["nnz_phase"]
+            out["cpu_baseline"] = {"value": cu / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"first {n_sample} of {len(regions)} regions of {args.workload} once ({cu} units, {dt:.2f} s), C++ port of the reference loops (oracle mode 1), {cores} threads over regions"}
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

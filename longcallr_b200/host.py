@@ -143,6 +143,31 @@ class ReadSet:
             self._ptr = None
 
 
+class ArrayReadSet:
+    """A read set over caller-owned numpy arrays (same attributes as ReadSet); used for pinned staging buffers."""
+
+    FIELDS = (("tid", "<i4"), ("pos", "<i4"), ("flag", "<u2"), ("mapq", "u1"), ("ts", "i1"), ("de", "<f4"),
+              ("seq_off", "<u8"), ("cig_off", "<u8"), ("seq", "u1"), ("qual", "u1"), ("cigar", "<u4"))
+
+    def __init__(self, contig_names, contig_lens, **arrays):
+        self.contig_names = list(contig_names)
+        self.contig_lens = np.asarray(contig_lens, dtype="<u8")
+        for name, dt in self.FIELDS:
+            setattr(self, name, np.ascontiguousarray(arrays[name], dtype=dt))
+        self.n_reads = len(self.pos)
+
+    @classmethod
+    def like(cls, reads, alloc):
+        """Copy `reads` into buffers obtained from alloc(nbytes) -> writable uint8 numpy array (e.g. pinned memory)."""
+        arrays = {}
+        for name, dt in cls.FIELDS:
+            src = np.ascontiguousarray(getattr(reads, name), dtype=dt)
+            buf = alloc(max(src.nbytes, 1))[: src.nbytes].view(dt)
+            buf[...] = src
+            arrays[name] = buf
+        return cls(reads.contig_names, reads.contig_lens, **arrays)
+
+
 class Reference:
     """FASTA contigs, bytes as in the file (src/util.rs:214-222)."""
 
@@ -180,7 +205,7 @@ class Synthetic:
     def __init__(self, **kw):
         cfg = abi.SynthConfig()
         defaults = dict(seed=20251017, contig_len=1_000_000, n_contigs=1, platform=1, depth=30.0, n_het=1000, n_edit=0,
-                        max_exons=6, max_intron=20000, both_strands=1, single_region=0, n_threads=os.cpu_count() or 1)
+                        max_exons=6, max_intron=20000, max_gap=3000, both_strands=1, single_region=0, n_threads=os.cpu_count() or 1)
         defaults.update(kw)
         for k, v in defaults.items():
             setattr(cfg, k, v)
@@ -206,10 +231,27 @@ class Synthetic:
             self._ptr = None
 
 
+def reads_struct(reads):
+    """An lcr_reads view of any read set (the returned object keeps the arrays alive)."""
+    if isinstance(reads, ReadSet):
+        return reads._ptr
+    r = abi.Reads()
+    names = (C.c_char_p * len(reads.contig_names))(*[n.encode() for n in reads.contig_names])
+    lens = np.ascontiguousarray(reads.contig_lens, dtype="<u8")
+    r.n_reads = reads.n_reads
+    r.n_contigs = len(reads.contig_names)
+    r.contig_names = names
+    r.contig_lens = lens.ctypes.data
+    for name, _ in ArrayReadSet.FIELDS:
+        setattr(r, name, getattr(reads, name).ctypes.data)
+    r._keep = (names, lens, reads)
+    return C.pointer(r)
+
+
 def find_regions(reads, params, truncation=False, truncation_coverage=200000):
     """Isolated regions (src/util.rs:236-332) with the read range of each; numpy REGION_DTYPE array."""
     out = C.POINTER(abi.RegionList)()
-    rc = host_lib().lcr_host_find_regions(reads._ptr, C.byref(params), int(truncation), truncation_coverage, C.byref(out))
+    rc = host_lib().lcr_host_find_regions(reads_struct(reads), C.byref(params), int(truncation), truncation_coverage, C.byref(out))
     if rc:
         raise LcrError(rc, "lcr_host_find_regions")
     n = out.contents.n_regions

@@ -13,24 +13,9 @@ FP_FIELDS = ("variant_quality", "genotype_quality", "phase_score", "genotype_pro
 FP_TOL = 1e-5  # north_star: "within 1e-5 on FP likelihood/QUAL fields"
 
 
-class ArrayReads:
-    """A read set backed by plain numpy arrays (same attributes as host.ReadSet)."""
-
-    def __init__(self, contig_names, contig_lens, tid, pos, flag, mapq, ts, de, seq_off, cig_off, seq, qual, cigar):
-        self.contig_names = list(contig_names)
-        self.contig_lens = np.asarray(contig_lens, dtype="<u8")
-        self.tid = np.ascontiguousarray(tid, dtype="<i4")
-        self.pos = np.ascontiguousarray(pos, dtype="<i4")
-        self.flag = np.ascontiguousarray(flag, dtype="<u2")
-        self.mapq = np.ascontiguousarray(mapq, dtype="u1")
-        self.ts = np.ascontiguousarray(ts, dtype="i1")
-        self.de = np.ascontiguousarray(de, dtype="<f4")
-        self.seq_off = np.ascontiguousarray(seq_off, dtype="<u8")
-        self.cig_off = np.ascontiguousarray(cig_off, dtype="<u8")
-        self.seq = np.ascontiguousarray(seq, dtype="u1")
-        self.qual = np.ascontiguousarray(qual, dtype="u1")
-        self.cigar = np.ascontiguousarray(cigar, dtype="<u4")
-        self.n_reads = len(self.pos)
+def ArrayReads(contig_names, contig_lens, tid, pos, flag, mapq, ts, de, seq_off, cig_off, seq, qual, cigar):
+    return host.ArrayReadSet(contig_names, contig_lens, tid=tid, pos=pos, flag=flag, mapq=mapq, ts=ts, de=de, seq_off=seq_off,
+                             cig_off=cig_off, seq=seq, qual=qual, cigar=cigar)
 
 
 def cigar_ops(s):
@@ -99,7 +84,7 @@ def compare_results(a, b, what=""):
         same_inf = np.isinf(x) & np.isinf(y) & (np.sign(x) == np.sign(y))
         ok = same_inf | (np.abs(x - y) <= FP_TOL) | (np.isnan(x) & np.isnan(y))
         assert ok.all(), f"{what} cand.{f}: max diff {np.nanmax(np.abs(x - y)[~same_inf])}"
-        inexact += int((a.cand[f].view(np.uint8) != b.cand[f].view(np.uint8)).any())
+        inexact += int((np.ascontiguousarray(a.cand[f]).view(np.uint8) != np.ascontiguousarray(b.cand[f]).view(np.uint8)).any())
     np.testing.assert_array_equal(a.hp, b.hp, err_msg=what + " hp")
     np.testing.assert_array_equal(a.ps, b.ps, err_msg=what + " ps")
     np.testing.assert_array_equal(a.is_fragment, b.is_fragment, err_msg=what + " is_fragment")
