@@ -75,6 +75,11 @@ int h2d(lcr_ctx *ctx, T **dst, const T *src, size_t n, uint64_t *bytes) {
     return 0;
 }
 
+__global__ void k_scatter_winners(uint32_t n, const uint32_t *slot, const long long *prob, const uint32_t *cfg, long long *out_prob, uint32_t *out_cfg) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out_prob[slot[i]] = prob[i]; out_cfg[slot[i]] = cfg[i]; }
+}
+
 __global__ void k_init_pairs(LcrPairEntry *t, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { t[i].key = ~0ull; t[i].cis = 0; t[i].trans = 0; }
@@ -134,6 +139,8 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     if ((rc = exclusive_scan_u32(ctx, elem_count, elem_scan, (size_t)n_slots + 1))) return rc;
     if ((rc = exclusive_scan_u32(ctx, cover_count, cover_off, (size_t)n_cand + 1))) return rc;
     db->timing.kernel_launches += 1; /* own kernels only; cub scans are library code */
+    lcr_launch_region_frag_ranges(n_regions, db->slot_off, frag_scan, db->rstate, st);
+    db->timing.kernel_launches += 1;
     uint32_t n_frag_total = 0, n_elem_total = 0;
     std::vector<LcrRegionState> hrs(n_regions);
     TRY(cudaMemcpyAsync(&n_frag_total, frag_scan + n_slots, 4, cudaMemcpyDeviceToHost, st));
@@ -155,8 +162,6 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
         table_size += cap;
     }
     TRY(cudaMemcpyAsync(db->rstate, hrs.data(), sizeof(LcrRegionState) * n_regions, cudaMemcpyHostToDevice, st));
-    lcr_launch_region_frag_ranges(n_regions, db->slot_off, frag_scan, db->rstate, st);
-    db->timing.kernel_launches += 1;
     db->n_frag = n_frag_total;
     db->n_elem = n_elem_total;
     DALLOC(frag_slot, (size_t)n_frag_total + 1);
@@ -225,6 +230,70 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     DALLOC(pa.blk_q, n_cand); DALLOC(pa.blk_qflip, n_cand);
     DALLOC(pa.tag, n_frag_total); DALLOC(pa.best_tag, n_frag_total); DALLOC(pa.fp, n_frag_total); DALLOC(pa.assign, n_frag_total);
     pa.hp = db->hp; pa.ps = db->ps;
+    /* enumeration search (regions with at most min(max_enum_snps, 10) candidates): one warp per configuration */
+    uint32_t *es_base = nullptr, *es_cfg = nullptr, *work_region = nullptr, *work_chunk = nullptr;
+    long long *es_prob = nullptr;
+    {
+        const uint32_t per_cta = lcr_enum_cfgs_per_cta();
+        const uint32_t NF_SMALL = 2048, NF_BIG = 16384;
+        std::vector<uint32_t> base(n_regions + 1, 0), wr[2], wc[2];
+        uint32_t nfmax[2] = {0, 0};
+        std::vector<uint32_t> bin(n_regions, 2);
+        for (uint32_t r = 0; r < n_regions; ++r) {
+            const LcrRegionState &s = hrs[r];
+            uint32_t chunks = 0;
+            if (s.status == 0 && s.n_cand && s.n_cand <= ctx->P.max_enum_snps && s.n_cand <= 10 && s.n_frag <= NF_BIG) {
+                chunks = ((1u << s.n_cand) + per_cta - 1) / per_cta;
+                bin[r] = s.n_frag <= NF_SMALL ? 0 : 1;
+            }
+            base[r + 1] = base[r] + chunks;
+        }
+        /* work items of one bin are contiguous in launch order; outputs are addressed through a per-item slot */
+        std::vector<uint32_t> slot_of;
+        const uint32_t n_work_total = base[n_regions];
+        if (n_work_total) {
+            std::vector<uint32_t> all_region, all_chunk, out_slot;
+            for (int b = 0; b < 2; ++b)
+                for (uint32_t r = 0; r < n_regions; ++r)
+                    if (bin[r] == (uint32_t)b) {
+                        nfmax[b] = std::max(nfmax[b], hrs[r].n_frag);
+                        for (uint32_t ck = 0; ck < base[r + 1] - base[r]; ++ck) { wr[b].push_back(r); wc[b].push_back(ck); }
+                    }
+            DALLOC(es_base, (size_t)n_regions + 1);
+            DALLOC(es_cfg, n_work_total);
+            DALLOC(es_prob, n_work_total);
+            DALLOC(work_region, n_work_total);
+            DALLOC(work_chunk, n_work_total);
+            TRY(cudaMemcpyAsync(es_base, base.data(), sizeof(uint32_t) * (n_regions + 1), cudaMemcpyHostToDevice, st));
+            /* launch bin by bin; each bin writes its winners into a scratch in launch order, scattered afterwards */
+            uint32_t off = 0;
+            std::vector<uint32_t> order_region, order_chunk;
+            for (int b = 0; b < 2; ++b) { order_region.insert(order_region.end(), wr[b].begin(), wr[b].end()); order_chunk.insert(order_chunk.end(), wc[b].begin(), wc[b].end()); }
+            TRY(cudaMemcpyAsync(work_region, order_region.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
+            TRY(cudaMemcpyAsync(work_chunk, order_chunk.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
+            long long *tmp_prob = nullptr;
+            uint32_t *tmp_cfg = nullptr, *d_slot = nullptr;
+            DALLOC(tmp_prob, n_work_total);
+            DALLOC(tmp_cfg, n_work_total);
+            DALLOC(d_slot, n_work_total);
+            std::vector<uint32_t> slot(n_work_total);
+            for (uint32_t i = 0; i < n_work_total; ++i) slot[i] = base[order_region[i]] + order_chunk[i];
+            TRY(cudaMemcpyAsync(d_slot, slot.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
+            TRY(cudaStreamSynchronize(st)); /* the host vectors above go out of scope */
+            for (int b = 0; b < 2; ++b) {
+                const uint32_t nw = (uint32_t)wr[b].size();
+                if (!nw) continue;
+                int e = lcr_launch_enum_search(pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, st);
+                if (e) { ctx->last_error = "k_enum_search launch failed"; ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
+                db->timing.kernel_launches += 1;
+                off += nw;
+            }
+            k_scatter_winners<<<(n_work_total + 127) / 128, 128, 0, st>>>(n_work_total, d_slot, tmp_prob, tmp_cfg, es_prob, es_cfg);
+            db->timing.kernel_launches += 1;
+            DFREE(tmp_prob); DFREE(tmp_cfg); DFREE(d_slot);
+            pa.es_base = es_base; pa.es_prob = es_prob; pa.es_cfg = es_cfg;
+        }
+    }
     lcr_launch_phase(pa, st);
     db->timing.kernel_launches += 1;
     cudaEvent_t ev_end;
@@ -259,6 +328,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     DFREE(pa.hap); DFREE(pa.gen); DFREE(pa.best_hap); DFREE(pa.best_gen); DFREE(pa.phase0); DFREE(pa.conserved);
     DFREE(pa.label); DFREE(pa.rank); DFREE(pa.work); DFREE(pa.blk_q); DFREE(pa.blk_qflip);
     DFREE(pa.tag); DFREE(pa.best_tag); DFREE(pa.fp); DFREE(pa.assign);
+    DFREE(es_base); DFREE(es_cfg); DFREE(es_prob); DFREE(work_region); DFREE(work_chunk);
     return LCR_OK;
 }
 

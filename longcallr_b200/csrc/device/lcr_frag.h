@@ -71,6 +71,10 @@ struct PhaseArgs {
     /* outputs per read */
     int8_t *hp;
     uint32_t *ps;
+    /* winners of the warp-per-configuration enumeration search (phase_enum.cu), per (region, chunk) */
+    const uint32_t *es_base; /* [n_regions+1] or null */
+    const long long *es_prob;
+    const uint32_t *es_cfg;
 };
 
 void lcr_launch_frag_count(const FragArgs &a, cudaStream_t st);
@@ -82,5 +86,9 @@ void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrR
 void lcr_launch_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj, cudaStream_t st);
 void lcr_launch_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region, cudaStream_t st);
 void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st);
+size_t lcr_enum_smem_bytes(uint32_t nf_cap);
+uint32_t lcr_enum_cfgs_per_cta();
+int lcr_launch_enum_search(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+                           long long *out_prob, uint32_t *out_cfg, cudaStream_t st);
 
 #endif

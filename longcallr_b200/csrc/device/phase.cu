@@ -192,7 +192,23 @@ __device__ void init_assignment(Ctx &x, uint32_t call) { /* phase.rs:673-680 */
 }
 
 /* phase.rs:1097-1122: all 2^n starting haplotypes */
-__device__ void phase_enum(Ctx &x) {
+__device__ bool phase_enum(Ctx &x) {
+    /* the search kernel already ran every configuration: replay the winner only */
+    if (x.a.es_base && x.a.es_base[x.reg + 1] > x.a.es_base[x.reg]) {
+        long long bp = 0;
+        uint32_t cfg = NONE32;
+        for (uint32_t w = x.a.es_base[x.reg]; w < x.a.es_base[x.reg + 1]; ++w) {
+            const uint32_t cw = x.a.es_cfg[w];
+            if (cw == NONE32) continue;
+            if (cfg == NONE32 || x.a.es_prob[w] > bp || (x.a.es_prob[w] == bp && cw < cfg)) { bp = x.a.es_prob[w]; cfg = cw; }
+        }
+        for (uint32_t i = x.tid; i < x.n; i += PB) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
+        init_assignment(x, cfg);
+        init_genotype(x);
+        __syncthreads();
+        cross_optimize(x, false, true);
+        return true;
+    }
     long long best = 0;
     bool have = false;
     const uint32_t n_cfg = 1u << x.n;
@@ -205,6 +221,7 @@ __device__ void phase_enum(Ctx &x) {
         if (!have || prob > best) { best = prob; have = true; save_best(x); }
     }
     load_best(x);
+    return false;
 }
 
 /* does fragment k carry, before SNP idx in its row, an element outside the block rooted at `root`? (phase.rs:1334-1338) */
@@ -592,7 +609,8 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     }
     __syncthreads();
     uint64_t n_calls;
-    if (x.n <= a.P.max_enum_snps) { phase_enum(x); n_calls = 1ull << x.n; }
+    bool counted_elsewhere = false;
+    if (x.n <= a.P.max_enum_snps) { counted_elsewhere = phase_enum(x); n_calls = 1ull << x.n; }
     else { phase_ld(x); n_calls = 1ull + 2ull * (x.n / 4 + 1); }
     for (uint32_t i = x.tid; i < x.n; i += PB) { x.c[i].haplotype = x.hap[i]; x.c[i].genotype = x.gen[i]; }
     __syncthreads();
@@ -606,7 +624,7 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     assign_reads(x, true);
     assign_snps(x);
     phase_sets(x);
-    if (x.tid == 0) {
+    if (x.tid == 0 && !counted_elsewhere) {
         atomicAdd((unsigned long long *)&a.stats->n_cross_optimize, (unsigned long long)n_calls);
         atomicAdd((unsigned long long *)&a.stats->n_sweep_iters, x.n_iters);
     }

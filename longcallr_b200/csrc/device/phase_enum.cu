@@ -1,0 +1,253 @@
+/*
+ * phase_enum.cu — the 2^n starting-haplotype enumeration of SNPFrag::phase (src/phase.rs:1097-1122),
+ * one warp per configuration.
+ *
+ * Every configuration is an independent cross_optimize run (src/phase.rs:810-976) from its own
+ * random haplotags, so the 2^n runs of a region spread over warps and CTAs; only the winning
+ * configuration index comes back (strict `>` in enumeration order == highest objective, lowest
+ * index on ties) and k_phase replays that single configuration to materialise the state.
+ *
+ * The region's fragment matrix is staged once per CTA in shared memory as one 64-bit word per
+ * read (n <= 10 sites x 6 bits: sign and capped quality + 1), haplotags are one bit per read per
+ * warp, SNP state lives in registers.  With sigma, delta, p in {-1, +1}:
+ *   read k flips to   sign( sum_i p_ki * delta_i * W_ki )      over its heterozygous phase sites
+ *   site i compares   C_i +- delta_i * M_i  (M_i = sum_k p_ki * sigma_k * W_ki), R_i, V_i
+ * where W = log10(1 - eps) - log10(eps) in fixed point and C, R, V are per-column constants.
+ */
+#include "lcr_frag.h"
+
+#define EW 8            /* warps per CTA */
+#define ECFG_PER_WARP 8 /* configurations per warp */
+#define EMAXN 10
+
+namespace {
+
+struct EnumShared {
+    long long W[32], OK[32], ERR[32];
+    long long C[EMAXN], R[EMAXN], V[EMAXN];
+    uint32_t cov[EMAXN];
+    long long best_prob[EW];
+    uint32_t best_cfg[EW];
+    unsigned long long iters[EW];
+};
+
+__global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+                                                         long long *out_prob, uint32_t *out_cfg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ EnumShared S;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t reg = work_region[blockIdx.x], chunk = work_chunk[blockIdx.x];
+    const LcrRegionState rs = a.rstate[reg];
+    const uint32_t n = rs.n_cand, nf = rs.n_frag, cb = rs.cand_begin, fb = rs.frag_begin;
+    const uint32_t words = (nf_cap + 31) / 32;
+    unsigned long long *rows = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint32_t *rrel = reinterpret_cast<uint32_t *>(rows + nf_cap);
+    uint32_t *sig = rrel + nf_cap + warp * words;
+    const lcr_candidate *c = a.cand + cb;
+    const LcrDeviceTables &T = *a.tables;
+    const uint64_t region_key = lcr_region_key(a.regions[reg].tid, a.regions[reg].start);
+    const uint32_t slot0 = a.slot_off[reg];
+
+    if (tid < 32) {
+        const uint32_t q = tid < 31 ? tid : 30;
+        S.OK[tid] = T.fx_ok[q];
+        S.ERR[tid] = T.fx_err[q];
+        S.W[tid] = T.fx_ok[q] - T.fx_err[q];
+    }
+    if (tid < EMAXN) { S.C[tid] = 0; S.R[tid] = 0; S.V[tid] = 0; S.cov[tid] = 0; }
+    /* stage the rows: bit 63 = fragment used for phasing, 6 bits per site: (q + 1) | 32 when p < 0 */
+    for (uint32_t k = tid; k < nf; k += EW * 32) {
+        const uint32_t f = fb + k;
+        unsigned long long row = a.frag_links[f] >= a.P.min_linkers ? (1ull << 63) : 0ull;
+        for (uint32_t e = a.frag_elem_off[f]; e < a.frag_elem_off[f + 1]; ++e) {
+            const int8_t cell = a.elem_cell[e];
+            const uint32_t code = cell > 0 ? (uint32_t)cell : ((uint32_t)(-cell) | 32u);
+            row |= (unsigned long long)code << (6 * a.elem_snp[e]);
+        }
+        rows[k] = row;
+        rrel[k] = a.frag_slot[f] - slot0;
+    }
+    uint32_t phase0 = 0; /* for_phasing mask */
+    int gen0[EMAXN];
+#pragma unroll
+    for (int i = 0; i < EMAXN; ++i) {
+        gen0[i] = 1;
+        if ((uint32_t)i < n) {
+            if (c[i].flags & LCR_CF_FOR_PHASING) phase0 |= 1u << i;
+            const int vt = c[i].variant_type;
+            gen0[i] = vt == 0 ? 1 : (vt == 1 ? 0 : -1); /* init_genotype, phase.rs:682-691 */
+        }
+    }
+    __syncthreads();
+    /* column constants over the fragments used for phasing: C = sum(ok + err), R = homref sum, V = homvar sum */
+    for (uint32_t i = warp; i < n; i += EW) {
+        long long C = 0, R = 0, V = 0;
+        uint32_t cov = 0;
+        for (uint32_t k = lane; k < nf; k += 32) {
+            const unsigned long long row = rows[k];
+            const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
+            if (!(row >> 63) || !code) continue;
+            const uint32_t q = (code & 31u) - 1u;
+            const bool neg = code & 32u;
+            C += S.OK[q] + S.ERR[q];
+            R += neg ? S.ERR[q] : S.OK[q];
+            V += neg ? S.OK[q] : S.ERR[q];
+            cov++;
+        }
+        for (int o = 16; o; o >>= 1) {
+            C += __shfl_xor_sync(0xffffffffu, C, o);
+            R += __shfl_xor_sync(0xffffffffu, R, o);
+            V += __shfl_xor_sync(0xffffffffu, V, o);
+            cov += __shfl_xor_sync(0xffffffffu, cov, o);
+        }
+        if (lane == 0) { S.C[i] = C; S.R[i] = R; S.V[i] = V; S.cov[i] = cov; }
+    }
+    __syncthreads();
+
+    const uint32_t n_cfg = 1u << n;
+    long long best_prob = 0;
+    uint32_t best_cfg = 0xffffffffu;
+    unsigned long long iters = 0;
+    const uint32_t nwords = (nf + 31) / 32;
+    for (uint32_t j = 0; j < ECFG_PER_WARP; ++j) {
+        const uint32_t cfg = chunk * (EW * ECFG_PER_WARP) + warp * ECFG_PER_WARP + j;
+        if (cfg >= n_cfg) break;
+        uint32_t dneg = cfg; /* bit i set: delta_i = -1 */
+        int eta[EMAXN];
+#pragma unroll
+        for (int i = 0; i < EMAXN; ++i) eta[i] = gen0[i];
+        /* init_assignment (phase.rs:673-680) */
+        for (uint32_t w = 0; w < nwords; ++w) {
+            const uint32_t k = w * 32 + lane;
+            bool neg = false;
+            if (k < nf && (rows[k] >> 63)) neg = lcr_uniform(a.P.seed, region_key, LCR_RNG_INIT_SIGMA, cfg, rrel[k]) < 0.5;
+            const uint32_t word = __ballot_sync(0xffffffffu, neg);
+            if (lane == 0) sig[w] = word;
+        }
+        __syncwarp();
+        long long M[EMAXN];
+        bool hg_increase = true, ht_increase = true;
+        int num_iters = 0;
+        while (hg_increase | ht_increase) {
+            ++iters;
+#pragma unroll
+            for (int i = 0; i < EMAXN; ++i) M[i] = 0;
+            bool any_flip = false;
+            uint32_t hetmask = 0;
+#pragma unroll
+            for (int i = 0; i < EMAXN; ++i)
+                if (eta[i] == 0) hetmask |= 1u << i;
+            hetmask &= phase0;
+            for (uint32_t w = 0; w < nwords; ++w) {
+                const uint32_t k = w * 32 + lane;
+                const uint32_t word = sig[w];
+                bool neg = (word >> lane) & 1u;
+                unsigned long long row = 0;
+                if (k < nf) row = rows[k];
+                const bool active = row >> 63;
+                if (active) {
+                    long long v = 0; /* sum_i p * delta * W over heterozygous phase sites */
+#pragma unroll
+                    for (int i = 0; i < EMAXN; ++i) {
+                        const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
+                        if (code && ((hetmask >> i) & 1u)) {
+                            const long long Wq = S.W[(code & 31u) - 1u];
+                            const bool minus = ((code >> 5) ^ (dneg >> i)) & 1u;
+                            v += minus ? -Wq : Wq;
+                        }
+                    }
+                    if (v != 0) {
+                        const bool nneg = v < 0;
+                        if (nneg != neg) { any_flip = true; neg = nneg; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < EMAXN; ++i) {
+                        const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
+                        if (code && ((phase0 >> i) & 1u)) {
+                            const long long Wq = S.W[(code & 31u) - 1u];
+                            const bool minus = ((code >> 5) & 1u) ^ (neg ? 1u : 0u);
+                            M[i] += minus ? -Wq : Wq;
+                        }
+                    }
+                }
+                const uint32_t nword = __ballot_sync(0xffffffffu, neg);
+                if (lane == 0) sig[w] = nword;
+            }
+            __syncwarp();
+            any_flip = __any_sync(0xffffffffu, any_flip);
+#pragma unroll
+            for (int i = 0; i < EMAXN; ++i)
+                if ((uint32_t)i < n)
+                    for (int o = 16; o; o >>= 1) M[i] += __shfl_xor_sync(0xffffffffu, M[i], o);
+            if (!any_flip) ht_increase = false;
+            else { ht_increase = true; hg_increase = true; }
+            /* delta / eta sweep with_genotype (phase.rs:905-921); all lanes hold the same sums */
+            bool better = false;
+#pragma unroll
+            for (int i = 0; i < EMAXN; ++i) {
+                if ((uint32_t)i >= n || !((phase0 >> i) & 1u) || !S.cov[i]) continue;
+                const long long dM = ((dneg >> i) & 1u) ? -M[i] : M[i];
+                const long long ph2 = 2 * (T.fx_prior_het - (long long)S.cov[i] * T.fx_log10_2);
+                const long long L0 = S.C[i] + dM + ph2, L1 = S.C[i] - dM + ph2;
+                const long long L2 = 2 * (S.R[i] + T.fx_prior_homref), L3 = 2 * (S.V[i] + T.fx_prior_homvar);
+                const long long L_old = eta[i] == 0 ? L0 : (eta[i] == 1 ? L2 : L3);
+                long long mx = L0 > L1 ? L0 : L1;
+                const long long m2 = L2 > L3 ? L2 : L3;
+                mx = mx > m2 ? mx : m2;
+                long long L_new;
+                if (L0 == mx) { eta[i] = 0; L_new = L0; }
+                else if (L1 == mx) { dneg ^= 1u << i; eta[i] = 0; L_new = L1; }
+                else if (L2 == mx) { eta[i] = 1; L_new = L2; }
+                else { eta[i] = -1; L_new = L3; }
+                if (L_new > L_old) better = true;
+            }
+            if (!better) hg_increase = false;
+            else { hg_increase = true; ht_increase = true; }
+            if (++num_iters > 20) break;
+        }
+        /* cal_overall_probability from the column sums of the final state */
+        long long prob2 = 0;
+#pragma unroll
+        for (int i = 0; i < EMAXN; ++i) {
+            if ((uint32_t)i >= n || !((phase0 >> i) & 1u) || !S.cov[i]) continue;
+            const long long dM = ((dneg >> i) & 1u) ? -M[i] : M[i];
+            prob2 += eta[i] == 0 ? (S.C[i] + dM) : (eta[i] == 1 ? 2 * S.R[i] : 2 * S.V[i]);
+        }
+        const long long prob = prob2 / 2;
+        if (best_cfg == 0xffffffffu || prob > best_prob) { best_prob = prob; best_cfg = cfg; }
+    }
+    if (lane == 0) { S.best_prob[warp] = best_prob; S.best_cfg[warp] = best_cfg; S.iters[warp] = iters; }
+    __syncthreads();
+    if (tid == 0) {
+        long long bp = 0;
+        uint32_t bc = 0xffffffffu;
+        unsigned long long it = 0;
+        uint32_t ncfg_done = 0;
+        for (int w = 0; w < EW; ++w) {
+            it += S.iters[w];
+            if (S.best_cfg[w] == 0xffffffffu) continue;
+            if (bc == 0xffffffffu || S.best_prob[w] > bp) { bp = S.best_prob[w]; bc = S.best_cfg[w]; }
+        }
+        const uint32_t first = chunk * (EW * ECFG_PER_WARP);
+        ncfg_done = n_cfg > first ? (n_cfg - first < EW * ECFG_PER_WARP ? n_cfg - first : EW * ECFG_PER_WARP) : 0;
+        out_prob[blockIdx.x] = bp;
+        out_cfg[blockIdx.x] = bc;
+        atomicAdd((unsigned long long *)&a.stats->n_sweep_iters, it);
+        atomicAdd((unsigned long long *)&a.stats->n_cross_optimize, (unsigned long long)ncfg_done);
+    }
+}
+
+} // namespace
+
+size_t lcr_enum_smem_bytes(uint32_t nf_cap) { return (size_t)nf_cap * 12 + (size_t)EW * ((nf_cap + 31) / 32) * 4 + 16; }
+uint32_t lcr_enum_cfgs_per_cta() { return EW * ECFG_PER_WARP; }
+
+int lcr_launch_enum_search(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+                           long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
+    if (!n_work) return 0;
+    const size_t smem = lcr_enum_smem_bytes(nf_cap);
+    cudaError_t e = cudaFuncSetAttribute(k_enum_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_enum_search<<<n_work, EW * 32, smem, st>>>(a, work_region, work_chunk, nf_cap, out_prob, out_cfg);
+    return 0;
+}
