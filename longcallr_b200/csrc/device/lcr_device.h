@@ -27,7 +27,7 @@
 #include "lcr_contract.h"
 
 #define LCR_TILE 512        /* positions per pileup tile == threads per pileup CTA */
-#define LCR_ROWS 64         /* read rows staged in shared memory per chunk          */
+#define LCR_ROWS 128        /* reads staged in shared memory per chunk (8-bit column counters: < 256) */
 #define LCR_CODE_NONE 7u    /* row byte: (q << 3) | code; code 0-3 ACGT, 4 other base, 5 deletion, 6 intron, 7 nothing */
 
 struct LcrItem {            /* part of one read inside one tile (20 B) */

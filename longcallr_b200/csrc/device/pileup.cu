@@ -147,6 +147,9 @@ struct PileArgs {
     uint32_t *cand_count;
     lcr_stats *stats;
     uint32_t *pl_acgt, *pl_fwd, *pl_d, *pl_n, *pl_ts; /* debug planes or null */
+    struct PreCand *pre;
+    uint32_t pre_cap;
+    uint32_t *pre_count;
 };
 
 __device__ __forceinline__ int base_code_dev(uint8_t b) {
@@ -190,6 +193,7 @@ struct SiteCounters {
 };
 
 /* candidate.rs:75-463 for one position; returns true and fills `o` when the site becomes a candidate */
+template <bool PRE>
 __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const SiteCounters &s, uint8_t ref_base, lcr_candidate &o) {
     const uint32_t total = s.cnt[0] + s.cnt[1] + s.cnt[2] + s.cnt[3];
     if (total < P.min_depth || total > P.max_depth) return false;
@@ -247,6 +251,7 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
         }
     }
     if (!(ref_base == 'A' || ref_base == 'C' || ref_base == 'G' || ref_base == 'T')) return false;
+    if (PRE) return true; /* count-based filters passed; the likelihood needs the per-base qualities */
     const double NEG_INF = lcr_u2d(0xfff0000000000000ULL);
     double ll[3];
     ll[0] = (s.q0flags & 2) ? NEG_INF : lcr_fx_to_f64(s.ll0);
@@ -306,144 +311,211 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     return true;
 }
 
+/* shared-memory row byte of the tile kernel:
+     bits 0-2  0-3 = A,C,G,T   4 = other read base   5 = deletion   6 = intron   7 = nothing
+     bit  3    base quality >= min_baseq
+     bit  4    read on the forward strand
+     bits 5-6  transcript strand of the read: 1 forward, 2 reverse (util.rs:803-819)              */
+#define ROW_NONE 7u
+#define SUBTILE 128
+#define NSUB (LCR_TILE / SUBTILE)
+#define PWARPS (LCR_TILE / 32)
+
+struct PreCand { /* a site that passed every count-based filter; its likelihood is computed by k_site_ll */
+    uint32_t tile, col;
+    uint32_t cnt[4], pass[4], fwd[4], ts[2], d, n;
+};
+
 __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
-    __shared__ __align__(16) uint8_t rows[LCR_ROWS][LCR_TILE];
+    extern __shared__ __align__(16) uint8_t rows_raw[]; /* LCR_ROWS x LCR_TILE row bytes */
+    uint8_t (*rows)[LCR_TILE] = reinterpret_cast<uint8_t (*)[LCR_TILE]>(rows_raw);
+    __shared__ __align__(16) ulonglong2 lut[256];
     __shared__ uint8_t ref_s[LCR_TILE];
-    __shared__ uint32_t row_meta[LCR_ROWS]; /* bit 31: forward strand; low bits: ts increment packed 16|16 */
-    __shared__ int64_t tab0[64], tab2[64];
+    __shared__ int32_t s_col[PWARPS][33];
+    __shared__ int32_t s_rp[PWARPS][33];
+    __shared__ uint8_t s_typ[PWARPS][32];
+    __shared__ uint32_t fill[NSUB];
     __shared__ unsigned long long s_bases;
     __shared__ int s_err;
 
     const uint32_t tile = blockIdx.x;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = LCR_TILE / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t reg = a.tile_region[tile];
     const lcr_region R = a.regions[reg];
     const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
-    const int64_t tile_start = (int64_t)(tile - a.tile_base[reg]) * LCR_TILE;
-    const int64_t tile_end = tile_start + LCR_TILE < vec_size ? tile_start + LCR_TILE : vec_size;
+    const int32_t tile_start = (int32_t)((tile - a.tile_base[reg]) * LCR_TILE);
+    const int32_t tile_end = (int64_t)tile_start + LCR_TILE < vec_size ? tile_start + LCR_TILE : (int32_t)vec_size;
     const uint32_t npos = (uint32_t)(tile_end - tile_start);
     if (tid == 0) s_err = a.rstate[reg].status; /* one read, so the whole CTA takes the same branch */
     __syncthreads();
     if (s_err != 0) return;
     const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start;
 
-    if (tid < 64) {
-        const uint32_t q = tid & 31;
-        const bool is_ref = tid >= 32;
-        const int64_t E = a.tables->gl_fx_err[q], K = a.tables->gl_fx_ok[q];
-        tab0[tid] = is_ref ? E : K;
-        tab2[tid] = is_ref ? K : E;
+    if (tid < 256) { /* per-code increments of the sixteen 8-bit column counters */
+        const uint32_t b = tid & 7u, pass = (tid >> 3) & 1u, fwd = (tid >> 4) & 1u, ts = (tid >> 5) & 3u;
+        unsigned long long x = 0, y = 0;
+        if (b < 4u) {
+            x |= 1ull << (8 * b);
+            x |= (unsigned long long)pass << (32 + 8 * b);
+            y |= (unsigned long long)fwd << (8 * b);
+        }
+        if (b <= 4u) {
+            if (ts == 1u) y |= 1ull << 32;
+            else if (ts == 2u) y |= 1ull << 40;
+        }
+        if (b == 5u) y |= 1ull << 48;
+        if (b == 6u) y |= 1ull << 56;
+        lut[tid] = make_ulonglong2(x, y);
     }
     if (tid == 0) s_bases = 0;
     const uint8_t ref_base = tid < npos ? ref[tid] : (uint8_t)'N';
     ref_s[tid] = ref_base;
-    const uint32_t refc = (ref_base == 'A') ? 0u : (ref_base == 'C') ? 1u : (ref_base == 'G') ? 2u : (ref_base == 'T') ? 3u : 8u;
     const uint32_t minq = (uint32_t)a.P.min_baseq;
+    const int64_t dist_end = (int64_t)a.P.distance_to_read_end;
 
-    SiteCounters sc;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { sc.cnt[i] = 0; sc.pass[i] = 0; sc.fwd[i] = 0; }
-    sc.ts[0] = sc.ts[1] = 0; sc.d = 0; sc.n = 0; sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
+    uint32_t cnt[4] = {0, 0, 0, 0}, pas[4] = {0, 0, 0, 0}, fwd[4] = {0, 0, 0, 0}, tsc[2] = {0, 0}, dcnt = 0, ncnt = 0;
 
     const uint32_t it0 = a.tile_off[tile], it1 = a.tile_off[tile + 1];
     unsigned long long my_bases = 0;
     for (uint32_t base_it = it0; base_it < it1; base_it += LCR_ROWS) {
-        const uint32_t nrows = (it1 - base_it) < LCR_ROWS ? (it1 - base_it) : LCR_ROWS;
-        /* clear the staged rows */
+        const uint32_t nitems = (it1 - base_it) < LCR_ROWS ? (it1 - base_it) : LCR_ROWS;
         {
-            uint4 fill;
-            fill.x = fill.y = fill.z = fill.w = 0x07070707u;
-            uint4 *r4 = reinterpret_cast<uint4 *>(&rows[0][0]);
-            const uint32_t n16 = nrows * (LCR_TILE / 16);
-            for (uint32_t i = tid; i < n16; i += LCR_TILE) r4[i] = fill;
+            uint4 fillv;
+            fillv.x = fillv.y = fillv.z = fillv.w = 0x07070707u;
+            uint4 *r4 = reinterpret_cast<uint4 *>(rows_raw);
+            const uint32_t n16 = nitems * (LCR_TILE / 16);
+            for (uint32_t i = tid; i < n16; i += LCR_TILE) r4[i] = fillv;
+            if (tid < NSUB) fill[tid] = 0;
         }
         __syncthreads();
-        /* phase 1: one warp per item writes its bases into a row */
-        for (uint32_t row = warp; row < nrows; row += nwarps) {
-            const LcrItem it = a.items[base_it + row];
-            const uint32_t slot = it.slot;
-            const uint32_t read = R.read_begin + (slot - a.slot_off[reg]);
+        /* phase 1: one warp per item; lanes are consecutive reference columns */
+        for (uint32_t itx = warp; itx < nitems; itx += PWARPS) {
+            const LcrItem it = a.items[base_it + itx];
+            const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
             const uint64_t s0 = a.seq_off[read];
             const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
             const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
-            const uint64_t c0 = a.cig_off[read], c1 = a.cig_off[read + 1];
-            const uint32_t ncig = (uint32_t)(c1 - c0);
+            const uint64_t c0 = a.cig_off[read];
+            const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
             const uint32_t *cig = a.cigar + c0;
             const int64_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int64_t)(cig[0] >> 4) : 0;
             const int64_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int64_t)(cig[ncig - 1] >> 4) : 0;
-            if (lane == 0) {
+            const int64_t rb = seq_len - trail;
+            uint32_t rconst;
+            {
                 const int strand = (a.flag[read] & 0x10) ? 1 : 0;
                 const int8_t ts = a.ts[read];
-                uint32_t tsinc = 0; /* util.rs:803-819 */
-                if (ts == '+') tsinc = strand == 0 ? 1u : (1u << 16);
-                else if (ts == '-') tsinc = strand == 0 ? (1u << 16) : 1u;
-                row_meta[row] = tsinc | (strand == 0 ? 0x80000000u : 0u);
+                uint32_t tcode = 0;
+                if (ts == '+') tcode = strand == 0 ? 1u : 2u;
+                else if (ts == '-') tcode = strand == 0 ? 2u : 1u;
+                rconst = (strand == 0 ? 16u : 0u) | (tcode << 5);
             }
-            int64_t fpos = it.fpos;
+            int32_t fpos = it.fpos;
             int64_t rpos = it.rpos;
             uint32_t ci = it.cig, off = it.opoff;
-            uint8_t *dst = &rows[row][0];
+            uint32_t slots = 0xffffffffu; /* row of this item in each sub-tile, allocated on first touch */
+            bool bad = false;
             while (ci < ncig && fpos < tile_end) {
-                const uint32_t op = cig[ci], opc = op & 0xf;
-                const int64_t len = (int64_t)(op >> 4) - (int64_t)off;
-                if (opc == 4 || opc == 5) { ++ci; off = 0; continue; }
-                if (opc == 1) { rpos += len; ++ci; off = 0; continue; }
-                const int64_t seg = len < tile_end - fpos ? len : tile_end - fpos;
-                if (opc == 0 || opc == 7 || opc == 8) {
-                    if (rpos + seg > seq_len) { s_err = LCR_ERR_BAD_CIGAR; break; }
-                    for (int64_t i = lane; i < seg; i += 32) {
-                        const int64_t rp = rpos + i;
-                        const uint32_t col = (uint32_t)(fpos - tile_start + i);
-                        const uint8_t b = __ldg(seq + rp);
-                        uint32_t q = __ldg(qual + rp);
-                        q = q < LCR_MAX_BASE_QUALITY ? q : LCR_MAX_BASE_QUALITY;
-                        if (!base_masked(a.P, seq, rp, seq_len, lead, trail, ref_s[col])) {
-                            const int bc = base_code_dev(b);
-                            dst[col] = (uint8_t)((q << 3) | (bc >= 0 ? (uint32_t)bc : 4u));
-                        }
+                /* one batch of up to 32 CIGAR ops: a lane per op, prefix sums give every op its first column / read offset */
+                uint32_t opc = 15, len = 0;
+                if (ci + lane < ncig) {
+                    const uint32_t op = cig[ci + lane];
+                    opc = op & 0xf;
+                    len = op >> 4;
+                    if (lane == 0) len -= off;
+                }
+                const bool consuming = opc == 0 || opc == 2 || opc == 3 || opc == 7 || opc == 8;
+                const bool is_m = opc == 0 || opc == 7 || opc == 8;
+                if (opc != 15 && !consuming && opc != 1 && opc != 4 && opc != 5) bad = true;
+                int32_t rl = consuming ? (int32_t)len : 0, ql = (is_m || opc == 1) ? (int32_t)len : 0;
+                int32_t rs = rl, qs = ql;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int32_t r2 = __shfl_up_sync(0xffffffffu, rs, o), q2 = __shfl_up_sync(0xffffffffu, qs, o);
+                    if ((int)lane >= o) { rs += r2; qs += q2; }
+                }
+                const int32_t tot_r = __shfl_sync(0xffffffffu, rs, 31), tot_q = __shfl_sync(0xffffffffu, qs, 31);
+                s_col[warp][lane] = fpos + rs - rl;
+                s_rp[warp][lane] = (int32_t)rpos + qs - ql;
+                s_typ[warp][lane] = consuming ? (uint8_t)(is_m ? 0 : opc) : (uint8_t)255;
+                if (lane == 0) s_col[warp][32] = fpos + tot_r;
+                bad = __any_sync(0xffffffffu, bad);
+                if (bad) break;
+                __syncwarp();
+                const int32_t colB = fpos + tot_r < tile_end ? fpos + tot_r : tile_end;
+                if (is_m) { /* aligned bases of this batch that fall inside the tile (stats: n_aligned_bases) */
+                    const int32_t a0 = s_col[warp][lane], b0 = a0 + (int32_t)len;
+                    const int32_t lo = a0 > fpos ? a0 : fpos, hi = b0 < colB ? b0 : colB;
+                    if (hi > lo) my_bases += (unsigned long long)(hi - lo);
+                    if ((int64_t)s_rp[warp][lane] + (hi > lo ? hi - a0 : 0) > seq_len) bad = true;
+                }
+                bad = __any_sync(0xffffffffu, bad);
+                if (bad) break;
+                /* rows of this item in the sub-tiles this batch reaches (allocated on first touch, warp-uniform) */
+                if (colB > fpos) {
+                    const uint32_t subA = (uint32_t)(fpos - tile_start) / SUBTILE, subB = (uint32_t)(colB - 1 - tile_start) / SUBTILE;
+                    for (uint32_t sidx = subA; sidx <= subB; ++sidx) {
+                        if (((slots >> (8 * sidx)) & 0xffu) != 0xffu) continue;
+                        uint32_t v = 0;
+                        if (lane == 0) v = atomicAdd(&fill[sidx], 1u);
+                        v = __shfl_sync(0xffffffffu, v, 0);
+                        slots = (slots & ~(0xffu << (8 * sidx))) | (v << (8 * sidx));
                     }
-                    if (lane == 0) my_bases += (unsigned long long)seg;
-                    rpos += seg;
-                } else if (opc == 2 || opc == 3) {
-                    const uint8_t code = opc == 2 ? 5 : 6;
-                    for (int64_t i = lane; i < seg; i += 32) dst[fpos - tile_start + i] = code;
-                } else { s_err = LCR_ERR_BAD_CIGAR; break; }
-                fpos += seg;
-                if (seg == len) { ++ci; off = 0; } else break;
+                }
+                for (int32_t c = fpos + (int32_t)lane; c < colB; c += 32) {
+                    /* the op covering column c: last op that starts at or before c */
+                    uint32_t lo = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1)
+                        if (s_col[warp][lo + step] <= c) lo += step;
+                    const uint32_t typ = s_typ[warp][lo];
+                    const uint32_t colr = (uint32_t)(c - tile_start);
+                    uint32_t code;
+                    if (typ == 0) {
+                        const int64_t rp = (int64_t)s_rp[warp][lo] + (c - s_col[warp][lo]);
+                        const uint8_t b = __ldg(seq + rp);
+                        const uint32_t q = __ldg(qual + rp);
+                        const int64_t d0 = rp - lead, d1 = rp - rb;
+                        const bool near_end = (d0 < 0 ? -d0 : d0) < dist_end || (d1 < 0 ? -d1 : d1) < dist_end;
+                        bool masked = false;
+                        if (near_end) masked = base_masked(a.P, seq, rp, seq_len, lead, trail, ref_s[colr]);
+                        const int bc = base_code_dev(b);
+                        code = masked ? ROW_NONE : ((bc >= 0 ? (uint32_t)bc : 4u) | ((q < 30u ? q : 30u) >= minq ? 8u : 0u) | rconst);
+                    } else code = typ == 2 ? 5u : 6u;
+                    rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)code;
+                }
+                fpos += tot_r;
+                rpos += tot_q;
+                ci += 32;
+                off = 0;
+                __syncwarp();
             }
+            if (bad) s_err = LCR_ERR_BAD_CIGAR;
         }
         __syncthreads();
-        /* phase 2: every thread walks the column of its position */
-        uint32_t c8 = 0, p8 = 0, f8 = 0, ts16 = 0, dn16 = 0;
-        for (uint32_t row = 0; row < nrows; ++row) {
-            const uint32_t code = rows[row][tid];
-            if (code == LCR_CODE_NONE) continue;
-            const uint32_t meta = row_meta[row];
-            const uint32_t b = code & 7u, q = code >> 3;
-            if (b <= 4u) ts16 += meta & 0x7fffffffu;
-            if (b < 4u) {
-                const uint32_t sh = b * 8u;
-                c8 += 1u << sh;
-                p8 += (q >= minq ? 1u : 0u) << sh;
-                f8 += (meta >> 31) << sh;
-                const bool is_ref = (b == refc);
-                const uint32_t idx = q + (is_ref ? 32u : 0u);
-                sc.ll0 += tab0[idx];
-                sc.ll2 += tab2[idx];
-                if (q == 0) sc.q0flags |= is_ref ? 1u : 2u;
-            } else if (b == 5u) dn16 += 1u;
-            else if (b == 6u) dn16 += 1u << 16;
-        }
+        /* phase 2: every thread sums the column of its position over the rows of its sub-tile */
+        {
+            unsigned long long acc0 = 0, acc1 = 0;
+            const uint32_t nrow = fill[tid / SUBTILE];
+            for (uint32_t row = 0; row < nrow; ++row) {
+                const ulonglong2 v = lut[rows[row][tid]];
+                acc0 += v.x;
+                acc1 += v.y;
+            }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            sc.cnt[i] += (c8 >> (8 * i)) & 0xffu;
-            sc.pass[i] += (p8 >> (8 * i)) & 0xffu;
-            sc.fwd[i] += (f8 >> (8 * i)) & 0xffu;
+            for (int i = 0; i < 4; ++i) {
+                cnt[i] += (uint32_t)(acc0 >> (8 * i)) & 0xffu;
+                pas[i] += (uint32_t)(acc0 >> (32 + 8 * i)) & 0xffu;
+                fwd[i] += (uint32_t)(acc1 >> (8 * i)) & 0xffu;
+            }
+            tsc[0] += (uint32_t)(acc1 >> 32) & 0xffu;
+            tsc[1] += (uint32_t)(acc1 >> 40) & 0xffu;
+            dcnt += (uint32_t)(acc1 >> 48) & 0xffu;
+            ncnt += (uint32_t)(acc1 >> 56) & 0xffu;
         }
-        sc.ts[0] += ts16 & 0xffffu; sc.ts[1] += ts16 >> 16;
-        sc.d += dn16 & 0xffffu; sc.n += dn16 >> 16;
         __syncthreads();
     }
+    my_bases = __reduce_add_sync(0xffffffffu, (uint32_t)my_bases);
     if (lane == 0 && my_bases) atomicAdd(&s_bases, my_bases);
     __syncthreads();
     if (tid == 0) {
@@ -451,21 +523,107 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
         if (s_err) atomicMin(&a.rstate[reg].status, s_err);
     }
     if (tid >= npos) return;
-    sc.n += a.tile_full_n[tile];
+    ncnt += a.tile_full_n[tile];
     if (a.pl_acgt) {
         const uint64_t g = a.pos_off[reg] + (uint64_t)tile_start + tid;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = sc.cnt[i]; a.pl_fwd[g * 4 + i] = sc.fwd[i]; }
-        a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
+        for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = cnt[i]; a.pl_fwd[g * 4 + i] = fwd[i]; }
+        a.pl_d[g] = dcnt; a.pl_n[g] = ncnt; a.pl_ts[g * 2] = tsc[0]; a.pl_ts[g * 2 + 1] = tsc[1];
     }
+    SiteCounters sc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sc.cnt[i] = cnt[i]; sc.pass[i] = pas[i]; sc.fwd[i] = fwd[i]; }
+    sc.ts[0] = tsc[0]; sc.ts[1] = tsc[1]; sc.d = dcnt; sc.n = ncnt; sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
+    lcr_candidate dummy;
+    if (site_call<true>(a.P, *a.tables, sc, ref_base, dummy)) {
+        const uint32_t k = atomicAdd(a.pre_count, 1u);
+        if (k < a.pre_cap) {
+            PreCand pc;
+            pc.tile = tile; pc.col = tid;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pc.cnt[i] = cnt[i]; pc.pass[i] = pas[i]; pc.fwd[i] = fwd[i]; }
+            pc.ts[0] = tsc[0]; pc.ts[1] = tsc[1]; pc.d = dcnt; pc.n = ncnt;
+            a.pre[k] = pc;
+        }
+    }
+}
+
+/* exact genotype likelihood of the sites that passed the count filters: one warp per site, lanes over the
+   reads of the site's tile (candidate.rs:236-282 over the same unmasked bases the pileup counted) */
+__global__ void __launch_bounds__(256) k_site_ll(PileArgs a, uint32_t n_pre) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_pre) return;
+    const PreCand pc = a.pre[w];
+    const uint32_t tile = pc.tile;
+    const uint32_t reg = a.tile_region[tile];
+    const lcr_region R = a.regions[reg];
+    const int32_t tile_start = (int32_t)((tile - a.tile_base[reg]) * LCR_TILE);
+    const int32_t col = tile_start + (int32_t)pc.col;
+    const uint8_t ref_base = a.ref_table[R.tid][((int64_t)R.start - 1) + col];
+    const int refc = (ref_base == 'A') ? 0 : (ref_base == 'C') ? 1 : (ref_base == 'G') ? 2 : (ref_base == 'T') ? 3 : 8;
+    long long ll0 = 0, ll2 = 0;
+    uint32_t q0flags = 0;
+    for (uint32_t idx = a.tile_off[tile] + lane; idx < a.tile_off[tile + 1]; idx += 32) {
+        const LcrItem it = a.items[idx];
+        const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
+        const uint64_t s0 = a.seq_off[read];
+        const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
+        const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
+        const uint64_t c0 = a.cig_off[read];
+        const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
+        const uint32_t *cig = a.cigar + c0;
+        const int64_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int64_t)(cig[0] >> 4) : 0;
+        const int64_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int64_t)(cig[ncig - 1] >> 4) : 0;
+        int32_t fpos = it.fpos;
+        int64_t rpos = it.rpos;
+        uint32_t off = it.opoff;
+        for (uint32_t ci = it.cig; ci < ncig && fpos <= col; ++ci, off = 0) {
+            const uint32_t op = cig[ci], opc = op & 0xf;
+            const int32_t len = (int32_t)(op >> 4) - (int32_t)off;
+            if (opc == 4 || opc == 5) continue;
+            if (opc == 1) { rpos += len; continue; }
+            const bool is_m = opc == 0 || opc == 7 || opc == 8;
+            if (col < fpos + len) {
+                if (is_m) {
+                    const int64_t rp = rpos + (col - fpos);
+                    if (rp < seq_len) {
+                        const uint8_t b = seq[rp];
+                        const uint32_t rq = qual[rp];
+                        const uint32_t q = rq < LCR_MAX_BASE_QUALITY ? rq : LCR_MAX_BASE_QUALITY;
+                        const int bc = base_code_dev(b);
+                        if (bc >= 0 && !base_masked(a.P, seq, rp, seq_len, lead, trail, ref_base)) {
+                            const bool is_ref = bc == refc;
+                            const long long E = a.tables->gl_fx_err[q], K = a.tables->gl_fx_ok[q];
+                            ll0 += is_ref ? E : K;
+                            ll2 += is_ref ? K : E;
+                            if (q == 0) q0flags |= is_ref ? 1u : 2u;
+                        }
+                    }
+                }
+                break;
+            }
+            fpos += len;
+            if (is_m) rpos += len;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        ll0 += __shfl_xor_sync(0xffffffffu, ll0, o);
+        ll2 += __shfl_xor_sync(0xffffffffu, ll2, o);
+        q0flags |= __shfl_xor_sync(0xffffffffu, q0flags, o);
+    }
+    if (lane != 0) return;
+    SiteCounters sc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sc.cnt[i] = pc.cnt[i]; sc.pass[i] = pc.pass[i]; sc.fwd[i] = pc.fwd[i]; }
+    sc.ts[0] = pc.ts[0]; sc.ts[1] = pc.ts[1]; sc.d = pc.d; sc.n = pc.n; sc.ll0 = ll0; sc.ll2 = ll2; sc.q0flags = q0flags;
     lcr_candidate o;
-    if (site_call(a.P, *a.tables, sc, ref_base, o)) {
+    if (site_call<false>(a.P, *a.tables, sc, ref_base, o)) {
         const uint32_t k = atomicAdd(a.cand_count, 1u);
         if (k < a.cand_cap) {
-            o.pos = (int64_t)R.start - 1 + tile_start + tid;
+            o.pos = (int64_t)R.start - 1 + col;
             o.region = reg;
             a.cand[k] = o;
-            a.cand_key[k] = ((uint64_t)reg << 32) | (uint64_t)(tile_start + tid);
+            a.cand_key[k] = ((uint64_t)reg << 32) | (uint64_t)(uint32_t)col;
         }
     }
 }
@@ -590,62 +748,76 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         db->timing.kernel_launches += 1;
     }
 
-    /* fused pileup + site genotyping */
-    uint32_t cand_cap = (uint32_t)std::min<uint64_t>(db->n_pos, db->n_pos / 8 + 4096);
-    if (!cand_cap) cand_cap = 1;
+    /* tile pileup (counts + count-based site filters), then the exact likelihood of the surviving sites */
+    uint32_t pre_cap = (uint32_t)std::min<uint64_t>(db->n_pos, db->n_pos / 8 + 4096);
+    if (!pre_cap) pre_cap = 1;
+    PreCand *pre = nullptr;
     lcr_candidate *cand_raw = nullptr;
     uint64_t *cand_key = nullptr;
-    uint32_t *cand_count = nullptr;
-    TRY(cudaMallocAsync(&cand_count, sizeof(uint32_t), st));
+    uint32_t *counters = nullptr; /* [0] pre-candidates, [1] candidates */
+    TRY(cudaMallocAsync(&counters, 2 * sizeof(uint32_t), st));
     cudaEvent_t ev0, ev1;
     TRY(cudaEventCreate(&ev0));
     TRY(cudaEventCreate(&ev1));
-    uint32_t n_cand = 0;
+    const size_t tile_smem = (size_t)LCR_ROWS * LCR_TILE;
+    TRY(cudaFuncSetAttribute(k_pileup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    PileArgs ka{};
+    ka.P = ctx->P;
+    ka.regions = db->regions;
+    ka.slot_off = db->slot_off; ka.slot_region = db->slot_region; ka.tile_base = db->tile_base; ka.tile_region = db->tile_region;
+    ka.pos_off = db->pos_off;
+    ka.flag = db->flag; ka.ts = db->ts; ka.seq_off = db->seq_off; ka.cig_off = db->cig_off;
+    ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
+    ka.ref_table = ctx->d_ref_table;
+    ka.tile_off = tile_off; ka.tile_full_n = tile_full_n; ka.items = items;
+    ka.tables = ctx->d_tables;
+    ka.rstate = db->rstate;
+    ka.stats = db->d_stats;
+    ka.pl_acgt = db->pl_acgt; ka.pl_fwd = db->pl_fwd; ka.pl_d = db->pl_d; ka.pl_n = db->pl_n; ka.pl_ts = db->pl_ts;
+    ka.pre_count = counters; ka.cand_count = counters + 1;
+    uint32_t n_pre = 0, n_cand = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        TRY(cudaMallocAsync(&cand_raw, sizeof(lcr_candidate) * (size_t)cand_cap, st));
-        TRY(cudaMallocAsync(&cand_key, sizeof(uint64_t) * (size_t)cand_cap, st));
-        TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t), st));
-        PileArgs ka{};
-        ka.P = ctx->P;
-        ka.regions = db->regions;
-        ka.slot_off = db->slot_off; ka.slot_region = db->slot_region; ka.tile_base = db->tile_base; ka.tile_region = db->tile_region;
-        ka.pos_off = db->pos_off;
-        ka.flag = db->flag; ka.ts = db->ts; ka.seq_off = db->seq_off; ka.cig_off = db->cig_off;
-        ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
-        ka.ref_table = ctx->d_ref_table;
-        ka.tile_off = tile_off; ka.tile_full_n = tile_full_n; ka.items = items;
-        ka.tables = ctx->d_tables;
-        ka.rstate = db->rstate;
-        ka.cand = cand_raw; ka.cand_key = cand_key; ka.cand_cap = cand_cap; ka.cand_count = cand_count;
-        ka.stats = db->d_stats;
-        ka.pl_acgt = db->pl_acgt; ka.pl_fwd = db->pl_fwd; ka.pl_d = db->pl_d; ka.pl_n = db->pl_n; ka.pl_ts = db->pl_ts;
+        TRY(cudaMallocAsync(&pre, sizeof(PreCand) * (size_t)pre_cap, st));
+        TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), st));
+        ka.pre = pre; ka.pre_cap = pre_cap;
         if (attempt == 1) TRY(cudaMemsetAsync(&db->d_stats->n_aligned_bases, 0, sizeof(uint64_t), st));
         TRY(cudaEventRecord(ev0, st));
         if (n_tiles) {
-            k_pileup_tile<<<n_tiles, LCR_TILE, 0, st>>>(ka);
+            k_pileup_tile<<<n_tiles, LCR_TILE, tile_smem, st>>>(ka);
             db->timing.kernel_launches += 1;
         }
         TRY(cudaEventRecord(ev1, st));
-        TRY(cudaMemcpyAsync(&n_cand, cand_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(&n_pre, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));
         TRY(cudaGetLastError());
-        if (n_cand <= cand_cap) break;
-        TRY(cudaFreeAsync(cand_raw, st));
-        TRY(cudaFreeAsync(cand_key, st));
-        cand_cap = n_cand;
+        if (n_pre <= pre_cap) break;
+        TRY(cudaFreeAsync(pre, st));
+        pre_cap = n_pre;
     }
     float ms = 0;
     TRY(cudaEventElapsedTime(&ms, ev0, ev1));
     db->timing.ms_pileup_kernel = ms;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    /* algorithmic bytes of the tile kernel: base + qual per aligned base, CIGAR, items, reference, candidates */
+    const uint32_t cand_cap = n_pre ? n_pre : 1;
+    TRY(cudaMallocAsync(&cand_raw, sizeof(lcr_candidate) * (size_t)cand_cap, st));
+    TRY(cudaMallocAsync(&cand_key, sizeof(uint64_t) * (size_t)cand_cap, st));
+    ka.cand = cand_raw; ka.cand_key = cand_key; ka.cand_cap = cand_cap;
+    if (n_pre) {
+        k_site_ll<<<(uint32_t)(((uint64_t)n_pre * 32 + 255) / 256), 256, 0, st>>>(ka, n_pre);
+        db->timing.kernel_launches += 1;
+    }
+    /* algorithmic bytes of the tile kernel: base + qual per aligned base, CIGAR, items, reference, surviving sites */
     {
         lcr_stats hs;
+        TRY(cudaMemcpyAsync(&n_cand, counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         TRY(cudaMemcpyAsync(&hs, db->d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));
-        db->timing.pileup_alg_bytes = 2ull * hs.n_aligned_bases + 4ull * db->n_cigar + sizeof(LcrItem) * (uint64_t)n_items + db->n_pos + sizeof(lcr_candidate) * (uint64_t)n_cand;
+        TRY(cudaGetLastError());
+        db->timing.pileup_alg_bytes = 2ull * hs.n_aligned_bases + 4ull * db->n_cigar + sizeof(LcrItem) * (uint64_t)n_items + db->n_pos + sizeof(PreCand) * (uint64_t)n_pre;
     }
+    TRY(cudaFreeAsync(pre, st));
+    uint32_t *cand_count = counters;
 
     /* sort candidates by (region, position) */
     db->n_cand = n_cand;
