@@ -75,6 +75,18 @@ int h2d(lcr_ctx *ctx, T **dst, const T *src, size_t n, uint64_t *bytes) {
     return 0;
 }
 
+template <class T>
+int h2d_padded(lcr_ctx *ctx, T **dst, const T *src, size_t n, size_t pad, uint64_t *bytes) {
+    int rc = dalloc(ctx, dst, n + pad);
+    if (rc) return rc;
+    LCR_CUDA_TRY(ctx, cudaMemsetAsync(*dst + n, 0, sizeof(T) * pad, ctx->stream));
+    if (n) {
+        LCR_CUDA_TRY(ctx, cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+        if (bytes) *bytes += sizeof(T) * n;
+    }
+    return 0;
+}
+
 __global__ void k_scatter_winners(uint32_t n, const uint32_t *slot, const long long *prob, const uint32_t *cfg, long long *out_prob, uint32_t *out_cfg) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { out_prob[slot[i]] = prob[i]; out_cfg[slot[i]] = cfg[i]; }
@@ -389,6 +401,11 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     t.log10_2 = ctx->luts.log10_2;
     for (int i = 0; i < 3; ++i) t.gl_prior_log[i] = ctx->luts.gl_prior_log[i];
     t.sor_threshold = ctx->luts.sor_threshold;
+    for (uint32_t n = 0; n <= 30; ++n) {
+        t.binom_reject[n] = 0;
+        for (uint32_t k = 0; k <= n; ++k)
+            if (lcr_binom_two_tailed_lt_0p05(k, n)) t.binom_reject[n] |= 1u << k;
+    }
     if (cudaMalloc(&ctx->d_tables, sizeof t) != cudaSuccess || cudaMemcpy(ctx->d_tables, &t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -478,8 +495,9 @@ int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) {
     UP(de, b->de, b->n_reads);
     if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
     else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
-    UP(seq, b->seq, n_bases);
-    UP(qual, b->qual, n_bases);
+    /* seq / qual carry 16 bytes of slack: the tile kernel reads them as aligned 32-bit words */
+    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 16, &bytes);
+    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 16, &bytes);
     UP(cigar, b->cigar, n_cig);
     UP(slot_off, slot_off.data(), slot_off.size());
     UP(slot_region, slot_region.data(), slot_region.size());

@@ -57,6 +57,7 @@ struct LcrDeviceTables {    /* what the kernels need from lcr_luts, in device-fr
     double log10_2;
     double gl_prior_log[3];
     float sor_threshold;
+    uint32_t binom_reject[32]; /* bit k of [n]: two-tailed binomial(k; n, 0.5) < 0.05 (candidate.rs:37-47, n <= 30) */
 };
 
 struct lcr_ctx {

@@ -162,26 +162,46 @@ __device__ __forceinline__ int base_code_dev(uint8_t b) {
     }
 }
 
-/* util.rs:737-789: end trim (ONT) and poly-A / homopolymer mask near the clipped read ends */
-__device__ __forceinline__ bool base_masked(const lcr_params &P, const uint8_t *seq, int64_t curr, int64_t seq_len, int64_t lead, int64_t trail, uint8_t ref_base) {
-    const int64_t dist_end = (int64_t)P.distance_to_read_end;
-    const int64_t read_end_boundary = seq_len - trail;
-    const int64_t d0 = curr - lead, d1 = curr - read_end_boundary;
+/* util.rs:737-789: end trim (ONT) and poly-A / homopolymer mask near the clipped read ends.
+   The reference scans the polya windows [ti, ti + polya), ti in [curr - polya, curr + 1], for one made
+   of a single letter X in {A,T,C,G} different from the reference base.  Every such window contains
+   curr - 1 or curr + 1, so it is enough to grow the homopolymer run around those two anchors inside
+   [curr - polya, curr + polya] and compare its length with polya. */
+__device__ __forceinline__ bool base_masked(const lcr_params &P, const uint8_t *seq, int64_t curr64, int64_t seq_len64, int64_t lead64, int64_t trail64, uint8_t ref_base) {
+    const int32_t curr = (int32_t)curr64, seq_len = (int32_t)seq_len64, lead = (int32_t)lead64, trail = (int32_t)trail64;
+    const int32_t dist_end = (int32_t)(P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : P.distance_to_read_end);
+    const int32_t d0 = curr - lead, d1 = curr - (seq_len - trail);
     const bool near_end = (d0 < 0 ? -d0 : d0) < dist_end || (d1 < 0 ? -d1 : d1) < dist_end;
     if (!near_end) return false;
     if (P.platform == 1) return true;
-    const int64_t polya = (int64_t)P.polya_tail_length;
-    for (int64_t ti = curr - polya; ti <= curr + 1; ++ti) {
-        if (ti < 0 || ti + polya - 1 >= seq_len) continue;
-        int64_t pa = 0, pt = 0, pc = 0, pg = 0;
-        for (int64_t tj = 0; tj < polya; ++tj) {
-            const uint8_t b = __ldg(seq + ti + tj);
-            if (b == 'A' && ref_base != 'A') pa++;
-            else if (b == 'T' && ref_base != 'T') pt++;
-            else if (b == 'C' && ref_base != 'C') pc++;
-            else if (b == 'G' && ref_base != 'G') pg++;
+    const int32_t polya = (int32_t)(P.polya_tail_length > 0x3fffffffu ? 0x3fffffffu : P.polya_tail_length);
+    if (polya < 2) { /* literal form for degenerate window lengths */
+        for (int32_t ti = curr - polya; ti <= curr + 1; ++ti) {
+            if (ti < 0 || ti + polya - 1 >= seq_len) continue;
+            int32_t pa = 0, pt = 0, pc = 0, pg = 0;
+            for (int32_t tj = 0; tj < polya; ++tj) {
+                const uint8_t b = __ldg(seq + ti + tj);
+                if (b == 'A' && ref_base != 'A') pa++;
+                else if (b == 'T' && ref_base != 'T') pt++;
+                else if (b == 'C' && ref_base != 'C') pc++;
+                else if (b == 'G' && ref_base != 'G') pg++;
+            }
+            if (pa >= polya || pt >= polya || pc >= polya || pg >= polya) return true;
         }
-        if (pa >= polya || pt >= polya || pc >= polya || pg >= polya) return true;
+        return false;
+    }
+    const int32_t lo = curr - polya > 0 ? curr - polya : 0;
+    const int32_t hi = curr + polya + 1 < seq_len ? curr + polya + 1 : seq_len; /* exclusive */
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int32_t anchor = side == 0 ? curr - 1 : curr + 1;
+        if (anchor < lo || anchor >= hi) continue;
+        const uint8_t X = __ldg(seq + anchor);
+        if (!(X == 'A' || X == 'T' || X == 'C' || X == 'G') || X == ref_base) continue;
+        int32_t s0 = anchor, e0 = anchor + 1;
+        while (s0 > lo && __ldg(seq + s0 - 1) == X) --s0;
+        while (e0 < hi && e0 - s0 < polya && __ldg(seq + e0) == X) ++e0;
+        if (e0 - s0 >= polya) return true;
     }
     return false;
 }
@@ -246,7 +266,7 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
         }
         if (sor > T.sor_threshold) return false;
         if (alt_num == 1) {
-            if (af + ar <= 30 && lcr_binom_two_tailed_lt_0p05((uint32_t)af, (uint32_t)(af + ar))) return false;
+            if (af + ar <= 30 && ((T.binom_reject[af + ar] >> af) & 1u)) return false;
             if ((int64_t)af * (int64_t)ar == 0) return false;
         }
     }
@@ -335,6 +355,7 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
     __shared__ int32_t s_rp[PWARPS][33];
     __shared__ uint8_t s_typ[PWARPS][32];
     __shared__ uint32_t fill[NSUB];
+    __shared__ uint32_t next_item;
     __shared__ unsigned long long s_bases;
     __shared__ int s_err;
 
@@ -371,7 +392,6 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
     const uint8_t ref_base = tid < npos ? ref[tid] : (uint8_t)'N';
     ref_s[tid] = ref_base;
     const uint32_t minq = (uint32_t)a.P.min_baseq;
-    const int64_t dist_end = (int64_t)a.P.distance_to_read_end;
 
     uint32_t cnt[4] = {0, 0, 0, 0}, pas[4] = {0, 0, 0, 0}, fwd[4] = {0, 0, 0, 0}, tsc[2] = {0, 0}, dcnt = 0, ncnt = 0;
 
@@ -386,21 +406,30 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
             const uint32_t n16 = nitems * (LCR_TILE / 16);
             for (uint32_t i = tid; i < n16; i += LCR_TILE) r4[i] = fillv;
             if (tid < NSUB) fill[tid] = 0;
+            if (tid == 0) next_item = 0;
         }
         __syncthreads();
-        /* phase 1: one warp per item; lanes are consecutive reference columns */
-        for (uint32_t itx = warp; itx < nitems; itx += PWARPS) {
+        /* phase 1: one warp per item.  A batch of up to 32 CIGAR ops is scanned (lane per op) into the first
+           column / first read offset of every reference-consuming op; columns are then produced either
+           4 per lane from word loads (long runs away from the read ends) or 1 per lane with the op of
+           each column found from a ballot over the op starts. */
+        for (;;) {
+            uint32_t itx = 0;
+            if (lane == 0) itx = atomicAdd(&next_item, 1u);
+            itx = __shfl_sync(0xffffffffu, itx, 0);
+            if (itx >= nitems) break;
             const LcrItem it = a.items[base_it + itx];
             const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
             const uint64_t s0 = a.seq_off[read];
-            const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
+            const int32_t seq_len = (int32_t)(a.seq_off[read + 1] - s0);
             const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
             const uint64_t c0 = a.cig_off[read];
             const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
             const uint32_t *cig = a.cigar + c0;
-            const int64_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int64_t)(cig[0] >> 4) : 0;
-            const int64_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int64_t)(cig[ncig - 1] >> 4) : 0;
-            const int64_t rb = seq_len - trail;
+            const int32_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int32_t)(cig[0] >> 4) : 0;
+            const int32_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int32_t)(cig[ncig - 1] >> 4) : 0;
+            const int32_t rb = seq_len - trail;
+            const int32_t dend = (int32_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
             uint32_t rconst;
             {
                 const int strand = (a.flag[read] & 0x10) ? 1 : 0;
@@ -411,12 +440,11 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                 rconst = (strand == 0 ? 16u : 0u) | (tcode << 5);
             }
             int32_t fpos = it.fpos;
-            int64_t rpos = it.rpos;
+            int32_t rpos = (int32_t)it.rpos;
             uint32_t ci = it.cig, off = it.opoff;
             uint32_t slots = 0xffffffffu; /* row of this item in each sub-tile, allocated on first touch */
             bool bad = false;
             while (ci < ncig && fpos < tile_end) {
-                /* one batch of up to 32 CIGAR ops: a lane per op, prefix sums give every op its first column / read offset */
                 uint32_t opc = 15, len = 0;
                 if (ci + lane < ncig) {
                     const uint32_t op = cig[ci + lane];
@@ -427,7 +455,7 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                 const bool consuming = opc == 0 || opc == 2 || opc == 3 || opc == 7 || opc == 8;
                 const bool is_m = opc == 0 || opc == 7 || opc == 8;
                 if (opc != 15 && !consuming && opc != 1 && opc != 4 && opc != 5) bad = true;
-                int32_t rl = consuming ? (int32_t)len : 0, ql = (is_m || opc == 1) ? (int32_t)len : 0;
+                const int32_t rl = consuming ? (int32_t)len : 0, ql = (is_m || opc == 1) ? (int32_t)len : 0;
                 int32_t rs = rl, qs = ql;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -435,23 +463,32 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                     if ((int)lane >= o) { rs += r2; qs += q2; }
                 }
                 const int32_t tot_r = __shfl_sync(0xffffffffu, rs, 31), tot_q = __shfl_sync(0xffffffffu, qs, 31);
-                s_col[warp][lane] = fpos + rs - rl;
-                s_rp[warp][lane] = (int32_t)rpos + qs - ql;
-                s_typ[warp][lane] = consuming ? (uint8_t)(is_m ? 0 : opc) : (uint8_t)255;
-                if (lane == 0) s_col[warp][32] = fpos + tot_r;
-                bad = __any_sync(0xffffffffu, bad);
-                if (bad) break;
-                __syncwarp();
-                const int32_t colB = fpos + tot_r < tile_end ? fpos + tot_r : tile_end;
-                if (is_m) { /* aligned bases of this batch that fall inside the tile (stats: n_aligned_bases) */
-                    const int32_t a0 = s_col[warp][lane], b0 = a0 + (int32_t)len;
+                /* compact the reference-consuming ops */
+                const bool keep = consuming && rl > 0;
+                const uint32_t keepmask = __ballot_sync(0xffffffffu, keep);
+                const uint32_t ncomp = __popc(keepmask);
+                if (keep) {
+                    const uint32_t k = __popc(keepmask & ((1u << lane) - 1u));
+                    s_col[warp][k] = fpos + rs - rl;
+                    s_rp[warp][k] = rpos + qs - ql;
+                    s_typ[warp][k] = (uint8_t)(is_m ? 0 : opc);
+                }
+                const int32_t batch_end = fpos + tot_r;
+                if (lane == 0) s_col[warp][ncomp] = batch_end;
+                const int32_t colB = batch_end < tile_end ? batch_end : tile_end;
+                if (is_m) { /* aligned bases of this batch inside the tile (n_aligned_bases) + bounds */
+                    const int32_t a0 = fpos + rs - rl, b0 = a0 + rl;
                     const int32_t lo = a0 > fpos ? a0 : fpos, hi = b0 < colB ? b0 : colB;
-                    if (hi > lo) my_bases += (unsigned long long)(hi - lo);
-                    if ((int64_t)s_rp[warp][lane] + (hi > lo ? hi - a0 : 0) > seq_len) bad = true;
+                    if (hi > lo) {
+                        my_bases += (unsigned long long)(hi - lo);
+                        if (rpos + qs - ql + (hi - a0) > seq_len) bad = true;
+                    }
                 }
                 bad = __any_sync(0xffffffffu, bad);
                 if (bad) break;
-                /* rows of this item in the sub-tiles this batch reaches (allocated on first touch, warp-uniform) */
+                __syncwarp();
+                const int32_t mystart = lane < ncomp ? s_col[warp][lane] : 0x7fffffff;
+                /* rows of this item in the sub-tiles this batch reaches */
                 if (colB > fpos) {
                     const uint32_t subA = (uint32_t)(fpos - tile_start) / SUBTILE, subB = (uint32_t)(colB - 1 - tile_start) / SUBTILE;
                     for (uint32_t sidx = subA; sidx <= subB; ++sidx) {
@@ -462,29 +499,79 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                         slots = (slots & ~(0xffu << (8 * sidx))) | (v << (8 * sidx));
                     }
                 }
-                for (int32_t c = fpos + (int32_t)lane; c < colB; c += 32) {
-                    /* the op covering column c: last op that starts at or before c */
-                    uint32_t lo = 0;
-#pragma unroll
-                    for (int step = 16; step; step >>= 1)
-                        if (s_col[warp][lo + step] <= c) lo += step;
-                    const uint32_t typ = s_typ[warp][lo];
-                    const uint32_t colr = (uint32_t)(c - tile_start);
-                    uint32_t code;
-                    if (typ == 0) {
-                        const int64_t rp = (int64_t)s_rp[warp][lo] + (c - s_col[warp][lo]);
-                        const uint8_t b = __ldg(seq + rp);
-                        const uint32_t q = __ldg(qual + rp);
-                        const int64_t d0 = rp - lead, d1 = rp - rb;
-                        const bool near_end = (d0 < 0 ? -d0 : d0) < dist_end || (d1 < 0 ? -d1 : d1) < dist_end;
-                        bool masked = false;
-                        if (near_end) masked = base_masked(a.P, seq, rp, seq_len, lead, trail, ref_s[colr]);
-                        const int bc = base_code_dev(b);
-                        code = masked ? ROW_NONE : ((bc >= 0 ? (uint32_t)bc : 4u) | ((q < 30u ? q : 30u) >= minq ? 8u : 0u) | rconst);
-                    } else code = typ == 2 ? 5u : 6u;
-                    rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)code;
+                int32_t cb = fpos;
+                while (cb < colB) {
+                    const int32_t first = (int32_t)__popc(__ballot_sync(0xffffffffu, mystart <= cb)) - 1;
+                    const int32_t op_col = s_col[warp][first], op_end = s_col[warp][first + 1];
+                    const uint32_t op_typ = s_typ[warp][first];
+                    const int32_t op_rp = s_rp[warp][first];
+                    const uint32_t colr0 = (uint32_t)(cb - tile_start);
+                    /* long run inside one op: 4 columns per lane */
+                    int32_t run = (op_end < colB ? op_end : colB) - cb;
+                    if (op_typ == 0) {
+                        const int32_t rp0 = op_rp + (cb - op_col);
+                        /* stay clear of the read-end zones |rp - lead| < D, |rp - rb| < D (util.rs:745-757) */
+                        if (rp0 < lead + dend) run = 0;
+                        else if (rp0 + run > rb - dend + 1) run = rb - dend + 1 - rp0;
+                    }
+                    if (run >= 64 && (colr0 & 3u) == 0) {
+                        const int32_t n4 = (run > 128 ? 128 : run) & ~3;
+                        if ((int32_t)(4 * lane) < n4) {
+                            const uint32_t colr = colr0 + 4 * lane;
+                            uint32_t code4;
+                            if (op_typ == 0) {
+                                const int32_t rp = op_rp + (cb - op_col) + 4 * (int32_t)lane;
+                                const uintptr_t sa = (uintptr_t)(seq + rp), qa = (uintptr_t)(qual + rp);
+                                const uint32_t *sw = (const uint32_t *)(sa & ~(uintptr_t)3), *qw = (const uint32_t *)(qa & ~(uintptr_t)3);
+                                const uint32_t w = __funnelshift_r(__ldg(sw), __ldg(sw + 1), (uint32_t)(sa & 3) * 8);
+                                const uint32_t qv = __funnelshift_r(__ldg(qw), __ldg(qw + 1), (uint32_t)(qa & 3) * 8);
+                                /* A,C,G,T -> 0..3 from bits 1-2 of the letter; anything else -> 4 */
+                                const uint32_t t = (w >> 1) & 0x03030303u;
+                                uint32_t c4 = t ^ ((t >> 1) & 0x01010101u);
+                                const uint32_t canon = __byte_perm(0x54474341u, 0, (c4 & 0x3u) | ((c4 >> 4) & 0x30u) | ((c4 >> 8) & 0x300u) | ((c4 >> 12) & 0x3000u));
+                                const uint32_t x = (w & 0xdfdfdfdfu) ^ canon;
+                                const uint32_t nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;
+                                c4 = (c4 & ~(nz * 7u)) | (nz * 4u);
+                                /* quality >= min_baseq per byte (qualities are < 128) */
+                                const uint32_t ge = (((qv & 0x7f7f7f7fu) | 0x80808080u) - minq * 0x01010101u) | (qv & 0x80808080u);
+                                const uint32_t pass4 = minq > 30u ? 0u : ((ge >> 4) & 0x08080808u);
+                                code4 = c4 | pass4 | (rconst * 0x01010101u);
+                            } else code4 = (op_typ == 2 ? 5u : 6u) * 0x01010101u;
+                            *reinterpret_cast<uint32_t *>(&rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr]) = code4;
+                        }
+                        cb += n4;
+                        continue;
+                    }
+                    /* one column per lane; the window ends where the columns become 4-aligned again */
+                    int32_t win = 32 - (int32_t)(colr0 & 3u);
+                    if (win > colB - cb) win = colB - cb;
+                    const int32_t rel = mystart - cb;
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? (1u << rel) : 0u);
+                    if ((int32_t)lane < win) {
+                        const int32_t c = cb + (int32_t)lane;
+                        const int32_t idx = first + (int32_t)__popc(starts & (0xffffffffu >> (31 - lane)));
+                        const uint32_t typ = s_typ[warp][idx];
+                        const uint32_t colr = colr0 + lane;
+                        uint32_t code;
+                        if (typ == 0) {
+                            const int32_t rp = s_rp[warp][idx] + (c - s_col[warp][idx]);
+                            const uint32_t b = __ldg(seq + rp);
+                            const uint32_t q = __ldg(qual + rp);
+                            const int32_t d0 = rp - lead, d1 = rp - rb;
+                            const bool near_end = (d0 < 0 ? -d0 : d0) < dend || (d1 < 0 ? -d1 : d1) < dend;
+                            bool masked = false;
+                            if (near_end) masked = base_masked(a.P, seq, rp, seq_len, lead, trail, ref_s[colr]);
+                            const uint32_t t = (b >> 1) & 3u;
+                            const uint32_t bc = t ^ (t >> 1);
+                            const uint32_t up = b & 0xdfu;
+                            const bool valid = up == ((0x54474341u >> (8 * bc)) & 0xffu);
+                            code = masked ? ROW_NONE : ((valid ? bc : 4u) | ((q < 30u ? q : 30u) >= minq ? 8u : 0u) | rconst);
+                        } else code = typ == 2 ? 5u : 6u;
+                        rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)code;
+                    }
+                    cb += win;
                 }
-                fpos += tot_r;
+                fpos = batch_end;
                 rpos += tot_q;
                 ci += 32;
                 off = 0;
