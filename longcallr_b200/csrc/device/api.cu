@@ -561,6 +561,9 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     TRY(cudaMemsetAsync(db->slot_flags, 0, db->n_slots ? db->n_slots : 1, st));
     if (ctx->P.flags & LCR_FLAG_EMIT_PLANES) {
         DALLOC(db->pl_acgt, db->n_pos * 4); DALLOC(db->pl_fwd, db->n_pos * 4); DALLOC(db->pl_d, db->n_pos); DALLOC(db->pl_n, db->n_pos); DALLOC(db->pl_ts, db->n_pos * 2);
+        const size_t np1 = db->n_pos ? db->n_pos : 1; /* regions that fail on the device keep zeroed planes */
+        TRY(cudaMemsetAsync(db->pl_acgt, 0, 16 * np1 / (db->n_pos ? 1 : 4), st)); TRY(cudaMemsetAsync(db->pl_fwd, 0, 16 * np1 / (db->n_pos ? 1 : 4), st));
+        TRY(cudaMemsetAsync(db->pl_d, 0, 4 * np1, st)); TRY(cudaMemsetAsync(db->pl_n, 0, 4 * np1, st)); TRY(cudaMemsetAsync(db->pl_ts, 0, 8 * np1 / (db->n_pos ? 1 : 2), st));
     }
     int rc = lcr_stage_pileup_impl(ctx, db, db->slot_flags);
     if (rc) return rc;
@@ -646,21 +649,27 @@ int lcr_fetch(lcr_ctx *ctx, lcr_device_batch *dbb, lcr_result **out) {
     }
     if ((ctx->P.flags & LCR_FLAG_EMIT_FRAGMENTS) && !(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) {
         const FragDebug &fd = db->extra.fragdbg;
-        const size_t nf = fd.frag_slot.size();
+        /* fragments of regions that failed are not reported (the reference would have panicked there) */
         box->frag_off.assign(nr + 1, 0);
-        for (uint32_t r = 0; r < nr; ++r) box->frag_off[r + 1] = hrs[r].frag_begin + hrs[r].n_frag;
-        for (uint32_t r = 0; r < nr; ++r) box->frag_off[r + 1] = std::max(box->frag_off[r + 1], box->frag_off[r]);
-        box->frag_read.resize(nf);
-        for (size_t f = 0; f < nf; ++f) {
-            const uint32_t slot = fd.frag_slot[f];
-            const uint32_t r = (uint32_t)(std::upper_bound(db->h_slot_off.begin(), db->h_slot_off.end(), slot) - db->h_slot_off.begin()) - 1;
-            box->frag_read[f] = db->extra.h_regions[r].read_begin + (slot - db->h_slot_off[r]);
+        box->elem_off.assign(1, 0);
+        for (uint32_t r = 0; r < nr; ++r) {
+            if (hrs[r].status == 0) {
+                for (uint32_t f = hrs[r].frag_begin; f < hrs[r].frag_begin + hrs[r].n_frag; ++f) {
+                    const uint32_t slot = fd.frag_slot[f];
+                    box->frag_read.push_back(db->extra.h_regions[r].read_begin + (slot - db->h_slot_off[r]));
+                    for (uint32_t e = fd.frag_elem_off[f]; e < fd.frag_elem_off[f + 1]; ++e) {
+                        box->elem_snp.push_back(fd.elem_snp[e]);
+                        box->elem_cell.push_back(fd.elem_cell[e]);
+                        box->elem_base.push_back(fd.elem_base[e]);
+                    }
+                    box->elem_off.push_back(box->elem_snp.size());
+                }
+            }
+            box->frag_off[r + 1] = (uint32_t)box->frag_read.size();
         }
-        box->elem_off.assign(fd.frag_elem_off.begin(), fd.frag_elem_off.end());
-        if (box->elem_off.empty()) box->elem_off.push_back(0);
-        box->elem_snp = fd.elem_snp; box->elem_cell = fd.elem_cell; box->elem_base = fd.elem_base;
+        const size_t nf = box->frag_read.size();
         res.fragments.n_frag = nf;
-        res.fragments.n_elem = fd.elem_snp.size();
+        res.fragments.n_elem = box->elem_snp.size();
         res.fragments.frag_off = box->frag_off.data();
         res.fragments.frag_read = box->frag_read.data();
         res.fragments.elem_off = box->elem_off.data();

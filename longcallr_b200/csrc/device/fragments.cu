@@ -119,8 +119,8 @@ __global__ void k_frag_fill(FragArgs a) {
     a.frag_slot[f] = slot;
     a.frag_elem_off[f] = e0;
     if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
+    if (rs.status != 0 || !rs.n_cand) { a.frag_links[f] = 0; return; } /* a failed region reports no fragments */
     a.is_fragment[read] = 1;
-    if (rs.status != 0 || !rs.n_cand) { a.frag_links[f] = 0; return; }
     const lcr_candidate *c = a.cand + rs.cand_begin;
     uint32_t k = 0, links = 0;
     const uint32_t floc = f - rs.frag_begin;

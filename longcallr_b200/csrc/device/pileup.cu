@@ -927,8 +927,10 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         TRY(cudaFreeAsync(perm_in, st));
         TRY(cudaFreeAsync(perm_out, st));
     }
-    k_cand_finalize<<<(db->n_regions + 63) / 64, 64, 0, st>>>(ctx->P, db->n_regions, keys_sorted, n_cand, db->cand, db->rstate);
-    db->timing.kernel_launches += 1;
+    if (db->n_regions) {
+        k_cand_finalize<<<(db->n_regions + 63) / 64, 64, 0, st>>>(ctx->P, db->n_regions, keys_sorted, n_cand, db->cand, db->rstate);
+        db->timing.kernel_launches += 1;
+    }
     TRY(cudaFreeAsync(keys_sorted, st));
     TRY(cudaFreeAsync(cand_raw, st));
     TRY(cudaFreeAsync(cand_key, st));

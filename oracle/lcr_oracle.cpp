@@ -1452,7 +1452,11 @@ struct Worker {
         std::vector<BaseFreq> pile;
         int st = pileup(pile);
         out.st.n_positions = (uint64_t)(reg.end - reg.start);
-        if (st) { out.status = st; return; }
+        if (st) { /* the reference panics here; the contract reports the status, no candidates, zeroed planes */
+            out.status = st;
+            if (P.flags & LCR_FLAG_EMIT_PLANES) out.pileup.assign((size_t)(reg.end - reg.start), BaseFreq());
+            return;
+        }
         get_candidate_snps(pile);
         if (P.flags & LCR_FLAG_EMIT_PLANES) out.pileup = std::move(pile);
         else std::vector<BaseFreq>().swap(pile);
