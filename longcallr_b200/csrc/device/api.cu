@@ -246,41 +246,39 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     uint32_t *es_base = nullptr, *es_cfg = nullptr, *work_region = nullptr, *work_chunk = nullptr;
     long long *es_prob = nullptr;
     {
-        const uint32_t per_cta = lcr_enum_cfgs_per_cta();
-        const uint32_t NF_SMALL = 2048, NF_BIG = 16384;
-        std::vector<uint32_t> base(n_regions + 1, 0), wr[2], wc[2];
-        uint32_t nfmax[2] = {0, 0};
-        std::vector<uint32_t> bin(n_regions, 2);
+        /* bins: launch shape (by number of configurations) x fragment-count class (shared memory footprint) */
+        const uint32_t NF_SMALL = 1024, NF_BIG = 16384;
+        const int NBIN = 8;
+        std::vector<uint32_t> base(n_regions + 1, 0), wr[NBIN], wc[NBIN];
+        uint32_t nfmax[NBIN] = {0, 0, 0, 0, 0, 0, 0, 0};
+        std::vector<int> bin(n_regions, -1);
         for (uint32_t r = 0; r < n_regions; ++r) {
             const LcrRegionState &s = hrs[r];
             uint32_t chunks = 0;
             if (s.status == 0 && s.n_cand && s.n_cand <= ctx->P.max_enum_snps && s.n_cand <= 10 && s.n_frag <= NF_BIG) {
+                const int shape = lcr_enum_shape_for(s.n_cand);
+                const uint32_t per_cta = lcr_enum_cfgs_per_cta(shape);
                 chunks = ((1u << s.n_cand) + per_cta - 1) / per_cta;
-                bin[r] = s.n_frag <= NF_SMALL ? 0 : 1;
+                bin[r] = shape * 2 + (s.n_frag <= NF_SMALL ? 0 : 1);
             }
             base[r + 1] = base[r] + chunks;
         }
-        /* work items of one bin are contiguous in launch order; outputs are addressed through a per-item slot */
-        std::vector<uint32_t> slot_of;
         const uint32_t n_work_total = base[n_regions];
         if (n_work_total) {
-            std::vector<uint32_t> all_region, all_chunk, out_slot;
-            for (int b = 0; b < 2; ++b)
-                for (uint32_t r = 0; r < n_regions; ++r)
-                    if (bin[r] == (uint32_t)b) {
-                        nfmax[b] = std::max(nfmax[b], hrs[r].n_frag);
-                        for (uint32_t ck = 0; ck < base[r + 1] - base[r]; ++ck) { wr[b].push_back(r); wc[b].push_back(ck); }
-                    }
+            for (uint32_t r = 0; r < n_regions; ++r)
+                if (bin[r] >= 0) {
+                    nfmax[bin[r]] = std::max(nfmax[bin[r]], hrs[r].n_frag);
+                    for (uint32_t ck = 0; ck < base[r + 1] - base[r]; ++ck) { wr[bin[r]].push_back(r); wc[bin[r]].push_back(ck); }
+                }
             DALLOC(es_base, (size_t)n_regions + 1);
             DALLOC(es_cfg, n_work_total);
             DALLOC(es_prob, n_work_total);
             DALLOC(work_region, n_work_total);
             DALLOC(work_chunk, n_work_total);
             TRY(cudaMemcpyAsync(es_base, base.data(), sizeof(uint32_t) * (n_regions + 1), cudaMemcpyHostToDevice, st));
-            /* launch bin by bin; each bin writes its winners into a scratch in launch order, scattered afterwards */
-            uint32_t off = 0;
+            /* each bin writes its winners in launch order; they are scattered to (region, chunk) order afterwards */
             std::vector<uint32_t> order_region, order_chunk;
-            for (int b = 0; b < 2; ++b) { order_region.insert(order_region.end(), wr[b].begin(), wr[b].end()); order_chunk.insert(order_chunk.end(), wc[b].begin(), wc[b].end()); }
+            for (int b = 0; b < NBIN; ++b) { order_region.insert(order_region.end(), wr[b].begin(), wr[b].end()); order_chunk.insert(order_chunk.end(), wc[b].begin(), wc[b].end()); }
             TRY(cudaMemcpyAsync(work_region, order_region.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
             TRY(cudaMemcpyAsync(work_chunk, order_chunk.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
             long long *tmp_prob = nullptr;
@@ -292,10 +290,11 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
             for (uint32_t i = 0; i < n_work_total; ++i) slot[i] = base[order_region[i]] + order_chunk[i];
             TRY(cudaMemcpyAsync(d_slot, slot.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
             TRY(cudaStreamSynchronize(st)); /* the host vectors above go out of scope */
-            for (int b = 0; b < 2; ++b) {
+            uint32_t off = 0;
+            for (int b = 0; b < NBIN; ++b) {
                 const uint32_t nw = (uint32_t)wr[b].size();
                 if (!nw) continue;
-                int e = lcr_launch_enum_search(pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, st);
+                int e = lcr_launch_enum_search(b / 2, pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, st);
                 if (e) { ctx->last_error = "k_enum_search launch failed"; ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
                 db->timing.kernel_launches += 1;
                 off += nw;

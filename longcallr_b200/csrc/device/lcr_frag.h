@@ -86,9 +86,9 @@ void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrR
 void lcr_launch_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj, cudaStream_t st);
 void lcr_launch_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region, cudaStream_t st);
 void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st);
-size_t lcr_enum_smem_bytes(uint32_t nf_cap);
-uint32_t lcr_enum_cfgs_per_cta();
-int lcr_launch_enum_search(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+int lcr_enum_shape_for(uint32_t n_cand);
+uint32_t lcr_enum_cfgs_per_cta(int shape);
+int lcr_launch_enum_search(int shape, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                            long long *out_prob, uint32_t *out_cfg, cudaStream_t st);
 
 #endif

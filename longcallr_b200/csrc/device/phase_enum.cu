@@ -16,9 +16,8 @@
  */
 #include "lcr_frag.h"
 
-#define EW 8            /* warps per CTA */
-#define ECFG_PER_WARP 8 /* configurations per warp */
 #define EMAXN 10
+#define EW_MAX 8
 
 namespace {
 
@@ -26,11 +25,14 @@ struct EnumShared {
     long long W[32], OK[32], ERR[32];
     long long C[EMAXN], R[EMAXN], V[EMAXN];
     uint32_t cov[EMAXN];
-    long long best_prob[EW];
-    uint32_t best_cfg[EW];
-    unsigned long long iters[EW];
+    long long best_prob[EW_MAX];
+    uint32_t best_cfg[EW_MAX];
+    unsigned long long iters[EW_MAX];
 };
 
+/* EW warps per CTA, ECFG_PER_WARP configurations per warp (strided over the chunk so that warps stay balanced);
+   small regions use small CTAs so that many of them share an SM */
+template <int EW, int ECFG_PER_WARP>
 __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                                                          long long *out_prob, uint32_t *out_cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
     unsigned long long iters = 0;
     const uint32_t nwords = (nf + 31) / 32;
     for (uint32_t j = 0; j < ECFG_PER_WARP; ++j) {
-        const uint32_t cfg = chunk * (EW * ECFG_PER_WARP) + warp * ECFG_PER_WARP + j;
+        const uint32_t cfg = chunk * (EW * ECFG_PER_WARP) + j * EW + warp;
         if (cfg >= n_cfg) break;
         uint32_t dneg = cfg; /* bit i set: delta_i = -1 */
         int eta[EMAXN];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
         for (int w = 0; w < EW; ++w) {
             it += S.iters[w];
             if (S.best_cfg[w] == 0xffffffffu) continue;
-            if (bc == 0xffffffffu || S.best_prob[w] > bp) { bp = S.best_prob[w]; bc = S.best_cfg[w]; }
+            if (bc == 0xffffffffu || S.best_prob[w] > bp || (S.best_prob[w] == bp && S.best_cfg[w] < bc)) { bp = S.best_prob[w]; bc = S.best_cfg[w]; }
         }
         const uint32_t first = chunk * (EW * ECFG_PER_WARP);
         ncfg_done = n_cfg > first ? (n_cfg - first < EW * ECFG_PER_WARP ? n_cfg - first : EW * ECFG_PER_WARP) : 0;
@@ -239,15 +241,30 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
 
 } // namespace
 
-size_t lcr_enum_smem_bytes(uint32_t nf_cap) { return (size_t)nf_cap * 12 + (size_t)EW * ((nf_cap + 31) / 32) * 4 + 16; }
-uint32_t lcr_enum_cfgs_per_cta() { return EW * ECFG_PER_WARP; }
+/* launch shapes by number of configurations: {warps per CTA, configurations per warp} */
+static const int SHAPES[4][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}};
 
-int lcr_launch_enum_search(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+int lcr_enum_shape_for(uint32_t n_cand) { return n_cand <= 2 ? 0 : (n_cand == 3 ? 1 : (n_cand == 4 ? 2 : 3)); }
+uint32_t lcr_enum_cfgs_per_cta(int shape) { return (uint32_t)(SHAPES[shape][0] * SHAPES[shape][1]); }
+static size_t smem_bytes(uint32_t nf_cap, int ew) { return (size_t)nf_cap * 12 + (size_t)ew * ((nf_cap + 31) / 32) * 4 + 16; }
+
+template <int EW, int CPW>
+static int launch_shape(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+                        long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
+    const size_t smem = smem_bytes(nf_cap, EW);
+    cudaError_t e = cudaFuncSetAttribute(k_enum_search<EW, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_enum_search<EW, CPW><<<n_work, EW * 32, smem, st>>>(a, work_region, work_chunk, nf_cap, out_prob, out_cfg);
+    return 0;
+}
+
+int lcr_launch_enum_search(int shape, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                            long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
     if (!n_work) return 0;
-    const size_t smem = lcr_enum_smem_bytes(nf_cap);
-    cudaError_t e = cudaFuncSetAttribute(k_enum_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    k_enum_search<<<n_work, EW * 32, smem, st>>>(a, work_region, work_chunk, nf_cap, out_prob, out_cfg);
-    return 0;
+    switch (shape) {
+        case 0: return launch_shape<1, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 1: return launch_shape<2, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 2: return launch_shape<4, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        default: return launch_shape<8, 8>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+    }
 }
