@@ -10,6 +10,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -85,6 +86,13 @@ int h2d_padded(lcr_ctx *ctx, T **dst, const T *src, size_t n, size_t pad, uint64
         if (bytes) *bytes += sizeof(T) * n;
     }
     return 0;
+}
+
+/* fragment count from which an LD-path region gets the cooperative whole-GPU kernel (LCR_BIG_REGION_FRAGS overrides: tests) */
+static uint32_t big_frag_threshold() {
+    const char *e = getenv("LCR_BIG_REGION_FRAGS");
+    if (e && *e) return (uint32_t)strtoul(e, nullptr, 10);
+    return 8192;
 }
 
 __global__ void k_scatter_winners(uint32_t n, const uint32_t *slot, const long long *prob, const uint32_t *cfg, long long *out_prob, uint32_t *out_cfg) {
@@ -305,8 +313,29 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
             pa.es_base = es_base; pa.es_prob = es_prob; pa.es_cfg = es_cfg;
         }
     }
+    /* regions too large for one CTA take the whole GPU, one after the other */
+    uint8_t *big_region = nullptr;
+    void *bcast = nullptr;
+    std::vector<uint32_t> big_list;
+    {
+        std::vector<uint8_t> big(n_regions, 0);
+        for (uint32_t r = 0; r < n_regions; ++r)
+            if (hrs[r].status == 0 && hrs[r].n_cand > ctx->P.max_enum_snps && hrs[r].n_frag >= big_frag_threshold()) { big[r] = 1; big_list.push_back(r); }
+        if (!big_list.empty()) {
+            DALLOC(big_region, n_regions);
+            TRY(cudaMemcpyAsync(big_region, big.data(), n_regions, cudaMemcpyHostToDevice, st));
+            TRY(cudaStreamSynchronize(st));
+            TRY(cudaMallocAsync(&bcast, lcr_phase_bcast_bytes(), st));
+            pa.big_region = big_region;
+        }
+    }
     lcr_launch_phase(pa, st);
     db->timing.kernel_launches += 1;
+    for (uint32_t r : big_list) {
+        int e = lcr_launch_phase_grid(pa, r, bcast, ctx->sm_count, st);
+        if (e) { ctx->last_error = std::string("k_phase_grid: ") + cudaGetErrorString((cudaError_t)e); ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
+        db->timing.kernel_launches += 1;
+    }
     cudaEvent_t ev_end;
     TRY(cudaEventCreate(&ev_end));
     TRY(cudaEventRecord(ev_end, st));
@@ -340,6 +369,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     DFREE(pa.label); DFREE(pa.rank); DFREE(pa.work); DFREE(pa.blk_q); DFREE(pa.blk_qflip);
     DFREE(pa.tag); DFREE(pa.best_tag); DFREE(pa.fp); DFREE(pa.assign);
     DFREE(es_base); DFREE(es_cfg); DFREE(es_prob); DFREE(work_region); DFREE(work_chunk);
+    DFREE(big_region); DFREE(bcast);
     return LCR_OK;
 }
 

@@ -72,6 +72,7 @@ struct PhaseArgs {
     int8_t *hp;
     uint32_t *ps;
     /* winners of the warp-per-configuration enumeration search (phase_enum.cu), per (region, chunk) */
+    const uint8_t *big_region; /* [n_regions] 1: handled by the cooperative whole-GPU kernel, or null */
     const uint32_t *es_base; /* [n_regions+1] or null */
     const long long *es_prob;
     const uint32_t *es_cfg;
@@ -86,6 +87,8 @@ void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrR
 void lcr_launch_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj, cudaStream_t st);
 void lcr_launch_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region, cudaStream_t st);
 void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st);
+int lcr_launch_phase_grid(const PhaseArgs &a, uint32_t reg, void *bcast_scratch, int sm_count, cudaStream_t st);
+size_t lcr_phase_bcast_bytes();
 int lcr_enum_shape_for(uint32_t n_cand);
 uint32_t lcr_enum_cfgs_per_cta(int shape);
 int lcr_launch_enum_search(int shape, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,

@@ -17,17 +17,35 @@
  * order-independent integer reduction: reads flip on the sign of sum(p * sigma * delta * W[q])
  * over their heterozygous sites, SNPs pick the arg-max of four integer column sums.
  */
+#include <cooperative_groups.h>
+
 #include "lcr_frag.h"
 
-#define PB 256
+namespace cg = cooperative_groups;
+
+#define PB 256          /* threads per CTA of the per-region kernel */
+#define PBG 512         /* threads per CTA of the cooperative (whole-GPU) kernel */
 #define NONE32 0xffffffffu
 
 namespace {
+
+/* values every thread of the team must agree on; lives in shared memory (one CTA per region) or in
+   global memory (cooperative kernel: the whole grid works on one large region) */
+struct TeamBcast {
+    int flag[3];
+    long long acc[3];
+    uint32_t root0;
+    int decision;
+};
 
 struct Ctx {
     const PhaseArgs &a;
     const LcrDeviceTables &T;
     uint32_t reg, n, nf, cb, fb, tid;
+    uint32_t nthreads;  /* team size: PB, or gridDim.x * PBG */
+    bool grid;          /* team is the whole cooperative grid */
+    uint32_t epoch_any, epoch_sum; /* number of tany() / tsum() calls so far (same in every thread) */
+    TeamBcast *bc;
     lcr_candidate *c;
     uint64_t region_key;
     uint32_t slot0;
@@ -48,14 +66,38 @@ __device__ __forceinline__ int64_t aki_fx(const LcrDeviceTables &T, int sigma, i
 __device__ __forceinline__ int cell_p(int8_t cell) { return cell > 0 ? 1 : -1; }
 __device__ __forceinline__ int cell_q(int8_t cell) { return (cell > 0 ? cell : -cell) - 1; }
 
-__device__ long long block_sum(Ctx &x, long long v) {
+/* team barrier */
+__device__ __forceinline__ void tsync(Ctx &x) {
+    if (x.grid) cg::this_grid().sync();
+    else __syncthreads();
+}
+/* team-wide OR (also a barrier).  Grid teams rotate three flag slots so that a reset never races a later write. */
+__device__ int tany(Ctx &x, int v) {
+    if (!x.grid) return __syncthreads_or(v);
+    const uint32_t k = x.epoch_any++;
+    if (v) x.bc->flag[k % 3] = 1;
+    cg::this_grid().sync();
+    const int r = *(volatile int *)&x.bc->flag[k % 3];
+    if (x.tid == 0) x.bc->flag[(k + 2) % 3] = 0;
+    return r;
+}
+/* team-wide sum (also a barrier) */
+__device__ long long tsum(Ctx &x, long long v) {
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     __syncthreads();
-    if ((x.tid & 31) == 0) x.sh[x.tid >> 5] = v;
+    const uint32_t lt = threadIdx.x;
+    if ((lt & 31) == 0) x.sh[lt >> 5] = v;
     __syncthreads();
     long long r = 0;
-    for (int w = 0; w < PB / 32; ++w) r += x.sh[w];
+    const uint32_t nw = blockDim.x / 32;
+    for (uint32_t w = 0; w < nw; ++w) r += x.sh[w];
     __syncthreads();
+    if (!x.grid) return r;
+    const uint32_t k = x.epoch_sum++;
+    if (lt == 0 && r) atomicAdd((unsigned long long *)&x.bc->acc[k % 3], (unsigned long long)r);
+    cg::this_grid().sync();
+    r = *(volatile long long *)&x.bc->acc[k % 3];
+    if (x.tid == 0) x.bc->acc[(k + 2) % 3] = 0;
     return r;
 }
 
@@ -87,7 +129,7 @@ __device__ __forceinline__ void col_L(const LcrDeviceTables &T, const ColFx &c, 
 /* cal_overall_probability (phase.rs:257-276) */
 __device__ long long objective(Ctx &x) {
     long long s = 0;
-    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
         if (!x.fp[k] || x.tag[k] == 0) continue;
         const int sg = x.tag[k];
         for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
@@ -97,7 +139,7 @@ __device__ long long objective(Ctx &x) {
             s += aki_fx(x.T, sg, x.hap[i], x.gen[i], cell_p(cell), cell_q(cell));
         }
     }
-    return block_sum(x, s);
+    return tsum(x, s);
 }
 
 /* cross_optimize (phase.rs:810-976) */
@@ -108,7 +150,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
         x.n_iters++;
         int better = 0;
         /* sigma sweep (phase.rs:823-868) */
-        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
             if (!x.fp[k]) continue;
             const int sg = x.tag[k];
             if (sg == 0) continue;
@@ -123,12 +165,12 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             }
             if (diff < 0) { x.tag[k] = (int8_t)(-sg); better = 1; }
         }
-        better = __syncthreads_or(better);
+        better = tany(x, better);
         if (!better) ht_increase = false;
         else { ht_increase = true; hg_increase = true; }
         /* delta / eta sweep (phase.rs:872-958) */
         better = 0;
-        for (uint32_t i = x.tid; i < x.n; i += PB) {
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
             if (!x.phase0[i]) continue;
             if (keep_conserved && x.conserved[i]) continue;
             const int d = x.hap[i], eta = x.gen[i];
@@ -162,7 +204,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             x.gen[i] = (int8_t)ne;
             if (L_new > L_old) better = 1;
         }
-        better = __syncthreads_or(better);
+        better = tany(x, better);
         if (!better) hg_increase = false;
         else { hg_increase = true; ht_increase = true; }
         if (++num_iters > 20) break;
@@ -171,23 +213,23 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
 }
 
 __device__ void save_best(Ctx &x) {
-    for (uint32_t i = x.tid; i < x.n; i += PB) { x.best_hap[i] = x.hap[i]; x.best_gen[i] = x.gen[i]; }
-    for (uint32_t k = x.tid; k < x.nf; k += PB) x.best_tag[k] = x.tag[k];
-    __syncthreads();
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.best_hap[i] = x.hap[i]; x.best_gen[i] = x.gen[i]; }
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) x.best_tag[k] = x.tag[k];
+    tsync(x);
 }
 __device__ void load_best(Ctx &x) {
-    for (uint32_t i = x.tid; i < x.n; i += PB) { x.hap[i] = x.best_hap[i]; x.gen[i] = x.best_gen[i]; }
-    for (uint32_t k = x.tid; k < x.nf; k += PB) x.tag[k] = x.best_tag[k];
-    __syncthreads();
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.hap[i] = x.best_hap[i]; x.gen[i] = x.best_gen[i]; }
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) x.tag[k] = x.best_tag[k];
+    tsync(x);
 }
 __device__ void init_genotype(Ctx &x) { /* phase.rs:682-691 */
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const int vt = x.c[i].variant_type;
         x.gen[i] = (int8_t)(vt == 0 ? 1 : (vt == 1 ? 0 : ((vt == 2 || vt == 3) ? -1 : x.gen[i])));
     }
 }
 __device__ void init_assignment(Ctx &x, uint32_t call) { /* phase.rs:673-680 */
-    for (uint32_t k = x.tid; k < x.nf; k += PB)
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads)
         if (x.fp[k]) x.tag[k] = uniform(x, LCR_RNG_INIT_SIGMA, call, read_rel(x, k)) < 0.5 ? -1 : 1;
 }
 
@@ -202,10 +244,10 @@ __device__ bool phase_enum(Ctx &x) {
             if (cw == NONE32) continue;
             if (cfg == NONE32 || x.a.es_prob[w] > bp || (x.a.es_prob[w] == bp && cw < cfg)) { bp = x.a.es_prob[w]; cfg = cw; }
         }
-        for (uint32_t i = x.tid; i < x.n; i += PB) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
         init_assignment(x, cfg);
         init_genotype(x);
-        __syncthreads();
+        tsync(x);
         cross_optimize(x, false, true);
         return true;
     }
@@ -213,10 +255,10 @@ __device__ bool phase_enum(Ctx &x) {
     bool have = false;
     const uint32_t n_cfg = 1u << x.n;
     for (uint32_t cfg = 0; cfg < n_cfg; ++cfg) {
-        for (uint32_t i = x.tid; i < x.n; i += PB) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
         init_assignment(x, cfg);
         init_genotype(x);
-        __syncthreads();
+        tsync(x);
         const long long prob = cross_optimize(x, false, true);
         if (!have || prob > best) { best = prob; have = true; save_best(x); }
     }
@@ -236,9 +278,9 @@ __device__ __forceinline__ bool flip_read_of(const Ctx &x, uint32_t k, uint32_t 
 
 /* cross_optimize_by_block (phase.rs:1298-1394); block scores are sums of round((1 - L1/D) * 2^40) */
 __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
-    for (uint32_t i = x.tid; i < x.n; i += PB) { x.blk_q[i] = 0; x.blk_qflip[i] = 0; }
-    __syncthreads();
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.blk_q[i] = 0; x.blk_qflip[i] = 0; }
+    tsync(x);
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const uint32_t root = x.label[i];
         if (root == NONE32) continue;
         const int d = x.hap[i], eta = x.gen[i];
@@ -260,11 +302,11 @@ __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
         atomicAdd((unsigned long long *)&x.blk_q[root], (unsigned long long)__double2ll_rn(t0 * 1099511627776.0));
         atomicAdd((unsigned long long *)&x.blk_qflip[root], (unsigned long long)__double2ll_rn(t1 * 1099511627776.0));
     }
-    __syncthreads();
+    tsync(x);
     /* haplotags: only the last block of ld_blocks (the component of the lowest LD node) survives the
        per-block rewrite of tmp_haplotag (phase.rs:1365-1378) */
     if (root0 != NONE32 && x.blk_q[root0] < x.blk_qflip[root0]) {
-        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
             if (!x.fp[k] || x.tag[k] == 0) continue;
             uint32_t best_idx = NONE32, best_rank = 0;
             for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
@@ -276,11 +318,11 @@ __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
             if (flip_read_of(x, k, best_idx, root0)) x.tag[k] = (int8_t)(-x.tag[k]);
         }
     }
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const uint32_t root = x.label[i];
         if (root != NONE32 && x.blk_q[root] < x.blk_qflip[root]) x.hap[i] = (int8_t)(-x.hap[i]);
     }
-    __syncthreads();
+    tsync(x);
     return objective(x);
 }
 
@@ -290,14 +332,13 @@ __device__ void phase_ld(Ctx &x) {
     const uint32_t adj_base = adj_off[0];
     const uint32_t *adj = x.a.adj;
     /* init_haplotypes_LD2 (phase.rs:600-652) */
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         x.hap[i] = uniform(x, LCR_RNG_INIT_DELTA, 0, i) < 0.5 ? 1 : -1;
         x.label[i] = NONE32;
         x.rank[i] = 0;
         x.conserved[i] = adj_off[i + 1] > adj_off[i] ? 1 : 0;
     }
-    __syncthreads();
-    __shared__ uint32_t s_root0;
+    tsync(x);
     if (x.tid == 0) {
         /* Bfs from the first node of every block: a node takes its sign from the neighbour that was
            dequeued first, which is the node that discovered it */
@@ -336,14 +377,14 @@ __device__ void phase_ld(Ctx &x) {
                 }
             }
         }
-        s_root0 = root0;
+        x.bc->root0 = root0;
         (void)adj_base;
     }
-    __syncthreads();
-    const uint32_t root0 = s_root0;
+    tsync(x);
+    const uint32_t root0 = *(volatile uint32_t *)&x.bc->root0;
     init_genotype(x);
     init_assignment(x, 0);
-    __syncthreads();
+    tsync(x);
     long long best = cross_optimize(x, true, false);
     save_best(x);
     load_best(x);
@@ -352,20 +393,20 @@ __device__ void phase_ld(Ctx &x) {
     load_best(x);
     for (uint32_t t = 0; t <= x.n / 4; ++t) {
         const bool flip = (t & 1u) == 1u;
-        for (uint32_t i = x.tid; i < x.n; i += PB) {
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
             const double rg = uniform(x, LCR_RNG_PERTURB_DELTA, t, i);
             if (rg < 0.1) x.hap[i] = flip ? 1 : -1;
             else if (rg >= 0.9) x.hap[i] = flip ? -1 : 1;
         }
-        __syncthreads();
+        tsync(x);
         prob = cross_optimize(x, false, false);
         if (prob > best) { best = prob; save_best(x); }
         load_best(x);
-        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
             if (!x.fp[k] || x.tag[k] == 0) continue;
             if (uniform(x, LCR_RNG_PERTURB_SIGMA, t, read_rel(x, k)) < 0.1) x.tag[k] = (int8_t)(-x.tag[k]);
         }
-        __syncthreads();
+        tsync(x);
         prob = cross_optimize(x, false, false);
         if (prob > best) { best = prob; save_best(x); }
         load_best(x);
@@ -374,7 +415,7 @@ __device__ void phase_ld(Ctx &x) {
 
 /* assign_reads_haplotype (snpfrags.rs:548-625) */
 __device__ void assign_reads(Ctx &x, bool record) {
-    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
         if (!x.fp[k]) continue;
         const int sg = x.tag[k];
         long long A = 0, B = 0;
@@ -404,7 +445,7 @@ __device__ void assign_reads(Ctx &x, bool record) {
             x.a.hp[read] = (int8_t)asg;
         }
     }
-    __syncthreads();
+    tsync(x);
 }
 
 /* -10 log10(1 - cal_phase_score_log) from three column sums (phase.rs:238-255, snpfrags.rs:483) */
@@ -415,7 +456,7 @@ __device__ __forceinline__ double phase_score_from(long long L1, long long L2, l
 
 /* assign_snp_haplotype_genotype (snpfrags.rs:378-546) */
 __device__ void assign_snps(Ctx &x) {
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         lcr_candidate &s = x.c[i];
         if (!(s.flags & LCR_CF_FOR_PHASING)) { s.flags |= LCR_CF_NON_SELECTED; continue; }
         if (x.cover_off[i + 1] == x.cover_off[i]) { s.flags |= LCR_CF_SINGLE; continue; }
@@ -448,20 +489,19 @@ __device__ void assign_snps(Ctx &x) {
         if (hap1 >= 1 && hap2 >= 1) s.phase_score = phase_score_from(s.haplotype == 1 ? Lp : Lm, Lp, Lm);
         else s.phase_score = 0.19940219;
     }
-    __syncthreads();
+    tsync(x);
 }
 
 /* eval_rna_edit_var_phase / eval_low_frac_var_phase (snpfrags.rs:191-376), candidates visited in list order */
 __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
     const float mps = x.a.P.min_phase_score - 3.0f;
-    __shared__ int s_decision;
     for (uint32_t ti = 0; ti < x.n; ++ti) {
         lcr_candidate &s = x.c[ti];
         if (!(s.flags & list_flag)) continue;
-        if (x.cover_off[ti + 1] == x.cover_off[ti]) { if (x.tid == 0) s.flags |= LCR_CF_SINGLE; __syncthreads(); continue; }
-        if (s.variant_type != 1) { if (x.tid == 0) s.flags |= LCR_CF_NON_SELECTED; __syncthreads(); continue; }
+        if (x.cover_off[ti + 1] == x.cover_off[ti]) { if (x.tid == 0) s.flags |= LCR_CF_SINGLE; tsync(x); continue; }
+        if (s.variant_type != 1) { if (x.tid == 0) s.flags |= LCR_CF_NON_SELECTED; tsync(x); continue; }
         long long Lp = 0, Lm = 0, h1 = 0, h2 = 0, cnt = 0;
-        for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += PB) {
+        for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += x.nthreads) {
             const uint32_t k = x.a.cover_frag[w];
             if (!x.fp[k] || x.assign[k] == 0 || x.frag_links[k] < x.a.P.min_linkers) continue;
             if (x.assign[k] == 1) h1++; else if (x.assign[k] == 2) h2++;
@@ -471,7 +511,7 @@ __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
             Lm += aki_fx(x.T, sg, -1, 0, p, q);
             cnt++;
         }
-        Lp = block_sum(x, Lp); Lm = block_sum(x, Lm); h1 = block_sum(x, h1); h2 = block_sum(x, h2); cnt = block_sum(x, cnt);
+        Lp = tsum(x, Lp); Lm = tsum(x, Lm); h1 = tsum(x, h1); h2 = tsum(x, h2); cnt = tsum(x, cnt);
         if (x.tid == 0) {
             int decision = 0;
             if (cnt == 0 || h1 < 2 || h2 < 2) s.flags |= LCR_CF_SINGLE;
@@ -494,32 +534,32 @@ __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
                     else s.flags |= LCR_CF_RNA_EDITING;
                 }
             }
-            s_decision = decision;
+            x.bc->decision = decision;
         }
-        __syncthreads();
-        if (s_decision) {
-            for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += PB) {
+        tsync(x);
+        if (*(volatile int *)&x.bc->decision) {
+            for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += x.nthreads) {
                 const uint32_t k = x.a.cover_frag[w];
                 x.fp[k] = 1;
                 if (x.tag[k] == 0 || x.assign[k] == 0) x.tag[k] = uniform(x, LCR_RNG_RESCUE_SIGMA, ti, read_rel(x, k)) < 0.5 ? -1 : 1;
             }
         }
-        __syncthreads();
+        tsync(x);
     }
 }
 
 /* assign_phase_set (snpfrags.rs:628-733): a read links the nodes it sees with the same p * delta */
 __device__ void phase_sets(Ctx &x) {
     const double mps = (double)x.a.P.min_phase_score;
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const lcr_candidate &s = x.c[i];
         const bool node = s.genotype == 0 && s.variant_type == 1 && !(s.flags & (LCR_CF_DENSE | LCR_CF_RNA_EDITING)) && !(s.phase_score < mps);
         x.label[i] = node ? i : NONE32;
     }
-    __syncthreads();
+    tsync(x);
     for (;;) {
         int changed = 0;
-        for (uint32_t k = x.tid; k < x.nf; k += PB) {
+        for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
             if (!x.fp[k] || x.assign[k] == 0) continue;
             uint32_t mn[2] = {NONE32, NONE32};
             for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
@@ -538,19 +578,19 @@ __device__ void phase_sets(Ctx &x) {
             }
         }
         /* pointer jumping */
-        __syncthreads();
-        for (uint32_t i = x.tid; i < x.n; i += PB) {
+        tsync(x);
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
             uint32_t l = x.label[i];
             if (l == NONE32) continue;
             while (x.label[l] < l) l = x.label[l];
             if (l < x.label[i]) { x.label[i] = l; changed = 1; }
         }
-        if (!__syncthreads_or(changed)) break;
+        if (!tany(x, changed)) break;
     }
-    for (uint32_t i = x.tid; i < x.n; i += PB)
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads)
         if (x.label[i] != NONE32) x.c[i].phase_set = (uint32_t)(x.c[x.label[i]].pos + 1);
     /* components are visited in descending order of their first node; a read keeps the first id it meets */
-    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
         if (!x.fp[k] || x.assign[k] == 0) continue;
         uint32_t cnt[2] = {0, 0}, root[2] = {0, 0}, nn = 0;
         for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
@@ -571,19 +611,17 @@ __device__ void phase_sets(Ctx &x) {
             x.a.ps[read] = (uint32_t)(x.c[best].pos + 1);
         }
     }
-    __syncthreads();
+    tsync(x);
 }
 
-__global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
-    __shared__ long long sh[PB / 32 * 2];
-    const uint32_t reg = blockIdx.x;
-    const LcrRegionState rs = a.rstate[reg];
-    if (rs.status != 0 || rs.n_cand == 0) return;
-    Ctx x{a, *a.tables};
-    x.reg = reg; x.n = rs.n_cand; x.nf = rs.n_frag; x.cb = rs.cand_begin; x.fb = rs.frag_begin; x.tid = threadIdx.x;
+/* the whole worker body after the fragment matrix exists: phase(), then thread.rs:168-201 */
+__device__ void run_region(Ctx &x) {
+    const PhaseArgs &a = x.a;
+    const LcrRegionState rs = a.rstate[x.reg];
+    x.n = rs.n_cand; x.nf = rs.n_frag; x.cb = rs.cand_begin; x.fb = rs.frag_begin;
     x.c = a.cand + x.cb;
-    x.region_key = lcr_region_key(a.regions[reg].tid, a.regions[reg].start);
-    x.slot0 = a.slot_off[reg];
+    x.region_key = lcr_region_key(a.regions[x.reg].tid, a.regions[x.reg].start);
+    x.slot0 = a.slot_off[x.reg];
     x.hap = a.hap + x.cb; x.gen = a.gen + x.cb; x.best_hap = a.best_hap + x.cb; x.best_gen = a.best_gen + x.cb;
     x.phase0 = a.phase0 + x.cb; x.conserved = a.conserved + x.cb;
     x.label = a.label + x.cb; x.rank = a.rank + x.cb;
@@ -593,27 +631,28 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     x.cover_off = a.cover_off + x.cb;
     x.adj_off = a.adj_off ? a.adj_off + x.cb : nullptr;
     x.work = (a.adj_off && a.work) ? a.work + (a.adj_off[x.cb] + x.cb) : nullptr;
-    x.sh = sh;
     x.n_iters = 0;
+    x.epoch_any = 0;
+    x.epoch_sum = 0;
 
-    for (uint32_t i = x.tid; i < x.n; i += PB) {
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         x.hap[i] = 0;
         x.gen[i] = x.c[i].genotype;
         x.phase0[i] = (x.c[i].flags & LCR_CF_FOR_PHASING) ? 1 : 0;
         x.conserved[i] = 0;
     }
-    for (uint32_t k = x.tid; k < x.nf; k += PB) {
+    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
         x.tag[k] = 0;
         x.assign[k] = 0;
         x.fp[k] = x.frag_links[k] >= a.P.min_linkers ? 1 : 0;
     }
-    __syncthreads();
+    tsync(x);
     uint64_t n_calls;
     bool counted_elsewhere = false;
     if (x.n <= a.P.max_enum_snps) { counted_elsewhere = phase_enum(x); n_calls = 1ull << x.n; }
     else { phase_ld(x); n_calls = 1ull + 2ull * (x.n / 4 + 1); }
-    for (uint32_t i = x.tid; i < x.n; i += PB) { x.c[i].haplotype = x.hap[i]; x.c[i].genotype = x.gen[i]; }
-    __syncthreads();
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.c[i].haplotype = x.hap[i]; x.c[i].genotype = x.gen[i]; }
+    tsync(x);
     /* thread.rs:168-201 */
     assign_reads(x, false);
     assign_snps(x);
@@ -630,8 +669,45 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     }
 }
 
+/* one CTA per region (everything except the few regions handed to the cooperative kernel) */
+__global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
+    __shared__ long long sh[32];
+    __shared__ TeamBcast bc;
+    const uint32_t reg = blockIdx.x;
+    const LcrRegionState rs = a.rstate[reg];
+    if (rs.status != 0 || rs.n_cand == 0 || (a.big_region && a.big_region[reg])) return;
+    Ctx x{a, *a.tables};
+    x.reg = reg; x.tid = threadIdx.x; x.nthreads = PB; x.grid = false; x.bc = &bc; x.sh = sh;
+    run_region(x);
+}
+
+/* the whole GPU on one large region: every sweep is a grid-wide pass over the fragment matrix in L2,
+   grid.sync() between passes, no host round trips (SURVEY.md section 7 "ragged work", BASELINE config 5) */
+__global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, uint32_t reg, TeamBcast *gbc) {
+    __shared__ long long sh[32];
+    Ctx x{a, *a.tables};
+    x.reg = reg; x.tid = blockIdx.x * blockDim.x + threadIdx.x; x.nthreads = gridDim.x * blockDim.x; x.grid = true; x.bc = gbc; x.sh = sh;
+    run_region(x);
+}
+
 } // namespace
 
 void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st) {
     if (a.n_regions) k_phase<<<a.n_regions, PB, 0, st>>>(a);
 }
+
+int lcr_launch_phase_grid(const PhaseArgs &a, uint32_t reg, void *bcast_scratch, int sm_count, cudaStream_t st) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_phase_grid, PBG, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    if (occ > 2) occ = 2;
+    e = cudaMemsetAsync(bcast_scratch, 0, sizeof(TeamBcast), st);
+    if (e != cudaSuccess) return (int)e;
+    PhaseArgs args = a;
+    TeamBcast *gbc = reinterpret_cast<TeamBcast *>(bcast_scratch);
+    void *params[] = {&args, &reg, &gbc};
+    e = cudaLaunchCooperativeKernel((void *)k_phase_grid, dim3((unsigned)(sm_count * occ)), dim3(PBG), params, 0, st);
+    return (int)e;
+}
+size_t lcr_phase_bcast_bytes() { return sizeof(TeamBcast); }

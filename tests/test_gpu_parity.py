@@ -145,3 +145,20 @@ def test_full_size_invariants_cfg2():
     # whole-run checksum equals the oracle's on the same input (contract mode, all host threads)
     want = ob.run(p, batch, refs, mode=0, threads=os.cpu_count() or 1)
     helpers.compare_results(got, want, "cfg2 full size")
+
+
+def test_cooperative_grid_kernel_matches_oracle(monkeypatch):
+    """Large LD-path regions run on the whole GPU (k_phase_grid); force that path on a small stress case."""
+    monkeypatch.setenv("LCR_BIG_REGION_FRAGS", "64")
+    syn = host.Synthetic(seed=6, contig_len=40_000, n_contigs=1, platform=0, depth=150.0, n_het=300, n_edit=20, max_intron=500, both_strands=0, single_region=1, n_threads=4)
+    p = host.params_preset("hifi-masseq", seed=12, flags=abi.LCR_FLAG_EMIT_FRAGMENTS)
+    regions, _ = host.find_regions(syn.reads, p)
+    got, want = run_both(p, syn.reads, syn.reference.for_reads(syn.reads), regions)
+    assert want.cand_off[-1] > 100 and got.stats["n_fragments"] > 1000
+    helpers.compare_results(got, want, "grid kernel")
+    # a mix: synthetic genes where only some regions exceed the threshold
+    syn = host.Synthetic(seed=13, contig_len=150_000, n_contigs=1, platform=1, depth=40.0, n_het=200, n_edit=30, both_strands=1, max_intron=300, max_gap=600, n_threads=4)
+    p = host.params_preset("ont-cdna", seed=5)
+    regions, _ = host.find_regions(syn.reads, p)
+    got, want = run_both(p, syn.reads, syn.reference.for_reads(syn.reads), regions)
+    helpers.compare_results(got, want, "grid kernel mixed")
