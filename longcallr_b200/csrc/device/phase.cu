@@ -117,6 +117,15 @@ __device__ __forceinline__ void col_add(const LcrDeviceTables &T, ColFx &c, int 
     c.homvar += aki_fx(T, sigma, delta, -1, p, q);
     c.cov++;
 }
+__device__ __forceinline__ void col_reduce(ColFx &c) { /* all lanes end up with the warp totals */
+    for (int o = 16; o; o >>= 1) {
+        c.het_d += __shfl_xor_sync(0xffffffffu, c.het_d, o);
+        c.het_nd += __shfl_xor_sync(0xffffffffu, c.het_nd, o);
+        c.homref += __shfl_xor_sync(0xffffffffu, c.homref, o);
+        c.homvar += __shfl_xor_sync(0xffffffffu, c.homvar, o);
+        c.cov += __shfl_xor_sync(0xffffffffu, c.cov, o);
+    }
+}
 __device__ __forceinline__ void col_L(const LcrDeviceTables &T, const ColFx &c, long long L[4], long long &D) {
     const long long ph = T.fx_prior_het - (long long)c.cov * T.fx_log10_2;
     L[0] = c.het_d + ph;
@@ -170,17 +179,20 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
         else { ht_increase = true; hg_increase = true; }
         /* delta / eta sweep (phase.rs:872-958) */
         better = 0;
-        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
+        /* one warp per SNP: lanes stride the column, five shuffled sums */
+        for (uint32_t i = x.tid >> 5; i < x.n; i += x.nthreads >> 5) {
             if (!x.phase0[i]) continue;
             if (keep_conserved && x.conserved[i]) continue;
             const int d = x.hap[i], eta = x.gen[i];
             ColFx col;
-            for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
+            for (uint32_t w = x.cover_off[i] + (x.tid & 31); w < x.cover_off[i + 1]; w += 32) {
                 const uint32_t k = x.a.cover_frag[w];
                 if (!x.fp[k] || x.tag[k] == 0) continue;
                 const int8_t cell = x.a.cover_cell[w];
                 col_add(x.T, col, x.tag[k], d, cell_p(cell), cell_q(cell));
             }
+            col_reduce(col);
+            if ((x.tid & 31) != 0) continue;
             if (!col.cov) continue;
             long long L[4], D;
             col_L(x.T, col, L, D);
@@ -454,20 +466,24 @@ __device__ __forceinline__ double phase_score_from(long long L1, long long L2, l
     return -10.0 * lcr_log10(1.0 - v);
 }
 
-/* assign_snp_haplotype_genotype (snpfrags.rs:378-546) */
+/* assign_snp_haplotype_genotype (snpfrags.rs:378-546): one warp per SNP, lane 0 writes the record */
 __device__ void assign_snps(Ctx &x) {
-    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
+    const uint32_t lane = x.tid & 31;
+    for (uint32_t i = x.tid >> 5; i < x.n; i += x.nthreads >> 5) {
         lcr_candidate &s = x.c[i];
-        if (!(s.flags & LCR_CF_FOR_PHASING)) { s.flags |= LCR_CF_NON_SELECTED; continue; }
-        if (x.cover_off[i + 1] == x.cover_off[i]) { s.flags |= LCR_CF_SINGLE; continue; }
+        const uint16_t flags0 = s.flags;
+        const int vt0 = s.variant_type;
         const int d = s.haplotype;
+        __syncwarp();
+        if (!(flags0 & LCR_CF_FOR_PHASING)) { if (lane == 0) s.flags = flags0 | LCR_CF_NON_SELECTED; continue; }
+        if (x.cover_off[i + 1] == x.cover_off[i]) { if (lane == 0) s.flags = flags0 | LCR_CF_SINGLE; continue; }
         ColFx col;
         long long Lp = 0, Lm = 0; /* het sums for delta = +1 / -1 */
         int hap1 = 0, hap2 = 0;
-        for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
+        for (uint32_t w = x.cover_off[i] + lane; w < x.cover_off[i + 1]; w += 32) {
             const uint32_t k = x.a.cover_frag[w];
             if (!x.fp[k] || x.frag_links[k] < x.a.P.min_linkers) continue;
-            if (s.variant_type == 1 && x.assign[k] == 0) continue;
+            if (vt0 == 1 && x.assign[k] == 0) continue;
             if (x.assign[k] == 1) hap1++; else if (x.assign[k] == 2) hap2++;
             const int8_t cell = x.a.cover_cell[w];
             const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
@@ -475,7 +491,15 @@ __device__ void assign_snps(Ctx &x) {
             Lp += aki_fx(x.T, sg, 1, 0, p, q);
             Lm += aki_fx(x.T, sg, -1, 0, p, q);
         }
-        if (!col.cov) { s.flags |= LCR_CF_NON_SELECTED; continue; }
+        col_reduce(col);
+        for (int o = 16; o; o >>= 1) {
+            Lp += __shfl_xor_sync(0xffffffffu, Lp, o);
+            Lm += __shfl_xor_sync(0xffffffffu, Lm, o);
+            hap1 += __shfl_xor_sync(0xffffffffu, hap1, o);
+            hap2 += __shfl_xor_sync(0xffffffffu, hap2, o);
+        }
+        if (lane != 0) continue;
+        if (!col.cov) { s.flags = flags0 | LCR_CF_NON_SELECTED; continue; }
         long long L[4], D;
         col_L(x.T, col, L, D);
         long long mx = L[0] > L[1] ? L[0] : L[1];
@@ -484,8 +508,8 @@ __device__ void assign_snps(Ctx &x) {
         if (L[0] == mx) { s.haplotype = (int8_t)d; s.genotype = 0; s.variant_type = 1; }
         else if (L[1] == mx) { s.haplotype = (int8_t)(-d); s.genotype = 0; s.variant_type = 1; }
         else if (L[2] == mx) { s.haplotype = (int8_t)d; s.genotype = 1; s.variant_type = 0; }
-        else { s.haplotype = (int8_t)d; s.genotype = -1; if (s.variant_type != 2 && s.variant_type != 3) s.variant_type = 2; }
-        if (s.genotype != 0) { s.flags |= LCR_CF_NON_SELECTED; continue; }
+        else { s.haplotype = (int8_t)d; s.genotype = -1; if (vt0 != 2 && vt0 != 3) s.variant_type = 2; }
+        if (s.genotype != 0) { s.flags = flags0 | LCR_CF_NON_SELECTED; continue; }
         if (hap1 >= 1 && hap2 >= 1) s.phase_score = phase_score_from(s.haplotype == 1 ? Lp : Lm, Lp, Lm);
         else s.phase_score = 0.19940219;
     }
