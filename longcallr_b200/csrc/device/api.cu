@@ -243,8 +243,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     pa.elem_snp = elem_snp; pa.elem_cell = elem_cell;
     pa.cover_off = cover_off; pa.cover_frag = cover_frag; pa.cover_cell = cover_cell;
     pa.adj_off = adj_off; pa.adj = adj;
-    DALLOC(pa.hap, n_cand); DALLOC(pa.gen, n_cand); DALLOC(pa.best_hap, n_cand); DALLOC(pa.best_gen, n_cand);
-    DALLOC(pa.phase0, n_cand); DALLOC(pa.conserved, n_cand);
+    DALLOC(pa.st, n_cand); DALLOC(pa.best_hap, n_cand); DALLOC(pa.best_gen, n_cand);
     DALLOC(pa.label, n_cand); DALLOC(pa.rank, n_cand);
     DALLOC(pa.work, (size_t)adj_total + n_cand + 1);
     DALLOC(pa.blk_q, n_cand); DALLOC(pa.blk_qflip, n_cand);
@@ -365,7 +364,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     DFREE(cover_count); DFREE(cover_off); DFREE(cover_cursor); DFREE(cover_frag); DFREE(cover_cell);
     DFREE(frag_slot); DFREE(frag_elem_off); DFREE(frag_links); DFREE(elem_snp); DFREE(elem_cell); DFREE(elem_base);
     DFREE(table); DFREE(entry_region); DFREE(deg); DFREE(adj_off); DFREE(adj_cursor); DFREE(adj);
-    DFREE(pa.hap); DFREE(pa.gen); DFREE(pa.best_hap); DFREE(pa.best_gen); DFREE(pa.phase0); DFREE(pa.conserved);
+    DFREE(pa.st); DFREE(pa.best_hap); DFREE(pa.best_gen);
     DFREE(pa.label); DFREE(pa.rank); DFREE(pa.work); DFREE(pa.blk_q); DFREE(pa.blk_qflip);
     DFREE(pa.tag); DFREE(pa.best_tag); DFREE(pa.fp); DFREE(pa.assign);
     DFREE(es_base); DFREE(es_cfg); DFREE(es_prob); DFREE(work_region); DFREE(work_chunk);

@@ -61,8 +61,8 @@ struct PhaseArgs {
     /* LD graph (regions with more than max_enum_snps candidates) */
     const uint32_t *adj_off, *adj;
     /* state, per candidate (global index) */
-    int8_t *hap, *gen, *best_hap, *best_gen;
-    uint8_t *phase0, *conserved;
+    char4 *st; /* delta, eta, for_phasing at the start of phase(), conserved */
+    int8_t *best_hap, *best_gen;
     uint32_t *label, *rank, *work; /* work: adj_total + n_cand entries per region segment */
     long long *blk_q, *blk_qflip;
     /* state, per fragment (global index) */

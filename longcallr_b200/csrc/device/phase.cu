@@ -50,8 +50,10 @@ struct Ctx {
     uint64_t region_key;
     uint32_t slot0;
     /* region views */
-    int8_t *hap, *gen, *best_hap, *best_gen, *tag, *best_tag;
-    uint8_t *phase0, *conserved, *fp, *assign;
+    char4 *st;   /* per SNP: x = delta (haplotype), y = eta (genotype), z = for_phasing when phase() started, w = conserved */
+    int8_t *best_hap, *best_gen, *tag, *best_tag;
+    uint8_t *fp, *assign;
+    const long long *OK, *ERR, *W; /* shared-memory copies of the fixed-point tables; W = ok - err */
     uint32_t *label, *rank, *work;
     long long *blk_q, *blk_qflip;
     const uint32_t *frag_slot, *frag_elem_off, *frag_links, *cover_off, *adj_off;
@@ -59,9 +61,9 @@ struct Ctx {
     unsigned long long n_iters;
 };
 
-__device__ __forceinline__ int64_t aki_fx(const LcrDeviceTables &T, int sigma, int delta, int eta, int p, int q) {
+__device__ __forceinline__ int64_t aki_tab(const long long *OK, const long long *ERR, int sigma, int delta, int eta, int p, int q) {
     const int x = eta == 0 ? sigma * delta : eta;
-    return p == x ? T.fx_ok[q] : T.fx_err[q];
+    return p == x ? OK[q] : ERR[q];
 }
 __device__ __forceinline__ int cell_p(int8_t cell) { return cell > 0 ? 1 : -1; }
 __device__ __forceinline__ int cell_q(int8_t cell) { return (cell > 0 ? cell : -cell) - 1; }
@@ -105,16 +107,19 @@ __device__ __forceinline__ double uniform(const Ctx &x, uint32_t stream, uint32_
     return lcr_uniform(x.a.P.seed, x.region_key, stream, call, idx);
 }
 __device__ __forceinline__ uint32_t read_rel(const Ctx &x, uint32_t k) { return x.frag_slot[k] - x.slot0; }
+__device__ __forceinline__ int64_t aki_fx(const Ctx &x, int sigma, int delta, int eta, int p, int q) { return aki_tab(x.OK, x.ERR, sigma, delta, eta, p, q); }
 
 struct ColFx {
     long long het_d = 0, het_nd = 0, homref = 0, homvar = 0;
     uint32_t cov = 0;
+    const long long *OK, *ERR;
+    __device__ __forceinline__ ColFx(const Ctx &x) : OK(x.OK), ERR(x.ERR) {}
 };
 __device__ __forceinline__ void col_add(const LcrDeviceTables &T, ColFx &c, int sigma, int delta, int p, int q) {
-    c.het_d += aki_fx(T, sigma, delta, 0, p, q);
-    c.het_nd += aki_fx(T, sigma, -delta, 0, p, q);
-    c.homref += aki_fx(T, sigma, delta, 1, p, q);
-    c.homvar += aki_fx(T, sigma, delta, -1, p, q);
+    c.het_d += aki_tab(c.OK, c.ERR, sigma, delta, 0, p, q);
+    c.het_nd += aki_tab(c.OK, c.ERR, sigma, -delta, 0, p, q);
+    c.homref += aki_tab(c.OK, c.ERR, sigma, delta, 1, p, q);
+    c.homvar += aki_tab(c.OK, c.ERR, sigma, delta, -1, p, q);
     c.cov++;
 }
 __device__ __forceinline__ void col_reduce(ColFx &c) { /* all lanes end up with the warp totals */
@@ -142,10 +147,10 @@ __device__ long long objective(Ctx &x) {
         if (!x.fp[k] || x.tag[k] == 0) continue;
         const int sg = x.tag[k];
         for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
-            const uint32_t i = x.a.elem_snp[e];
-            if (!x.phase0[i]) continue;
+            const char4 st = x.st[x.a.elem_snp[e]];
+            if (!st.z) continue;
             const int8_t cell = x.a.elem_cell[e];
-            s += aki_fx(x.T, sg, x.hap[i], x.gen[i], cell_p(cell), cell_q(cell));
+            s += aki_fx(x, sg, st.x, st.y, cell_p(cell), cell_q(cell));
         }
     }
     return tsum(x, s);
@@ -165,12 +170,11 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             if (sg == 0) continue;
             long long diff = 0;
             for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
-                const uint32_t i = x.a.elem_snp[e];
-                if (!x.phase0[i] || x.gen[i] != 0) continue;
+                const char4 st = x.st[x.a.elem_snp[e]];
+                if (!st.z || st.y != 0) continue;
                 const int8_t cell = x.a.elem_cell[e];
-                const int q = cell_q(cell);
-                const long long W = x.T.fx_ok[q] - x.T.fx_err[q];
-                diff += (cell_p(cell) == sg * x.hap[i]) ? W : -W;
+                const long long W = x.W[cell_q(cell)];
+                diff += (cell_p(cell) == sg * st.x) ? W : -W;
             }
             if (diff < 0) { x.tag[k] = (int8_t)(-sg); better = 1; }
         }
@@ -181,10 +185,10 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
         better = 0;
         /* one warp per SNP: lanes stride the column, five shuffled sums */
         for (uint32_t i = x.tid >> 5; i < x.n; i += x.nthreads >> 5) {
-            if (!x.phase0[i]) continue;
-            if (keep_conserved && x.conserved[i]) continue;
-            const int d = x.hap[i], eta = x.gen[i];
-            ColFx col;
+            if (!x.st[i].z) continue;
+            if (keep_conserved && x.st[i].w) continue;
+            const int d = x.st[i].x, eta = x.st[i].y;
+            ColFx col(x);
             for (uint32_t w = x.cover_off[i] + (x.tid & 31); w < x.cover_off[i + 1]; w += 32) {
                 const uint32_t k = x.a.cover_frag[w];
                 if (!x.fp[k] || x.tag[k] == 0) continue;
@@ -212,8 +216,8 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             } else {
                 if (L[2] >= L[3]) { nd = d; ne = 1; L_new = L[2]; } else { nd = d; ne = -1; L_new = L[3]; }
             }
-            x.hap[i] = (int8_t)nd;
-            x.gen[i] = (int8_t)ne;
+            x.st[i].x = (int8_t)nd;
+            x.st[i].y = (int8_t)ne;
             if (L_new > L_old) better = 1;
         }
         better = tany(x, better);
@@ -225,19 +229,19 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
 }
 
 __device__ void save_best(Ctx &x) {
-    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.best_hap[i] = x.hap[i]; x.best_gen[i] = x.gen[i]; }
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.best_hap[i] = x.st[i].x; x.best_gen[i] = x.st[i].y; }
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) x.best_tag[k] = x.tag[k];
     tsync(x);
 }
 __device__ void load_best(Ctx &x) {
-    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.hap[i] = x.best_hap[i]; x.gen[i] = x.best_gen[i]; }
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.st[i].x = x.best_hap[i]; x.st[i].y = x.best_gen[i]; }
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) x.tag[k] = x.best_tag[k];
     tsync(x);
 }
 __device__ void init_genotype(Ctx &x) { /* phase.rs:682-691 */
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const int vt = x.c[i].variant_type;
-        x.gen[i] = (int8_t)(vt == 0 ? 1 : (vt == 1 ? 0 : ((vt == 2 || vt == 3) ? -1 : x.gen[i])));
+        x.st[i].y = (int8_t)(vt == 0 ? 1 : (vt == 1 ? 0 : ((vt == 2 || vt == 3) ? -1 : x.st[i].y)));
     }
 }
 __device__ void init_assignment(Ctx &x, uint32_t call) { /* phase.rs:673-680 */
@@ -256,7 +260,7 @@ __device__ bool phase_enum(Ctx &x) {
             if (cw == NONE32) continue;
             if (cfg == NONE32 || x.a.es_prob[w] > bp || (x.a.es_prob[w] == bp && cw < cfg)) { bp = x.a.es_prob[w]; cfg = cw; }
         }
-        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.st[i].x = ((cfg >> i) & 1u) ? -1 : 1;
         init_assignment(x, cfg);
         init_genotype(x);
         tsync(x);
@@ -267,7 +271,7 @@ __device__ bool phase_enum(Ctx &x) {
     bool have = false;
     const uint32_t n_cfg = 1u << x.n;
     for (uint32_t cfg = 0; cfg < n_cfg; ++cfg) {
-        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.hap[i] = ((cfg >> i) & 1u) ? -1 : 1;
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.st[i].x = ((cfg >> i) & 1u) ? -1 : 1;
         init_assignment(x, cfg);
         init_genotype(x);
         tsync(x);
@@ -295,8 +299,8 @@ __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const uint32_t root = x.label[i];
         if (root == NONE32) continue;
-        const int d = x.hap[i], eta = x.gen[i];
-        ColFx c0, c1;
+        const int d = x.st[i].x, eta = x.st[i].y;
+        ColFx c0(x), c1(x);
         for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
             const uint32_t k = x.a.cover_frag[w];
             if (!x.fp[k] || x.tag[k] == 0) continue;
@@ -332,7 +336,7 @@ __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
     }
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         const uint32_t root = x.label[i];
-        if (root != NONE32 && x.blk_q[root] < x.blk_qflip[root]) x.hap[i] = (int8_t)(-x.hap[i]);
+        if (root != NONE32 && x.blk_q[root] < x.blk_qflip[root]) x.st[i].x = (int8_t)(-x.st[i].x);
     }
     tsync(x);
     return objective(x);
@@ -345,10 +349,10 @@ __device__ void phase_ld(Ctx &x) {
     const uint32_t *adj = x.a.adj;
     /* init_haplotypes_LD2 (phase.rs:600-652) */
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
-        x.hap[i] = uniform(x, LCR_RNG_INIT_DELTA, 0, i) < 0.5 ? 1 : -1;
+        x.st[i].x = uniform(x, LCR_RNG_INIT_DELTA, 0, i) < 0.5 ? 1 : -1;
         x.label[i] = NONE32;
         x.rank[i] = 0;
-        x.conserved[i] = adj_off[i + 1] > adj_off[i] ? 1 : 0;
+        x.st[i].w = adj_off[i + 1] > adj_off[i] ? 1 : 0;
     }
     tsync(x);
     if (x.tid == 0) {
@@ -361,7 +365,7 @@ __device__ void phase_ld(Ctx &x) {
             if (root0 == NONE32) root0 = r;
             uint32_t qh = 0, qt = 0;
             x.label[r] = r;
-            x.hap[r] = 1;
+            x.st[r].x = 1;
             queue[qt++] = r;
             while (qh < qt) {
                 const uint32_t nx = queue[qh++];
@@ -369,7 +373,7 @@ __device__ void phase_ld(Ctx &x) {
                     const uint32_t v = adj[w] & 0x7fffffffu;
                     if (x.label[v] != NONE32) continue;
                     x.label[v] = r;
-                    x.hap[v] = (adj[w] & 0x80000000u) ? (int8_t)(-x.hap[nx]) : x.hap[nx];
+                    x.st[v].x = (adj[w] & 0x80000000u) ? (int8_t)(-x.st[nx].x) : x.st[nx].x;
                     queue[qt++] = v;
                 }
             }
@@ -407,8 +411,8 @@ __device__ void phase_ld(Ctx &x) {
         const bool flip = (t & 1u) == 1u;
         for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
             const double rg = uniform(x, LCR_RNG_PERTURB_DELTA, t, i);
-            if (rg < 0.1) x.hap[i] = flip ? 1 : -1;
-            else if (rg >= 0.9) x.hap[i] = flip ? -1 : 1;
+            if (rg < 0.1) x.st[i].x = flip ? 1 : -1;
+            else if (rg >= 0.9) x.st[i].x = flip ? -1 : 1;
         }
         tsync(x);
         prob = cross_optimize(x, false, false);
@@ -436,8 +440,8 @@ __device__ void assign_reads(Ctx &x, bool record) {
             const lcr_candidate &s = x.c[x.a.elem_snp[e]];
             if (!(s.flags & LCR_CF_FOR_PHASING) || s.haplotype == 0 || s.genotype != 0) continue;
             const int8_t cell = x.a.elem_cell[e];
-            A += aki_fx(x.T, sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
-            B += aki_fx(x.T, -sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
+            A += aki_fx(x, sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
+            B += aki_fx(x, -sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
             cnt++;
         }
         int asg = 0;
@@ -477,7 +481,7 @@ __device__ void assign_snps(Ctx &x) {
         __syncwarp();
         if (!(flags0 & LCR_CF_FOR_PHASING)) { if (lane == 0) s.flags = flags0 | LCR_CF_NON_SELECTED; continue; }
         if (x.cover_off[i + 1] == x.cover_off[i]) { if (lane == 0) s.flags = flags0 | LCR_CF_SINGLE; continue; }
-        ColFx col;
+        ColFx col(x);
         long long Lp = 0, Lm = 0; /* het sums for delta = +1 / -1 */
         int hap1 = 0, hap2 = 0;
         for (uint32_t w = x.cover_off[i] + lane; w < x.cover_off[i + 1]; w += 32) {
@@ -488,8 +492,8 @@ __device__ void assign_snps(Ctx &x) {
             const int8_t cell = x.a.cover_cell[w];
             const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
             col_add(x.T, col, sg, d, p, q);
-            Lp += aki_fx(x.T, sg, 1, 0, p, q);
-            Lm += aki_fx(x.T, sg, -1, 0, p, q);
+            Lp += aki_fx(x, sg, 1, 0, p, q);
+            Lm += aki_fx(x, sg, -1, 0, p, q);
         }
         col_reduce(col);
         for (int o = 16; o; o >>= 1) {
@@ -531,8 +535,8 @@ __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
             if (x.assign[k] == 1) h1++; else if (x.assign[k] == 2) h2++;
             const int8_t cell = x.a.cover_cell[w];
             const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
-            Lp += aki_fx(x.T, sg, 1, 0, p, q);
-            Lm += aki_fx(x.T, sg, -1, 0, p, q);
+            Lp += aki_fx(x, sg, 1, 0, p, q);
+            Lm += aki_fx(x, sg, -1, 0, p, q);
             cnt++;
         }
         Lp = tsum(x, Lp); Lm = tsum(x, Lm); h1 = tsum(x, h1); h2 = tsum(x, h2); cnt = tsum(x, cnt);
@@ -638,6 +642,16 @@ __device__ void phase_sets(Ctx &x) {
     tsync(x);
 }
 
+__device__ __forceinline__ void load_tables(const PhaseArgs &a, long long (*tabs)[32]) {
+    if (threadIdx.x < 32) {
+        const uint32_t q = threadIdx.x < 31 ? threadIdx.x : 30;
+        tabs[0][threadIdx.x] = a.tables->fx_ok[q];
+        tabs[1][threadIdx.x] = a.tables->fx_err[q];
+        tabs[2][threadIdx.x] = a.tables->fx_ok[q] - a.tables->fx_err[q];
+    }
+    __syncthreads();
+}
+
 /* the whole worker body after the fragment matrix exists: phase(), then thread.rs:168-201 */
 __device__ void run_region(Ctx &x) {
     const PhaseArgs &a = x.a;
@@ -646,8 +660,7 @@ __device__ void run_region(Ctx &x) {
     x.c = a.cand + x.cb;
     x.region_key = lcr_region_key(a.regions[x.reg].tid, a.regions[x.reg].start);
     x.slot0 = a.slot_off[x.reg];
-    x.hap = a.hap + x.cb; x.gen = a.gen + x.cb; x.best_hap = a.best_hap + x.cb; x.best_gen = a.best_gen + x.cb;
-    x.phase0 = a.phase0 + x.cb; x.conserved = a.conserved + x.cb;
+    x.st = a.st + x.cb; x.best_hap = a.best_hap + x.cb; x.best_gen = a.best_gen + x.cb;
     x.label = a.label + x.cb; x.rank = a.rank + x.cb;
     x.blk_q = a.blk_q + x.cb; x.blk_qflip = a.blk_qflip + x.cb;
     x.tag = a.tag + x.fb; x.best_tag = a.best_tag + x.fb; x.fp = a.fp + x.fb; x.assign = a.assign + x.fb;
@@ -660,10 +673,10 @@ __device__ void run_region(Ctx &x) {
     x.epoch_sum = 0;
 
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
-        x.hap[i] = 0;
-        x.gen[i] = x.c[i].genotype;
-        x.phase0[i] = (x.c[i].flags & LCR_CF_FOR_PHASING) ? 1 : 0;
-        x.conserved[i] = 0;
+        x.st[i].x = 0;
+        x.st[i].y = x.c[i].genotype;
+        x.st[i].z = (x.c[i].flags & LCR_CF_FOR_PHASING) ? 1 : 0;
+        x.st[i].w = 0;
     }
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
         x.tag[k] = 0;
@@ -675,7 +688,7 @@ __device__ void run_region(Ctx &x) {
     bool counted_elsewhere = false;
     if (x.n <= a.P.max_enum_snps) { counted_elsewhere = phase_enum(x); n_calls = 1ull << x.n; }
     else { phase_ld(x); n_calls = 1ull + 2ull * (x.n / 4 + 1); }
-    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.c[i].haplotype = x.hap[i]; x.c[i].genotype = x.gen[i]; }
+    for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.c[i].haplotype = x.st[i].x; x.c[i].genotype = x.st[i].y; }
     tsync(x);
     /* thread.rs:168-201 */
     assign_reads(x, false);
@@ -696,12 +709,15 @@ __device__ void run_region(Ctx &x) {
 /* one CTA per region (everything except the few regions handed to the cooperative kernel) */
 __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     __shared__ long long sh[32];
+    __shared__ long long tabs[3][32];
     __shared__ TeamBcast bc;
     const uint32_t reg = blockIdx.x;
     const LcrRegionState rs = a.rstate[reg];
     if (rs.status != 0 || rs.n_cand == 0 || (a.big_region && a.big_region[reg])) return;
     Ctx x{a, *a.tables};
     x.reg = reg; x.tid = threadIdx.x; x.nthreads = PB; x.grid = false; x.bc = &bc; x.sh = sh;
+    load_tables(a, tabs);
+    x.OK = tabs[0]; x.ERR = tabs[1]; x.W = tabs[2];
     run_region(x);
 }
 
@@ -709,7 +725,10 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
    grid.sync() between passes, no host round trips (SURVEY.md section 7 "ragged work", BASELINE config 5) */
 __global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, uint32_t reg, TeamBcast *gbc) {
     __shared__ long long sh[32];
+    __shared__ long long tabs[3][32];
     Ctx x{a, *a.tables};
+    load_tables(a, tabs);
+    x.OK = tabs[0]; x.ERR = tabs[1]; x.W = tabs[2];
     x.reg = reg; x.tid = blockIdx.x * blockDim.x + threadIdx.x; x.nthreads = gridDim.x * blockDim.x; x.grid = true; x.bc = gbc; x.sh = sh;
     run_region(x);
 }
