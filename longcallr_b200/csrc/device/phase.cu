@@ -143,10 +143,11 @@ __device__ __forceinline__ void col_L(const LcrDeviceTables &T, const ColFx &c, 
 /* cal_overall_probability (phase.rs:257-276) */
 __device__ long long objective(Ctx &x) {
     long long s = 0;
-    for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
+    /* eight lanes per fragment row */
+    for (uint32_t k = x.tid >> 3; k < x.nf; k += x.nthreads >> 3) {
         if (!x.fp[k] || x.tag[k] == 0) continue;
         const int sg = x.tag[k];
-        for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
+        for (uint32_t e = x.frag_elem_off[k] + (x.tid & 7); e < x.frag_elem_off[k + 1]; e += 8) {
             const char4 st = x.st[x.a.elem_snp[e]];
             if (!st.z) continue;
             const int8_t cell = x.a.elem_cell[e];
@@ -164,19 +165,28 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
         x.n_iters++;
         int better = 0;
         /* sigma sweep (phase.rs:823-868) */
-        for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
-            if (!x.fp[k]) continue;
-            const int sg = x.tag[k];
-            if (sg == 0) continue;
+        /* eight lanes per fragment row; the row sum is shuffled together inside the group */
+        for (uint32_t k0 = 0; k0 < x.nf; k0 += x.nthreads >> 3) {
+            const uint32_t k = k0 + (x.tid >> 3);
             long long diff = 0;
-            for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
-                const char4 st = x.st[x.a.elem_snp[e]];
-                if (!st.z || st.y != 0) continue;
-                const int8_t cell = x.a.elem_cell[e];
-                const long long W = x.W[cell_q(cell)];
-                diff += (cell_p(cell) == sg * st.x) ? W : -W;
+            int sg = 0;
+            if (k < x.nf && x.fp[k]) sg = x.tag[k];
+            if (sg != 0) {
+                for (uint32_t e = x.frag_elem_off[k] + (x.tid & 7); e < x.frag_elem_off[k + 1]; e += 8) {
+                    const char4 st = x.st[x.a.elem_snp[e]];
+                    if (!st.z || st.y != 0) continue;
+                    const int8_t cell = x.a.elem_cell[e];
+                    const long long W = x.W[cell_q(cell)];
+                    diff += (cell_p(cell) == sg * st.x) ? W : -W;
+                }
             }
-            if (diff < 0) { x.tag[k] = (int8_t)(-sg); better = 1; }
+            diff += __shfl_xor_sync(0xffffffffu, diff, 1);
+            diff += __shfl_xor_sync(0xffffffffu, diff, 2);
+            diff += __shfl_xor_sync(0xffffffffu, diff, 4);
+            if (sg != 0 && diff < 0) {
+                if ((x.tid & 7) == 0) x.tag[k] = (int8_t)(-sg);
+                better = 1;
+            }
         }
         better = tany(x, better);
         if (!better) ht_increase = false;
