@@ -346,6 +346,21 @@ struct PreCand { /* a site that passed every count-based filter; its likelihood 
     uint32_t cnt[4], pass[4], fwd[4], ts[2], d, n;
 };
 
+/* 4 read bases + 4 qualities (little-endian words) -> 4 row bytes */
+__device__ __forceinline__ uint32_t codes4(uint32_t w, uint32_t qv, uint32_t minq, uint32_t rconst4) {
+    /* A,C,G,T -> 0..3 from bits 1-2 of the letter; anything else -> 4 */
+    const uint32_t t = (w >> 1) & 0x03030303u;
+    uint32_t c4 = t ^ ((t >> 1) & 0x01010101u);
+    const uint32_t canon = __byte_perm(0x54474341u, 0, (c4 & 0x3u) | ((c4 >> 4) & 0x30u) | ((c4 >> 8) & 0x300u) | ((c4 >> 12) & 0x3000u));
+    const uint32_t x = (w & 0xdfdfdfdfu) ^ canon;
+    const uint32_t nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;
+    c4 = (c4 & ~(nz * 7u)) | (nz * 4u);
+    /* quality >= min_baseq per byte */
+    const uint32_t ge = (((qv & 0x7f7f7f7fu) | 0x80808080u) - minq * 0x01010101u) | (qv & 0x80808080u);
+    const uint32_t pass4 = minq > 30u ? 0u : ((ge >> 4) & 0x08080808u);
+    return c4 | pass4 | rconst4;
+}
+
 __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
     extern __shared__ __align__(16) uint8_t rows_raw[]; /* LCR_ROWS x LCR_TILE row bytes */
     uint8_t (*rows)[LCR_TILE] = reinterpret_cast<uint8_t (*)[LCR_TILE]>(rows_raw);
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                 }
                 const int32_t tot_r = __shfl_sync(0xffffffffu, rs, 31), tot_q = __shfl_sync(0xffffffffu, qs, 31);
                 /* compact the reference-consuming ops */
-                const bool keep = consuming && rl > 0;
+                const bool keep = consuming && rl > 0 && (fpos + rs - rl) < tile_end;
                 const uint32_t keepmask = __ballot_sync(0xffffffffu, keep);
                 const uint32_t ncomp = __popc(keepmask);
                 if (keep) {
@@ -487,7 +502,6 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                 bad = __any_sync(0xffffffffu, bad);
                 if (bad) break;
                 __syncwarp();
-                const int32_t mystart = lane < ncomp ? s_col[warp][lane] : 0x7fffffff;
                 /* rows of this item in the sub-tiles this batch reaches */
                 if (colB > fpos) {
                     const uint32_t subA = (uint32_t)(fpos - tile_start) / SUBTILE, subB = (uint32_t)(colB - 1 - tile_start) / SUBTILE;
@@ -499,77 +513,107 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
                         slots = (slots & ~(0xffu << (8 * sidx))) | (v << (8 * sidx));
                     }
                 }
-                int32_t cb = fpos;
-                while (cb < colB) {
-                    const int32_t first = (int32_t)__popc(__ballot_sync(0xffffffffu, mystart <= cb)) - 1;
-                    const int32_t op_col = s_col[warp][first], op_end = s_col[warp][first + 1];
-                    const uint32_t op_typ = s_typ[warp][first];
-                    const int32_t op_rp = s_rp[warp][first];
-                    const uint32_t colr0 = (uint32_t)(cb - tile_start);
-                    /* long run inside one op: 4 columns per lane */
-                    int32_t run = (op_end < colB ? op_end : colB) - cb;
-                    if (op_typ == 0) {
-                        const int32_t rp0 = op_rp + (cb - op_col);
-                        /* stay clear of the read-end zones |rp - lead| < D, |rp - rb| < D (util.rs:745-757) */
-                        if (rp0 < lead + dend) run = 0;
-                        else if (rp0 + run > rb - dend + 1) run = rb - dend + 1 - rp0;
-                    }
-                    if (run >= 64 && (colr0 & 3u) == 0) {
-                        const int32_t n4 = (run > 128 ? 128 : run) & ~3;
-                        if ((int32_t)(4 * lane) < n4) {
-                            const uint32_t colr = colr0 + 4 * lane;
-                            uint32_t code4;
-                            if (op_typ == 0) {
-                                const int32_t rp = op_rp + (cb - op_col) + 4 * (int32_t)lane;
-                                const uintptr_t sa = (uintptr_t)(seq + rp), qa = (uintptr_t)(qual + rp);
-                                const uint32_t *sw = (const uint32_t *)(sa & ~(uintptr_t)3), *qw = (const uint32_t *)(qa & ~(uintptr_t)3);
-                                const uint32_t w = __funnelshift_r(__ldg(sw), __ldg(sw + 1), (uint32_t)(sa & 3) * 8);
-                                const uint32_t qv = __funnelshift_r(__ldg(qw), __ldg(qw + 1), (uint32_t)(qa & 3) * 8);
-                                /* A,C,G,T -> 0..3 from bits 1-2 of the letter; anything else -> 4 */
-                                const uint32_t t = (w >> 1) & 0x03030303u;
-                                uint32_t c4 = t ^ ((t >> 1) & 0x01010101u);
-                                const uint32_t canon = __byte_perm(0x54474341u, 0, (c4 & 0x3u) | ((c4 >> 4) & 0x30u) | ((c4 >> 8) & 0x300u) | ((c4 >> 12) & 0x3000u));
-                                const uint32_t x = (w & 0xdfdfdfdfu) ^ canon;
-                                const uint32_t nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;
-                                c4 = (c4 & ~(nz * 7u)) | (nz * 4u);
-                                /* quality >= min_baseq per byte (qualities are < 128) */
-                                const uint32_t ge = (((qv & 0x7f7f7f7fu) | 0x80808080u) - minq * 0x01010101u) | (qv & 0x80808080u);
-                                const uint32_t pass4 = minq > 30u ? 0u : ((ge >> 4) & 0x08080808u);
-                                code4 = c4 | pass4 | (rconst * 0x01010101u);
-                            } else code4 = (op_typ == 2 ? 5u : 6u) * 0x01010101u;
-                            *reinterpret_cast<uint32_t *>(&rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr]) = code4;
-                        }
-                        cb += n4;
-                        continue;
-                    }
-                    /* one column per lane; the window ends where the columns become 4-aligned again */
-                    int32_t win = 32 - (int32_t)(colr0 & 3u);
-                    if (win > colB - cb) win = colB - cb;
-                    const int32_t rel = mystart - cb;
+                /* every kept op is one run inside [fpos, colB); cut each run into 16-byte aligned chunks of the read
+                   (or 16 columns of a D / N run) and let every lane take one chunk */
+                int32_t run_a = 0, run_n = 0, run_rp = 0, run_al = 0;
+                uint32_t run_typ = 0, nch = 0;
+                if (lane < ncomp) {
+                    const int32_t st = s_col[warp][lane], en = s_col[warp][lane + 1];
+                    run_a = st > fpos ? st : fpos;
+                    const int32_t bb = en < colB ? en : colB;
+                    run_n = bb - run_a;
+                    run_typ = s_typ[warp][lane];
+                    run_rp = s_rp[warp][lane] + (run_a - st);
+                    if (run_typ == 0) run_al = (int32_t)((uintptr_t)(seq + run_rp) & 15u);
+                    nch = (uint32_t)(run_al + run_n + 15) >> 4;
+                }
+                uint32_t chs = nch; /* inclusive scan of the chunk counts */
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v2 = __shfl_up_sync(0xffffffffu, chs, o);
+                    if ((int)lane >= o) chs += v2;
+                }
+                const uint32_t n_chunks = __shfl_sync(0xffffffffu, chs, 31);
+                const int32_t mychoff = lane < ncomp ? (int32_t)(chs - nch) : 0x7fffffff;
+                const uint32_t rconst4 = rconst * 0x01010101u;
+                for (uint32_t base = 0; base < n_chunks; base += 32) {
+                    const int32_t first = (int32_t)__popc(__ballot_sync(0xffffffffu, mychoff <= (int32_t)base)) - 1;
+                    const int32_t rel = mychoff - (int32_t)base;
                     const uint32_t starts = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? (1u << rel) : 0u);
-                    if ((int32_t)lane < win) {
-                        const int32_t c = cb + (int32_t)lane;
-                        const int32_t idx = first + (int32_t)__popc(starts & (0xffffffffu >> (31 - lane)));
-                        const uint32_t typ = s_typ[warp][idx];
-                        const uint32_t colr = colr0 + lane;
-                        uint32_t code;
-                        if (typ == 0) {
-                            const int32_t rp = s_rp[warp][idx] + (c - s_col[warp][idx]);
-                            const uint32_t b = __ldg(seq + rp);
-                            const uint32_t q = __ldg(qual + rp);
-                            const int32_t d0 = rp - lead, d1 = rp - rb;
-                            const bool near_end = (d0 < 0 ? -d0 : d0) < dend || (d1 < 0 ? -d1 : d1) < dend;
-                            bool masked = false;
-                            if (near_end) masked = base_masked(a.P, seq, rp, seq_len, lead, trail, ref_s[colr]);
-                            const uint32_t t = (b >> 1) & 3u;
-                            const uint32_t bc = t ^ (t >> 1);
-                            const uint32_t up = b & 0xdfu;
-                            const bool valid = up == ((0x54474341u >> (8 * bc)) & 0xffu);
-                            code = masked ? ROW_NONE : ((valid ? bc : 4u) | ((q < 30u ? q : 30u) >= minq ? 8u : 0u) | rconst);
-                        } else code = typ == 2 ? 5u : 6u;
-                        rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)code;
+                    const int32_t k = first + (int32_t)__popc(starts & (0xffffffffu >> (31 - lane)));
+                    /* run parameters of my chunk come from the lane that owns run k */
+                    const int32_t k_a = __shfl_sync(0xffffffffu, run_a, k), k_n = __shfl_sync(0xffffffffu, run_n, k);
+                    const int32_t k_rp = __shfl_sync(0xffffffffu, run_rp, k), k_al = __shfl_sync(0xffffffffu, run_al, k);
+                    const uint32_t k_typ = __shfl_sync(0xffffffffu, run_typ, k);
+                    const int32_t k_off = __shfl_sync(0xffffffffu, mychoff, k);
+                    const uint32_t g = base + lane;
+                    if (g < n_chunks) {
+                        const int32_t c = (int32_t)g - k_off;              /* chunk index inside the run */
+                        const int32_t lo = c == 0 ? k_al : 0;
+                        int32_t hi = k_al + k_n - 16 * c;
+                        if (hi > 16) hi = 16;
+                        uint32_t w0, w1, w2, w3;
+                        if (k_typ == 0) {
+                            const uintptr_t sa = ((uintptr_t)(seq + k_rp) & ~(uintptr_t)15) + (uintptr_t)(16 * c);
+                            const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(sa));
+                            const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(sa + (uintptr_t)(qual - seq)));
+                            w0 = codes4(sv.x, qv.x, minq, rconst4); w1 = codes4(sv.y, qv.y, minq, rconst4);
+                            w2 = codes4(sv.z, qv.z, minq, rconst4); w3 = codes4(sv.w, qv.w, minq, rconst4);
+                        } else w0 = w1 = w2 = w3 = (k_typ == 2 ? 5u : 6u) * 0x01010101u;
+                        /* byte j of the chunk is column k_a - k_al + 16 c + j */
+                        const uint32_t colr0 = (uint32_t)(k_a - k_al + 16 * c - tile_start);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t wj = j < 4 ? w0 : (j < 8 ? w1 : (j < 12 ? w2 : w3));
+                            if (j >= lo && j < hi) {
+                                const uint32_t colr = colr0 + (uint32_t)j;
+                                rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)(wj >> (8 * (j & 3)));
+                            }
+                        }
                     }
-                    cb += win;
+                }
+                /* read-end zones (util.rs:745-789): bases with |rp - lead| < D or |rp - rb| < D are trimmed (ONT) or tested
+                   for poly-A / homopolymer runs; one lane per zone base of this batch */
+                if (dend > 0) {
+                    const int32_t zlo = lead + dend, zhi = rb - dend; /* rp < zlo or rp > zhi lies in a zone */
+                    int32_t z0n = 0, z1n = 0, z1s = 0;                   /* zone bases of my run: [run_rp, run_rp+z0n) and [z1s, z1s+z1n) */
+                    if (lane < ncomp && run_typ == 0) {
+                        const int32_t e0 = run_rp + run_n < zlo ? run_rp + run_n : zlo;
+                        z0n = e0 > run_rp ? e0 - run_rp : 0;
+                        z1s = run_rp + z0n > zhi + 1 ? run_rp + z0n : zhi + 1;
+                        z1n = run_rp + run_n > z1s ? run_rp + run_n - z1s : 0;
+                    }
+                    uint32_t zc = (uint32_t)(z0n + z1n), zs = zc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v2 = __shfl_up_sync(0xffffffffu, zs, o);
+                        if ((int)lane >= o) zs += v2;
+                    }
+                    const uint32_t n_z = __shfl_sync(0xffffffffu, zs, 31);
+                    if (n_z) {
+                        __syncwarp();
+                        s_rp[warp][lane] = (int32_t)(zs - zc); /* exclusive offsets; s_rp / s_col are free again after the chunk pass */
+                        __syncwarp();
+                        for (uint32_t base = 0; base < n_z; base += 32) {
+                            const uint32_t g = base + lane;
+                            /* owner run: last lane whose offset is <= g and that has zone bases */
+                            uint32_t lo_k = 0;
+#pragma unroll
+                            for (int step = 16; step; step >>= 1)
+                                if (lo_k + step < 32 && (uint32_t)s_rp[warp][lo_k + step] <= g) lo_k += step;
+                            const int32_t k_rp = __shfl_sync(0xffffffffu, run_rp, lo_k), k_a = __shfl_sync(0xffffffffu, run_a, lo_k);
+                            const int32_t k_z0n = __shfl_sync(0xffffffffu, z0n, lo_k), k_z1s = __shfl_sync(0xffffffffu, z1s, lo_k);
+                            const uint32_t k_off = (uint32_t)__shfl_sync(0xffffffffu, s_rp[warp][lane], lo_k);
+                            if (g < n_z) {
+                                const int32_t idx = (int32_t)(g - k_off);
+                                const int32_t r = idx < k_z0n ? k_rp + idx : k_z1s + (idx - k_z0n);
+                                const uint32_t colr = (uint32_t)(k_a + (r - k_rp) - tile_start);
+                                if (base_masked(a.P, seq, r, seq_len, lead, trail, ref_s[colr]))
+                                    rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)ROW_NONE;
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
                 fpos = batch_end;
                 rpos += tot_q;
