@@ -297,14 +297,24 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
             for (uint32_t i = 0; i < n_work_total; ++i) slot[i] = base[order_region[i]] + order_chunk[i];
             TRY(cudaMemcpyAsync(d_slot, slot.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
             TRY(cudaStreamSynchronize(st)); /* the host vectors above go out of scope */
+            /* the bins are independent: fork them onto side streams so that small and large shapes overlap */
             uint32_t off = 0;
+            TRY(cudaEventRecord(ctx->ev_fork, st));
+            int used = 0;
             for (int b = 0; b < NBIN; ++b) {
                 const uint32_t nw = (uint32_t)wr[b].size();
                 if (!nw) continue;
-                int e = lcr_launch_enum_search(b / 2, pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, st);
+                cudaStream_t ss = ctx->side[used % 4];
+                TRY(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+                int e = lcr_launch_enum_search(b / 2, pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, ss);
                 if (e) { ctx->last_error = "k_enum_search launch failed"; ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
                 db->timing.kernel_launches += 1;
                 off += nw;
+                ++used;
+            }
+            for (int i = 0; i < 4 && i < used; ++i) {
+                TRY(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+                TRY(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
             }
             k_scatter_winners<<<(n_work_total + 127) / 128, 128, 0, st>>>(n_work_total, d_slot, tmp_prob, tmp_cfg, es_prob, es_cfg);
             db->timing.kernel_launches += 1;
@@ -410,6 +420,11 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LCR_ERR_CUDA; }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 4; ++i) {
+        cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
     /* keep freed blocks in the stream-ordered pool between runs */
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -451,6 +466,8 @@ void lcr_destroy(lcr_ctx *ctx) {
     if (ctx->d_ref_table) cudaFree(ctx->d_ref_table);
     if (ctx->d_ref_len) cudaFree(ctx->d_ref_len);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    for (int i = 0; i < 4; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -64,6 +64,8 @@ struct lcr_ctx {
     lcr_params P;
     int device;
     cudaStream_t stream;
+    cudaStream_t side[4];      /* independent launches of one stage fork onto these and join back */
+    cudaEvent_t ev_fork, ev_join[4];
     lcr_luts luts;
     LcrDeviceTables *d_tables; /* device copy */
     std::vector<uint8_t *> d_ref;
