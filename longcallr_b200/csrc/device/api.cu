@@ -540,9 +540,9 @@ int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) {
     UP(de, b->de, b->n_reads);
     if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
     else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
-    /* seq / qual carry 16 bytes of slack: the tile kernel reads them as aligned 32-bit words */
-    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 16, &bytes);
-    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 16, &bytes);
+    /* seq / qual carry 32 bytes of slack: the tile kernel reads aligned 16-byte blocks plus the following word */
+    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 32, &bytes);
+    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 32, &bytes);
     UP(cigar, b->cigar, n_cig);
     UP(slot_off, slot_off.data(), slot_off.size());
     UP(slot_region, slot_region.data(), slot_region.size());

@@ -76,7 +76,7 @@ __global__ void k_frag_count(FragArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.n_slots) return;
     uint32_t isfrag = 0, nelem = 0;
-    if (a.slot_flags[slot]) {
+    if (a.slot_flags[slot] & 1) {
         const uint32_t reg = a.slot_region[slot];
         const LcrRegionState rs = a.rstate[reg];
         if (rs.status == 0 && rs.n_cand) {

@@ -30,9 +30,10 @@ struct PrepArgs {
     const uint8_t *mapq;
     const float *de;
     const uint64_t *seq_off, *cig_off;
+    const uint8_t *seq;
     const uint32_t *cigar;
     LcrRegionState *rstate;
-    uint8_t *slot_flags;
+    uint8_t *slot_flags;   /* bit 0: passes the read filter and overlaps the window; bit 1: the poly-A test needs the exact path */
     uint32_t *tile_count;  /* COUNT: items per tile; FILL: cursor */
     const uint32_t *tile_off;
     uint32_t *tile_full_n; /* whole-tile intron covers */
@@ -65,9 +66,39 @@ __global__ void k_slot_prep(PrepArgs a) {
         }
         const int64_t p = a.pos[read];
         const bool in_window = p < (int64_t)R.end && p + (rlen ? rlen : 1) > (int64_t)R.start;
-        a.slot_flags[slot] = (pass && in_window) ? 1 : 0;
-        if (!(pass && in_window)) return;
-    } else if (!a.slot_flags[slot]) return;
+        if (!(pass && in_window)) { a.slot_flags[slot] = 0; return; }
+        /* util.rs:754-789 can only mask a base when a homopolymer window of polya_tail_length letters lies within
+           polya_tail_length of a read-end zone: reads without one skip the per-base test in k_seg_build */
+        uint8_t fl_out = 1;
+        if (a.P.platform != 1 && a.P.distance_to_read_end > 0) {
+            const int64_t polya = (int64_t)(a.P.polya_tail_length > 0x3fffffffu ? 0x3fffffffu : a.P.polya_tail_length);
+            bool has_run = polya < 2;
+            if (!has_run) {
+                const int64_t dend = (int64_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
+                const int64_t lead = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (int64_t)(a.cigar[c0] >> 4) : 0;
+                const int64_t trail = (c1 > c0 && (a.cigar[c1 - 1] & 0xf) == 4) ? (int64_t)(a.cigar[c1 - 1] >> 4) : 0;
+                const int64_t rb = (int64_t)l_seq - trail;
+                const uint8_t *seq = a.seq + a.seq_off[read];
+                const int64_t centre[2] = {lead, rb};
+                for (int z = 0; z < 2 && !has_run; ++z) {
+                    int64_t lo = centre[z] - dend + 1 - polya, hi = centre[z] + dend + polya; /* [lo, hi) */
+                    if (lo < 0) lo = 0;
+                    if (hi > (int64_t)l_seq) hi = (int64_t)l_seq;
+                    int64_t run = 0;
+                    uint8_t prev = 0;
+                    for (int64_t i = lo; i < hi; ++i) {
+                        const uint8_t b = __ldg(seq + i);
+                        const bool letter = b == 'A' || b == 'C' || b == 'G' || b == 'T';
+                        run = letter ? (b == prev ? run + 1 : 1) : 0;
+                        prev = b;
+                        if (run >= polya) { has_run = true; break; }
+                    }
+                }
+            }
+            if (has_run) fl_out |= 2;
+        }
+        a.slot_flags[slot] = fl_out;
+    } else if (!(a.slot_flags[slot] & 1)) return;
 
     const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
     const int64_t fv_start = (int64_t)R.start - 1;
@@ -125,32 +156,6 @@ __global__ void k_slot_prep(PrepArgs a) {
 }
 
 /* ------------------------------------------------------------------------- */
-
-struct PileArgs {
-    lcr_params P;
-    const lcr_region *regions;
-    const uint32_t *slot_off, *slot_region, *tile_base, *tile_region;
-    const uint64_t *pos_off;
-    const uint16_t *flag;
-    const int8_t *ts;
-    const uint64_t *seq_off, *cig_off;
-    const uint8_t *seq, *qual;
-    const uint32_t *cigar;
-    const uint8_t *const *ref_table;
-    const uint32_t *tile_off, *tile_full_n;
-    const LcrItem *items;
-    const LcrDeviceTables *tables;
-    LcrRegionState *rstate;
-    lcr_candidate *cand;
-    uint64_t *cand_key;
-    uint32_t cand_cap;
-    uint32_t *cand_count;
-    lcr_stats *stats;
-    uint32_t *pl_acgt, *pl_fwd, *pl_d, *pl_n, *pl_ts; /* debug planes or null */
-    struct PreCand *pre;
-    uint32_t pre_cap;
-    uint32_t *pre_count;
-};
 
 __device__ __forceinline__ int base_code_dev(uint8_t b) {
     switch (b) {
@@ -331,51 +336,253 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     return true;
 }
 
-/* shared-memory row byte of the tile kernel:
-     bits 0-2  0-3 = A,C,G,T   4 = other read base   5 = deletion   6 = intron   7 = nothing
-     bit  3    base quality >= min_baseq
-     bit  4    read on the forward strand
-     bits 5-6  transcript strand of the read: 1 forward, 2 reverse (util.rs:803-819)              */
-#define ROW_NONE 7u
-#define SUBTILE 128
-#define NSUB (LCR_TILE / SUBTILE)
-#define PWARPS (LCR_TILE / 32)
+/* ------------------------------------------------------------------------- *
+ * Tile pileup, version 3: segments -> one-hot row planes -> carry-save column sums.
+ *
+ * k_seg_build (thread per item) turns the part of a read inside a tile into *segments*: maximal runs of
+ * unmasked aligned bases (M/=/X), deleted positions (D) or intron positions (N) on consecutive columns.
+ * The read-end trim (ONT) and the poly-A / homopolymer mask (util.rs:737-789) are applied here, by cutting
+ * M runs at masked bases, so the tile kernel has no per-base special cases.
+ *
+ * k_pileup_tile (CTA per tile) stages up to PT_ROWS items as two byte planes per (row, column):
+ *     plane X   bit 0-3  base is A,C,G,T          bit 4-7  ... and base quality >= min_baseq
+ *     plane Y   bit 0-3  A,C,G,T on a forward read; bit 4 / 5 transcript strand forward / reverse
+ *               (util.rs:803-819, any base letter); bit 6 deletion; bit 7 intron
+ * one lane per 16-byte block of the read (aligned 128-bit loads of seq and qual, bytes rotated to the
+ * column alignment with PRMT, codes built four columns at a time), then every thread sums one 32-bit column
+ * word (4 columns x 8 indicators) over the rows with a Harley-Seal carry-save adder tree: ~2.4 logic
+ * instructions per row for 32 counters.  Counters are unpacked once per tile (once per 255 rows on deep tiles).
+ * ------------------------------------------------------------------------- */
+#define PT_THREADS 256
+#define PT_ROWS 64
+#define PT_SEGS 512
+#define PT_WORDS (LCR_TILE / 4)
+#define SEG_M 0u
+#define SEG_D 1u
+#define SEG_N 2u
+
+struct LcrSeg {             /* 16 B */
+    uint64_t spos;          /* M: offset of the first base in the seq / qual pools */
+    uint32_t row_typ;       /* bits 0-1 type, bit 2 forward strand, bits 3-4 transcript strand code, bits 8-31 row (item index in its tile) */
+    uint16_t col;           /* first column inside the tile */
+    uint16_t len;           /* 1 .. LCR_TILE */
+};
 
 struct PreCand { /* a site that passed every count-based filter; its likelihood is computed by k_site_ll */
     uint32_t tile, col;
     uint32_t cnt[4], pass[4], fwd[4], ts[2], d, n;
 };
 
-/* 4 read bases + 4 qualities (little-endian words) -> 4 row bytes */
-__device__ __forceinline__ uint32_t codes4(uint32_t w, uint32_t qv, uint32_t minq, uint32_t rconst4) {
-    /* A,C,G,T -> 0..3 from bits 1-2 of the letter; anything else -> 4 */
-    const uint32_t t = (w >> 1) & 0x03030303u;
-    uint32_t c4 = t ^ ((t >> 1) & 0x01010101u);
-    const uint32_t canon = __byte_perm(0x54474341u, 0, (c4 & 0x3u) | ((c4 >> 4) & 0x30u) | ((c4 >> 8) & 0x300u) | ((c4 >> 12) & 0x3000u));
-    const uint32_t x = (w & 0xdfdfdfdfu) ^ canon;
-    const uint32_t nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;
-    c4 = (c4 & ~(nz * 7u)) | (nz * 4u);
-    /* quality >= min_baseq per byte */
-    const uint32_t ge = (((qv & 0x7f7f7f7fu) | 0x80808080u) - minq * 0x01010101u) | (qv & 0x80808080u);
-    const uint32_t pass4 = minq > 30u ? 0u : ((ge >> 4) & 0x08080808u);
-    return c4 | pass4 | rconst4;
+struct SegArgs {
+    lcr_params P;
+    uint32_t n_items;
+    const lcr_region *regions;
+    const uint32_t *slot_off, *slot_region, *tile_base;
+    const uint16_t *flag;
+    const int8_t *ts;
+    const uint64_t *seq_off, *cig_off;
+    const uint8_t *seq;
+    const uint32_t *cigar;
+    const uint8_t *const *ref_table;
+    const uint8_t *slot_flags;
+    const uint32_t *tile_off;
+    const LcrItem *items;
+    LcrRegionState *rstate;
+    lcr_stats *stats;
+    uint32_t *seg_count;       /* COUNT: out */
+    const uint32_t *seg_off;   /* FILL: in   */
+    LcrSeg *segs;
+    uint32_t *deep_flag;       /* set when a tile has more than 255 items */
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_seg_build(SegArgs a) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nseg = 0, nb = 0;
+    if (idx < a.n_items) {
+        const LcrItem it = a.items[idx];
+        const uint32_t reg = a.slot_region[it.slot];
+        if (a.rstate[reg].status == 0) {
+            const lcr_region R = a.regions[reg];
+            const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
+            const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
+            const int32_t tile_local = it.fpos / LCR_TILE;
+            const int32_t tile_start = tile_local * LCR_TILE;
+            const int32_t tile_end = (int64_t)tile_start + LCR_TILE < vec_size ? tile_start + LCR_TILE : (int32_t)vec_size;
+            const uint32_t row = idx - a.tile_off[a.tile_base[reg] + (uint32_t)tile_local];
+            if (!FILL && row == 255u) *a.deep_flag = 1u;
+            const uint64_t s0 = a.seq_off[read];
+            const int32_t seq_len = (int32_t)(a.seq_off[read + 1] - s0);
+            const uint8_t *seq = a.seq + s0;
+            const uint64_t c0 = a.cig_off[read];
+            const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
+            const uint32_t *cig = a.cigar + c0;
+            const int32_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int32_t)(cig[0] >> 4) : 0;
+            const int32_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int32_t)(cig[ncig - 1] >> 4) : 0;
+            const int32_t rb = seq_len - trail;
+            const int32_t dend = (int32_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
+            const bool ont = a.P.platform == 1;
+            const bool zones = dend > 0 && (ont || (a.slot_flags[it.slot] & 2));
+            uint32_t rowtyp = row << 8;
+            {
+                const int strand = (a.flag[read] & 0x10) ? 1 : 0;
+                const int8_t ts = a.ts[read];
+                uint32_t tcode = 0;
+                if (ts == '+') tcode = strand == 0 ? 1u : 2u;
+                else if (ts == '-') tcode = strand == 0 ? 2u : 1u;
+                rowtyp |= (strand == 0 ? 4u : 0u) | (tcode << 3);
+            }
+            /* zone bounds in read coordinates, ordered by their first base (int64: lead - dend may leave int32) */
+            int64_t zlo[2] = {(int64_t)lead - dend + 1, (int64_t)rb - dend + 1}, zhi[2] = {(int64_t)lead + dend - 1, (int64_t)rb + dend - 1};
+            if (zlo[1] < zlo[0]) { int64_t t = zlo[0]; zlo[0] = zlo[1]; zlo[1] = t; t = zhi[0]; zhi[0] = zhi[1]; zhi[1] = t; }
+            const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1);
+            LcrSeg *out = FILL ? a.segs + a.seg_off[idx] : nullptr;
+            int32_t fpos = it.fpos, rpos = (int32_t)it.rpos;
+            uint32_t off = it.opoff;
+            bool bad = false;
+            for (uint32_t ci = it.cig; ci < ncig && fpos < tile_end; ++ci, off = 0) {
+                const uint32_t op = cig[ci], opc = op & 0xf;
+                const int32_t len = (int32_t)((op >> 4) - off);
+                if (opc == 4 || opc == 5) continue;
+                if (opc == 1) { rpos += len; continue; }
+                if (!is_ref_consuming(opc)) { bad = true; break; }
+                const bool is_m = opc == 0 || opc == 7 || opc == 8;
+                const int32_t n = fpos + len < tile_end ? len : tile_end - fpos; /* columns of this op inside the tile */
+                if (n > 0) {
+                    const uint32_t colr = (uint32_t)(fpos - tile_start);
+                    if (!is_m) {
+                        if (FILL) {
+                            LcrSeg s;
+                            s.spos = 0; s.row_typ = rowtyp | (opc == 2 ? SEG_D : SEG_N); s.col = (uint16_t)colr; s.len = (uint16_t)n;
+                            out[nseg] = s;
+                        }
+                        nseg++;
+                    } else {
+                        if ((int64_t)rpos + n > (int64_t)seq_len) { bad = true; break; }
+                        nb += (uint32_t)n;
+                        const int32_t ra = rpos, rbnd = rpos + n;
+                        int32_t start = ra;
+                        auto emit = [&](int32_t x, int32_t y) {
+                            if (y <= x) return;
+                            if (FILL) {
+                                LcrSeg s;
+                                s.spos = s0 + (uint64_t)x; s.row_typ = rowtyp | SEG_M; s.col = (uint16_t)(colr + (uint32_t)(x - ra)); s.len = (uint16_t)(y - x);
+                                out[nseg] = s;
+                            }
+                            nseg++;
+                        };
+                        if (zones) {
+                            int64_t prev_hi = -0x7fffffffffffLL;
+                            for (int k = 0; k < 2; ++k) {
+                                int64_t lo = zlo[k] > (int64_t)ra ? zlo[k] : (int64_t)ra;
+                                if (lo <= prev_hi) lo = prev_hi + 1;
+                                const int64_t hi = zhi[k] < (int64_t)rbnd - 1 ? zhi[k] : (int64_t)rbnd - 1;
+                                for (int64_t rp = lo; rp <= hi; ++rp) {
+                                    const bool m = ont || base_masked(a.P, seq, rp, seq_len, lead, trail, ref[fpos + ((int32_t)rp - ra)]);
+                                    if (m) { emit(start, (int32_t)rp); start = (int32_t)rp + 1; }
+                                }
+                                if (zhi[k] > prev_hi) prev_hi = zhi[k];
+                            }
+                        }
+                        emit(start, rbnd);
+                    }
+                }
+                fpos += len;
+                if (is_m) rpos += len;
+            }
+            if (bad) { atomicMin(&a.rstate[reg].status, (int32_t)LCR_ERR_BAD_CIGAR); nseg = 0; nb = 0; }
+        }
+    }
+    if (!FILL) {
+        if (idx < a.n_items) a.seg_count[idx] = nseg;
+    } else {
+        nb = __reduce_add_sync(0xffffffffu, nb); /* < 2^32: 32 items x 512 columns */
+        if ((threadIdx.x & 31) == 0 && nb) atomicAdd((unsigned long long *)&a.stats->n_aligned_bases, (unsigned long long)nb);
+    }
 }
 
-__global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
-    extern __shared__ __align__(16) uint8_t rows_raw[]; /* LCR_ROWS x LCR_TILE row bytes */
-    uint8_t (*rows)[LCR_TILE] = reinterpret_cast<uint8_t (*)[LCR_TILE]>(rows_raw);
-    __shared__ __align__(16) ulonglong2 lut[256];
-    __shared__ uint8_t ref_s[LCR_TILE];
-    __shared__ int32_t s_col[PWARPS][33];
-    __shared__ int32_t s_rp[PWARPS][33];
-    __shared__ uint8_t s_typ[PWARPS][32];
-    __shared__ uint32_t fill[NSUB];
-    __shared__ uint32_t next_item;
-    __shared__ unsigned long long s_bases;
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
+    return r;
+}
+/* carry-save adder: (hi, lo) = x + y + z per bit */
+#define CSA(hi, lo, x, y, z) do { const uint32_t x__ = (x), y__ = (y), z__ = (z); hi = lop3_maj(x__, y__, z__); lo = lop3_xor3(x__, y__, z__); } while (0)
+
+/* PTX prmt in its generic form: bit 3 of a selector nibble replicates the sign bit of the selected byte
+   (__byte_perm is specified to ignore that bit) */
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+/* 4 read bases + 4 qualities (column order) -> plane bytes */
+__device__ __forceinline__ void onehot4(uint32_t s, uint32_t q, uint32_t minq4, uint32_t pass_allow, uint32_t fmask, uint32_t tsb, uint32_t &x, uint32_t &y) {
+    /* PRMT as an 8-entry table on the low three bits of each letter: A=..001 C=..011 T=..100 G=..111 */
+    const uint32_t t = s & 0x07070707u;
+    const uint32_t u = t | (t >> 4);
+    const uint32_t sel = __byte_perm(u, 0, 0x4420);
+    uint32_t oh = __byte_perm(0x02000100u, 0x04000008u, sel);
+    const uint32_t canon = __byte_perm(0x43004100u, 0x47000054u, sel);
+    const uint32_t d = (s & 0xdfdfdfdfu) ^ canon;                       /* non-zero byte: not exactly that letter (either case) */
+    const uint32_t nz = ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d;
+    oh &= ~prmt_sign(nz);                                          /* 0xff where bit 7 of the byte is set */
+    const uint32_t ge = ((((q & 0x7f7f7f7fu) | 0x80808080u) - minq4) | q);
+    const uint32_t pm = prmt_sign(ge) & pass_allow;
+    x = oh | ((oh << 4) & pm);
+    y = (oh & fmask) | tsb;
+}
+
+struct PileArgs {
+    lcr_params P;
+    const lcr_region *regions;
+    const uint32_t *slot_off, *slot_region, *tile_base, *tile_region;
+    const uint64_t *pos_off;
+    const uint16_t *flag;
+    const int8_t *ts;
+    const uint64_t *seq_off, *cig_off;
+    const uint8_t *seq, *qual;
+    const uint32_t *cigar;
+    const uint8_t *const *ref_table;
+    const uint32_t *tile_off, *tile_full_n;
+    const LcrItem *items;
+    const uint32_t *seg_off;
+    const LcrSeg *segs;
+    const LcrDeviceTables *tables;
+    LcrRegionState *rstate;
+    lcr_candidate *cand;
+    uint64_t *cand_key;
+    uint32_t cand_cap;
+    uint32_t *cand_count;
+    lcr_stats *stats;
+    uint32_t *pl_acgt, *pl_fwd, *pl_d, *pl_n, *pl_ts; /* debug planes or null */
+    PreCand *pre;
+    uint32_t pre_cap;
+    uint32_t *pre_count;
+};
+
+template <bool DEEP>
+__global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
+    extern __shared__ __align__(16) uint32_t pt_smem[];
+    uint32_t *planes = pt_smem;                                           /* [2][PT_ROWS][PT_WORDS] */
+    LcrSeg *s_seg = reinterpret_cast<LcrSeg *>(pt_smem + 2 * PT_ROWS * PT_WORDS);
+    uint32_t *s_out8 = reinterpret_cast<uint32_t *>(s_seg);               /* [16][PT_WORDS], aliases the segment stage */
+    uint32_t *s_choff = pt_smem + 2 * PT_ROWS * PT_WORDS + PT_SEGS * 4;   /* [PT_SEGS + 1] */
+    uint32_t *s_out32 = s_choff + PT_SEGS + 4;                            /* DEEP: [16][LCR_TILE] */
+    __shared__ uint32_t s_wsum[PT_THREADS / 32];
+    __shared__ uint32_t s_bounds[2];
     __shared__ int s_err;
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t it0 = a.tile_off[tile], it1 = a.tile_off[tile + 1];
+    if (((it1 - it0) > 255u) != DEEP) return;
     const uint32_t reg = a.tile_region[tile];
     const lcr_region R = a.regions[reg];
     const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
@@ -385,296 +592,259 @@ __global__ void __launch_bounds__(LCR_TILE, 2) k_pileup_tile(PileArgs a) {
     if (tid == 0) s_err = a.rstate[reg].status; /* one read, so the whole CTA takes the same branch */
     __syncthreads();
     if (s_err != 0) return;
-    const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start;
+    if (DEEP)
+        for (uint32_t i = tid; i < 16 * LCR_TILE; i += PT_THREADS) s_out32[i] = 0;
 
-    if (tid < 256) { /* per-code increments of the sixteen 8-bit column counters */
-        const uint32_t b = tid & 7u, pass = (tid >> 3) & 1u, fwd = (tid >> 4) & 1u, ts = (tid >> 5) & 3u;
-        unsigned long long x = 0, y = 0;
-        if (b < 4u) {
-            x |= 1ull << (8 * b);
-            x |= (unsigned long long)pass << (32 + 8 * b);
-            y |= (unsigned long long)fwd << (8 * b);
-        }
-        if (b <= 4u) {
-            if (ts == 1u) y |= 1ull << 32;
-            else if (ts == 2u) y |= 1ull << 40;
-        }
-        if (b == 5u) y |= 1ull << 48;
-        if (b == 6u) y |= 1ull << 56;
-        lut[tid] = make_ulonglong2(x, y);
-    }
-    if (tid == 0) s_bases = 0;
-    const uint8_t ref_base = tid < npos ? ref[tid] : (uint8_t)'N';
-    ref_s[tid] = ref_base;
     const uint32_t minq = (uint32_t)a.P.min_baseq;
+    const uint32_t minq4 = (minq > 30u ? 0u : minq) * 0x01010101u;
+    const uint32_t pass_allow = minq > 30u ? 0u : 0xffffffffu;
+    const uint8_t *seqp = a.seq, *qualp = a.qual;
 
-    uint32_t cnt[4] = {0, 0, 0, 0}, pas[4] = {0, 0, 0, 0}, fwd[4] = {0, 0, 0, 0}, tsc[2] = {0, 0}, dcnt = 0, ncnt = 0;
+    /* carry-save state of this thread's column word: plane (tid / PT_WORDS), word (tid % PT_WORDS) */
+    uint32_t ones = 0, twos = 0, fours = 0, eights = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+    uint32_t acc_rows = 0;
+    const uint32_t my_plane = tid / PT_WORDS, my_word = tid % PT_WORDS;
+    uint32_t cnt8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt8[i] = 0;
 
-    const uint32_t it0 = a.tile_off[tile], it1 = a.tile_off[tile + 1];
-    unsigned long long my_bases = 0;
-    for (uint32_t base_it = it0; base_it < it1; base_it += LCR_ROWS) {
-        const uint32_t nitems = (it1 - base_it) < LCR_ROWS ? (it1 - base_it) : LCR_ROWS;
+    auto flush = [&]() { /* bit-sliced counters -> 4 x 8-bit fields per indicator */
+        const uint32_t lv[8] = {ones, twos, fours, eights, s4, s5, s6, s7};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cnt8[i] = 0;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            if ((acc_rows >> l) != 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cnt8[i] += ((lv[l] >> i) & 0x01010101u) << l;
+            }
+        }
+        ones = twos = fours = eights = s4 = s5 = s6 = s7 = 0;
+        acc_rows = 0;
+    };
+
+    for (uint32_t base_it = it0; base_it < it1; base_it += PT_ROWS) {
+        const uint32_t nrow = (it1 - base_it) < PT_ROWS ? (it1 - base_it) : PT_ROWS;
+        const uint32_t row_base = base_it - it0;
+        if (DEEP && acc_rows + nrow > 255u) {
+            flush();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
+        }
+        __syncthreads(); /* the previous batch's column sums are done with the planes */
         {
-            uint4 fillv;
-            fillv.x = fillv.y = fillv.z = fillv.w = 0x07070707u;
-            uint4 *r4 = reinterpret_cast<uint4 *>(rows_raw);
-            const uint32_t n16 = nitems * (LCR_TILE / 16);
-            for (uint32_t i = tid; i < n16; i += LCR_TILE) r4[i] = fillv;
-            if (tid < NSUB) fill[tid] = 0;
-            if (tid == 0) next_item = 0;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint4 *p4 = reinterpret_cast<uint4 *>(planes);
+            for (uint32_t i = tid; i < nrow * (PT_WORDS / 4); i += PT_THREADS) {
+                p4[i] = z;
+                p4[PT_ROWS * (PT_WORDS / 4) + i] = z;
+            }
+            if (tid == 0) { s_bounds[0] = a.seg_off[base_it]; s_bounds[1] = a.seg_off[base_it + nrow]; }
         }
         __syncthreads();
-        /* phase 1: one warp per item.  A batch of up to 32 CIGAR ops is scanned (lane per op) into the first
-           column / first read offset of every reference-consuming op; columns are then produced either
-           4 per lane from word loads (long runs away from the read ends) or 1 per lane with the op of
-           each column found from a ballot over the op starts. */
-        for (;;) {
-            uint32_t itx = 0;
-            if (lane == 0) itx = atomicAdd(&next_item, 1u);
-            itx = __shfl_sync(0xffffffffu, itx, 0);
-            if (itx >= nitems) break;
-            const LcrItem it = a.items[base_it + itx];
-            const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
-            const uint64_t s0 = a.seq_off[read];
-            const int32_t seq_len = (int32_t)(a.seq_off[read + 1] - s0);
-            const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
-            const uint64_t c0 = a.cig_off[read];
-            const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
-            const uint32_t *cig = a.cigar + c0;
-            const int32_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int32_t)(cig[0] >> 4) : 0;
-            const int32_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int32_t)(cig[ncig - 1] >> 4) : 0;
-            const int32_t rb = seq_len - trail;
-            const int32_t dend = (int32_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
-            uint32_t rconst;
+        const uint32_t seg_lo = s_bounds[0], seg_hi = s_bounds[1];
+        for (uint32_t sb = seg_lo; sb < seg_hi; sb += PT_SEGS) {
+            const uint32_t ns = (seg_hi - sb) < PT_SEGS ? (seg_hi - sb) : PT_SEGS;
+            if (sb != seg_lo) __syncthreads();
+            /* stage the segments and scan their block counts */
+            uint32_t nch[PT_SEGS / PT_THREADS], mysum = 0;
+#pragma unroll
+            for (int qd = 0; qd < PT_SEGS / PT_THREADS; ++qd) {
+                const uint32_t i = tid * (PT_SEGS / PT_THREADS) + qd;
+                uint32_t n = 0;
+                if (i < ns) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + sb + i));
+                    reinterpret_cast<uint4 *>(s_seg)[i] = raw;
+                    const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
+                    if ((raw.z & 3u) == SEG_M) {
+                        const uint32_t al = raw.x & 15u, e = (al - col) & 3u;
+                        const uint32_t last = al + len - 1u, cl = last >> 4;
+                        n = cl + 1u - (((last & 15u) < e && cl > 0u) ? 1u : 0u);
+                    } else n = (((col & 15u) + len - 1u) >> 4) + 1u;
+                }
+                nch[qd] = n;
+                mysum += n;
+            }
+            uint32_t incl = mysum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < PT_THREADS / 32; ++w) {
+                const uint32_t v = s_wsum[w];
+                if (w < (int)warp) wbase += v;
+                total += v;
+            }
             {
-                const int strand = (a.flag[read] & 0x10) ? 1 : 0;
-                const int8_t ts = a.ts[read];
-                uint32_t tcode = 0;
-                if (ts == '+') tcode = strand == 0 ? 1u : 2u;
-                else if (ts == '-') tcode = strand == 0 ? 2u : 1u;
-                rconst = (strand == 0 ? 16u : 0u) | (tcode << 5);
+                uint32_t run = wbase + incl - mysum;
+#pragma unroll
+                for (int qd = 0; qd < PT_SEGS / PT_THREADS; ++qd) {
+                    s_choff[tid * (PT_SEGS / PT_THREADS) + qd] = run;
+                    run += nch[qd];
+                }
             }
-            int32_t fpos = it.fpos;
-            int32_t rpos = (int32_t)it.rpos;
-            uint32_t ci = it.cig, off = it.opoff;
-            uint32_t slots = 0xffffffffu; /* row of this item in each sub-tile, allocated on first touch */
-            bool bad = false;
-            while (ci < ncig && fpos < tile_end) {
-                uint32_t opc = 15, len = 0;
-                if (ci + lane < ncig) {
-                    const uint32_t op = cig[ci + lane];
-                    opc = op & 0xf;
-                    len = op >> 4;
-                    if (lane == 0) len -= off;
-                }
-                const bool consuming = opc == 0 || opc == 2 || opc == 3 || opc == 7 || opc == 8;
-                const bool is_m = opc == 0 || opc == 7 || opc == 8;
-                if (opc != 15 && !consuming && opc != 1 && opc != 4 && opc != 5) bad = true;
-                const int32_t rl = consuming ? (int32_t)len : 0, ql = (is_m || opc == 1) ? (int32_t)len : 0;
-                int32_t rs = rl, qs = ql;
+            __syncthreads();
+            /* one lane per 16-byte block of a segment */
+            for (uint32_t g = tid; g < total; g += PT_THREADS) {
+                uint32_t k = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int32_t r2 = __shfl_up_sync(0xffffffffu, rs, o), q2 = __shfl_up_sync(0xffffffffu, qs, o);
-                    if ((int)lane >= o) { rs += r2; qs += q2; }
-                }
-                const int32_t tot_r = __shfl_sync(0xffffffffu, rs, 31), tot_q = __shfl_sync(0xffffffffu, qs, 31);
-                /* compact the reference-consuming ops */
-                const bool keep = consuming && rl > 0 && (fpos + rs - rl) < tile_end;
-                const uint32_t keepmask = __ballot_sync(0xffffffffu, keep);
-                const uint32_t ncomp = __popc(keepmask);
-                if (keep) {
-                    const uint32_t k = __popc(keepmask & ((1u << lane) - 1u));
-                    s_col[warp][k] = fpos + rs - rl;
-                    s_rp[warp][k] = rpos + qs - ql;
-                    s_typ[warp][k] = (uint8_t)(is_m ? 0 : opc);
-                }
-                const int32_t batch_end = fpos + tot_r;
-                if (lane == 0) s_col[warp][ncomp] = batch_end;
-                const int32_t colB = batch_end < tile_end ? batch_end : tile_end;
-                if (is_m) { /* aligned bases of this batch inside the tile (n_aligned_bases) + bounds */
-                    const int32_t a0 = fpos + rs - rl, b0 = a0 + rl;
-                    const int32_t lo = a0 > fpos ? a0 : fpos, hi = b0 < colB ? b0 : colB;
-                    if (hi > lo) {
-                        my_bases += (unsigned long long)(hi - lo);
-                        if (rpos + qs - ql + (hi - a0) > seq_len) bad = true;
+                for (uint32_t step = PT_SEGS / 2; step; step >>= 1)
+                    if (k + step < ns && s_choff[k + step] <= g) k += step;
+                const uint32_t c = g - s_choff[k];
+                const uint4 raw = reinterpret_cast<const uint4 *>(s_seg)[k];
+                const uint32_t typ = raw.z & 3u, col = raw.w & 0xffffu, len = raw.w >> 16;
+                uint32_t *rx = planes + ((raw.z >> 8) - row_base) * PT_WORDS, *ry = rx + PT_ROWS * PT_WORDS;
+                uint32_t x[4], y[4];
+                int32_t W0, e, vlo, vhi; /* first owned column word; window offset of its first byte; valid window bytes [vlo, vhi) */
+                if (typ == SEG_M) {
+                    const uint64_t spos = ((uint64_t)raw.y << 32) | raw.x;
+                    const uint32_t al = raw.x & 15u;
+                    const uint64_t blk = (spos & ~(uint64_t)15) + 16ull * c;
+                    const int32_t D0 = (int32_t)col - (int32_t)al + 16 * (int32_t)c; /* column of window byte 0 */
+                    e = (int32_t)((al - col) & 3u);
+                    W0 = (D0 + e) >> 2;
+                    vlo = (int32_t)al - 16 * (int32_t)c;
+                    vhi = vlo + (int32_t)len;
+                    const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(seqp + blk));
+                    const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(qualp + blk));
+                    const uint32_t s4w = __ldg(reinterpret_cast<const uint32_t *>(seqp + blk + 16));
+                    const uint32_t q4w = __ldg(reinterpret_cast<const uint32_t *>(qualp + blk + 16));
+                    const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u;
+                    const uint32_t tsb = ((raw.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
+                    const uint32_t rot = 0x3210u + 0x1111u * (uint32_t)e;
+                    onehot4(__byte_perm(sv.x, sv.y, rot), __byte_perm(qv.x, qv.y, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
+                    onehot4(__byte_perm(sv.y, sv.z, rot), __byte_perm(qv.y, qv.z, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
+                    onehot4(__byte_perm(sv.z, sv.w, rot), __byte_perm(qv.z, qv.w, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
+                    onehot4(__byte_perm(sv.w, s4w, rot), __byte_perm(qv.w, q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                    if (c == 0 && (int32_t)al < e) {
+                        /* bytes [al, e) of the first block fall into the column word before W0 */
+                        uint32_t x0, y0;
+                        onehot4(sv.x, qv.x, minq4, pass_allow, fmask, tsb, x0, y0);
+                        uint8_t *bx = reinterpret_cast<uint8_t *>(rx + (W0 - 1)), *by = reinterpret_cast<uint8_t *>(ry + (W0 - 1));
+                        for (int32_t j = (int32_t)al; j < e && j < vhi; ++j) {
+                            bx[4 + j - e] = (uint8_t)(x0 >> (8 * j));
+                            by[4 + j - e] = (uint8_t)(y0 >> (8 * j));
+                        }
                     }
+                } else {
+                    const int32_t B0 = (int32_t)(col & ~15u) + 16 * (int32_t)c;
+                    W0 = B0 >> 2;
+                    e = 0;
+                    vlo = (int32_t)col - B0;
+                    vhi = vlo + (int32_t)len;
+                    const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
+                    x[0] = x[1] = x[2] = x[3] = 0;
+                    y[0] = y[1] = y[2] = y[3] = v;
                 }
-                bad = __any_sync(0xffffffffu, bad);
-                if (bad) break;
-                __syncwarp();
-                /* rows of this item in the sub-tiles this batch reaches */
-                if (colB > fpos) {
-                    const uint32_t subA = (uint32_t)(fpos - tile_start) / SUBTILE, subB = (uint32_t)(colB - 1 - tile_start) / SUBTILE;
-                    for (uint32_t sidx = subA; sidx <= subB; ++sidx) {
-                        if (((slots >> (8 * sidx)) & 0xffu) != 0xffu) continue;
-                        uint32_t v = 0;
-                        if (lane == 0) v = atomicAdd(&fill[sidx], 1u);
-                        v = __shfl_sync(0xffffffffu, v, 0);
-                        slots = (slots & ~(0xffu << (8 * sidx))) | (v << (8 * sidx));
-                    }
-                }
-                /* every kept op is one run inside [fpos, colB); cut each run into 16-byte aligned chunks of the read
-                   (or 16 columns of a D / N run) and let every lane take one chunk */
-                int32_t run_a = 0, run_n = 0, run_rp = 0, run_al = 0;
-                uint32_t run_typ = 0, nch = 0;
-                if (lane < ncomp) {
-                    const int32_t st = s_col[warp][lane], en = s_col[warp][lane + 1];
-                    run_a = st > fpos ? st : fpos;
-                    const int32_t bb = en < colB ? en : colB;
-                    run_n = bb - run_a;
-                    run_typ = s_typ[warp][lane];
-                    run_rp = s_rp[warp][lane] + (run_a - st);
-                    if (run_typ == 0) run_al = (int32_t)((uintptr_t)(seq + run_rp) & 15u);
-                    nch = (uint32_t)(run_al + run_n + 15) >> 4;
-                }
-                uint32_t chs = nch; /* inclusive scan of the chunk counts */
+                if (vlo <= e && e + 16 <= vhi) {
+                    if (typ == SEG_M) { rx[W0] = x[0]; rx[W0 + 1] = x[1]; rx[W0 + 2] = x[2]; rx[W0 + 3] = x[3]; }
+                    ry[W0] = y[0]; ry[W0 + 1] = y[1]; ry[W0 + 2] = y[2]; ry[W0 + 3] = y[3];
+                } else {
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v2 = __shfl_up_sync(0xffffffffu, chs, o);
-                    if ((int)lane >= o) chs += v2;
-                }
-                const uint32_t n_chunks = __shfl_sync(0xffffffffu, chs, 31);
-                const int32_t mychoff = lane < ncomp ? (int32_t)(chs - nch) : 0x7fffffff;
-                const uint32_t rconst4 = rconst * 0x01010101u;
-                for (uint32_t base = 0; base < n_chunks; base += 32) {
-                    const int32_t first = (int32_t)__popc(__ballot_sync(0xffffffffu, mychoff <= (int32_t)base)) - 1;
-                    const int32_t rel = mychoff - (int32_t)base;
-                    const uint32_t starts = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? (1u << rel) : 0u);
-                    const int32_t k = first + (int32_t)__popc(starts & (0xffffffffu >> (31 - lane)));
-                    /* run parameters of my chunk come from the lane that owns run k */
-                    const int32_t k_a = __shfl_sync(0xffffffffu, run_a, k), k_n = __shfl_sync(0xffffffffu, run_n, k);
-                    const int32_t k_rp = __shfl_sync(0xffffffffu, run_rp, k), k_al = __shfl_sync(0xffffffffu, run_al, k);
-                    const uint32_t k_typ = __shfl_sync(0xffffffffu, run_typ, k);
-                    const int32_t k_off = __shfl_sync(0xffffffffu, mychoff, k);
-                    const uint32_t g = base + lane;
-                    if (g < n_chunks) {
-                        const int32_t c = (int32_t)g - k_off;              /* chunk index inside the run */
-                        const int32_t lo = c == 0 ? k_al : 0;
-                        int32_t hi = k_al + k_n - 16 * c;
-                        if (hi > 16) hi = 16;
-                        uint32_t w0, w1, w2, w3;
-                        if (k_typ == 0) {
-                            const uintptr_t sa = ((uintptr_t)(seq + k_rp) & ~(uintptr_t)15) + (uintptr_t)(16 * c);
-                            const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(sa));
-                            const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(sa + (uintptr_t)(qual - seq)));
-                            w0 = codes4(sv.x, qv.x, minq, rconst4); w1 = codes4(sv.y, qv.y, minq, rconst4);
-                            w2 = codes4(sv.z, qv.z, minq, rconst4); w3 = codes4(sv.w, qv.w, minq, rconst4);
-                        } else w0 = w1 = w2 = w3 = (k_typ == 2 ? 5u : 6u) * 0x01010101u;
-                        /* byte j of the chunk is column k_a - k_al + 16 c + j */
-                        const uint32_t colr0 = (uint32_t)(k_a - k_al + 16 * c - tile_start);
+                    for (int t = 0; t < 4; ++t) {
+                        const int32_t u0 = e + 4 * t;
+                        if (vlo <= u0 && u0 + 4 <= vhi) {
+                            if (typ == SEG_M) rx[W0 + t] = x[t];
+                            ry[W0 + t] = y[t];
+                        } else if (u0 < vhi && u0 + 4 > vlo) {
+                            uint8_t *bx = reinterpret_cast<uint8_t *>(rx + (W0 + t)), *by = reinterpret_cast<uint8_t *>(ry + (W0 + t));
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t wj = j < 4 ? w0 : (j < 8 ? w1 : (j < 12 ? w2 : w3));
-                            if (j >= lo && j < hi) {
-                                const uint32_t colr = colr0 + (uint32_t)j;
-                                rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)(wj >> (8 * (j & 3)));
-                            }
+                            for (int b = 0; b < 4; ++b)
+                                if (u0 + b >= vlo && u0 + b < vhi) {
+                                    if (typ == SEG_M) bx[b] = (uint8_t)(x[t] >> (8 * b));
+                                    by[b] = (uint8_t)(y[t] >> (8 * b));
+                                }
                         }
                     }
                 }
-                /* read-end zones (util.rs:745-789): bases with |rp - lead| < D or |rp - rb| < D are trimmed (ONT) or tested
-                   for poly-A / homopolymer runs; one lane per zone base of this batch */
-                if (dend > 0) {
-                    const int32_t zlo = lead + dend, zhi = rb - dend; /* rp < zlo or rp > zhi lies in a zone */
-                    int32_t z0n = 0, z1n = 0, z1s = 0;                   /* zone bases of my run: [run_rp, run_rp+z0n) and [z1s, z1s+z1n) */
-                    if (lane < ncomp && run_typ == 0) {
-                        const int32_t e0 = run_rp + run_n < zlo ? run_rp + run_n : zlo;
-                        z0n = e0 > run_rp ? e0 - run_rp : 0;
-                        z1s = run_rp + z0n > zhi + 1 ? run_rp + z0n : zhi + 1;
-                        z1n = run_rp + run_n > z1s ? run_rp + run_n - z1s : 0;
-                    }
-                    uint32_t zc = (uint32_t)(z0n + z1n), zs = zc;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t v2 = __shfl_up_sync(0xffffffffu, zs, o);
-                        if ((int)lane >= o) zs += v2;
-                    }
-                    const uint32_t n_z = __shfl_sync(0xffffffffu, zs, 31);
-                    if (n_z) {
-                        __syncwarp();
-                        s_rp[warp][lane] = (int32_t)(zs - zc); /* exclusive offsets; s_rp / s_col are free again after the chunk pass */
-                        __syncwarp();
-                        for (uint32_t base = 0; base < n_z; base += 32) {
-                            const uint32_t g = base + lane;
-                            /* owner run: last lane whose offset is <= g and that has zone bases */
-                            uint32_t lo_k = 0;
-#pragma unroll
-                            for (int step = 16; step; step >>= 1)
-                                if (lo_k + step < 32 && (uint32_t)s_rp[warp][lo_k + step] <= g) lo_k += step;
-                            const int32_t k_rp = __shfl_sync(0xffffffffu, run_rp, lo_k), k_a = __shfl_sync(0xffffffffu, run_a, lo_k);
-                            const int32_t k_z0n = __shfl_sync(0xffffffffu, z0n, lo_k), k_z1s = __shfl_sync(0xffffffffu, z1s, lo_k);
-                            const uint32_t k_off = (uint32_t)__shfl_sync(0xffffffffu, s_rp[warp][lane], lo_k);
-                            if (g < n_z) {
-                                const int32_t idx = (int32_t)(g - k_off);
-                                const int32_t r = idx < k_z0n ? k_rp + idx : k_z1s + (idx - k_z0n);
-                                const uint32_t colr = (uint32_t)(k_a + (r - k_rp) - tile_start);
-                                if (base_masked(a.P, seq, r, seq_len, lead, trail, ref_s[colr]))
-                                    rows[(slots >> (8 * (colr / SUBTILE))) & 0xffu][colr] = (uint8_t)ROW_NONE;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                fpos = batch_end;
-                rpos += tot_q;
-                ci += 32;
-                off = 0;
-                __syncwarp();
             }
-            if (bad) s_err = LCR_ERR_BAD_CIGAR;
         }
         __syncthreads();
-        /* phase 2: every thread sums the column of its position over the rows of its sub-tile */
+        /* column sums of this batch: Harley-Seal blocks of 16 rows */
         {
-            unsigned long long acc0 = 0, acc1 = 0;
-            const uint32_t nrow = fill[tid / SUBTILE];
-            for (uint32_t row = 0; row < nrow; ++row) {
-                const ulonglong2 v = lut[rows[row][tid]];
-                acc0 += v.x;
-                acc1 += v.y;
-            }
+            const uint32_t *pl = planes + my_plane * (PT_ROWS * PT_WORDS) + my_word;
+            for (uint32_t r0 = 0; r0 < nrow; r0 += 16) {
+                uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                cnt[i] += (uint32_t)(acc0 >> (8 * i)) & 0xffu;
-                pas[i] += (uint32_t)(acc0 >> (32 + 8 * i)) & 0xffu;
-                fwd[i] += (uint32_t)(acc1 >> (8 * i)) & 0xffu;
+                for (int j = 0; j < 16; ++j) w[j] = (r0 + j < nrow) ? pl[(r0 + j) * PT_WORDS] : 0u;
+                uint32_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
+                CSA(t2a, ones, ones, w[0], w[1]);
+                CSA(t2b, ones, ones, w[2], w[3]);
+                CSA(t4a, twos, twos, t2a, t2b);
+                CSA(t2a, ones, ones, w[4], w[5]);
+                CSA(t2b, ones, ones, w[6], w[7]);
+                CSA(t4b, twos, twos, t2a, t2b);
+                CSA(t8a, fours, fours, t4a, t4b);
+                CSA(t2a, ones, ones, w[8], w[9]);
+                CSA(t2b, ones, ones, w[10], w[11]);
+                CSA(t4a, twos, twos, t2a, t2b);
+                CSA(t2a, ones, ones, w[12], w[13]);
+                CSA(t2b, ones, ones, w[14], w[15]);
+                CSA(t4b, twos, twos, t2a, t2b);
+                CSA(t8b, fours, fours, t4a, t4b);
+                CSA(t16, eights, eights, t8a, t8b);
+                /* ripple the sixteens into the upper bit slices */
+                uint32_t cy = t16, tt;
+                tt = s4 & cy; s4 ^= cy; cy = tt;
+                tt = s5 & cy; s5 ^= cy; cy = tt;
+                tt = s6 & cy; s6 ^= cy; cy = tt;
+                s7 ^= cy;
             }
-            tsc[0] += (uint32_t)(acc1 >> 32) & 0xffu;
-            tsc[1] += (uint32_t)(acc1 >> 40) & 0xffu;
-            dcnt += (uint32_t)(acc1 >> 48) & 0xffu;
-            ncnt += (uint32_t)(acc1 >> 56) & 0xffu;
+            acc_rows += nrow;
         }
-        __syncthreads();
     }
-    my_bases = __reduce_add_sync(0xffffffffu, (uint32_t)my_bases);
-    if (lane == 0 && my_bases) atomicAdd(&s_bases, my_bases);
+    flush();
+    __syncthreads(); /* the segment stage is free: it becomes the 8-bit counter exchange */
+    if (DEEP) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_out8[(my_plane * 8 + i) * PT_WORDS + my_word] = cnt8[i];
+    }
     __syncthreads();
-    if (tid == 0) {
-        if (s_bases) atomicAdd((unsigned long long *)&a.stats->n_aligned_bases, s_bases);
-        if (s_err) atomicMin(&a.rstate[reg].status, s_err);
-    }
-    if (tid >= npos) return;
-    ncnt += a.tile_full_n[tile];
-    if (a.pl_acgt) {
-        const uint64_t g = a.pos_off[reg] + (uint64_t)tile_start + tid;
+    const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start;
+    for (uint32_t colr = tid; colr < npos; colr += PT_THREADS) {
+        uint32_t v[16];
+        if (DEEP) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = cnt[i]; a.pl_fwd[g * 4 + i] = fwd[i]; }
-        a.pl_d[g] = dcnt; a.pl_n[g] = ncnt; a.pl_ts[g * 2] = tsc[0]; a.pl_ts[g * 2 + 1] = tsc[1];
-    }
-    SiteCounters sc;
+            for (int i = 0; i < 16; ++i) v[i] = s_out32[i * LCR_TILE + colr];
+        } else {
+            const uint8_t *o8 = reinterpret_cast<const uint8_t *>(s_out8);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { sc.cnt[i] = cnt[i]; sc.pass[i] = pas[i]; sc.fwd[i] = fwd[i]; }
-    sc.ts[0] = tsc[0]; sc.ts[1] = tsc[1]; sc.d = dcnt; sc.n = ncnt; sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
-    lcr_candidate dummy;
-    if (site_call<true>(a.P, *a.tables, sc, ref_base, dummy)) {
-        const uint32_t k = atomicAdd(a.pre_count, 1u);
-        if (k < a.pre_cap) {
-            PreCand pc;
-            pc.tile = tile; pc.col = tid;
+            for (int i = 0; i < 16; ++i) v[i] = o8[i * LCR_TILE + colr];
+        }
+        SiteCounters sc;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { pc.cnt[i] = cnt[i]; pc.pass[i] = pas[i]; pc.fwd[i] = fwd[i]; }
-            pc.ts[0] = tsc[0]; pc.ts[1] = tsc[1]; pc.d = dcnt; pc.n = ncnt;
-            a.pre[k] = pc;
+        for (int i = 0; i < 4; ++i) { sc.cnt[i] = v[i]; sc.pass[i] = v[4 + i]; sc.fwd[i] = v[8 + i]; }
+        sc.ts[0] = v[12]; sc.ts[1] = v[13]; sc.d = v[14]; sc.n = v[15] + a.tile_full_n[tile];
+        sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
+        if (a.pl_acgt) {
+            const uint64_t g = a.pos_off[reg] + (uint64_t)tile_start + colr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = sc.cnt[i]; a.pl_fwd[g * 4 + i] = sc.fwd[i]; }
+            a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
+        }
+        lcr_candidate dummy;
+        if (site_call<true>(a.P, *a.tables, sc, ref[colr], dummy)) {
+            const uint32_t k = atomicAdd(a.pre_count, 1u);
+            if (k < a.pre_cap) {
+                PreCand pc;
+                pc.tile = tile; pc.col = colr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { pc.cnt[i] = sc.cnt[i]; pc.pass[i] = sc.pass[i]; pc.fwd[i] = sc.fwd[i]; }
+                pc.ts[0] = sc.ts[0]; pc.ts[1] = sc.ts[1]; pc.d = sc.d; pc.n = sc.n;
+                a.pre[k] = pc;
+            }
         }
     }
 }
@@ -821,7 +991,7 @@ __global__ void k_cand_finalize(lcr_params P, uint32_t n_regions, const uint64_t
 
 __global__ void k_count_pass(const uint8_t *slot_flags, uint32_t n_slots, lcr_stats *stats) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t v = (i < n_slots && slot_flags[i]) ? 1u : 0u;
+    uint32_t v = (i < n_slots && (slot_flags[i] & 1)) ? 1u : 0u;
     v = __reduce_add_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long *)&stats->n_reads_pass, (unsigned long long)v);
 }
@@ -852,7 +1022,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     pa.regions = db->regions;
     pa.slot_off = db->slot_off; pa.slot_region = db->slot_region; pa.tile_base = db->tile_base;
     pa.pos = db->pos; pa.flag = db->flag; pa.mapq = db->mapq; pa.de = db->de;
-    pa.seq_off = db->seq_off; pa.cig_off = db->cig_off; pa.cigar = db->cigar;
+    pa.seq_off = db->seq_off; pa.cig_off = db->cig_off; pa.seq = db->seq; pa.cigar = db->cigar;
     pa.rstate = db->rstate;
     pa.slot_flags = slot_flags;
     pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n; pa.items = nullptr;
@@ -879,6 +1049,51 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         db->timing.kernel_launches += 1;
     }
 
+    /* segments: count per item, scan, fill (k_seg_build) */
+    uint32_t *seg_count = nullptr, *seg_off = nullptr, *deep_flag = nullptr;
+    LcrSeg *segs = nullptr;
+    TRY(cudaMallocAsync(&seg_count, sizeof(uint32_t) * ((size_t)n_items + 2), st));
+    TRY(cudaMallocAsync(&seg_off, sizeof(uint32_t) * ((size_t)n_items + 2), st));
+    TRY(cudaMemsetAsync(seg_count + n_items, 0, 2 * sizeof(uint32_t), st));
+    deep_flag = seg_count + n_items + 1;
+    SegArgs sa{};
+    sa.P = ctx->P;
+    sa.n_items = n_items;
+    sa.regions = db->regions;
+    sa.slot_off = db->slot_off; sa.slot_region = db->slot_region; sa.tile_base = db->tile_base;
+    sa.flag = db->flag; sa.ts = db->ts; sa.seq_off = db->seq_off; sa.cig_off = db->cig_off;
+    sa.seq = db->seq; sa.cigar = db->cigar;
+    sa.ref_table = ctx->d_ref_table;
+    sa.slot_flags = slot_flags;
+    sa.tile_off = tile_off; sa.items = items;
+    sa.rstate = db->rstate; sa.stats = db->d_stats;
+    sa.seg_count = seg_count; sa.seg_off = seg_off; sa.segs = nullptr; sa.deep_flag = deep_flag;
+    const uint32_t sg = (n_items + 127) / 128;
+    if (sg) {
+        k_seg_build<false><<<sg, 128, 0, st>>>(sa);
+        db->timing.kernel_launches += 1;
+    }
+    {
+        size_t sb2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, sb2, seg_count, seg_off, n_items + 1, st);
+        void *tmp2 = nullptr;
+        TRY(cudaMallocAsync(&tmp2, sb2 ? sb2 : 16, st));
+        TRY(cub::DeviceScan::ExclusiveSum(tmp2, sb2, seg_count, seg_off, n_items + 1, st));
+        TRY(cudaFreeAsync(tmp2, st));
+    }
+    uint32_t seg_tail[2] = {0, 0}; /* total segments, deep-tile flag */
+    TRY(cudaMemcpyAsync(&seg_tail[0], seg_off + n_items, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&seg_tail[1], deep_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    const uint32_t n_segs = seg_tail[0];
+    const bool any_deep = seg_tail[1] != 0;
+    TRY(cudaMallocAsync(&segs, sizeof(LcrSeg) * (size_t)(n_segs ? n_segs : 1), st));
+    sa.segs = segs;
+    if (sg) {
+        k_seg_build<true><<<sg, 128, 0, st>>>(sa);
+        db->timing.kernel_launches += 1;
+    }
+
     /* tile pileup (counts + count-based site filters), then the exact likelihood of the surviving sites */
     uint32_t pre_cap = (uint32_t)std::min<uint64_t>(db->n_pos, db->n_pos / 8 + 4096);
     if (!pre_cap) pre_cap = 1;
@@ -890,8 +1105,10 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     cudaEvent_t ev0, ev1;
     TRY(cudaEventCreate(&ev0));
     TRY(cudaEventCreate(&ev1));
-    const size_t tile_smem = (size_t)LCR_ROWS * LCR_TILE;
-    TRY(cudaFuncSetAttribute(k_pileup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    const size_t tile_smem = sizeof(uint32_t) * (2 * PT_ROWS * PT_WORDS + PT_SEGS * 4 + PT_SEGS + 4);
+    const size_t tile_smem_deep = tile_smem + sizeof(uint32_t) * 16 * LCR_TILE;
+    TRY(cudaFuncSetAttribute(k_pileup_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    TRY(cudaFuncSetAttribute(k_pileup_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_deep));
     PileArgs ka{};
     ka.P = ctx->P;
     ka.regions = db->regions;
@@ -901,6 +1118,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
     ka.ref_table = ctx->d_ref_table;
     ka.tile_off = tile_off; ka.tile_full_n = tile_full_n; ka.items = items;
+    ka.seg_off = seg_off; ka.segs = segs;
     ka.tables = ctx->d_tables;
     ka.rstate = db->rstate;
     ka.stats = db->d_stats;
@@ -911,11 +1129,14 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         TRY(cudaMallocAsync(&pre, sizeof(PreCand) * (size_t)pre_cap, st));
         TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), st));
         ka.pre = pre; ka.pre_cap = pre_cap;
-        if (attempt == 1) TRY(cudaMemsetAsync(&db->d_stats->n_aligned_bases, 0, sizeof(uint64_t), st));
         TRY(cudaEventRecord(ev0, st));
         if (n_tiles) {
-            k_pileup_tile<<<n_tiles, LCR_TILE, tile_smem, st>>>(ka);
+            k_pileup_tile<false><<<n_tiles, PT_THREADS, tile_smem, st>>>(ka);
             db->timing.kernel_launches += 1;
+            if (any_deep) {
+                k_pileup_tile<true><<<n_tiles, PT_THREADS, tile_smem_deep, st>>>(ka);
+                db->timing.kernel_launches += 1;
+            }
         }
         TRY(cudaEventRecord(ev1, st));
         TRY(cudaMemcpyAsync(&n_pre, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -945,7 +1166,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         TRY(cudaMemcpyAsync(&hs, db->d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));
         TRY(cudaGetLastError());
-        db->timing.pileup_alg_bytes = 2ull * hs.n_aligned_bases + 4ull * db->n_cigar + sizeof(LcrItem) * (uint64_t)n_items + db->n_pos + sizeof(PreCand) * (uint64_t)n_pre;
+        db->timing.pileup_alg_bytes = 2ull * hs.n_aligned_bases + 4ull * db->n_cigar + 32ull * db->n_reads + db->n_pos + sizeof(PreCand) * (uint64_t)n_pre;
     }
     TRY(cudaFreeAsync(pre, st));
     uint32_t *cand_count = counters;
@@ -980,6 +1201,9 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaFreeAsync(cand_key, st));
     TRY(cudaFreeAsync(cand_count, st));
     TRY(cudaFreeAsync(items, st));
+    TRY(cudaFreeAsync(segs, st));
+    TRY(cudaFreeAsync(seg_count, st));
+    TRY(cudaFreeAsync(seg_off, st));
     TRY(cudaFreeAsync(tmp, st));
     TRY(cudaFreeAsync(tile_count, st));
     TRY(cudaFreeAsync(tile_off, st));
