@@ -20,140 +20,7 @@
 
 namespace {
 
-struct PrepArgs {
-    lcr_params P;
-    uint32_t n_slots;
-    const lcr_region *regions;
-    const uint32_t *slot_off, *slot_region, *tile_base;
-    const int32_t *pos;
-    const uint16_t *flag;
-    const uint8_t *mapq;
-    const float *de;
-    const uint64_t *seq_off, *cig_off;
-    const uint8_t *seq;
-    const uint32_t *cigar;
-    LcrRegionState *rstate;
-    uint8_t *slot_flags;   /* bit 0: passes the read filter and overlaps the window; bit 1: the poly-A test needs the exact path */
-    uint32_t *tile_count;  /* COUNT: items per tile; FILL: cursor */
-    const uint32_t *tile_off;
-    uint32_t *tile_full_n; /* whole-tile intron covers */
-    LcrItem *items;
-};
-
 __device__ __forceinline__ bool is_ref_consuming(uint32_t opc) { return opc == 0 || opc == 2 || opc == 3 || opc == 7 || opc == 8; }
-
-template <bool FILL>
-__global__ void k_slot_prep(PrepArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= a.n_slots) return;
-    const uint32_t reg = a.slot_region[slot];
-    if (a.rstate[reg].status != 0) return;
-    const lcr_region R = a.regions[reg];
-    const uint32_t read = R.read_begin + (slot - a.slot_off[reg]);
-    const uint64_t c0 = a.cig_off[read], c1 = a.cig_off[read + 1];
-    if (!FILL) {
-        /* util.rs:652-668 */
-        const uint64_t l_seq = a.seq_off[read + 1] - a.seq_off[read];
-        const uint16_t fl = a.flag[read];
-        bool pass = !((int32_t)a.mapq[read] < a.P.min_mapq || l_seq < (uint64_t)a.P.min_read_length || (fl & 0x4) || (fl & 0x100) || (fl & 0x800));
-        const float de = a.de[read];
-        if (!(de != de) && de >= a.P.divergence) pass = false;
-        /* fetch((chr, start, end)): pos < end && bam_endpos > start on the region's own numbers */
-        int64_t rlen = 0;
-        for (uint64_t c = c0; c < c1; ++c) {
-            const uint32_t op = a.cigar[c];
-            if (is_ref_consuming(op & 0xf)) rlen += op >> 4;
-        }
-        const int64_t p = a.pos[read];
-        const bool in_window = p < (int64_t)R.end && p + (rlen ? rlen : 1) > (int64_t)R.start;
-        if (!(pass && in_window)) { a.slot_flags[slot] = 0; return; }
-        /* util.rs:754-789 can only mask a base when a homopolymer window of polya_tail_length letters lies within
-           polya_tail_length of a read-end zone: reads without one skip the per-base test in k_seg_build */
-        uint8_t fl_out = 1;
-        if (a.P.platform != 1 && a.P.distance_to_read_end > 0) {
-            const int64_t polya = (int64_t)(a.P.polya_tail_length > 0x3fffffffu ? 0x3fffffffu : a.P.polya_tail_length);
-            bool has_run = polya < 2;
-            if (!has_run) {
-                const int64_t dend = (int64_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
-                const int64_t lead = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (int64_t)(a.cigar[c0] >> 4) : 0;
-                const int64_t trail = (c1 > c0 && (a.cigar[c1 - 1] & 0xf) == 4) ? (int64_t)(a.cigar[c1 - 1] >> 4) : 0;
-                const int64_t rb = (int64_t)l_seq - trail;
-                const uint8_t *seq = a.seq + a.seq_off[read];
-                const int64_t centre[2] = {lead, rb};
-                for (int z = 0; z < 2 && !has_run; ++z) {
-                    int64_t lo = centre[z] - dend + 1 - polya, hi = centre[z] + dend + polya; /* [lo, hi) */
-                    if (lo < 0) lo = 0;
-                    if (hi > (int64_t)l_seq) hi = (int64_t)l_seq;
-                    int64_t run = 0;
-                    uint8_t prev = 0;
-                    for (int64_t i = lo; i < hi; ++i) {
-                        const uint8_t b = __ldg(seq + i);
-                        const bool letter = b == 'A' || b == 'C' || b == 'G' || b == 'T';
-                        run = letter ? (b == prev ? run + 1 : 1) : 0;
-                        prev = b;
-                        if (run >= polya) { has_run = true; break; }
-                    }
-                }
-            }
-            if (has_run) fl_out |= 2;
-        }
-        a.slot_flags[slot] = fl_out;
-    } else if (!(a.slot_flags[slot] & 1)) return;
-
-    const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
-    const int64_t fv_start = (int64_t)R.start - 1;
-    const uint32_t tb = a.tile_base[reg];
-    int64_t fpos = (int64_t)a.pos[read] - fv_start;
-    uint32_t rpos = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (a.cigar[c0] >> 4) : 0; /* leading_softclips */
-    int64_t last_tile = -1;
-    for (uint64_t c = c0; c < c1; ++c) {
-        const uint32_t op = a.cigar[c], opc = op & 0xf, len = op >> 4;
-        if (opc == 4 || opc == 5) continue;
-        if (opc == 1) {
-            if (fpos >= vec_size && fpos >= 1) break;
-            rpos += len;
-            continue;
-        }
-        if (!is_ref_consuming(opc)) { /* util.rs:943-945 panics */
-            atomicMin(&a.rstate[reg].status, (int32_t)LCR_ERR_BAD_CIGAR);
-            return;
-        }
-        const bool is_m = (opc == 0 || opc == 7 || opc == 8);
-        const int64_t lo = fpos, hi = fpos + (int64_t)len;
-        if (lo >= vec_size) { /* the walk is over; later ops cannot reach the window */
-            fpos = hi;
-            continue;
-        }
-        if (hi > 0) {
-            const int64_t a0 = lo < 0 ? 0 : lo, b0 = hi < vec_size ? hi : vec_size;
-            for (int64_t t = a0 / LCR_TILE; t * LCR_TILE < b0; ++t) {
-                const int64_t ts = a0 > t * LCR_TILE ? a0 : t * LCR_TILE;
-                const int64_t tile_end = (t + 1) * LCR_TILE < vec_size ? (t + 1) * LCR_TILE : vec_size;
-                const int64_t te = b0 < tile_end ? b0 : tile_end;
-                if (opc == 3 && ts == t * LCR_TILE && te == tile_end && t > last_tile) {
-                    if (FILL) atomicAdd(&a.tile_full_n[tb + t], 1u);
-                    continue;
-                }
-                if (t > last_tile) {
-                    last_tile = t;
-                    if (!FILL) atomicAdd(&a.tile_count[tb + t], 1u);
-                    else {
-                        const uint32_t k = a.tile_off[tb + t] + atomicAdd(&a.tile_count[tb + t], 1u);
-                        LcrItem it;
-                        it.slot = slot;
-                        it.cig = (uint32_t)(c - c0);
-                        it.opoff = (uint32_t)(ts - lo);
-                        it.rpos = is_m ? rpos + (uint32_t)(ts - lo) : rpos;
-                        it.fpos = (int32_t)ts;
-                        a.items[k] = it;
-                    }
-                }
-            }
-        }
-        fpos = hi;
-        if (is_m) rpos += len;
-    }
-}
 
 /* ------------------------------------------------------------------------- */
 
@@ -222,23 +89,22 @@ template <bool PRE>
 __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const SiteCounters &s, uint8_t ref_base, lcr_candidate &o) {
     const uint32_t total = s.cnt[0] + s.cnt[1] + s.cnt[2] + s.cnt[3];
     if (total < P.min_depth || total > P.max_depth) return false;
-    /* get_two_major_alleles: stable descending sort of (A,C,G,T) */
-    int ord[4] = {0, 1, 2, 3};
-#pragma unroll
-    for (int i = 1; i < 4; ++i) {
-        const int v = ord[i];
-        int j = i - 1;
-        while (j >= 0 && s.cnt[ord[j]] < s.cnt[v]) { ord[j + 1] = ord[j]; --j; }
-        ord[j + 1] = v;
-    }
-    const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    /* get_two_major_alleles: stable descending sort of (A,C,G,T); keys (count << 2 | 3 - index) through a 5-exchange network */
+    uint32_t k0 = (s.cnt[0] << 2) | 3u, k1 = (s.cnt[1] << 2) | 2u, k2 = (s.cnt[2] << 2) | 1u, k3 = s.cnt[3] << 2;
+#define LCR_CX(x, y) do { const uint32_t hi__ = max(x, y), lo__ = min(x, y); x = hi__; y = lo__; } while (0)
+    LCR_CX(k0, k1); LCR_CX(k2, k3); LCR_CX(k0, k2); LCR_CX(k1, k3); LCR_CX(k1, k2);
+#undef LCR_CX
+    const int ord[4] = {3 - (int)(k0 & 3u), 3 - (int)(k1 & 3u), 3 - (int)(k2 & 3u), 3 - (int)(k3 & 3u)};
+    const uint32_t oc[4] = {k0 >> 2, k1 >> 2, k2 >> 2, k3 >> 2}; /* counts in sorted order */
+    auto letter = [](int c) -> uint8_t { return (uint8_t)(0x54474341u >> (8 * c)); };                  /* "ACGT"[c] */
+    auto pick = [](const uint32_t (&v)[4], int i) -> uint32_t { return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3]; }; /* registers only */
     int i1 = ord[0], i2 = ord[1];
-    if ((uint8_t)ACGT[ord[0]] != ref_base && (uint8_t)ACGT[ord[1]] != ref_base) {
-        if (s.cnt[ord[2]] == s.cnt[ord[1]] && (uint8_t)ACGT[ord[2]] == ref_base) i2 = ord[2];
-        else if (s.cnt[ord[3]] == s.cnt[ord[1]] && (uint8_t)ACGT[ord[3]] == ref_base) i2 = ord[3];
+    uint32_t allele1_cnt = oc[0], allele2_cnt = oc[1];
+    if (letter(ord[0]) != ref_base && letter(ord[1]) != ref_base) {
+        if (oc[2] == oc[1] && letter(ord[2]) == ref_base) { i2 = ord[2]; allele2_cnt = oc[2]; }
+        else if (oc[3] == oc[1] && letter(ord[3]) == ref_base) { i2 = ord[3]; allele2_cnt = oc[3]; }
     }
-    const uint8_t allele1 = (uint8_t)ACGT[i1], allele2 = (uint8_t)ACGT[i2];
-    const uint32_t allele1_cnt = s.cnt[i1], allele2_cnt = s.cnt[i2];
+    const uint8_t allele1 = letter(i1), allele2 = letter(i2);
     const float allele1_freq = (float)allele1_cnt / (float)total;
     const float allele2_freq = (float)allele2_cnt / (float)total;
     uint8_t ref_allele_base;
@@ -258,15 +124,15 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     if (s.d >= alt_cnt[0]) return false;
     const uint32_t depth_incl = total + s.d + s.n;
     if ((float)(allele1_cnt + allele2_cnt) / (float)depth_incl < P.min_allele_freq_include_intron) return false;
-    if (allele1 != ref_base) { if (allele1_cnt > 0 && s.pass[i1] < 2) return false; }
-    else if (allele2 != ref_base) { if (allele2_cnt > 0 && s.pass[i2] < 2) return false; }
+    if (allele1 != ref_base) { if (allele1_cnt > 0 && pick(s.pass, i1) < 2) return false; }
+    else if (allele2 != ref_base) { if (allele2_cnt > 0 && pick(s.pass, i2) < 2) return false; }
     if (P.use_strand_bias) {
-        const int32_t rf = (int32_t)s.fwd[ref_code], rr = (int32_t)(s.cnt[ref_code] - s.fwd[ref_code]);
-        const int32_t af = (int32_t)s.fwd[alt_i[0]], ar = (int32_t)(s.cnt[alt_i[0]] - s.fwd[alt_i[0]]);
+        const int32_t rf = (int32_t)pick(s.fwd, ref_code), rr = (int32_t)(pick(s.cnt, ref_code) - pick(s.fwd, ref_code));
+        const int32_t af = (int32_t)pick(s.fwd, alt_i[0]), ar = (int32_t)(pick(s.cnt, alt_i[0]) - pick(s.fwd, alt_i[0]));
         float sor;
         if (alt_num == 1) sor = lcr_strand_odds_ratio(rf, rr, af, ar);
         else {
-            const int32_t bf = (int32_t)s.fwd[alt_i[1]], br = (int32_t)(s.cnt[alt_i[1]] - s.fwd[alt_i[1]]);
+            const int32_t bf = (int32_t)pick(s.fwd, alt_i[1]), br = (int32_t)(pick(s.cnt, alt_i[1]) - pick(s.fwd, alt_i[1]));
             sor = fmaxf(lcr_strand_odds_ratio(rf, rr, af, ar), lcr_strand_odds_ratio(rf, rr, bf, br));
         }
         if (sor > T.sor_threshold) return false;
@@ -306,7 +172,7 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
 
     uint16_t fl = 0;
     const int32_t fwd_ts = (int32_t)s.ts[0], rev_ts = (int32_t)s.ts[1];
-    const uint8_t alt0 = (uint8_t)ACGT[alt_i[0]];
+    const uint8_t alt0 = letter(alt_i[0]);
     bool keep = true;
     if (ref_allele_base == 'A' && alt0 == 'G' && (fwd_ts > rev_ts * 2 || (fwd_ts == 0 && rev_ts == 0)) && variant_type != 2) fl = LCR_CF_RNA_EDITING | LCR_CF_EDIT_LIST;
     else if (ref_allele_base == 'T' && alt0 == 'C' && (rev_ts > fwd_ts * 2 || (fwd_ts == 0 && rev_ts == 0)) && variant_type != 2) fl = LCR_CF_RNA_EDITING | LCR_CF_EDIT_LIST;
@@ -336,170 +202,285 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     return true;
 }
 
-/* ------------------------------------------------------------------------- *
- * Tile pileup, version 3: segments -> one-hot row planes -> carry-save column sums.
- *
- * k_seg_build (thread per item) turns the part of a read inside a tile into *segments*: maximal runs of
- * unmasked aligned bases (M/=/X), deleted positions (D) or intron positions (N) on consecutive columns.
- * The read-end trim (ONT) and the poly-A / homopolymer mask (util.rs:737-789) are applied here, by cutting
- * M runs at masked bases, so the tile kernel has no per-base special cases.
- *
- * k_pileup_tile (CTA per tile) stages up to PT_ROWS items as two byte planes per (row, column):
- *     plane X   bit 0-3  base is A,C,G,T          bit 4-7  ... and base quality >= min_baseq
- *     plane Y   bit 0-3  A,C,G,T on a forward read; bit 4 / 5 transcript strand forward / reverse
- *               (util.rs:803-819, any base letter); bit 6 deletion; bit 7 intron
- * one lane per 16-byte block of the read (aligned 128-bit loads of seq and qual, bytes rotated to the
- * column alignment with PRMT, codes built four columns at a time), then every thread sums one 32-bit column
- * word (4 columns x 8 indicators) over the rows with a Harley-Seal carry-save adder tree: ~2.4 logic
- * instructions per row for 32 counters.  Counters are unpacked once per tile (once per 255 rows on deep tiles).
- * ------------------------------------------------------------------------- */
-#define PT_THREADS 256
-#define PT_ROWS 64
-#define PT_SEGS 512
-#define PT_WORDS (LCR_TILE / 4)
-#define SEG_M 0u
-#define SEG_D 1u
-#define SEG_N 2u
-
-struct LcrSeg {             /* 16 B */
+struct LcrSeg {             /* 16 B: a run of unmasked aligned bases, deleted or intron positions of one read inside one tile */
     uint64_t spos;          /* M: offset of the first base in the seq / qual pools */
     uint32_t row_typ;       /* bits 0-1 type, bit 2 forward strand, bits 3-4 transcript strand code, bits 8-31 row (item index in its tile) */
     uint16_t col;           /* first column inside the tile */
     uint16_t len;           /* 1 .. LCR_TILE */
 };
+#define SEG_M 0u
+#define SEG_D 1u
+#define SEG_N 2u
+#define LCR_SLOT_RUNS 4     /* homopolymer runs remembered per read for the poly-A mask */
 
-struct PreCand { /* a site that passed every count-based filter; its likelihood is computed by k_site_ll */
-    uint32_t tile, col;
-    uint32_t cnt[4], pass[4], fwd[4], ts[2], d, n;
-};
-
-struct SegArgs {
+struct PrepArgs {
     lcr_params P;
-    uint32_t n_items;
+    uint32_t n_slots;
     const lcr_region *regions;
     const uint32_t *slot_off, *slot_region, *tile_base;
+    const int32_t *pos;
     const uint16_t *flag;
+    const uint8_t *mapq;
     const int8_t *ts;
+    const float *de;
     const uint64_t *seq_off, *cig_off;
     const uint8_t *seq;
     const uint32_t *cigar;
     const uint8_t *const *ref_table;
-    const uint8_t *slot_flags;
-    const uint32_t *tile_off;
-    const LcrItem *items;
     LcrRegionState *rstate;
     lcr_stats *stats;
-    uint32_t *seg_count;       /* COUNT: out */
-    const uint32_t *seg_off;   /* FILL: in   */
+    uint8_t *slot_flags;   /* bit 0: passes the read filter and overlaps the window; bit 1: has homopolymer runs near a read end;
+                              bit 2: more than LCR_SLOT_RUNS of them (every zone base takes the exact test) */
+    uint64_t *slot_runs;   /* [n_slots][LCR_SLOT_RUNS]: start << 32 | length, in read coordinates */
+    uint32_t *tile_count;  /* COUNT: items per tile; FILL: cursor */
+    const uint32_t *tile_off;
+    uint32_t *tile_full_n; /* whole-tile intron covers */
+    uint32_t *tile_segs;   /* COUNT: segments per tile; FILL: cursor */
+    uint32_t *deep_flag;   /* COUNT: set when some tile holds more than 255 items */
+    const uint32_t *tile_seg_off;
+    LcrItem *items;
     LcrSeg *segs;
-    uint32_t *deep_flag;       /* set when a tile has more than 255 items */
 };
 
+/* Read filter (util.rs:652-668), fetch window, and the decomposition of every passing read into per-tile items
+   (CIGAR checkpoints for k_site_ll) and segments (what k_pileup_tile streams).  The read-end trim (ONT) and the
+   poly-A / homopolymer mask (util.rs:737-789) are applied here by cutting M runs at masked bases.  Two passes
+   around an exclusive scan: COUNT sizes the per-tile lists, FILL writes them. */
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_seg_build(SegArgs a) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t nseg = 0, nb = 0;
-    if (idx < a.n_items) {
-        const LcrItem it = a.items[idx];
-        const uint32_t reg = a.slot_region[it.slot];
-        if (a.rstate[reg].status == 0) {
-            const lcr_region R = a.regions[reg];
-            const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
+__global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_bases = 0;
+    bool live = slot < a.n_slots;
+    uint32_t reg = 0;
+    if (live) {
+        reg = a.slot_region[slot];
+        if (a.rstate[reg].status != 0) live = false;
+    }
+    if (live) {
+        const lcr_region R = a.regions[reg];
+        const uint32_t read = R.read_begin + (slot - a.slot_off[reg]);
+        const uint64_t c0 = a.cig_off[read], c1 = a.cig_off[read + 1];
+        const uint64_t s0 = a.seq_off[read];
+        const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
+        const uint8_t *seq = a.seq + s0;
+        const int64_t lead = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (int64_t)(a.cigar[c0] >> 4) : 0; /* leading_softclips */
+        const int64_t trail = (c1 > c0 && (a.cigar[c1 - 1] & 0xf) == 4) ? (int64_t)(a.cigar[c1 - 1] >> 4) : 0;
+        const int64_t rb = seq_len - trail;
+        const int64_t dend = (int64_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
+        const bool ont = a.P.platform == 1;
+        uint8_t sflags;
+        uint64_t runs[LCR_SLOT_RUNS];
+#pragma unroll
+        for (int i = 0; i < LCR_SLOT_RUNS; ++i) runs[i] = 0;
+        if (!FILL) {
+            /* util.rs:652-668 */
+            const uint16_t fl = a.flag[read];
+            bool pass = !((int32_t)a.mapq[read] < a.P.min_mapq || (uint64_t)seq_len < (uint64_t)a.P.min_read_length || (fl & 0x4) || (fl & 0x100) || (fl & 0x800));
+            const float de = a.de[read];
+            if (!(de != de) && de >= a.P.divergence) pass = false;
+            /* fetch((chr, start, end)): pos < end && bam_endpos > start on the region's own numbers */
+            int64_t rlen = 0;
+            for (uint64_t c = c0; c < c1; ++c) {
+                const uint32_t op = a.cigar[c];
+                if (is_ref_consuming(op & 0xf)) rlen += op >> 4;
+            }
+            const int64_t p = a.pos[read];
+            const bool in_window = p < (int64_t)R.end && p + (rlen ? rlen : 1) > (int64_t)R.start;
+            sflags = (pass && in_window) ? 1 : 0;
+            if (sflags && !ont && dend > 0) {
+                /* util.rs:754-789 can only mask a base next to (or inside) a homopolymer run of polya_tail_length letters that
+                   lies within polya_tail_length of a read-end zone: remember those runs, the walk below tests only their bases */
+                const int64_t polya = (int64_t)(a.P.polya_tail_length > 0x3fffffffu ? 0x3fffffffu : a.P.polya_tail_length);
+                if (polya < 2 || rb < lead) sflags |= 6; /* degenerate window or overlapping clips: exact test on every zone base */
+                else {
+                    const int64_t centre[2] = {lead, rb};
+                    uint32_t nrun = 0;
+                    int64_t scanned_to = -1; /* runs ending at or before this index are already recorded */
+                    for (int z = 0; z < 2; ++z) {
+                        int64_t lo = centre[z] - dend + 1 - polya, hi = centre[z] + dend + polya; /* [lo, hi) */
+                        if (lo < 0) lo = 0;
+                        if (hi > seq_len) hi = seq_len;
+                        int64_t run = 0;
+                        uint8_t prev = 0;
+                        for (int64_t i = lo; i <= hi; ++i) {
+                            const uint8_t b = i < hi ? __ldg(seq + i) : (uint8_t)0;
+                            const bool letter = b == 'A' || b == 'C' || b == 'G' || b == 'T';
+                            if (letter && b == prev) { run++; continue; }
+                            if (run >= polya && i > scanned_to) { /* the run [i - run, i) just ended */
+                                if (nrun < LCR_SLOT_RUNS) runs[nrun] = ((uint64_t)(i - run) << 32) | (uint64_t)run;
+                                nrun++;
+                            }
+                            run = letter ? 1 : 0;
+                            prev = b;
+                        }
+                        if (hi > scanned_to) scanned_to = hi;
+                    }
+                    if (nrun) sflags |= 2;
+                    if (nrun > LCR_SLOT_RUNS) sflags |= 4;
+                }
+            }
+            a.slot_flags[slot] = sflags;
+            if (sflags & 2) {
+#pragma unroll
+                for (int i = 0; i < LCR_SLOT_RUNS; ++i) a.slot_runs[(size_t)slot * LCR_SLOT_RUNS + i] = runs[i];
+            }
+        } else {
+            sflags = a.slot_flags[slot];
+            if ((sflags & 6) == 2) {
+#pragma unroll
+                for (int i = 0; i < LCR_SLOT_RUNS; ++i) runs[i] = a.slot_runs[(size_t)slot * LCR_SLOT_RUNS + i];
+            }
+        }
+        if (sflags & 1) {
             const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
-            const int32_t tile_local = it.fpos / LCR_TILE;
-            const int32_t tile_start = tile_local * LCR_TILE;
-            const int32_t tile_end = (int64_t)tile_start + LCR_TILE < vec_size ? tile_start + LCR_TILE : (int32_t)vec_size;
-            const uint32_t row = idx - a.tile_off[a.tile_base[reg] + (uint32_t)tile_local];
-            if (!FILL && row == 255u) *a.deep_flag = 1u;
-            const uint64_t s0 = a.seq_off[read];
-            const int32_t seq_len = (int32_t)(a.seq_off[read + 1] - s0);
-            const uint8_t *seq = a.seq + s0;
-            const uint64_t c0 = a.cig_off[read];
-            const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
-            const uint32_t *cig = a.cigar + c0;
-            const int32_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int32_t)(cig[0] >> 4) : 0;
-            const int32_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int32_t)(cig[ncig - 1] >> 4) : 0;
-            const int32_t rb = seq_len - trail;
-            const int32_t dend = (int32_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
-            const bool ont = a.P.platform == 1;
-            const bool zones = dend > 0 && (ont || (a.slot_flags[it.slot] & 2));
-            uint32_t rowtyp = row << 8;
+            const int64_t fv_start = (int64_t)R.start - 1;
+            const uint32_t tb = a.tile_base[reg];
+            const uint8_t *ref = a.ref_table[R.tid] + fv_start;
+            uint32_t rowtyp_c;
             {
                 const int strand = (a.flag[read] & 0x10) ? 1 : 0;
                 const int8_t ts = a.ts[read];
                 uint32_t tcode = 0;
                 if (ts == '+') tcode = strand == 0 ? 1u : 2u;
                 else if (ts == '-') tcode = strand == 0 ? 2u : 1u;
-                rowtyp |= (strand == 0 ? 4u : 0u) | (tcode << 3);
+                rowtyp_c = (strand == 0 ? 4u : 0u) | (tcode << 3);
             }
-            /* zone bounds in read coordinates, ordered by their first base (int64: lead - dend may leave int32) */
-            int64_t zlo[2] = {(int64_t)lead - dend + 1, (int64_t)rb - dend + 1}, zhi[2] = {(int64_t)lead + dend - 1, (int64_t)rb + dend - 1};
+            /* read-end zones in read coordinates, ordered by their first base */
+            int64_t zlo[2] = {lead - dend + 1, rb - dend + 1}, zhi[2] = {lead + dend - 1, rb + dend - 1};
             if (zlo[1] < zlo[0]) { int64_t t = zlo[0]; zlo[0] = zlo[1]; zlo[1] = t; t = zhi[0]; zhi[0] = zhi[1]; zhi[1] = t; }
-            const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1);
-            LcrSeg *out = FILL ? a.segs + a.seg_off[idx] : nullptr;
-            int32_t fpos = it.fpos, rpos = (int32_t)it.rpos;
-            uint32_t off = it.opoff;
+            const int mask_mode = dend <= 0 ? 0 : ont ? 1 : (sflags & 4) ? 2 : (sflags & 2) ? 3 : 0;
+
+            int64_t fpos = (int64_t)a.pos[read] - fv_start;
+            int64_t rpos = lead;
+            int64_t last_tile = -1;
+            uint32_t row = 0, nseg_tile = 0; /* of the current tile */
             bool bad = false;
-            for (uint32_t ci = it.cig; ci < ncig && fpos < tile_end; ++ci, off = 0) {
-                const uint32_t op = cig[ci], opc = op & 0xf;
-                const int32_t len = (int32_t)((op >> 4) - off);
+            auto leave_tile = [&]() {
+                if (!FILL && last_tile >= 0 && nseg_tile) atomicAdd(&a.tile_segs[tb + last_tile], nseg_tile);
+                nseg_tile = 0;
+            };
+            for (uint64_t c = c0; c < c1 && !bad; ++c) {
+                const uint32_t op = a.cigar[c], opc = op & 0xf, len = op >> 4;
                 if (opc == 4 || opc == 5) continue;
-                if (opc == 1) { rpos += len; continue; }
-                if (!is_ref_consuming(opc)) { bad = true; break; }
-                const bool is_m = opc == 0 || opc == 7 || opc == 8;
-                const int32_t n = fpos + len < tile_end ? len : tile_end - fpos; /* columns of this op inside the tile */
-                if (n > 0) {
-                    const uint32_t colr = (uint32_t)(fpos - tile_start);
-                    if (!is_m) {
-                        if (FILL) {
-                            LcrSeg s;
-                            s.spos = 0; s.row_typ = rowtyp | (opc == 2 ? SEG_D : SEG_N); s.col = (uint16_t)colr; s.len = (uint16_t)n;
-                            out[nseg] = s;
+                if (opc == 1) {
+                    if (fpos >= vec_size && fpos >= 1) break;
+                    rpos += len;
+                    continue;
+                }
+                if (!is_ref_consuming(opc)) { bad = true; break; } /* util.rs:943-945 panics */
+                const bool is_m = (opc == 0 || opc == 7 || opc == 8);
+                const int64_t lo = fpos, hi = fpos + (int64_t)len;
+                if (lo >= vec_size) { /* the walk is over; later ops cannot reach the window */
+                    fpos = hi;
+                    continue;
+                }
+                if (hi > 0) {
+                    const int64_t a0 = lo < 0 ? 0 : lo, b0 = hi < vec_size ? hi : vec_size;
+                    for (int64_t t = a0 / LCR_TILE; t * LCR_TILE < b0; ++t) {
+                        const int64_t ts = a0 > t * LCR_TILE ? a0 : t * LCR_TILE;
+                        const int64_t tile_end = (t + 1) * LCR_TILE < vec_size ? (t + 1) * LCR_TILE : vec_size;
+                        const int64_t te = b0 < tile_end ? b0 : tile_end;
+                        if (opc == 3 && ts == t * LCR_TILE && te == tile_end && t > last_tile) {
+                            if (FILL) atomicAdd(&a.tile_full_n[tb + t], 1u);
+                            continue;
                         }
-                        nseg++;
-                    } else {
-                        if ((int64_t)rpos + n > (int64_t)seq_len) { bad = true; break; }
-                        nb += (uint32_t)n;
-                        const int32_t ra = rpos, rbnd = rpos + n;
-                        int32_t start = ra;
-                        auto emit = [&](int32_t x, int32_t y) {
-                            if (y <= x) return;
+                        if (t > last_tile) {
+                            leave_tile();
+                            last_tile = t;
+                            if (!FILL) { if (atomicAdd(&a.tile_count[tb + t], 1u) == 255u) *a.deep_flag = 1u; }
+                            else {
+                                row = atomicAdd(&a.tile_count[tb + t], 1u);
+                                LcrItem it;
+                                it.slot = slot;
+                                it.cig = (uint32_t)(c - c0);
+                                it.opoff = (uint32_t)(ts - lo);
+                                it.rpos = (uint32_t)(is_m ? rpos + (ts - lo) : rpos);
+                                it.fpos = (int32_t)ts;
+                                a.items[a.tile_off[tb + t] + row] = it;
+                            }
+                        }
+                        const uint32_t colr = (uint32_t)(ts - t * LCR_TILE);
+                        auto put = [&](uint32_t typ, uint64_t spos, uint32_t col, uint32_t n) {
                             if (FILL) {
                                 LcrSeg s;
-                                s.spos = s0 + (uint64_t)x; s.row_typ = rowtyp | SEG_M; s.col = (uint16_t)(colr + (uint32_t)(x - ra)); s.len = (uint16_t)(y - x);
-                                out[nseg] = s;
-                            }
-                            nseg++;
+                                s.spos = spos; s.row_typ = (row << 8) | rowtyp_c | typ; s.col = (uint16_t)col; s.len = (uint16_t)n;
+                                a.segs[a.tile_seg_off[tb + t] + atomicAdd(&a.tile_segs[tb + t], 1u)] = s;
+                            } else nseg_tile++;
                         };
-                        if (zones) {
-                            int64_t prev_hi = -0x7fffffffffffLL;
+                        if (!is_m) {
+                            put(opc == 2 ? SEG_D : SEG_N, 0, colr, (uint32_t)(te - ts));
+                            continue;
+                        }
+                        const int64_t pa = rpos + (ts - lo), pb = rpos + (te - lo); /* read coordinates of this piece */
+                        if (pb > seq_len) { bad = true; break; }
+                        n_bases += (uint32_t)(te - ts);
+                        int64_t start = pa;
+                        auto emit = [&](int64_t x, int64_t y) { /* unmasked stretch [x, y) */
+                            if (y > x) put(SEG_M, s0 + (uint64_t)x, colr + (uint32_t)(x - pa), (uint32_t)(y - x));
+                        };
+                        if (mask_mode == 1) { /* util.rs:745-751: every base of a zone */
                             for (int k = 0; k < 2; ++k) {
-                                int64_t lo = zlo[k] > (int64_t)ra ? zlo[k] : (int64_t)ra;
-                                if (lo <= prev_hi) lo = prev_hi + 1;
-                                const int64_t hi = zhi[k] < (int64_t)rbnd - 1 ? zhi[k] : (int64_t)rbnd - 1;
-                                for (int64_t rp = lo; rp <= hi; ++rp) {
-                                    const bool m = ont || base_masked(a.P, seq, rp, seq_len, lead, trail, ref[fpos + ((int32_t)rp - ra)]);
-                                    if (m) { emit(start, (int32_t)rp); start = (int32_t)rp + 1; }
-                                }
-                                if (zhi[k] > prev_hi) prev_hi = zhi[k];
+                                const int64_t zl = zlo[k] > start ? zlo[k] : start, zh = zhi[k] < pb - 1 ? zhi[k] : pb - 1;
+                                if (zl <= zh) { emit(start, zl); start = zh + 1; }
+                            }
+                        } else if (mask_mode == 2) { /* exact test on every zone base */
+                            for (int k = 0; k < 2; ++k) {
+                                const int64_t zl = zlo[k] > start ? zlo[k] : start, zh = zhi[k] < pb - 1 ? zhi[k] : pb - 1;
+                                for (int64_t rp = zl; rp <= zh; ++rp)
+                                    if (base_masked(a.P, seq, rp, seq_len, lead, trail, ref[ts + (rp - pa)])) { emit(start, rp); start = rp + 1; }
+                            }
+                        } else if (mask_mode == 3) { /* only bases inside or next to a remembered run can be masked */
+                            int64_t from = pa;
+#pragma unroll
+                            for (int j = 0; j < LCR_SLOT_RUNS; ++j) {
+                                const int64_t rs = (int64_t)(runs[j] >> 32), rn = (int64_t)(runs[j] & 0xffffffffu);
+                                if (rn == 0) continue;
+                                const int64_t zl = rs - 1 > from ? rs - 1 : from, zh = rs + rn < pb - 1 ? rs + rn : pb - 1;
+                                for (int64_t rp = zl; rp <= zh; ++rp)
+                                    if (base_masked(a.P, seq, rp, seq_len, lead, trail, ref[ts + (rp - pa)])) { emit(start, rp); start = rp + 1; }
+                                if (zh + 1 > from) from = zh + 1;
                             }
                         }
-                        emit(start, rbnd);
+                        emit(start, pb);
                     }
                 }
-                fpos += len;
+                fpos = hi;
                 if (is_m) rpos += len;
             }
-            if (bad) { atomicMin(&a.rstate[reg].status, (int32_t)LCR_ERR_BAD_CIGAR); nseg = 0; nb = 0; }
+            leave_tile();
+            if (bad) { atomicMin(&a.rstate[reg].status, (int32_t)LCR_ERR_BAD_CIGAR); n_bases = 0; }
         }
     }
-    if (!FILL) {
-        if (idx < a.n_items) a.seg_count[idx] = nseg;
-    } else {
-        nb = __reduce_add_sync(0xffffffffu, nb); /* < 2^32: 32 items x 512 columns */
-        if ((threadIdx.x & 31) == 0 && nb) atomicAdd((unsigned long long *)&a.stats->n_aligned_bases, (unsigned long long)nb);
+    if (FILL) {
+        n_bases = __reduce_add_sync(0xffffffffu, n_bases);
+        if ((threadIdx.x & 31) == 0 && n_bases) atomicAdd((unsigned long long *)&a.stats->n_aligned_bases, (unsigned long long)n_bases);
     }
 }
+
+/* ------------------------------------------------------------------------- *
+ * Tile pileup, version 3: segments -> one-hot row planes -> carry-save column sums.
+ *
+ * k_pileup_tile (CTA per tile) stages up to PT_ROWS items as two byte planes per (row, column):
+ *     plane X   bit 0-3  base is A,C,G,T          bit 4-7  ... and base quality >= min_baseq
+ *     plane Y   bit 0-3  A,C,G,T on a forward read; bit 4 / 5 transcript strand forward / reverse
+ *               (util.rs:803-819, any base letter); bit 6 deletion; bit 7 intron
+ * Whole column words (4 columns) of a segment are produced one lane per 16-byte block of the read: aligned
+ * 128-bit loads of seq and qual, bytes rotated to the column alignment with PRMT, codes built four columns at
+ * a time.  The up to three columns before / after the whole words of a segment are written byte-wise by one
+ * lane per segment.  Then every thread sums one 32-bit column word (4 columns x 8 indicators) over the rows
+ * with a Harley-Seal carry-save adder tree: ~2.4 logic instructions per row for 32 counters.  Counters are
+ * unpacked once per tile (once per 255 rows on deep tiles).
+ * ------------------------------------------------------------------------- */
+#define PT_THREADS 256
+#define PT_ROWS 56
+#define PT_SEGS 512
+#define PT_WORDS (LCR_TILE / 4)
+#define PT_TAB ((PT_SEGS * (LCR_TILE / 16 + 1)) / 8 + 8) /* one entry per 8 blocks */
+
+struct PreCand { /* a site that passed every count-based filter; its likelihood is computed by k_site_ll */
+    uint32_t tile, col;
+    uint32_t cnt[4], pass[4], fwd[4], ts[2], d, n;
+};
 
 __device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t z) {
     uint32_t r;
@@ -532,7 +513,7 @@ __device__ __forceinline__ void onehot4(uint32_t s, uint32_t q, uint32_t minq4, 
     const uint32_t canon = __byte_perm(0x43004100u, 0x47000054u, sel);
     const uint32_t d = (s & 0xdfdfdfdfu) ^ canon;                       /* non-zero byte: not exactly that letter (either case) */
     const uint32_t nz = ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d;
-    oh &= ~prmt_sign(nz);                                          /* 0xff where bit 7 of the byte is set */
+    oh &= ~prmt_sign(nz);
     const uint32_t ge = ((((q & 0x7f7f7f7fu) | 0x80808080u) - minq4) | q);
     const uint32_t pm = prmt_sign(ge) & pass_allow;
     x = oh | ((oh << 4) & pm);
@@ -552,7 +533,7 @@ struct PileArgs {
     const uint8_t *const *ref_table;
     const uint32_t *tile_off, *tile_full_n;
     const LcrItem *items;
-    const uint32_t *seg_off;
+    const uint32_t *tile_seg_off;
     const LcrSeg *segs;
     const LcrDeviceTables *tables;
     LcrRegionState *rstate;
@@ -571,12 +552,12 @@ template <bool DEEP>
 __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
     extern __shared__ __align__(16) uint32_t pt_smem[];
     uint32_t *planes = pt_smem;                                           /* [2][PT_ROWS][PT_WORDS] */
-    LcrSeg *s_seg = reinterpret_cast<LcrSeg *>(pt_smem + 2 * PT_ROWS * PT_WORDS);
+    uint4 *s_seg = reinterpret_cast<uint4 *>(pt_smem + 2 * PT_ROWS * PT_WORDS); /* [PT_SEGS] staged segments */
     uint32_t *s_out8 = reinterpret_cast<uint32_t *>(s_seg);               /* [16][PT_WORDS], aliases the segment stage */
-    uint32_t *s_choff = pt_smem + 2 * PT_ROWS * PT_WORDS + PT_SEGS * 4;   /* [PT_SEGS + 1] */
-    uint32_t *s_out32 = s_choff + PT_SEGS + 4;                            /* DEEP: [16][LCR_TILE] */
+    uint32_t *s_choff = pt_smem + 2 * PT_ROWS * PT_WORDS + PT_SEGS * 4;   /* [PT_SEGS + 1] first block of every staged segment */
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_choff + PT_SEGS + 4); /* [PT_TAB] segment of every 8th block */
+    uint32_t *s_out32 = s_choff + PT_SEGS + 4 + (PT_TAB + 1) / 2;         /* DEEP: [16][LCR_TILE] */
     __shared__ uint32_t s_wsum[PT_THREADS / 32];
-    __shared__ uint32_t s_bounds[2];
     __shared__ int s_err;
 
     const uint32_t tile = blockIdx.x;
@@ -599,6 +580,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
     const uint32_t minq4 = (minq > 30u ? 0u : minq) * 0x01010101u;
     const uint32_t pass_allow = minq > 30u ? 0u : 0xffffffffu;
     const uint8_t *seqp = a.seq, *qualp = a.qual;
+    const uint32_t seg_lo = a.tile_seg_off[tile], seg_hi = a.tile_seg_off[tile + 1];
+    const bool one_batch = (it1 - it0) <= PT_ROWS;
 
     /* carry-save state of this thread's column word: plane (tid / PT_WORDS), word (tid % PT_WORDS) */
     uint32_t ones = 0, twos = 0, fours = 0, eights = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
@@ -623,9 +606,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
         acc_rows = 0;
     };
 
-    for (uint32_t base_it = it0; base_it < it1; base_it += PT_ROWS) {
-        const uint32_t nrow = (it1 - base_it) < PT_ROWS ? (it1 - base_it) : PT_ROWS;
-        const uint32_t row_base = base_it - it0;
+    for (uint32_t row_base = 0; row_base < it1 - it0; row_base += PT_ROWS) {
+        const uint32_t nrow = (it1 - it0 - row_base) < PT_ROWS ? (it1 - it0 - row_base) : PT_ROWS;
         if (DEEP && acc_rows + nrow > 255u) {
             flush();
 #pragma unroll
@@ -641,28 +623,29 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
                 p4[i] = z;
                 p4[PT_ROWS * (PT_WORDS / 4) + i] = z;
             }
-            if (tid == 0) { s_bounds[0] = a.seg_off[base_it]; s_bounds[1] = a.seg_off[base_it + nrow]; }
         }
-        __syncthreads();
-        const uint32_t seg_lo = s_bounds[0], seg_hi = s_bounds[1];
         for (uint32_t sb = seg_lo; sb < seg_hi; sb += PT_SEGS) {
             const uint32_t ns = (seg_hi - sb) < PT_SEGS ? (seg_hi - sb) : PT_SEGS;
-            if (sb != seg_lo) __syncthreads();
-            /* stage the segments and scan their block counts */
+            __syncthreads(); /* planes zeroed / previous stage consumed */
+            /* stage the segments of this batch's rows and scan their block counts */
             uint32_t nch[PT_SEGS / PT_THREADS], mysum = 0;
 #pragma unroll
             for (int qd = 0; qd < PT_SEGS / PT_THREADS; ++qd) {
                 const uint32_t i = tid * (PT_SEGS / PT_THREADS) + qd;
                 uint32_t n = 0;
                 if (i < ns) {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + sb + i));
-                    reinterpret_cast<uint4 *>(s_seg)[i] = raw;
-                    const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
-                    if ((raw.z & 3u) == SEG_M) {
-                        const uint32_t al = raw.x & 15u, e = (al - col) & 3u;
-                        const uint32_t last = al + len - 1u, cl = last >> 4;
-                        n = cl + 1u - (((last & 15u) < e && cl > 0u) ? 1u : 0u);
-                    } else n = (((col & 15u) + len - 1u) >> 4) + 1u;
+                    uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + sb + i));
+                    const uint32_t rrow = (raw.z >> 8) - row_base;
+                    if (one_batch || rrow < nrow) {
+                        const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
+                        const uint32_t wlo = (col + 3u) >> 2, whi = (col + len) >> 2; /* whole column words [wlo, whi) */
+                        if (whi > wlo) {
+                            const uint32_t nw = whi - wlo;
+                            if ((raw.z & 3u) == SEG_M) n = ((((raw.x + 4u * wlo - col) & 15u) + 4u * nw - 4u) >> 4) + 1u;
+                            else n = (((wlo & 3u) + nw - 1u) >> 2) + 1u;
+                        }
+                    } else raw.w = 0; /* another batch's row: nothing to do here */
+                    s_seg[i] = raw;
                 }
                 nch[qd] = n;
                 mysum += n;
@@ -686,82 +669,83 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
                 uint32_t run = wbase + incl - mysum;
 #pragma unroll
                 for (int qd = 0; qd < PT_SEGS / PT_THREADS; ++qd) {
-                    s_choff[tid * (PT_SEGS / PT_THREADS) + qd] = run;
+                    const uint32_t i = tid * (PT_SEGS / PT_THREADS) + qd;
+                    s_choff[i] = run;
+                    for (uint32_t m = (run + 7u) >> 3; m * 8u < run + nch[qd]; ++m) s_tab[m] = (uint16_t)i;
                     run += nch[qd];
                 }
+                if (tid == PT_THREADS - 1) s_choff[PT_SEGS] = run;
             }
             __syncthreads();
-            /* one lane per 16-byte block of a segment */
+            /* whole column words: one lane per 16-byte block of a segment */
             for (uint32_t g = tid; g < total; g += PT_THREADS) {
-                uint32_t k = 0;
-#pragma unroll
-                for (uint32_t step = PT_SEGS / 2; step; step >>= 1)
-                    if (k + step < ns && s_choff[k + step] <= g) k += step;
+                uint32_t k = s_tab[g >> 3];
+                while (s_choff[k + 1] <= g) ++k;
                 const uint32_t c = g - s_choff[k];
-                const uint4 raw = reinterpret_cast<const uint4 *>(s_seg)[k];
+                const uint4 raw = s_seg[k];
                 const uint32_t typ = raw.z & 3u, col = raw.w & 0xffffu, len = raw.w >> 16;
+                const uint32_t wlo = (col + 3u) >> 2, whi = (col + len) >> 2;
                 uint32_t *rx = planes + ((raw.z >> 8) - row_base) * PT_WORDS, *ry = rx + PT_ROWS * PT_WORDS;
                 uint32_t x[4], y[4];
-                int32_t W0, e, vlo, vhi; /* first owned column word; window offset of its first byte; valid window bytes [vlo, vhi) */
+                uint32_t W0; /* first column word this lane produces */
                 if (typ == SEG_M) {
-                    const uint64_t spos = ((uint64_t)raw.y << 32) | raw.x;
-                    const uint32_t al = raw.x & 15u;
+                    const uint64_t spos = (((uint64_t)raw.y << 32) | raw.x) + (uint64_t)(4u * wlo - col); /* base of column 4 * wlo */
+                    const uint32_t al = (uint32_t)spos & 15u, e = al & 3u;
                     const uint64_t blk = (spos & ~(uint64_t)15) + 16ull * c;
-                    const int32_t D0 = (int32_t)col - (int32_t)al + 16 * (int32_t)c; /* column of window byte 0 */
-                    e = (int32_t)((al - col) & 3u);
-                    W0 = (D0 + e) >> 2;
-                    vlo = (int32_t)al - 16 * (int32_t)c;
-                    vhi = vlo + (int32_t)len;
+                    W0 = wlo + 4u * c - (al >> 2);
                     const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(seqp + blk));
                     const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(qualp + blk));
                     const uint32_t s4w = __ldg(reinterpret_cast<const uint32_t *>(seqp + blk + 16));
                     const uint32_t q4w = __ldg(reinterpret_cast<const uint32_t *>(qualp + blk + 16));
                     const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u;
                     const uint32_t tsb = ((raw.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
-                    const uint32_t rot = 0x3210u + 0x1111u * (uint32_t)e;
+                    const uint32_t rot = 0x3210u + 0x1111u * e;
                     onehot4(__byte_perm(sv.x, sv.y, rot), __byte_perm(qv.x, qv.y, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
                     onehot4(__byte_perm(sv.y, sv.z, rot), __byte_perm(qv.y, qv.z, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
                     onehot4(__byte_perm(sv.z, sv.w, rot), __byte_perm(qv.z, qv.w, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
                     onehot4(__byte_perm(sv.w, s4w, rot), __byte_perm(qv.w, q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
-                    if (c == 0 && (int32_t)al < e) {
-                        /* bytes [al, e) of the first block fall into the column word before W0 */
-                        uint32_t x0, y0;
-                        onehot4(sv.x, qv.x, minq4, pass_allow, fmask, tsb, x0, y0);
-                        uint8_t *bx = reinterpret_cast<uint8_t *>(rx + (W0 - 1)), *by = reinterpret_cast<uint8_t *>(ry + (W0 - 1));
-                        for (int32_t j = (int32_t)al; j < e && j < vhi; ++j) {
-                            bx[4 + j - e] = (uint8_t)(x0 >> (8 * j));
-                            by[4 + j - e] = (uint8_t)(y0 >> (8 * j));
-                        }
-                    }
                 } else {
-                    const int32_t B0 = (int32_t)(col & ~15u) + 16 * (int32_t)c;
-                    W0 = B0 >> 2;
-                    e = 0;
-                    vlo = (int32_t)col - B0;
-                    vhi = vlo + (int32_t)len;
+                    W0 = (wlo & ~3u) + 4u * c;
                     const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
                     x[0] = x[1] = x[2] = x[3] = 0;
                     y[0] = y[1] = y[2] = y[3] = v;
                 }
-                if (vlo <= e && e + 16 <= vhi) {
-                    if (typ == SEG_M) { rx[W0] = x[0]; rx[W0 + 1] = x[1]; rx[W0 + 2] = x[2]; rx[W0 + 3] = x[3]; }
-                    ry[W0] = y[0]; ry[W0 + 1] = y[1]; ry[W0 + 2] = y[2]; ry[W0 + 3] = y[3];
-                } else {
+                const uint32_t rel = W0 - wlo, span = whi - wlo; /* word W0 + t is whole iff rel + t < span (unsigned) */
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int32_t u0 = e + 4 * t;
-                        if (vlo <= u0 && u0 + 4 <= vhi) {
-                            if (typ == SEG_M) rx[W0 + t] = x[t];
-                            ry[W0 + t] = y[t];
-                        } else if (u0 < vhi && u0 + 4 > vlo) {
-                            uint8_t *bx = reinterpret_cast<uint8_t *>(rx + (W0 + t)), *by = reinterpret_cast<uint8_t *>(ry + (W0 + t));
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                if (u0 + b >= vlo && u0 + b < vhi) {
-                                    if (typ == SEG_M) bx[b] = (uint8_t)(x[t] >> (8 * b));
-                                    by[b] = (uint8_t)(y[t] >> (8 * b));
-                                }
-                        }
+                for (uint32_t t = 0; t < 4; ++t) {
+                    if (rel + t < span) {
+                        if (typ == SEG_M) rx[W0 + t] = x[t];
+                        ry[W0 + t] = y[t];
+                    }
+                }
+            }
+            /* the columns before and after the whole words: one lane per segment */
+            for (uint32_t i = tid; i < ns; i += PT_THREADS) {
+                const uint4 raw = s_seg[i];
+                const uint32_t typ = raw.z & 3u, col = raw.w & 0xffffu, len = raw.w >> 16;
+                if (len == 0) continue;
+                const uint32_t end = col + len, wlo = (col + 3u) >> 2, whi = end >> 2;
+                uint8_t *bx = reinterpret_cast<uint8_t *>(planes + ((raw.z >> 8) - row_base) * PT_WORDS), *by = bx + PT_ROWS * PT_WORDS * 4;
+                const uint32_t h1 = (4u * wlo < end) ? 4u * wlo : end;            /* head columns [col, h1) */
+                const uint32_t t0 = (whi >= wlo) ? 4u * whi : end;                /* tail columns [t0, end) */
+                const uint64_t spos = ((uint64_t)raw.y << 32) | raw.x;
+                const uint32_t fwd = raw.z & 4u, tsb = ((raw.z >> 3) & 3u) << 4;
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t pa = part == 0 ? col : t0, pb = part == 0 ? h1 : end;
+                    for (uint32_t p = pa; p < pb; ++p) {
+                        if (typ == SEG_M) {
+                            const uint8_t b = __ldg(seqp + spos + (p - col));
+                            const uint32_t q = __ldg(qualp + spos + (p - col));
+                            const int bc = base_code_dev(b);
+                            uint32_t xb = 0, yb = tsb;
+                            if (bc >= 0) {
+                                xb = 1u << bc;
+                                if (fwd) yb |= xb;
+                                if (pass_allow && q >= minq) xb |= 0x10u << bc;
+                            }
+                            bx[p] = (uint8_t)xb;
+                            by[p] = (uint8_t)yb;
+                        } else by[p] = typ == SEG_D ? (uint8_t)0x40 : (uint8_t)0x80;
                     }
                 }
             }
@@ -813,6 +797,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
     }
     __syncthreads();
     const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start;
+    const uint32_t full_n = a.tile_full_n[tile];
     for (uint32_t colr = tid; colr < npos; colr += PT_THREADS) {
         uint32_t v[16];
         if (DEEP) {
@@ -826,7 +811,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
         SiteCounters sc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { sc.cnt[i] = v[i]; sc.pass[i] = v[4 + i]; sc.fwd[i] = v[8 + i]; }
-        sc.ts[0] = v[12]; sc.ts[1] = v[13]; sc.d = v[14]; sc.n = v[15] + a.tile_full_n[tile];
+        sc.ts[0] = v[12]; sc.ts[1] = v[13]; sc.d = v[14]; sc.n = v[15] + full_n;
         sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
         if (a.pl_acgt) {
             const uint64_t g = a.pos_off[reg] + (uint64_t)tile_start + colr;
@@ -1008,89 +993,58 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
 int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flags) {
     cudaStream_t st = ctx->stream;
     const uint32_t n_tiles = db->n_tiles;
-    uint32_t *tile_count = nullptr, *tile_off = nullptr, *tile_full_n = nullptr;
+    /* per-tile counters: [0] items, [1] whole-tile intron covers, [2] segments; their scans: [0] items, [1] segments */
+    uint32_t *tile_cnt = nullptr, *tile_scan = nullptr;
+    uint64_t *slot_runs = nullptr;
     LcrItem *items = nullptr;
-    TRY(cudaMallocAsync(&tile_count, sizeof(uint32_t) * (n_tiles + 1), st));
-    TRY(cudaMallocAsync(&tile_off, sizeof(uint32_t) * (n_tiles + 1), st));
-    TRY(cudaMallocAsync(&tile_full_n, sizeof(uint32_t) * (n_tiles + 1), st));
-    TRY(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (n_tiles + 1), st));
-    TRY(cudaMemsetAsync(tile_full_n, 0, sizeof(uint32_t) * (n_tiles + 1), st));
+    LcrSeg *segs = nullptr;
+    const size_t tn = (size_t)n_tiles + 1;
+    TRY(cudaMallocAsync(&tile_cnt, sizeof(uint32_t) * (3 * tn + 1), st));
+    TRY(cudaMallocAsync(&tile_scan, sizeof(uint32_t) * 2 * tn, st));
+    TRY(cudaMallocAsync(&slot_runs, sizeof(uint64_t) * LCR_SLOT_RUNS * (size_t)(db->n_slots ? db->n_slots : 1), st));
+    TRY(cudaMemsetAsync(tile_cnt, 0, sizeof(uint32_t) * (3 * tn + 1), st));
+    uint32_t *tile_count = tile_cnt, *tile_full_n = tile_cnt + tn, *tile_segs = tile_cnt + 2 * tn;
+    uint32_t *tile_off = tile_scan, *tile_seg_off = tile_scan + tn;
 
     PrepArgs pa{};
     pa.P = ctx->P;
     pa.n_slots = db->n_slots;
     pa.regions = db->regions;
     pa.slot_off = db->slot_off; pa.slot_region = db->slot_region; pa.tile_base = db->tile_base;
-    pa.pos = db->pos; pa.flag = db->flag; pa.mapq = db->mapq; pa.de = db->de;
+    pa.pos = db->pos; pa.flag = db->flag; pa.mapq = db->mapq; pa.ts = db->ts; pa.de = db->de;
     pa.seq_off = db->seq_off; pa.cig_off = db->cig_off; pa.seq = db->seq; pa.cigar = db->cigar;
-    pa.rstate = db->rstate;
-    pa.slot_flags = slot_flags;
-    pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n; pa.items = nullptr;
+    pa.ref_table = ctx->d_ref_table;
+    pa.rstate = db->rstate; pa.stats = db->d_stats;
+    pa.slot_flags = slot_flags; pa.slot_runs = slot_runs;
+    pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n;
+    pa.tile_segs = tile_segs; pa.tile_seg_off = tile_seg_off; pa.deep_flag = tile_cnt + 3 * tn;
+    pa.items = nullptr; pa.segs = nullptr;
     const uint32_t pb = 128, pg = (db->n_slots + pb - 1) / pb;
     if (pg) {
         k_slot_prep<false><<<pg, pb, 0, st>>>(pa);
         k_count_pass<<<pg, pb, 0, st>>>(slot_flags, db->n_slots, db->d_stats);
         db->timing.kernel_launches += 2;
     }
-    /* exclusive scan of the per-tile item counts */
+    /* exclusive scans of the per-tile item and segment counts */
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_count, tile_off, n_tiles + 1, st);
     void *tmp = nullptr;
     TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_count, tile_off, n_tiles + 1, st));
-    uint32_t n_items = 0;
-    TRY(cudaMemcpyAsync(&n_items, tile_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_segs, tile_seg_off, n_tiles + 1, st));
+    uint32_t totals[3] = {0, 0, 0};
+    TRY(cudaMemcpyAsync(&totals[0], tile_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&totals[1], tile_seg_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&totals[2], tile_cnt + 3 * tn, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
+    const uint32_t n_items = totals[0], n_segs = totals[1];
     TRY(cudaMallocAsync(&items, sizeof(LcrItem) * (size_t)(n_items ? n_items : 1), st));
-    TRY(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (n_tiles + 1), st));
-    pa.items = items;
+    TRY(cudaMallocAsync(&segs, sizeof(LcrSeg) * (size_t)(n_segs ? n_segs : 1), st));
+    TRY(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * tn, st));
+    TRY(cudaMemsetAsync(tile_segs, 0, sizeof(uint32_t) * tn, st));
+    pa.items = items; pa.segs = segs;
     if (pg) {
         k_slot_prep<true><<<pg, pb, 0, st>>>(pa);
-        db->timing.kernel_launches += 1;
-    }
-
-    /* segments: count per item, scan, fill (k_seg_build) */
-    uint32_t *seg_count = nullptr, *seg_off = nullptr, *deep_flag = nullptr;
-    LcrSeg *segs = nullptr;
-    TRY(cudaMallocAsync(&seg_count, sizeof(uint32_t) * ((size_t)n_items + 2), st));
-    TRY(cudaMallocAsync(&seg_off, sizeof(uint32_t) * ((size_t)n_items + 2), st));
-    TRY(cudaMemsetAsync(seg_count + n_items, 0, 2 * sizeof(uint32_t), st));
-    deep_flag = seg_count + n_items + 1;
-    SegArgs sa{};
-    sa.P = ctx->P;
-    sa.n_items = n_items;
-    sa.regions = db->regions;
-    sa.slot_off = db->slot_off; sa.slot_region = db->slot_region; sa.tile_base = db->tile_base;
-    sa.flag = db->flag; sa.ts = db->ts; sa.seq_off = db->seq_off; sa.cig_off = db->cig_off;
-    sa.seq = db->seq; sa.cigar = db->cigar;
-    sa.ref_table = ctx->d_ref_table;
-    sa.slot_flags = slot_flags;
-    sa.tile_off = tile_off; sa.items = items;
-    sa.rstate = db->rstate; sa.stats = db->d_stats;
-    sa.seg_count = seg_count; sa.seg_off = seg_off; sa.segs = nullptr; sa.deep_flag = deep_flag;
-    const uint32_t sg = (n_items + 127) / 128;
-    if (sg) {
-        k_seg_build<false><<<sg, 128, 0, st>>>(sa);
-        db->timing.kernel_launches += 1;
-    }
-    {
-        size_t sb2 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, sb2, seg_count, seg_off, n_items + 1, st);
-        void *tmp2 = nullptr;
-        TRY(cudaMallocAsync(&tmp2, sb2 ? sb2 : 16, st));
-        TRY(cub::DeviceScan::ExclusiveSum(tmp2, sb2, seg_count, seg_off, n_items + 1, st));
-        TRY(cudaFreeAsync(tmp2, st));
-    }
-    uint32_t seg_tail[2] = {0, 0}; /* total segments, deep-tile flag */
-    TRY(cudaMemcpyAsync(&seg_tail[0], seg_off + n_items, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(&seg_tail[1], deep_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));
-    const uint32_t n_segs = seg_tail[0];
-    const bool any_deep = seg_tail[1] != 0;
-    TRY(cudaMallocAsync(&segs, sizeof(LcrSeg) * (size_t)(n_segs ? n_segs : 1), st));
-    sa.segs = segs;
-    if (sg) {
-        k_seg_build<true><<<sg, 128, 0, st>>>(sa);
         db->timing.kernel_launches += 1;
     }
 
@@ -1105,7 +1059,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     cudaEvent_t ev0, ev1;
     TRY(cudaEventCreate(&ev0));
     TRY(cudaEventCreate(&ev1));
-    const size_t tile_smem = sizeof(uint32_t) * (2 * PT_ROWS * PT_WORDS + PT_SEGS * 4 + PT_SEGS + 4);
+    const size_t tile_smem = sizeof(uint32_t) * (2 * PT_ROWS * PT_WORDS + PT_SEGS * 4 + PT_SEGS + 4 + (PT_TAB + 1) / 2);
     const size_t tile_smem_deep = tile_smem + sizeof(uint32_t) * 16 * LCR_TILE;
     TRY(cudaFuncSetAttribute(k_pileup_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
     TRY(cudaFuncSetAttribute(k_pileup_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_deep));
@@ -1118,13 +1072,15 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
     ka.ref_table = ctx->d_ref_table;
     ka.tile_off = tile_off; ka.tile_full_n = tile_full_n; ka.items = items;
-    ka.seg_off = seg_off; ka.segs = segs;
+    ka.tile_seg_off = tile_seg_off; ka.segs = segs;
     ka.tables = ctx->d_tables;
     ka.rstate = db->rstate;
     ka.stats = db->d_stats;
     ka.pl_acgt = db->pl_acgt; ka.pl_fwd = db->pl_fwd; ka.pl_d = db->pl_d; ka.pl_n = db->pl_n; ka.pl_ts = db->pl_ts;
     ka.pre_count = counters; ka.cand_count = counters + 1;
     uint32_t n_pre = 0, n_cand = 0;
+    /* tiles with more than 255 items take the variant with 32-bit column counters */
+    const bool any_deep = totals[2] != 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(cudaMallocAsync(&pre, sizeof(PreCand) * (size_t)pre_cap, st));
         TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), st));
@@ -1202,12 +1158,10 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaFreeAsync(cand_count, st));
     TRY(cudaFreeAsync(items, st));
     TRY(cudaFreeAsync(segs, st));
-    TRY(cudaFreeAsync(seg_count, st));
-    TRY(cudaFreeAsync(seg_off, st));
+    TRY(cudaFreeAsync(slot_runs, st));
     TRY(cudaFreeAsync(tmp, st));
-    TRY(cudaFreeAsync(tile_count, st));
-    TRY(cudaFreeAsync(tile_off, st));
-    TRY(cudaFreeAsync(tile_full_n, st));
+    TRY(cudaFreeAsync(tile_cnt, st));
+    TRY(cudaFreeAsync(tile_scan, st));
     TRY(cudaGetLastError());
     return LCR_OK;
 }
