@@ -24,14 +24,9 @@ __device__ __forceinline__ bool is_ref_consuming(uint32_t opc) { return opc == 0
 
 /* ------------------------------------------------------------------------- */
 
-__device__ __forceinline__ int base_code_dev(uint8_t b) {
-    switch (b) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        default: return -1;
-    }
+__device__ __forceinline__ int base_code_dev(uint8_t b) { /* A,C,G,T in either case -> 0..3, anything else -> -1 */
+    const uint32_t u = b & 0xdfu;
+    return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : -1;
 }
 
 /* util.rs:737-789: end trim (ONT) and poly-A / homopolymer mask near the clipped read ends.
@@ -89,6 +84,14 @@ template <bool PRE>
 __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const SiteCounters &s, uint8_t ref_base, lcr_candidate &o) {
     const uint32_t total = s.cnt[0] + s.cnt[1] + s.cnt[2] + s.cnt[3];
     if (total < P.min_depth || total > P.max_depth) return false;
+    /* two rejections of the cascade below, taken first because they settle most positions: the last test of the count
+       filters (candidate.rs:132, upper-case A/C/G/T only), and a column holding nothing but the reference base, whose
+       alternative allele has count 0 and fails `d >= alt count` (candidate.rs:165) */
+    if (!(ref_base == 'A' || ref_base == 'C' || ref_base == 'G' || ref_base == 'T')) return false;
+    {
+        const uint32_t rc = ref_base == 'A' ? s.cnt[0] : ref_base == 'C' ? s.cnt[1] : ref_base == 'G' ? s.cnt[2] : s.cnt[3];
+        if (rc == total) return false;
+    }
     /* get_two_major_alleles: stable descending sort of (A,C,G,T); keys (count << 2 | 3 - index) through a 5-exchange network */
     uint32_t k0 = (s.cnt[0] << 2) | 3u, k1 = (s.cnt[1] << 2) | 2u, k2 = (s.cnt[2] << 2) | 1u, k3 = s.cnt[3] << 2;
 #define LCR_CX(x, y) do { const uint32_t hi__ = max(x, y), lo__ = min(x, y); x = hi__; y = lo__; } while (0)
@@ -460,19 +463,18 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
 /* ------------------------------------------------------------------------- *
  * Tile pileup, version 3: segments -> one-hot row planes -> carry-save column sums.
  *
- * k_pileup_tile (CTA per tile) stages up to PT_ROWS items as two byte planes per (row, column):
+ * k_pileup_tile (CTA per tile) stages up to ROWS items as two byte planes per (row, column):
  *     plane X   bit 0-3  base is A,C,G,T          bit 4-7  ... and base quality >= min_baseq
  *     plane Y   bit 0-3  A,C,G,T on a forward read; bit 4 / 5 transcript strand forward / reverse
  *               (util.rs:803-819, any base letter); bit 6 deletion; bit 7 intron
  * Whole column words (4 columns) of a segment are produced one lane per 16-byte block of the read: aligned
- * 128-bit loads of seq and qual, bytes rotated to the column alignment with PRMT, codes built four columns at
- * a time.  The up to three columns before / after the whole words of a segment are written byte-wise by one
- * lane per segment.  Then every thread sums one 32-bit column word (4 columns x 8 indicators) over the rows
- * with a Harley-Seal carry-save adder tree: ~2.4 logic instructions per row for 32 counters.  Counters are
- * unpacked once per tile (once per 255 rows on deep tiles).
+ * 128-bit loads of seq and qual (issued one block ahead), bytes rotated to the column alignment with PRMT,
+ * codes built four columns at a time.  The up to three columns before / after the whole words of a segment
+ * are written byte-wise by one lane per segment.  Then every thread sums one 32-bit column word (4 columns x
+ * 8 indicators) over the rows with a Harley-Seal carry-save adder tree: ~2.4 logic instructions per row for
+ * 32 counters.  Counters are unpacked once per tile (once per 255 rows on deep tiles).
  * ------------------------------------------------------------------------- */
 #define PT_THREADS 256
-#define PT_ROWS 56
 #define PT_SEGS 512
 #define PT_WORDS (LCR_TILE / 4)
 #define PT_TAB ((PT_SEGS * (LCR_TILE / 16 + 1)) / 8 + 8) /* one entry per 8 blocks */
@@ -481,6 +483,45 @@ struct PreCand { /* a site that passed every count-based filter; its likelihood 
     uint32_t tile, col;
     uint32_t cnt[4], pass[4], fwd[4], ts[2], d, n;
 };
+
+struct __align__(16) LcrTileDesc { /* 48 B, one per tile (k_tile_desc) */
+    const uint8_t *ref;     /* reference base of column 0 */
+    uint64_t pos_g;         /* index of column 0 in the debug planes */
+    uint32_t it0, n_items;  /* items of the tile */
+    uint32_t seg_lo, n_segs;
+    uint32_t reg, npos;
+    uint32_t full_n;        /* introns covering the whole tile */
+    int32_t status;         /* of the region */
+};
+
+struct DescArgs {
+    uint32_t n_tiles;
+    const lcr_region *regions;
+    const uint32_t *tile_base, *tile_region, *tile_off, *tile_seg_off, *tile_full_n;
+    const uint64_t *pos_off;
+    const uint8_t *const *ref_table;
+    const LcrRegionState *rstate;
+    LcrTileDesc *desc;
+};
+
+__global__ void k_tile_desc(DescArgs a) {
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= a.n_tiles) return;
+    const uint32_t reg = a.tile_region[tile];
+    const lcr_region R = a.regions[reg];
+    const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
+    const int64_t tile_start = (int64_t)(tile - a.tile_base[reg]) * LCR_TILE;
+    const int64_t tile_end = tile_start + LCR_TILE < vec_size ? tile_start + LCR_TILE : vec_size;
+    LcrTileDesc d;
+    d.status = a.rstate[reg].status;
+    d.ref = d.status == 0 ? a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start : nullptr;
+    d.pos_g = a.pos_off[reg] + (uint64_t)tile_start;
+    d.it0 = a.tile_off[tile]; d.n_items = a.tile_off[tile + 1] - d.it0;
+    d.seg_lo = a.tile_seg_off[tile]; d.n_segs = a.tile_seg_off[tile + 1] - d.seg_lo;
+    d.reg = reg; d.npos = (uint32_t)(tile_end - tile_start);
+    d.full_n = a.tile_full_n[tile];
+    a.desc[tile] = d;
+}
 
 __device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t z) {
     uint32_t r;
@@ -524,16 +565,15 @@ struct PileArgs {
     lcr_params P;
     const lcr_region *regions;
     const uint32_t *slot_off, *slot_region, *tile_base, *tile_region;
-    const uint64_t *pos_off;
     const uint16_t *flag;
     const int8_t *ts;
     const uint64_t *seq_off, *cig_off;
     const uint8_t *seq, *qual;
     const uint32_t *cigar;
     const uint8_t *const *ref_table;
-    const uint32_t *tile_off, *tile_full_n;
+    const uint32_t *tile_off;
     const LcrItem *items;
-    const uint32_t *tile_seg_off;
+    const LcrTileDesc *desc;
     const LcrSeg *segs;
     const LcrDeviceTables *tables;
     LcrRegionState *rstate;
@@ -548,40 +588,50 @@ struct PileArgs {
     uint32_t *pre_count;
 };
 
-template <bool DEEP>
-__global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
+struct PtBlock { /* one 16-byte block of a segment, loads in flight */
+    uint4 sv, qv;
+    uint32_t s4w, q4w;
+    uint32_t z;        /* row_typ of the segment, row already relative to the batch */
+    uint32_t W0, rel, span, e;
+};
+
+template <int ROWS>
+constexpr size_t pt_smem_bytes(bool deep) {
+    return sizeof(uint32_t) * (2 * ROWS * PT_WORDS + PT_SEGS * 4 + PT_SEGS + 4 + (PT_TAB + 1) / 2 + (deep ? 16 * LCR_TILE : 0));
+}
+
+template <bool DEEP, int ROWS, int MINB>
+__global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
+    static_assert(ROWS % 16 == 0 && ROWS >= 16, "the column sums read whole blocks of 16 rows");
     extern __shared__ __align__(16) uint32_t pt_smem[];
-    uint32_t *planes = pt_smem;                                           /* [2][PT_ROWS][PT_WORDS] */
-    uint4 *s_seg = reinterpret_cast<uint4 *>(pt_smem + 2 * PT_ROWS * PT_WORDS); /* [PT_SEGS] staged segments */
-    uint32_t *s_out8 = reinterpret_cast<uint32_t *>(s_seg);               /* [16][PT_WORDS], aliases the segment stage */
-    uint32_t *s_choff = pt_smem + 2 * PT_ROWS * PT_WORDS + PT_SEGS * 4;   /* [PT_SEGS + 1] first block of every staged segment */
+    uint32_t *planes = pt_smem;                                           /* [2][ROWS][PT_WORDS] */
+    uint4 *s_seg = reinterpret_cast<uint4 *>(pt_smem + 2 * ROWS * PT_WORDS); /* [PT_SEGS] staged segments */
+    uint32_t *s_choff = pt_smem + 2 * ROWS * PT_WORDS + PT_SEGS * 4;      /* [PT_SEGS + 1] first block of every staged segment */
     uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_choff + PT_SEGS + 4); /* [PT_TAB] segment of every 8th block */
     uint32_t *s_out32 = s_choff + PT_SEGS + 4 + (PT_TAB + 1) / 2;         /* DEEP: [16][LCR_TILE] */
     __shared__ uint32_t s_wsum[PT_THREADS / 32];
-    __shared__ int s_err;
 
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t it0 = a.tile_off[tile], it1 = a.tile_off[tile + 1];
-    if (((it1 - it0) > 255u) != DEEP) return;
-    const uint32_t reg = a.tile_region[tile];
-    const lcr_region R = a.regions[reg];
-    const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
-    const int32_t tile_start = (int32_t)((tile - a.tile_base[reg]) * LCR_TILE);
-    const int32_t tile_end = (int64_t)tile_start + LCR_TILE < vec_size ? tile_start + LCR_TILE : (int32_t)vec_size;
-    const uint32_t npos = (uint32_t)(tile_end - tile_start);
-    if (tid == 0) s_err = a.rstate[reg].status; /* one read, so the whole CTA takes the same branch */
-    __syncthreads();
-    if (s_err != 0) return;
-    if (DEEP)
+    LcrTileDesc D;
+    {
+        const uint4 *dp = reinterpret_cast<const uint4 *>(a.desc + tile);
+        uint4 *dd = reinterpret_cast<uint4 *>(&D);
+        dd[0] = __ldg(dp); dd[1] = __ldg(dp + 1); dd[2] = __ldg(dp + 2);
+    }
+    if ((D.n_items > 255u) != DEEP || D.status != 0) return;
+    const uint32_t n_items = D.n_items, npos = D.npos;
+    if (DEEP) {
         for (uint32_t i = tid; i < 16 * LCR_TILE; i += PT_THREADS) s_out32[i] = 0;
+        __syncthreads();
+    }
 
     const uint32_t minq = (uint32_t)a.P.min_baseq;
     const uint32_t minq4 = (minq > 30u ? 0u : minq) * 0x01010101u;
     const uint32_t pass_allow = minq > 30u ? 0u : 0xffffffffu;
     const uint8_t *seqp = a.seq, *qualp = a.qual;
-    const uint32_t seg_lo = a.tile_seg_off[tile], seg_hi = a.tile_seg_off[tile + 1];
-    const bool one_batch = (it1 - it0) <= PT_ROWS;
+    const uint32_t seg_lo = D.seg_lo, seg_hi = D.seg_lo + D.n_segs;
+    const bool one_batch = n_items <= ROWS;
 
     /* carry-save state of this thread's column word: plane (tid / PT_WORDS), word (tid % PT_WORDS) */
     uint32_t ones = 0, twos = 0, fours = 0, eights = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
@@ -606,8 +656,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
         acc_rows = 0;
     };
 
-    for (uint32_t row_base = 0; row_base < it1 - it0; row_base += PT_ROWS) {
-        const uint32_t nrow = (it1 - it0 - row_base) < PT_ROWS ? (it1 - it0 - row_base) : PT_ROWS;
+    for (uint32_t row_base = 0; row_base < n_items; row_base += ROWS) {
+        const uint32_t nrow = (n_items - row_base) < (uint32_t)ROWS ? (n_items - row_base) : (uint32_t)ROWS;
         if (DEEP && acc_rows + nrow > 255u) {
             flush();
 #pragma unroll
@@ -615,18 +665,19 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
         }
-        __syncthreads(); /* the previous batch's column sums are done with the planes */
+        if (row_base) __syncthreads(); /* the previous batch's column sums are done with the planes */
         {
             const uint4 z = make_uint4(0, 0, 0, 0);
             uint4 *p4 = reinterpret_cast<uint4 *>(planes);
-            for (uint32_t i = tid; i < nrow * (PT_WORDS / 4); i += PT_THREADS) {
+            const uint32_t nz16 = ((nrow + 15u) & ~15u) * (PT_WORDS / 4); /* whole blocks of 16 rows */
+            for (uint32_t i = tid; i < nz16; i += PT_THREADS) {
                 p4[i] = z;
-                p4[PT_ROWS * (PT_WORDS / 4) + i] = z;
+                p4[ROWS * (PT_WORDS / 4) + i] = z;
             }
         }
         for (uint32_t sb = seg_lo; sb < seg_hi; sb += PT_SEGS) {
             const uint32_t ns = (seg_hi - sb) < PT_SEGS ? (seg_hi - sb) : PT_SEGS;
-            __syncthreads(); /* planes zeroed / previous stage consumed */
+            if (sb != seg_lo) __syncthreads(); /* previous stage consumed */
             /* stage the segments of this batch's rows and scan their block counts */
             uint32_t nch[PT_SEGS / PT_THREADS], mysum = 0;
 #pragma unroll
@@ -644,6 +695,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
                             if ((raw.z & 3u) == SEG_M) n = ((((raw.x + 4u * wlo - col) & 15u) + 4u * nw - 4u) >> 4) + 1u;
                             else n = (((wlo & 3u) + nw - 1u) >> 2) + 1u;
                         }
+                        raw.z = (raw.z & 0xffu) | (rrow << 8);
                     } else raw.w = 0; /* another batch's row: nothing to do here */
                     s_seg[i] = raw;
                 }
@@ -657,7 +709,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
                 if ((int)lane >= o) incl += v;
             }
             if (lane == 31) s_wsum[warp] = incl;
-            __syncthreads();
+            __syncthreads(); /* also: planes zeroed */
             uint32_t wbase = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < PT_THREADS / 32; ++w) {
@@ -677,87 +729,109 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
                 if (tid == PT_THREADS - 1) s_choff[PT_SEGS] = run;
             }
             __syncthreads();
-            /* whole column words: one lane per 16-byte block of a segment */
-            for (uint32_t g = tid; g < total; g += PT_THREADS) {
+            /* whole column words: one lane per 16-byte block of a segment, loads issued one block ahead */
+            auto fetch = [&](uint32_t g, PtBlock &b) {
                 uint32_t k = s_tab[g >> 3];
                 while (s_choff[k + 1] <= g) ++k;
                 const uint32_t c = g - s_choff[k];
                 const uint4 raw = s_seg[k];
-                const uint32_t typ = raw.z & 3u, col = raw.w & 0xffffu, len = raw.w >> 16;
+                const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
                 const uint32_t wlo = (col + 3u) >> 2, whi = (col + len) >> 2;
-                uint32_t *rx = planes + ((raw.z >> 8) - row_base) * PT_WORDS, *ry = rx + PT_ROWS * PT_WORDS;
-                uint32_t x[4], y[4];
-                uint32_t W0; /* first column word this lane produces */
-                if (typ == SEG_M) {
+                b.z = raw.z;
+                b.span = whi - wlo;
+                if ((raw.z & 3u) == SEG_M) {
                     const uint64_t spos = (((uint64_t)raw.y << 32) | raw.x) + (uint64_t)(4u * wlo - col); /* base of column 4 * wlo */
-                    const uint32_t al = (uint32_t)spos & 15u, e = al & 3u;
+                    const uint32_t al = (uint32_t)spos & 15u;
                     const uint64_t blk = (spos & ~(uint64_t)15) + 16ull * c;
-                    W0 = wlo + 4u * c - (al >> 2);
-                    const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(seqp + blk));
-                    const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(qualp + blk));
-                    const uint32_t s4w = __ldg(reinterpret_cast<const uint32_t *>(seqp + blk + 16));
-                    const uint32_t q4w = __ldg(reinterpret_cast<const uint32_t *>(qualp + blk + 16));
-                    const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u;
-                    const uint32_t tsb = ((raw.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
-                    const uint32_t rot = 0x3210u + 0x1111u * e;
-                    onehot4(__byte_perm(sv.x, sv.y, rot), __byte_perm(qv.x, qv.y, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
-                    onehot4(__byte_perm(sv.y, sv.z, rot), __byte_perm(qv.y, qv.z, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
-                    onehot4(__byte_perm(sv.z, sv.w, rot), __byte_perm(qv.z, qv.w, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
-                    onehot4(__byte_perm(sv.w, s4w, rot), __byte_perm(qv.w, q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                    b.e = al & 3u;
+                    b.W0 = wlo + 4u * c - (al >> 2);
+                    b.sv = __ldg(reinterpret_cast<const uint4 *>(seqp + blk));
+                    b.qv = __ldg(reinterpret_cast<const uint4 *>(qualp + blk));
+                    b.s4w = __ldg(reinterpret_cast<const uint32_t *>(seqp + blk + 16));
+                    b.q4w = __ldg(reinterpret_cast<const uint32_t *>(qualp + blk + 16));
                 } else {
-                    W0 = (wlo & ~3u) + 4u * c;
-                    const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
-                    x[0] = x[1] = x[2] = x[3] = 0;
-                    y[0] = y[1] = y[2] = y[3] = v;
+                    b.e = 0;
+                    b.W0 = (wlo & ~3u) + 4u * c;
                 }
-                const uint32_t rel = W0 - wlo, span = whi - wlo; /* word W0 + t is whole iff rel + t < span (unsigned) */
+                b.rel = b.W0 - wlo; /* word W0 + t is whole iff rel + t < span (unsigned) */
+            };
+            PtBlock cur, nxt;
+            if (tid < total) fetch(tid, cur);
+            for (uint32_t g = tid; g < total; g += PT_THREADS) {
+                const bool more = g + PT_THREADS < total;
+                if (more) fetch(g + PT_THREADS, nxt);
+                {
+                    const uint32_t typ = cur.z & 3u;
+                    uint32_t *rx = planes + (cur.z >> 8) * PT_WORDS + cur.W0, *ry = rx + ROWS * PT_WORDS;
+                    uint32_t x[4], y[4];
+                    if (typ == SEG_M) {
+                        const uint32_t fmask = (cur.z & 4u) ? 0x0f0f0f0fu : 0u;
+                        const uint32_t tsb = ((cur.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
+                        const uint32_t rot = 0x3210u + 0x1111u * cur.e;
+                        onehot4(__byte_perm(cur.sv.x, cur.sv.y, rot), __byte_perm(cur.qv.x, cur.qv.y, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
+                        onehot4(__byte_perm(cur.sv.y, cur.sv.z, rot), __byte_perm(cur.qv.y, cur.qv.z, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
+                        onehot4(__byte_perm(cur.sv.z, cur.sv.w, rot), __byte_perm(cur.qv.z, cur.qv.w, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
+                        onehot4(__byte_perm(cur.sv.w, cur.s4w, rot), __byte_perm(cur.qv.w, cur.q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                    } else {
+                        const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
+                        x[0] = x[1] = x[2] = x[3] = 0;
+                        y[0] = y[1] = y[2] = y[3] = v;
+                    }
 #pragma unroll
-                for (uint32_t t = 0; t < 4; ++t) {
-                    if (rel + t < span) {
-                        if (typ == SEG_M) rx[W0 + t] = x[t];
-                        ry[W0 + t] = y[t];
+                    for (uint32_t t = 0; t < 4; ++t) {
+                        if (cur.rel + t < cur.span) {
+                            if (typ == SEG_M) rx[t] = x[t];
+                            ry[t] = y[t];
+                        }
                     }
                 }
+                if (more) cur = nxt;
             }
-            /* the columns before and after the whole words: one lane per segment */
+            /* the columns before and after the whole words: one lane per segment, 4-byte windows of the read */
             for (uint32_t i = tid; i < ns; i += PT_THREADS) {
                 const uint4 raw = s_seg[i];
                 const uint32_t typ = raw.z & 3u, col = raw.w & 0xffffu, len = raw.w >> 16;
                 if (len == 0) continue;
                 const uint32_t end = col + len, wlo = (col + 3u) >> 2, whi = end >> 2;
-                uint8_t *bx = reinterpret_cast<uint8_t *>(planes + ((raw.z >> 8) - row_base) * PT_WORDS), *by = bx + PT_ROWS * PT_WORDS * 4;
+                uint8_t *bx = reinterpret_cast<uint8_t *>(planes + (raw.z >> 8) * PT_WORDS), *by = bx + ROWS * PT_WORDS * 4;
                 const uint32_t h1 = (4u * wlo < end) ? 4u * wlo : end;            /* head columns [col, h1) */
                 const uint32_t t0 = (whi >= wlo) ? 4u * whi : end;                /* tail columns [t0, end) */
-                const uint64_t spos = ((uint64_t)raw.y << 32) | raw.x;
-                const uint32_t fwd = raw.z & 4u, tsb = ((raw.z >> 3) & 3u) << 4;
-                for (int part = 0; part < 2; ++part) {
-                    const uint32_t pa = part == 0 ? col : t0, pb = part == 0 ? h1 : end;
-                    for (uint32_t p = pa; p < pb; ++p) {
-                        if (typ == SEG_M) {
-                            const uint8_t b = __ldg(seqp + spos + (p - col));
-                            const uint32_t q = __ldg(qualp + spos + (p - col));
-                            const int bc = base_code_dev(b);
-                            uint32_t xb = 0, yb = tsb;
-                            if (bc >= 0) {
-                                xb = 1u << bc;
-                                if (fwd) yb |= xb;
-                                if (pass_allow && q >= minq) xb |= 0x10u << bc;
-                            }
-                            bx[p] = (uint8_t)xb;
-                            by[p] = (uint8_t)yb;
-                        } else by[p] = typ == SEG_D ? (uint8_t)0x40 : (uint8_t)0x80;
+                if (h1 == col && t0 == end) continue;
+                if (typ == SEG_M) {
+                    const uint64_t spos = ((uint64_t)raw.y << 32) | raw.x;
+                    const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u, tsb = ((raw.z >> 3) & 3u) * 0x10101010u;
+                    const uint64_t ah = spos, at = spos + (t0 - col);
+                    const uint32_t *sh = reinterpret_cast<const uint32_t *>(seqp + (ah & ~(uint64_t)3)), *qh = reinterpret_cast<const uint32_t *>(qualp + (ah & ~(uint64_t)3));
+                    const uint32_t *st = reinterpret_cast<const uint32_t *>(seqp + (at & ~(uint64_t)3)), *qt = reinterpret_cast<const uint32_t *>(qualp + (at & ~(uint64_t)3));
+                    const uint32_t sh0 = __ldg(sh), sh1 = __ldg(sh + 1), qh0 = __ldg(qh), qh1 = __ldg(qh + 1);
+                    const uint32_t st0 = __ldg(st), st1 = __ldg(st + 1), qt0 = __ldg(qt), qt1 = __ldg(qt + 1);
+                    const uint32_t roth = 0x3210u + 0x1111u * ((uint32_t)ah & 3u), rott = 0x3210u + 0x1111u * ((uint32_t)at & 3u);
+                    uint32_t xh, yh, xt, yt;
+                    onehot4(__byte_perm(sh0, sh1, roth), __byte_perm(qh0, qh1, roth), minq4, pass_allow, fmask, tsb, xh, yh);
+                    onehot4(__byte_perm(st0, st1, rott), __byte_perm(qt0, qt1, rott), minq4, pass_allow, fmask, tsb, xt, yt);
+#pragma unroll
+                    for (uint32_t j = 0; j < 3; ++j) {
+                        if (col + j < h1) { bx[col + j] = (uint8_t)(xh >> (8 * j)); by[col + j] = (uint8_t)(yh >> (8 * j)); }
+                        if (t0 + j < end) { bx[t0 + j] = (uint8_t)(xt >> (8 * j)); by[t0 + j] = (uint8_t)(yt >> (8 * j)); }
+                    }
+                } else {
+                    const uint8_t v = typ == SEG_D ? (uint8_t)0x40 : (uint8_t)0x80;
+#pragma unroll
+                    for (uint32_t j = 0; j < 3; ++j) {
+                        if (col + j < h1) by[col + j] = v;
+                        if (t0 + j < end) by[t0 + j] = v;
                     }
                 }
             }
         }
         __syncthreads();
-        /* column sums of this batch: Harley-Seal blocks of 16 rows */
+        /* column sums of this batch: Harley-Seal blocks of 16 rows (rows up to the next multiple of 16 are zero) */
         {
-            const uint32_t *pl = planes + my_plane * (PT_ROWS * PT_WORDS) + my_word;
+            const uint32_t *pl = planes + my_plane * (ROWS * PT_WORDS) + my_word;
             for (uint32_t r0 = 0; r0 < nrow; r0 += 16) {
                 uint32_t w[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] = (r0 + j < nrow) ? pl[(r0 + j) * PT_WORDS] : 0u;
+                for (int j = 0; j < 16; ++j) w[j] = pl[(r0 + j) * PT_WORDS];
                 uint32_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
                 CSA(t2a, ones, ones, w[0], w[1]);
                 CSA(t2b, ones, ones, w[2], w[3]);
@@ -785,7 +859,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
         }
     }
     flush();
-    __syncthreads(); /* the segment stage is free: it becomes the 8-bit counter exchange */
+    /* counter exchange: 8-bit counters go to rows 0-7 of the thread's own plane, at its own word (only this thread ever
+       reads that word during the column sums, so no barrier is needed before the write) */
     if (DEEP) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -793,28 +868,27 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_pileup_tile(PileArgs a) {
             for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_out8[(my_plane * 8 + i) * PT_WORDS + my_word] = cnt8[i];
+        for (int i = 0; i < 8; ++i) planes[(my_plane * ROWS + i) * PT_WORDS + my_word] = cnt8[i];
     }
     __syncthreads();
-    const uint8_t *ref = a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start;
-    const uint32_t full_n = a.tile_full_n[tile];
+    const uint8_t *ref = D.ref;
     for (uint32_t colr = tid; colr < npos; colr += PT_THREADS) {
         uint32_t v[16];
         if (DEEP) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = s_out32[i * LCR_TILE + colr];
         } else {
-            const uint8_t *o8 = reinterpret_cast<const uint8_t *>(s_out8);
+            const uint8_t *o8 = reinterpret_cast<const uint8_t *>(planes);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = o8[i * LCR_TILE + colr];
+            for (int i = 0; i < 8; ++i) { v[i] = o8[i * LCR_TILE + colr]; v[8 + i] = o8[(ROWS + i) * LCR_TILE + colr]; }
         }
         SiteCounters sc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { sc.cnt[i] = v[i]; sc.pass[i] = v[4 + i]; sc.fwd[i] = v[8 + i]; }
-        sc.ts[0] = v[12]; sc.ts[1] = v[13]; sc.d = v[14]; sc.n = v[15] + full_n;
+        sc.ts[0] = v[12]; sc.ts[1] = v[13]; sc.d = v[14]; sc.n = v[15] + D.full_n;
         sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
         if (a.pl_acgt) {
-            const uint64_t g = a.pos_off[reg] + (uint64_t)tile_start + colr;
+            const uint64_t g = D.pos_g + colr;
 #pragma unroll
             for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = sc.cnt[i]; a.pl_fwd[g * 4 + i] = sc.fwd[i]; }
             a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
@@ -1059,20 +1133,33 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     cudaEvent_t ev0, ev1;
     TRY(cudaEventCreate(&ev0));
     TRY(cudaEventCreate(&ev1));
-    const size_t tile_smem = sizeof(uint32_t) * (2 * PT_ROWS * PT_WORDS + PT_SEGS * 4 + PT_SEGS + 4 + (PT_TAB + 1) / 2);
-    const size_t tile_smem_deep = tile_smem + sizeof(uint32_t) * 16 * LCR_TILE;
-    TRY(cudaFuncSetAttribute(k_pileup_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-    TRY(cudaFuncSetAttribute(k_pileup_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_deep));
+    LcrTileDesc *desc = nullptr;
+    TRY(cudaMallocAsync(&desc, sizeof(LcrTileDesc) * tn, st));
+    if (n_tiles) {
+        DescArgs da{};
+        da.n_tiles = n_tiles; da.regions = db->regions;
+        da.tile_base = db->tile_base; da.tile_region = db->tile_region; da.tile_off = tile_off; da.tile_seg_off = tile_seg_off; da.tile_full_n = tile_full_n;
+        da.pos_off = db->pos_off; da.ref_table = ctx->d_ref_table; da.rstate = db->rstate; da.desc = desc;
+        k_tile_desc<<<(n_tiles + 255) / 256, 256, 0, st>>>(da);
+        db->timing.kernel_launches += 1;
+    }
+    /* launch shape of the tile kernel: rows staged per batch / resident CTAs per SM (LCR_TILE_VARIANT: experiments) */
+    static const int variant = [] { const char *e = getenv("LCR_TILE_VARIANT"); return e && *e ? atoi(e) : 0; }();
+    void (*k_tile)(PileArgs) = variant == 1 ? k_pileup_tile<false, 32, 4> : k_pileup_tile<false, 48, 3>;
+    void (*k_tile_deep)(PileArgs) = variant == 1 ? k_pileup_tile<true, 32, 4> : k_pileup_tile<true, 48, 3>;
+    const size_t tile_smem = variant == 1 ? pt_smem_bytes<32>(false) : pt_smem_bytes<48>(false);
+    const size_t tile_smem_deep = variant == 1 ? pt_smem_bytes<32>(true) : pt_smem_bytes<48>(true);
+    TRY(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    TRY(cudaFuncSetAttribute(k_tile_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_deep));
     PileArgs ka{};
     ka.P = ctx->P;
     ka.regions = db->regions;
     ka.slot_off = db->slot_off; ka.slot_region = db->slot_region; ka.tile_base = db->tile_base; ka.tile_region = db->tile_region;
-    ka.pos_off = db->pos_off;
     ka.flag = db->flag; ka.ts = db->ts; ka.seq_off = db->seq_off; ka.cig_off = db->cig_off;
     ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
     ka.ref_table = ctx->d_ref_table;
-    ka.tile_off = tile_off; ka.tile_full_n = tile_full_n; ka.items = items;
-    ka.tile_seg_off = tile_seg_off; ka.segs = segs;
+    ka.tile_off = tile_off; ka.items = items;
+    ka.desc = desc; ka.segs = segs;
     ka.tables = ctx->d_tables;
     ka.rstate = db->rstate;
     ka.stats = db->d_stats;
@@ -1087,10 +1174,10 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         ka.pre = pre; ka.pre_cap = pre_cap;
         TRY(cudaEventRecord(ev0, st));
         if (n_tiles) {
-            k_pileup_tile<false><<<n_tiles, PT_THREADS, tile_smem, st>>>(ka);
+            k_tile<<<n_tiles, PT_THREADS, tile_smem, st>>>(ka);
             db->timing.kernel_launches += 1;
             if (any_deep) {
-                k_pileup_tile<true><<<n_tiles, PT_THREADS, tile_smem_deep, st>>>(ka);
+                k_tile_deep<<<n_tiles, PT_THREADS, tile_smem_deep, st>>>(ka);
                 db->timing.kernel_launches += 1;
             }
         }
@@ -1158,6 +1245,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaFreeAsync(cand_count, st));
     TRY(cudaFreeAsync(items, st));
     TRY(cudaFreeAsync(segs, st));
+    TRY(cudaFreeAsync(desc, st));
     TRY(cudaFreeAsync(slot_runs, st));
     TRY(cudaFreeAsync(tmp, st));
     TRY(cudaFreeAsync(tile_cnt, st));
