@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
     const uint32_t words = (nf_cap + 31) / 32;
     unsigned long long *rows = reinterpret_cast<unsigned long long *>(smem_raw);
     uint32_t *rrel = reinterpret_cast<uint32_t *>(rows + nf_cap);
-    uint32_t *sig = rrel + nf_cap + warp * words;
+    uint32_t *wm = rrel + nf_cap;            /* per 32 rows: sites some phasing row of the word carries (warp-uniform skips) */
+    uint32_t *sig = wm + words + warp * words;
     const lcr_candidate *c = a.cand + cb;
     const LcrDeviceTables &T = *a.tables;
     const uint64_t region_key = lcr_region_key(a.regions[reg].tid, a.regions[reg].start);
@@ -57,27 +58,32 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
         S.W[tid] = T.fx_ok[q] - T.fx_err[q];
     }
     if (tid < EMAXN) { S.C[tid] = 0; S.R[tid] = 0; S.V[tid] = 0; S.cov[tid] = 0; }
+    for (uint32_t w = tid; w < words; w += EW * 32) wm[w] = 0;
+    __syncthreads();
     /* stage the rows: bit 63 = fragment used for phasing, 6 bits per site: (q + 1) | 32 when p < 0 */
     for (uint32_t k = tid; k < nf; k += EW * 32) {
         const uint32_t f = fb + k;
         unsigned long long row = a.frag_links[f] >= a.P.min_linkers ? (1ull << 63) : 0ull;
+        uint32_t present = 0;
         for (uint32_t e = a.frag_elem_off[f]; e < a.frag_elem_off[f + 1]; ++e) {
             const int8_t cell = a.elem_cell[e];
             const uint32_t code = cell > 0 ? (uint32_t)cell : ((uint32_t)(-cell) | 32u);
             row |= (unsigned long long)code << (6 * a.elem_snp[e]);
+            if (code) present |= 1u << a.elem_snp[e];
         }
         rows[k] = row;
+        if ((row >> 63) && present) atomicOr(&wm[k >> 5], present);
         rrel[k] = a.frag_slot[f] - slot0;
     }
     uint32_t phase0 = 0; /* for_phasing mask */
-    int gen0[EMAXN];
+    uint32_t het0 = 0, pos0 = 0xffffffffu; /* init_genotype, phase.rs:682-691: type 0 -> eta 1, type 1 -> 0, else -1 */
 #pragma unroll
     for (int i = 0; i < EMAXN; ++i) {
-        gen0[i] = 1;
         if ((uint32_t)i < n) {
             if (c[i].flags & LCR_CF_FOR_PHASING) phase0 |= 1u << i;
             const int vt = c[i].variant_type;
-            gen0[i] = vt == 0 ? 1 : (vt == 1 ? 0 : -1); /* init_genotype, phase.rs:682-691 */
+            if (vt == 1) het0 |= 1u << i;
+            if (vt != 0) pos0 &= ~(1u << i);
         }
     }
     __syncthreads();
@@ -115,9 +121,7 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
         const uint32_t cfg = chunk * (EW * ECFG_PER_WARP) + j * EW + warp;
         if (cfg >= n_cfg) break;
         uint32_t dneg = cfg; /* bit i set: delta_i = -1 */
-        int eta[EMAXN];
-#pragma unroll
-        for (int i = 0; i < EMAXN; ++i) eta[i] = gen0[i];
+        uint32_t eta_het = het0, eta_pos = pos0; /* bit i: eta_i == 0 / eta_i == +1 (neither: -1) */
         /* init_assignment (phase.rs:673-680) */
         for (uint32_t w = 0; w < nwords; ++w) {
             const uint32_t k = w * 32 + lane;
@@ -135,37 +139,37 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
 #pragma unroll
             for (int i = 0; i < EMAXN; ++i) M[i] = 0;
             bool any_flip = false;
-            uint32_t hetmask = 0;
-#pragma unroll
-            for (int i = 0; i < EMAXN; ++i)
-                if (eta[i] == 0) hetmask |= 1u << i;
-            hetmask &= phase0;
+            const uint32_t hetmask = eta_het & phase0;
             for (uint32_t w = 0; w < nwords; ++w) {
                 const uint32_t k = w * 32 + lane;
                 const uint32_t word = sig[w];
+                const uint32_t wsites = wm[w];                 /* the same for the whole warp */
+                const uint32_t vs = wsites & hetmask, ms = wsites & phase0;
                 bool neg = (word >> lane) & 1u;
                 unsigned long long row = 0;
                 if (k < nf) row = rows[k];
                 const bool active = row >> 63;
-                if (active) {
-                    long long v = 0; /* sum_i p * delta * W over heterozygous phase sites */
+                long long v = 0; /* sum_i p * delta * W over heterozygous phase sites */
 #pragma unroll
-                    for (int i = 0; i < EMAXN; ++i) {
+                for (int i = 0; i < EMAXN; ++i) {
+                    if ((vs >> i) & 1u) {
                         const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
-                        if (code && ((hetmask >> i) & 1u)) {
+                        if (code) {
                             const long long Wq = S.W[(code & 31u) - 1u];
                             const bool minus = ((code >> 5) ^ (dneg >> i)) & 1u;
                             v += minus ? -Wq : Wq;
                         }
                     }
-                    if (v != 0) {
-                        const bool nneg = v < 0;
-                        if (nneg != neg) { any_flip = true; neg = nneg; }
-                    }
+                }
+                if (active && v != 0) {
+                    const bool nneg = v < 0;
+                    if (nneg != neg) { any_flip = true; neg = nneg; }
+                }
 #pragma unroll
-                    for (int i = 0; i < EMAXN; ++i) {
+                for (int i = 0; i < EMAXN; ++i) {
+                    if ((ms >> i) & 1u) {
                         const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
-                        if (code && ((phase0 >> i) & 1u)) {
+                        if (active && code) {
                             const long long Wq = S.W[(code & 31u) - 1u];
                             const bool minus = ((code >> 5) & 1u) ^ (neg ? 1u : 0u);
                             M[i] += minus ? -Wq : Wq;
@@ -183,38 +187,46 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
                     for (int o = 16; o; o >>= 1) M[i] += __shfl_xor_sync(0xffffffffu, M[i], o);
             if (!any_flip) ht_increase = false;
             else { ht_increase = true; hg_increase = true; }
-            /* delta / eta sweep with_genotype (phase.rs:905-921); all lanes hold the same sums */
-            bool better = false;
+            /* delta / eta sweep with_genotype (phase.rs:905-921): all lanes hold the same sums, lane i decides site i */
+            bool better = false, flip = false;
+            bool nhet = (eta_het >> lane) & 1u, npos = (eta_pos >> lane) & 1u;
+            if (lane < n && ((phase0 >> lane) & 1u) && S.cov[lane]) {
+                long long Mi = M[0];
 #pragma unroll
-            for (int i = 0; i < EMAXN; ++i) {
-                if ((uint32_t)i >= n || !((phase0 >> i) & 1u) || !S.cov[i]) continue;
-                const long long dM = ((dneg >> i) & 1u) ? -M[i] : M[i];
-                const long long ph2 = 2 * (T.fx_prior_het - (long long)S.cov[i] * T.fx_log10_2);
-                const long long L0 = S.C[i] + dM + ph2, L1 = S.C[i] - dM + ph2;
-                const long long L2 = 2 * (S.R[i] + T.fx_prior_homref), L3 = 2 * (S.V[i] + T.fx_prior_homvar);
-                const long long L_old = eta[i] == 0 ? L0 : (eta[i] == 1 ? L2 : L3);
+                for (int i = 1; i < EMAXN; ++i) Mi = (int)lane == i ? M[i] : Mi;
+                const long long dM = ((dneg >> lane) & 1u) ? -Mi : Mi;
+                const long long ph2 = 2 * (T.fx_prior_het - (long long)S.cov[lane] * T.fx_log10_2);
+                const long long L0 = S.C[lane] + dM + ph2, L1 = S.C[lane] - dM + ph2;
+                const long long L2 = 2 * (S.R[lane] + T.fx_prior_homref), L3 = 2 * (S.V[lane] + T.fx_prior_homvar);
+                const long long L_old = nhet ? L0 : (npos ? L2 : L3);
                 long long mx = L0 > L1 ? L0 : L1;
                 const long long m2 = L2 > L3 ? L2 : L3;
                 mx = mx > m2 ? mx : m2;
                 long long L_new;
-                if (L0 == mx) { eta[i] = 0; L_new = L0; }
-                else if (L1 == mx) { dneg ^= 1u << i; eta[i] = 0; L_new = L1; }
-                else if (L2 == mx) { eta[i] = 1; L_new = L2; }
-                else { eta[i] = -1; L_new = L3; }
-                if (L_new > L_old) better = true;
+                if (L0 == mx) { nhet = true; npos = false; L_new = L0; }
+                else if (L1 == mx) { flip = true; nhet = true; npos = false; L_new = L1; }
+                else if (L2 == mx) { nhet = false; npos = true; L_new = L2; }
+                else { nhet = false; npos = false; L_new = L3; }
+                better = L_new > L_old;
             }
+            dneg ^= __ballot_sync(0xffffffffu, flip);
+            eta_het = __ballot_sync(0xffffffffu, nhet);
+            eta_pos = __ballot_sync(0xffffffffu, npos);
+            better = __any_sync(0xffffffffu, better);
             if (!better) hg_increase = false;
             else { hg_increase = true; ht_increase = true; }
             if (++num_iters > 20) break;
         }
         /* cal_overall_probability from the column sums of the final state */
         long long prob2 = 0;
+        if (lane < n && ((phase0 >> lane) & 1u) && S.cov[lane]) {
+            long long Mi = M[0];
 #pragma unroll
-        for (int i = 0; i < EMAXN; ++i) {
-            if ((uint32_t)i >= n || !((phase0 >> i) & 1u) || !S.cov[i]) continue;
-            const long long dM = ((dneg >> i) & 1u) ? -M[i] : M[i];
-            prob2 += eta[i] == 0 ? (S.C[i] + dM) : (eta[i] == 1 ? 2 * S.R[i] : 2 * S.V[i]);
+            for (int i = 1; i < EMAXN; ++i) Mi = (int)lane == i ? M[i] : Mi;
+            const long long dM = ((dneg >> lane) & 1u) ? -Mi : Mi;
+            prob2 = ((eta_het >> lane) & 1u) ? (S.C[lane] + dM) : (((eta_pos >> lane) & 1u) ? 2 * S.R[lane] : 2 * S.V[lane]);
         }
+        for (int o = 16; o; o >>= 1) prob2 += __shfl_xor_sync(0xffffffffu, prob2, o);
         const long long prob = prob2 / 2;
         if (best_cfg == 0xffffffffu || prob > best_prob) { best_prob = prob; best_cfg = cfg; }
     }
@@ -246,7 +258,7 @@ static const int SHAPES[4][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}};
 
 int lcr_enum_shape_for(uint32_t n_cand) { return n_cand <= 2 ? 0 : (n_cand == 3 ? 1 : (n_cand == 4 ? 2 : 3)); }
 uint32_t lcr_enum_cfgs_per_cta(int shape) { return (uint32_t)(SHAPES[shape][0] * SHAPES[shape][1]); }
-static size_t smem_bytes(uint32_t nf_cap, int ew) { return (size_t)nf_cap * 12 + (size_t)ew * ((nf_cap + 31) / 32) * 4 + 16; }
+static size_t smem_bytes(uint32_t nf_cap, int ew) { return (size_t)nf_cap * 12 + (size_t)(ew + 1) * ((nf_cap + 31) / 32) * 4 + 16; }
 
 template <int EW, int CPW>
 static int launch_shape(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
