@@ -234,12 +234,11 @@ def main():
     h2d = d2h = 0
     for _ in range(args.steps):
         flush_l2()
-        h = eng.upload(batch)
-        eng.run_device(h)
-        rr = eng.fetch(h)
-        tt = eng.timing(h)
+        raw = eng.submit_raw(batch)  # the reference-facing call: host buffers in, host results out
+        rr = host.ResultView(raw)
+        eng.free_result(raw)
+        tt = eng.last_submit_timing()
         h2d, d2h = tt["h2d_bytes"], tt["d2h_bytes"]
-        eng.release(h)
     barrier()
     e2e_ms = (time.perf_counter() - e2e_t0) * 1e3
     n_cand_total = rr.n_cand

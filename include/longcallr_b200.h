@@ -229,6 +229,8 @@ typedef struct lcr_timing {
     uint64_t d2h_bytes;        /* bytes lcr_fetch copied                                   */
 } lcr_timing;
 int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out);
+/* accounting of the last lcr_submit on this context, summed over the chunks it was cut into */
+int lcr_last_submit_timing(lcr_ctx *ctx, lcr_timing *out);
 
 const char *lcr_strerror(int status);
 const char *lcr_last_error(lcr_ctx *ctx);

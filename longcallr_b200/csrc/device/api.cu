@@ -120,6 +120,7 @@ int exclusive_scan_u32(lcr_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n
 struct lcr_device_batch_full : lcr_device_batch {
     DbExtra extra;
     uint8_t *slot_flags = nullptr;
+    cudaEvent_t ready = nullptr; /* set by an asynchronous upload: the run waits for it */
 };
 
 static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
@@ -421,6 +422,8 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LCR_ERR_CUDA; }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    memset(&ctx->last_submit, 0, sizeof ctx->last_submit);
     for (int i = 0; i < 4; ++i) {
         cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
@@ -468,6 +471,7 @@ void lcr_destroy(lcr_ctx *ctx) {
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     for (int i = 0; i < 4; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -486,8 +490,14 @@ int lcr_set_reference(lcr_ctx *ctx, int32_t tid, const uint8_t *seq, uint64_t le
     return LCR_OK;
 }
 
-int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) {
+/* async: allocate and copy on the context's copy stream and record `ready` instead of waiting */
+static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out, bool async) {
     if (!ctx || !b || !out) return LCR_ERR_INVALID_ARG;
+    struct StreamSwap { /* the helpers above issue work on ctx->stream */
+        lcr_ctx *c; cudaStream_t saved; bool on;
+        StreamSwap(lcr_ctx *c_, bool on_) : c(c_), saved(c_->stream), on(on_) { if (on) c->stream = c->copy_stream; }
+        ~StreamSwap() { if (on) c->stream = saved; }
+    } swap_guard(ctx, async);
     if (ctx->sticky) return ctx->sticky;
     if (b->n_regions && !b->regions) return LCR_ERR_INVALID_ARG;
     if (b->n_reads && (!b->pos || !b->flag || !b->mapq || !b->ts || !b->de || !b->seq_off || !b->cig_off)) return LCR_ERR_INVALID_ARG;
@@ -532,26 +542,32 @@ int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) {
     uint64_t bytes = 0;
     int rc = 0;
 #define UP(field, src, n) if (!rc) rc = h2d(ctx, &db->field, src, (size_t)(n), &bytes)
-    UP(regions, b->regions, b->n_regions);
-    UP(pos, b->pos, b->n_reads);
-    UP(flag, b->flag, b->n_reads);
-    UP(mapq, b->mapq, b->n_reads);
-    UP(ts, b->ts, b->n_reads);
-    UP(de, b->de, b->n_reads);
-    if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
-    else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
-    /* seq / qual carry 32 bytes of slack: the tile kernel reads aligned 16-byte blocks plus the following word */
-    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 32, &bytes);
-    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 32, &bytes);
-    UP(cigar, b->cigar, n_cig);
+    /* the small host-side tables first (pageable sources: those copies wait for the stream), the caller's large arrays last,
+       so that an asynchronous upload returns while seq / qual are still in flight */
     UP(slot_off, slot_off.data(), slot_off.size());
     UP(slot_region, slot_region.data(), slot_region.size());
     UP(tile_base, tile_base.data(), tile_base.size());
     UP(tile_region, tile_region.data(), tile_region.size());
     UP(pos_off, pos_off.data(), pos_off.size());
+    UP(regions, b->regions, b->n_regions);
+    if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
+    else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
+    UP(pos, b->pos, b->n_reads);
+    UP(flag, b->flag, b->n_reads);
+    UP(mapq, b->mapq, b->n_reads);
+    UP(ts, b->ts, b->n_reads);
+    UP(de, b->de, b->n_reads);
+    UP(cigar, b->cigar, n_cig);
+    /* seq / qual carry 32 bytes of slack: the tile kernel reads aligned 16-byte blocks plus the following word */
+    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 32, &bytes);
+    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 32, &bytes);
 #undef UP
     if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaError_t e = cudaSuccess;
+        if (async) {
+            e = cudaEventCreateWithFlags(&db->ready, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(db->ready, ctx->stream);
+        } else e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
     }
     if (rc) { lcr_release(ctx, db); return rc; }
@@ -559,6 +575,8 @@ int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) {
     *out = db;
     return LCR_OK;
 }
+
+int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) { return upload_impl(ctx, b, out, false); }
 
 static void free_results(lcr_ctx *ctx, lcr_device_batch_full *db) {
     DFREE(db->rstate); DFREE(db->cand); DFREE(db->hp); DFREE(db->ps); DFREE(db->is_fragment); DFREE(db->d_stats);
@@ -574,6 +592,7 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
     TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    if (db->ready) TRY(cudaStreamWaitEvent(st, db->ready, 0));
     free_results(ctx, db);
     const uint64_t h2d_keep = db->h2d_bytes;
     memset(&db->timing, 0, sizeof db->timing);
@@ -739,6 +758,7 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); DFREE(db->qual); DFREE(db->cigar);
     DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
     cudaStreamSynchronize(ctx->stream);
+    if (db->ready) { cudaEventSynchronize(db->ready); cudaEventDestroy(db->ready); }
     delete db;
 }
 
@@ -748,14 +768,160 @@ int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out) {
     return LCR_OK;
 }
 
-int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
+int lcr_last_submit_timing(lcr_ctx *ctx, lcr_timing *out) {
+    if (!ctx || !out) return LCR_ERR_INVALID_ARG;
+    *out = ctx->last_submit;
+    return LCR_OK;
+}
+
+static void add_timing(lcr_timing &acc, const lcr_timing &t) {
+    acc.ms_total += t.ms_total; acc.ms_pileup += t.ms_pileup; acc.ms_pileup_kernel += t.ms_pileup_kernel;
+    acc.ms_fragments += t.ms_fragments; acc.ms_phase += t.ms_phase; acc.kernel_launches += t.kernel_launches;
+    acc.pileup_alg_bytes += t.pileup_alg_bytes; acc.h2d_bytes += t.h2d_bytes; acc.d2h_bytes += t.d2h_bytes;
+}
+
+static int submit_one(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
     lcr_device_batch *db = nullptr;
     int rc = lcr_upload(ctx, batch, &db);
     if (rc) return rc;
     rc = lcr_run_device(ctx, db);
     if (!rc) rc = lcr_fetch(ctx, db, out);
+    if (!rc) add_timing(ctx->last_submit, db->timing);
     lcr_release(ctx, db);
     return rc;
+}
+
+/* One chunk of a large submit: consecutive regions and the read rows they span, offsets rebased to the chunk. */
+struct SubmitChunk {
+    uint32_t r0, r1, read_lo, read_hi;
+    std::vector<lcr_region> regions;
+    std::vector<uint64_t> seq_off, cig_off;
+    lcr_batch view;
+};
+
+static size_t submit_chunk_bytes() { /* seq + qual bytes per chunk (LCR_SUBMIT_CHUNK_MB overrides: tests) */
+    const char *e = getenv("LCR_SUBMIT_CHUNK_MB");
+    if (e && *e) return (size_t)strtoull(e, nullptr, 10) << 20;
+    return (size_t)256 << 20;
+}
+
+/* The worker body for a batch of regions, host buffers in, host results out.  Large batches are cut into chunks of
+   consecutive regions; the host-to-device copies of chunk k+1 run on the copy stream while chunk k computes (regions are
+   independent, so the result is the same as one pass over the whole batch). */
+int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
+    if (!ctx || !batch || !out) return LCR_ERR_INVALID_ARG;
+    if (ctx->sticky) return ctx->sticky;
+    memset(&ctx->last_submit, 0, sizeof ctx->last_submit);
+    const size_t chunk_bytes = submit_chunk_bytes();
+    const uint64_t total_bases = batch->n_reads && batch->seq_off ? batch->seq_off[batch->n_reads] : 0;
+    const bool debug_out = ctx->P.flags & (LCR_FLAG_EMIT_PLANES | LCR_FLAG_EMIT_FRAGMENTS);
+    bool chunkable = !debug_out && batch->n_regions > 1 && 2 * total_bases > chunk_bytes + chunk_bytes / 2 && batch->regions && batch->seq_off && batch->cig_off;
+    std::vector<SubmitChunk> chunks;
+    if (chunkable) {
+        /* greedy cut by the bases of the reads each region spans; regions with unusable read ranges ride along */
+        uint32_t r = 0;
+        while (r < batch->n_regions) {
+            SubmitChunk ck;
+            ck.r0 = r;
+            ck.read_lo = 0xffffffffu; ck.read_hi = 0;
+            uint64_t bases = 0;
+            while (r < batch->n_regions) {
+                const lcr_region &g = batch->regions[r];
+                const bool ok = g.read_end >= g.read_begin && g.read_end <= batch->n_reads;
+                if (ok && g.read_end > g.read_begin) {
+                    const uint32_t lo = std::min(ck.read_lo, g.read_begin), hi = std::max(ck.read_hi, g.read_end);
+                    const uint64_t nb = batch->seq_off[hi] - batch->seq_off[lo];
+                    if (r > ck.r0 && 2 * nb > chunk_bytes) break;
+                    ck.read_lo = lo; ck.read_hi = hi; bases = nb;
+                }
+                ++r;
+            }
+            (void)bases;
+            ck.r1 = r;
+            if (ck.read_lo > ck.read_hi) { ck.read_lo = 0; ck.read_hi = 0; }
+            chunks.push_back(std::move(ck));
+        }
+        if (chunks.size() < 2) chunkable = false;
+    }
+    if (!chunkable) return submit_one(ctx, batch, out);
+
+    for (SubmitChunk &ck : chunks) {
+        const uint32_t nreads = ck.read_hi - ck.read_lo;
+        ck.regions.assign(batch->regions + ck.r0, batch->regions + ck.r1);
+        for (lcr_region &g : ck.regions) {
+            const bool ok = g.read_end >= g.read_begin && g.read_end <= batch->n_reads;
+            if (ok && g.read_end > g.read_begin) { g.read_begin -= ck.read_lo; g.read_end -= ck.read_lo; }
+            else if (ok) { g.read_begin = 0; g.read_end = 0; }
+            else { g.read_begin = 1; g.read_end = 0; } /* stays invalid */
+        }
+        ck.seq_off.resize((size_t)nreads + 1);
+        ck.cig_off.resize((size_t)nreads + 1);
+        const uint64_t sb = batch->seq_off[ck.read_lo], cb = batch->cig_off[ck.read_lo];
+        for (uint32_t i = 0; i <= nreads; ++i) { ck.seq_off[i] = batch->seq_off[ck.read_lo + i] - sb; ck.cig_off[i] = batch->cig_off[ck.read_lo + i] - cb; }
+        lcr_batch &v = ck.view;
+        v.n_regions = ck.r1 - ck.r0; v.n_reads = nreads; v.regions = ck.regions.data();
+        v.pos = batch->pos + ck.read_lo; v.flag = batch->flag + ck.read_lo; v.mapq = batch->mapq + ck.read_lo;
+        v.ts = batch->ts + ck.read_lo; v.de = batch->de + ck.read_lo;
+        v.seq_off = ck.seq_off.data(); v.cig_off = ck.cig_off.data();
+        v.seq = batch->seq ? batch->seq + sb : nullptr; v.qual = batch->qual ? batch->qual + sb : nullptr;
+        v.cigar = batch->cigar ? batch->cigar + cb : nullptr;
+    }
+
+    ResultBox *all = new (std::nothrow) ResultBox();
+    if (!all) return LCR_ERR_OOM;
+    all->cand_off.assign((size_t)batch->n_regions + 1, 0);
+    all->region_status.assign(batch->n_regions, 0);
+    all->hp.assign(batch->n_reads, (int8_t)-1);
+    all->ps.assign(batch->n_reads, 0);
+    all->is_fragment.assign(batch->n_reads, 0);
+    lcr_stats st{};
+    int rc = 0;
+    lcr_device_batch *cur = nullptr, *nxt = nullptr;
+    rc = upload_impl(ctx, &chunks[0].view, &cur, true);
+    for (size_t k = 0; k < chunks.size() && !rc; ++k) {
+        if (k + 1 < chunks.size()) rc = upload_impl(ctx, &chunks[k + 1].view, &nxt, true); /* overlaps the run below */
+        lcr_result *part = nullptr;
+        if (!rc) rc = lcr_run_device(ctx, cur);
+        if (!rc) rc = lcr_fetch(ctx, cur, &part);
+        if (!rc) {
+            const SubmitChunk &ck = chunks[k];
+            add_timing(ctx->last_submit, cur->timing);
+            const uint32_t base = (uint32_t)all->cand.size();
+            for (uint32_t i = 0; i < part->n_cand; ++i) {
+                lcr_candidate c = part->cand[i];
+                c.region += ck.r0;
+                all->cand.push_back(c);
+            }
+            for (uint32_t r = 0; r < part->n_regions; ++r) {
+                all->region_status[ck.r0 + r] = part->region_status[r];
+                all->cand_off[ck.r0 + r + 1] = base + part->cand_off[r + 1];
+            }
+            for (uint32_t i = 0; i < part->n_reads; ++i) {
+                const size_t g = (size_t)ck.read_lo + i;
+                if (part->hp[i] != -1) all->hp[g] = part->hp[i];
+                if (part->ps[i]) all->ps[g] = part->ps[i];
+                if (part->is_fragment[i]) all->is_fragment[g] = 1;
+            }
+            st.n_reads_pass += part->stats.n_reads_pass; st.n_aligned_bases += part->stats.n_aligned_bases;
+            st.n_positions += part->stats.n_positions; st.n_candidates += part->stats.n_candidates;
+            st.n_fragments += part->stats.n_fragments; st.nnz_phase += part->stats.nnz_phase;
+            st.n_cross_optimize += part->stats.n_cross_optimize; st.n_sweep_iters += part->stats.n_sweep_iters;
+            lcr_free_result(part);
+        }
+        if (cur) lcr_release(ctx, cur);
+        cur = nxt;
+        nxt = nullptr;
+    }
+    if (cur) lcr_release(ctx, cur);
+    if (nxt) lcr_release(ctx, nxt);
+    if (rc) { delete all; return rc; }
+    lcr_result &res = all->res;
+    res.n_regions = batch->n_regions; res.n_reads = batch->n_reads; res.n_cand = (uint32_t)all->cand.size();
+    res.cand_off = all->cand_off.data(); res.cand = all->cand.data(); res.region_status = all->region_status.data();
+    res.hp = all->hp.data(); res.ps = all->ps.data(); res.is_fragment = all->is_fragment.data();
+    res.stats = st;
+    *out = &all->res;
+    return LCR_OK;
 }
 
 } /* extern "C" */

@@ -65,6 +65,8 @@ struct lcr_ctx {
     int device;
     cudaStream_t stream;
     cudaStream_t side[4];      /* independent launches of one stage fork onto these and join back */
+    cudaStream_t copy_stream;  /* lcr_submit: the next chunk's host-to-device copies run here while the current chunk computes */
+    lcr_timing last_submit;    /* accounting of the last lcr_submit (lcr_last_submit_timing) */
     cudaEvent_t ev_fork, ev_join[4];
     lcr_luts luts;
     LcrDeviceTables *d_tables; /* device copy */

@@ -76,6 +76,7 @@ def cuda_lib():
         L.lcr_release.argtypes = [C.c_void_p, C.c_void_p]
         L.lcr_release.restype = None
         L.lcr_get_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Timing)]
+        L.lcr_last_submit_timing.argtypes = [C.c_void_p, C.POINTER(abi.Timing)]
         L.lcr_strerror.argtypes = [C.c_int]
         L.lcr_strerror.restype = C.c_char_p
         L.lcr_last_error.argtypes = [C.c_void_p]
@@ -408,6 +409,12 @@ class Engine:
     def timing(self, handle):
         t = abi.Timing()
         self._check(self.L.lcr_get_timing(self.ctx, handle, C.byref(t)), "lcr_get_timing")
+        return {k: getattr(t, k) for k, _ in abi.Timing._fields_}
+
+    def last_submit_timing(self):
+        """Accounting of the last submit / submit_raw (summed over the chunks lcr_submit cut the batch into)."""
+        t = abi.Timing()
+        self._check(self.L.lcr_last_submit_timing(self.ctx, C.byref(t)), "lcr_last_submit_timing")
         return {k: getattr(t, k) for k, _ in abi.Timing._fields_}
 
     def close(self):

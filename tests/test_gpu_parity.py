@@ -162,3 +162,25 @@ def test_cooperative_grid_kernel_matches_oracle(monkeypatch):
     regions, _ = host.find_regions(syn.reads, p)
     got, want = run_both(p, syn.reads, syn.reference.for_reads(syn.reads), regions)
     helpers.compare_results(got, want, "grid kernel mixed")
+
+
+def test_chunked_submit_matches_single_pass(monkeypatch):
+    """lcr_submit cuts large batches into chunks of regions and overlaps their uploads: same result as one pass, and as the oracle."""
+    syn = host.Synthetic(seed=21, contig_len=200_000, n_contigs=2, platform=0, depth=30.0, n_het=160, n_edit=30, both_strands=0, n_threads=4)
+    p = host.params_preset("hifi-masseq", seed=4)
+    regions, _ = host.find_regions(syn.reads, p)
+    refs = syn.reference.for_reads(syn.reads)
+    batch = host.BatchView(syn.reads, regions)
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
+    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", "100000")
+    whole = eng.submit(batch)
+    n_launch_whole = eng.last_submit_timing()["kernel_launches"]
+    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", "1")
+    parts = eng.submit(batch)
+    t = eng.last_submit_timing()
+    eng.close()
+    assert t["kernel_launches"] > 2 * n_launch_whole, "the batch was not cut into chunks"
+    helpers.compare_results(parts, whole, "chunked vs whole")
+    want = ob.run(p, batch, refs, mode=0)
+    helpers.compare_results(parts, want, "chunked vs oracle")
