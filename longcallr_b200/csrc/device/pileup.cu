@@ -234,14 +234,15 @@ struct PrepArgs {
     lcr_stats *stats;
     uint8_t *slot_flags;   /* bit 0: passes the read filter and overlaps the window; bit 1: has homopolymer runs near a read end;
                               bit 2: more than LCR_SLOT_RUNS of them (every zone base takes the exact test) */
-    uint64_t *slot_runs;   /* [n_slots][LCR_SLOT_RUNS]: start << 32 | length, in read coordinates */
+    uint64_t *slot_runs;   /* [n_slots][LCR_SLOT_RUNS]: start << 32 | length << 8 | letter, in read coordinates */
     uint32_t *tile_count;  /* COUNT: items per tile; FILL: cursor */
     const uint32_t *tile_off;
     uint32_t *tile_full_n; /* whole-tile intron covers */
-    uint32_t *tile_segs;   /* COUNT: segments per tile; FILL: cursor */
     uint32_t *deep_flag;   /* COUNT: set when some tile holds more than 255 items */
-    const uint32_t *tile_seg_off;
+    uint32_t *slot_segs;   /* COUNT: upper bound of the read's segments (exact but for poly-A cuts) */
+    const uint32_t *slot_seg_off; /* its exclusive scan: the read's segments are written there, in walk order, no atomics */
     LcrItem *items;
+    uint2 *item_segs;      /* FILL: per item (tile order), first segment and segment count */
     LcrSeg *segs;
 };
 
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
                             const bool letter = b == 'A' || b == 'C' || b == 'G' || b == 'T';
                             if (letter && b == prev) { run++; continue; }
                             if (run >= polya && i > scanned_to) { /* the run [i - run, i) just ended */
-                                if (nrun < LCR_SLOT_RUNS) runs[nrun] = ((uint64_t)(i - run) << 32) | (uint64_t)run;
+                                if (nrun < LCR_SLOT_RUNS) runs[nrun] = ((uint64_t)(i - run) << 32) | ((uint64_t)(run > 0xffffff ? 0xffffff : run) << 8) | (uint64_t)prev;
                                 nrun++;
                             }
                             run = letter ? 1 : 0;
@@ -356,11 +357,13 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
             int64_t fpos = (int64_t)a.pos[read] - fv_start;
             int64_t rpos = lead;
             int64_t last_tile = -1;
-            uint32_t row = 0, nseg_tile = 0; /* of the current tile */
+            uint32_t item_k = 0xffffffffu;                 /* FILL: index of the current item */
+            uint32_t seg_w = FILL ? a.slot_seg_off[slot] : 0; /* FILL: next segment slot of this read; COUNT: segments so far */
+            uint32_t seg_item0 = seg_w;                    /* first segment of the current item */
             bool bad = false;
             auto leave_tile = [&]() {
-                if (!FILL && last_tile >= 0 && nseg_tile) atomicAdd(&a.tile_segs[tb + last_tile], nseg_tile);
-                nseg_tile = 0;
+                if (FILL && item_k != 0xffffffffu) a.item_segs[item_k] = make_uint2(seg_item0, seg_w - seg_item0);
+                seg_item0 = seg_w;
             };
             for (uint64_t c = c0; c < c1 && !bad; ++c) {
                 const uint32_t op = a.cigar[c], opc = op & 0xf, len = op >> 4;
@@ -392,23 +395,24 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
                             last_tile = t;
                             if (!FILL) { if (atomicAdd(&a.tile_count[tb + t], 1u) == 255u) *a.deep_flag = 1u; }
                             else {
-                                row = atomicAdd(&a.tile_count[tb + t], 1u);
+                                item_k = a.tile_off[tb + t] + atomicAdd(&a.tile_count[tb + t], 1u);
                                 LcrItem it;
                                 it.slot = slot;
                                 it.cig = (uint32_t)(c - c0);
                                 it.opoff = (uint32_t)(ts - lo);
                                 it.rpos = (uint32_t)(is_m ? rpos + (ts - lo) : rpos);
                                 it.fpos = (int32_t)ts;
-                                a.items[a.tile_off[tb + t] + row] = it;
+                                a.items[item_k] = it;
                             }
                         }
                         const uint32_t colr = (uint32_t)(ts - t * LCR_TILE);
                         auto put = [&](uint32_t typ, uint64_t spos, uint32_t col, uint32_t n) {
                             if (FILL) {
                                 LcrSeg s;
-                                s.spos = spos; s.row_typ = (row << 8) | rowtyp_c | typ; s.col = (uint16_t)col; s.len = (uint16_t)n;
-                                a.segs[a.tile_seg_off[tb + t] + atomicAdd(&a.tile_segs[tb + t], 1u)] = s;
-                            } else nseg_tile++;
+                                s.spos = spos; s.row_typ = rowtyp_c | typ; s.col = (uint16_t)col; s.len = (uint16_t)n;
+                                a.segs[seg_w] = s;
+                            }
+                            seg_w++;
                         };
                         if (!is_m) {
                             put(opc == 2 ? SEG_D : SEG_N, 0, colr, (uint32_t)(te - ts));
@@ -426,21 +430,43 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
                                 const int64_t zl = zlo[k] > start ? zlo[k] : start, zh = zhi[k] < pb - 1 ? zhi[k] : pb - 1;
                                 if (zl <= zh) { emit(start, zl); start = zh + 1; }
                             }
-                        } else if (mask_mode == 2) { /* exact test on every zone base */
+                        } else if (mask_mode == 2) { /* exact test on every zone base (COUNT: every one may cut) */
                             for (int k = 0; k < 2; ++k) {
                                 const int64_t zl = zlo[k] > start ? zlo[k] : start, zh = zhi[k] < pb - 1 ? zhi[k] : pb - 1;
+                                if (!FILL) { if (zh >= zl) seg_w += (uint32_t)(zh - zl + 1); continue; }
                                 for (int64_t rp = zl; rp <= zh; ++rp)
                                     if (base_masked(a.P, seq, rp, seq_len, lead, trail, ref[ts + (rp - pa)])) { emit(start, rp); start = rp + 1; }
                             }
-                        } else if (mask_mode == 3) { /* only bases inside or next to a remembered run can be masked */
+                        } else if (mask_mode == 3) {
+                            /* only bases inside or next to a remembered run can be masked, and the test of util.rs:754-789 needs no
+                               sequence loads there: base rp is masked iff, for a run [rs, re) of a letter other than the reference base
+                               that holds rp - 1 or rp + 1, at least polya of its bases lie in [rp - polya, rp + polya] */
+                            const int64_t polya = (int64_t)a.P.polya_tail_length;
                             int64_t from = pa;
 #pragma unroll
                             for (int j = 0; j < LCR_SLOT_RUNS; ++j) {
-                                const int64_t rs = (int64_t)(runs[j] >> 32), rn = (int64_t)(runs[j] & 0xffffffffu);
+                                const int64_t rs = (int64_t)(runs[j] >> 32), rn = (int64_t)((runs[j] >> 8) & 0xffffffu);
                                 if (rn == 0) continue;
                                 const int64_t zl = rs - 1 > from ? rs - 1 : from, zh = rs + rn < pb - 1 ? rs + rn : pb - 1;
-                                for (int64_t rp = zl; rp <= zh; ++rp)
-                                    if (base_masked(a.P, seq, rp, seq_len, lead, trail, ref[ts + (rp - pa)])) { emit(start, rp); start = rp + 1; }
+                                if (!FILL) { if (zh >= zl) seg_w += (uint32_t)(zh - zl + 1); }
+                                else {
+                                    for (int64_t rp = zl; rp <= zh; ++rp) {
+                                        const int64_t d0 = rp - lead, d1 = rp - rb;
+                                        if (!((d0 < 0 ? -d0 : d0) < dend || (d1 < 0 ? -d1 : d1) < dend)) continue;
+                                        const uint8_t rbase = ref[ts + (rp - pa)];
+                                        const int64_t wlo = rp - polya > 0 ? rp - polya : 0, whi = rp + polya + 1 < seq_len ? rp + polya + 1 : seq_len;
+                                        bool m = false;
+#pragma unroll
+                                        for (int q = 0; q < LCR_SLOT_RUNS; ++q) { /* runs overlap or touch only when the two scans met: test all */
+                                            const int64_t qs = (int64_t)(runs[q] >> 32), qn = (int64_t)((runs[q] >> 8) & 0xffffffu), qe = qs + qn;
+                                            if (qn == 0 || (uint8_t)(runs[q] & 0xffu) == rbase) continue;
+                                            const bool anchored = (rp - 1 >= qs && rp - 1 < qe) || (rp + 1 >= qs && rp + 1 < qe);
+                                            const int64_t ov = (qe < whi ? qe : whi) - (qs > wlo ? qs : wlo);
+                                            if (anchored && ov >= polya) m = true;
+                                        }
+                                        if (m) { emit(start, rp); start = rp + 1; }
+                                    }
+                                }
                                 if (zh + 1 > from) from = zh + 1;
                             }
                         }
@@ -452,6 +478,7 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
             }
             leave_tile();
             if (bad) { atomicMin(&a.rstate[reg].status, (int32_t)LCR_ERR_BAD_CIGAR); n_bases = 0; }
+            if (!FILL) a.slot_segs[slot] = seg_w;
         }
     }
     if (FILL) {
@@ -475,9 +502,8 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
  * 32 counters.  Counters are unpacked once per tile (once per 255 rows on deep tiles).
  * ------------------------------------------------------------------------- */
 #define PT_THREADS 256
-#define PT_SEGS 512
 #define PT_WORDS (LCR_TILE / 4)
-#define PT_TAB ((PT_SEGS * (LCR_TILE / 16 + 1)) / 8 + 8) /* one entry per 8 blocks */
+#define PT_TAB(SEGS) (((SEGS) * (LCR_TILE / 16 + 1)) / 8 + 8) /* one entry per 8 blocks */
 
 struct PreCand { /* a site that passed every count-based filter; its likelihood is computed by k_site_ll */
     uint32_t tile, col;
@@ -488,7 +514,7 @@ struct __align__(16) LcrTileDesc { /* 48 B, one per tile (k_tile_desc) */
     const uint8_t *ref;     /* reference base of column 0 */
     uint64_t pos_g;         /* index of column 0 in the debug planes */
     uint32_t it0, n_items;  /* items of the tile */
-    uint32_t seg_lo, n_segs;
+    uint32_t seg_lo, n_segs; /* unused */
     uint32_t reg, npos;
     uint32_t full_n;        /* introns covering the whole tile */
     int32_t status;         /* of the region */
@@ -497,7 +523,7 @@ struct __align__(16) LcrTileDesc { /* 48 B, one per tile (k_tile_desc) */
 struct DescArgs {
     uint32_t n_tiles;
     const lcr_region *regions;
-    const uint32_t *tile_base, *tile_region, *tile_off, *tile_seg_off, *tile_full_n;
+    const uint32_t *tile_base, *tile_region, *tile_off, *tile_full_n;
     const uint64_t *pos_off;
     const uint8_t *const *ref_table;
     const LcrRegionState *rstate;
@@ -517,7 +543,7 @@ __global__ void k_tile_desc(DescArgs a) {
     d.ref = d.status == 0 ? a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start : nullptr;
     d.pos_g = a.pos_off[reg] + (uint64_t)tile_start;
     d.it0 = a.tile_off[tile]; d.n_items = a.tile_off[tile + 1] - d.it0;
-    d.seg_lo = a.tile_seg_off[tile]; d.n_segs = a.tile_seg_off[tile + 1] - d.seg_lo;
+    d.seg_lo = 0; d.n_segs = 0;
     d.reg = reg; d.npos = (uint32_t)(tile_end - tile_start);
     d.full_n = a.tile_full_n[tile];
     a.desc[tile] = d;
@@ -574,6 +600,7 @@ struct PileArgs {
     const uint32_t *tile_off;
     const LcrItem *items;
     const LcrTileDesc *desc;
+    const uint2 *item_segs;
     const LcrSeg *segs;
     const LcrDeviceTables *tables;
     LcrRegionState *rstate;
@@ -595,20 +622,22 @@ struct PtBlock { /* one 16-byte block of a segment, loads in flight */
     uint32_t W0, rel, span, e;
 };
 
-template <int ROWS>
+template <int ROWS, int SEGS>
 constexpr size_t pt_smem_bytes(bool deep) {
-    return sizeof(uint32_t) * (2 * ROWS * PT_WORDS + PT_SEGS * 4 + PT_SEGS + 4 + (PT_TAB + 1) / 2 + (deep ? 16 * LCR_TILE : 0));
+    return sizeof(uint32_t) * (2 * ROWS * PT_WORDS + SEGS * 4 + SEGS + 4 + (PT_TAB(SEGS) + 1) / 2 + (deep ? 16 * LCR_TILE : 0));
 }
 
-template <bool DEEP, int ROWS, int MINB>
+template <bool DEEP, int ROWS, int MINB, int SEGS>
 __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
+    constexpr int PT_SEGS = SEGS;
+    static_assert(SEGS % PT_THREADS == 0, "whole segments per thread in the stage");
     static_assert(ROWS % 16 == 0 && ROWS >= 16, "the column sums read whole blocks of 16 rows");
     extern __shared__ __align__(16) uint32_t pt_smem[];
     uint32_t *planes = pt_smem;                                           /* [2][ROWS][PT_WORDS] */
     uint4 *s_seg = reinterpret_cast<uint4 *>(pt_smem + 2 * ROWS * PT_WORDS); /* [PT_SEGS] staged segments */
     uint32_t *s_choff = pt_smem + 2 * ROWS * PT_WORDS + PT_SEGS * 4;      /* [PT_SEGS + 1] first block of every staged segment */
     uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_choff + PT_SEGS + 4); /* [PT_TAB] segment of every 8th block */
-    uint32_t *s_out32 = s_choff + PT_SEGS + 4 + (PT_TAB + 1) / 2;         /* DEEP: [16][LCR_TILE] */
+    uint32_t *s_out32 = s_choff + PT_SEGS + 4 + (PT_TAB(SEGS) + 1) / 2;   /* DEEP: [16][LCR_TILE] */
     __shared__ uint32_t s_wsum[PT_THREADS / 32];
 
     const uint32_t tile = blockIdx.x;
@@ -630,8 +659,9 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
     const uint32_t minq4 = (minq > 30u ? 0u : minq) * 0x01010101u;
     const uint32_t pass_allow = minq > 30u ? 0u : 0xffffffffu;
     const uint8_t *seqp = a.seq, *qualp = a.qual;
-    const uint32_t seg_lo = D.seg_lo, seg_hi = D.seg_lo + D.n_segs;
-    const bool one_batch = n_items <= ROWS;
+    static_assert(ROWS <= 64, "the item scan below handles two items per lane of one warp");
+    __shared__ uint32_t s_ioff[65]; /* first staged-segment index of every item of the batch, and the total */
+    __shared__ uint32_t s_ibeg[64]; /* first segment of every item of the batch */
 
     /* carry-save state of this thread's column word: plane (tid / PT_WORDS), word (tid % PT_WORDS) */
     uint32_t ones = 0, twos = 0, fours = 0, eights = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
@@ -649,7 +679,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
         for (int l = 0; l < 8; ++l) {
             if ((acc_rows >> l) != 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cnt8[i] += ((lv[l] >> i) & 0x01010101u) << l;
+                for (int i = 0; i < 8; ++i) cnt8[i] |= (i >= l ? lv[l] >> (i - l) : lv[l] << (l - i)) & (0x01010101u << l); /* bit l of 4 counters */
             }
         }
         ones = twos = fours = eights = s4 = s5 = s6 = s7 = 0;
@@ -666,6 +696,12 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
         }
         if (row_base) __syncthreads(); /* the previous batch's column sums are done with the planes */
+        /* the batch's items and where their segments start in the concatenated list (loads issued before the zero fill) */
+        uint2 e0 = make_uint2(0, 0), e1 = make_uint2(0, 0);
+        if (warp == 0) {
+            if (lane < nrow) e0 = a.item_segs[D.it0 + row_base + lane];
+            if (lane + 32 < nrow) e1 = a.item_segs[D.it0 + row_base + lane + 32];
+        }
         {
             const uint4 z = make_uint4(0, 0, 0, 0);
             uint4 *p4 = reinterpret_cast<uint4 *>(planes);
@@ -675,9 +711,23 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 p4[ROWS * (PT_WORDS / 4) + i] = z;
             }
         }
-        for (uint32_t sb = seg_lo; sb < seg_hi; sb += PT_SEGS) {
-            const uint32_t ns = (seg_hi - sb) < PT_SEGS ? (seg_hi - sb) : PT_SEGS;
-            if (sb != seg_lo) __syncthreads(); /* previous stage consumed */
+        if (warp == 0) {
+            uint32_t i0 = e0.y, i1 = e1.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v0 = __shfl_up_sync(0xffffffffu, i0, o), v1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if ((int)lane >= o) { i0 += v0; i1 += v1; }
+            }
+            const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+            s_ioff[lane] = i0 - e0.y; s_ibeg[lane] = e0.x;
+            s_ioff[lane + 32] = t0 + i1 - e1.y; s_ibeg[lane + 32] = e1.x;
+            if (lane == 0) s_ioff[64] = t0 + t1;
+        }
+        __syncthreads(); /* also: the previous batch's stage is consumed */
+        const uint32_t n_seg_batch = s_ioff[64];
+        for (uint32_t sb = 0; sb < n_seg_batch; sb += PT_SEGS) {
+            const uint32_t ns = (n_seg_batch - sb) < PT_SEGS ? (n_seg_batch - sb) : PT_SEGS;
+            if (sb) __syncthreads(); /* previous stage consumed */
             /* stage the segments of this batch's rows and scan their block counts */
             uint32_t nch[PT_SEGS / PT_THREADS], mysum = 0;
 #pragma unroll
@@ -685,18 +735,20 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 const uint32_t i = tid * (PT_SEGS / PT_THREADS) + qd;
                 uint32_t n = 0;
                 if (i < ns) {
-                    uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + sb + i));
-                    const uint32_t rrow = (raw.z >> 8) - row_base;
-                    if (one_batch || rrow < nrow) {
-                        const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
-                        const uint32_t wlo = (col + 3u) >> 2, whi = (col + len) >> 2; /* whole column words [wlo, whi) */
-                        if (whi > wlo) {
-                            const uint32_t nw = whi - wlo;
-                            if ((raw.z & 3u) == SEG_M) n = ((((raw.x + 4u * wlo - col) & 15u) + 4u * nw - 4u) >> 4) + 1u;
-                            else n = (((wlo & 3u) + nw - 1u) >> 2) + 1u;
-                        }
-                        raw.z = (raw.z & 0xffu) | (rrow << 8);
-                    } else raw.w = 0; /* another batch's row: nothing to do here */
+                    const uint32_t idx = sb + i;
+                    uint32_t j = 0; /* the item of staged segment idx: last j with s_ioff[j] <= idx */
+#pragma unroll
+                    for (uint32_t step = 32; step; step >>= 1)
+                        if (j + step < nrow && s_ioff[j + step] <= idx) j += step;
+                    uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + s_ibeg[j] + (idx - s_ioff[j])));
+                    const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
+                    const uint32_t wlo = (col + 3u) >> 2, whi = (col + len) >> 2; /* whole column words [wlo, whi) */
+                    if (whi > wlo) {
+                        const uint32_t nw = whi - wlo;
+                        if ((raw.z & 3u) == SEG_M) n = ((((raw.x + 4u * wlo - col) & 15u) + 4u * nw - 4u) >> 4) + 1u;
+                        else n = (((wlo & 3u) + nw - 1u) >> 2) + 1u;
+                    }
+                    raw.z = (raw.z & 0xffu) | (j << 8);
                     s_seg[i] = raw;
                 }
                 nch[qd] = n;
@@ -1067,18 +1119,21 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
 int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flags) {
     cudaStream_t st = ctx->stream;
     const uint32_t n_tiles = db->n_tiles;
-    /* per-tile counters: [0] items, [1] whole-tile intron covers, [2] segments; their scans: [0] items, [1] segments */
-    uint32_t *tile_cnt = nullptr, *tile_scan = nullptr;
+    /* per-tile counters: [0] items, [1] whole-tile intron covers (+ the deep-tile flag); per-slot segment bounds; their scans */
+    uint32_t *tile_cnt = nullptr, *tile_off = nullptr, *slot_segs = nullptr, *slot_seg_off = nullptr;
     uint64_t *slot_runs = nullptr;
     LcrItem *items = nullptr;
+    uint2 *item_segs = nullptr;
     LcrSeg *segs = nullptr;
-    const size_t tn = (size_t)n_tiles + 1;
-    TRY(cudaMallocAsync(&tile_cnt, sizeof(uint32_t) * (3 * tn + 1), st));
-    TRY(cudaMallocAsync(&tile_scan, sizeof(uint32_t) * 2 * tn, st));
+    const size_t tn = (size_t)n_tiles + 1, sn = (size_t)db->n_slots + 1;
+    TRY(cudaMallocAsync(&tile_cnt, sizeof(uint32_t) * (2 * tn + 1), st));
+    TRY(cudaMallocAsync(&tile_off, sizeof(uint32_t) * tn, st));
+    TRY(cudaMallocAsync(&slot_segs, sizeof(uint32_t) * sn, st));
+    TRY(cudaMallocAsync(&slot_seg_off, sizeof(uint32_t) * sn, st));
     TRY(cudaMallocAsync(&slot_runs, sizeof(uint64_t) * LCR_SLOT_RUNS * (size_t)(db->n_slots ? db->n_slots : 1), st));
-    TRY(cudaMemsetAsync(tile_cnt, 0, sizeof(uint32_t) * (3 * tn + 1), st));
-    uint32_t *tile_count = tile_cnt, *tile_full_n = tile_cnt + tn, *tile_segs = tile_cnt + 2 * tn;
-    uint32_t *tile_off = tile_scan, *tile_seg_off = tile_scan + tn;
+    TRY(cudaMemsetAsync(tile_cnt, 0, sizeof(uint32_t) * (2 * tn + 1), st));
+    TRY(cudaMemsetAsync(slot_segs, 0, sizeof(uint32_t) * sn, st));
+    uint32_t *tile_count = tile_cnt, *tile_full_n = tile_cnt + tn, *deep_flag = tile_cnt + 2 * tn;
 
     PrepArgs pa{};
     pa.P = ctx->P;
@@ -1090,33 +1145,36 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     pa.ref_table = ctx->d_ref_table;
     pa.rstate = db->rstate; pa.stats = db->d_stats;
     pa.slot_flags = slot_flags; pa.slot_runs = slot_runs;
-    pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n;
-    pa.tile_segs = tile_segs; pa.tile_seg_off = tile_seg_off; pa.deep_flag = tile_cnt + 3 * tn;
-    pa.items = nullptr; pa.segs = nullptr;
+    pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n; pa.deep_flag = deep_flag;
+    pa.slot_segs = slot_segs; pa.slot_seg_off = slot_seg_off;
+    pa.items = nullptr; pa.item_segs = nullptr; pa.segs = nullptr;
     const uint32_t pb = 128, pg = (db->n_slots + pb - 1) / pb;
     if (pg) {
         k_slot_prep<false><<<pg, pb, 0, st>>>(pa);
         k_count_pass<<<pg, pb, 0, st>>>(slot_flags, db->n_slots, db->d_stats);
         db->timing.kernel_launches += 2;
     }
-    /* exclusive scans of the per-tile item and segment counts */
-    size_t tmp_bytes = 0;
+    /* exclusive scans of the per-tile item counts and the per-read segment bounds */
+    size_t tmp_bytes = 0, tmp_bytes2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tile_count, tile_off, n_tiles + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes2, slot_segs, slot_seg_off, db->n_slots + 1, st);
+    if (tmp_bytes2 > tmp_bytes) tmp_bytes = tmp_bytes2;
     void *tmp = nullptr;
     TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_count, tile_off, n_tiles + 1, st));
-    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_segs, tile_seg_off, n_tiles + 1, st));
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, slot_segs, slot_seg_off, db->n_slots + 1, st));
     uint32_t totals[3] = {0, 0, 0};
     TRY(cudaMemcpyAsync(&totals[0], tile_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(&totals[1], tile_seg_off + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(&totals[2], tile_cnt + 3 * tn, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&totals[1], slot_seg_off + db->n_slots, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(&totals[2], deep_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     const uint32_t n_items = totals[0], n_segs = totals[1];
     TRY(cudaMallocAsync(&items, sizeof(LcrItem) * (size_t)(n_items ? n_items : 1), st));
+    TRY(cudaMallocAsync(&item_segs, sizeof(uint2) * (size_t)(n_items ? n_items : 1), st));
     TRY(cudaMallocAsync(&segs, sizeof(LcrSeg) * (size_t)(n_segs ? n_segs : 1), st));
     TRY(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * tn, st));
-    TRY(cudaMemsetAsync(tile_segs, 0, sizeof(uint32_t) * tn, st));
-    pa.items = items; pa.segs = segs;
+    TRY(cudaMemsetAsync(item_segs, 0, sizeof(uint2) * (size_t)(n_items ? n_items : 1), st));
+    pa.items = items; pa.item_segs = item_segs; pa.segs = segs;
     if (pg) {
         k_slot_prep<true><<<pg, pb, 0, st>>>(pa);
         db->timing.kernel_launches += 1;
@@ -1138,17 +1196,18 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     if (n_tiles) {
         DescArgs da{};
         da.n_tiles = n_tiles; da.regions = db->regions;
-        da.tile_base = db->tile_base; da.tile_region = db->tile_region; da.tile_off = tile_off; da.tile_seg_off = tile_seg_off; da.tile_full_n = tile_full_n;
+        da.tile_base = db->tile_base; da.tile_region = db->tile_region; da.tile_off = tile_off; da.tile_full_n = tile_full_n;
         da.pos_off = db->pos_off; da.ref_table = ctx->d_ref_table; da.rstate = db->rstate; da.desc = desc;
         k_tile_desc<<<(n_tiles + 255) / 256, 256, 0, st>>>(da);
         db->timing.kernel_launches += 1;
     }
     /* launch shape of the tile kernel: rows staged per batch / resident CTAs per SM (LCR_TILE_VARIANT: experiments) */
     static const int variant = [] { const char *e = getenv("LCR_TILE_VARIANT"); return e && *e ? atoi(e) : 0; }();
-    void (*k_tile)(PileArgs) = variant == 1 ? k_pileup_tile<false, 32, 4> : k_pileup_tile<false, 48, 3>;
-    void (*k_tile_deep)(PileArgs) = variant == 1 ? k_pileup_tile<true, 32, 4> : k_pileup_tile<true, 48, 3>;
-    const size_t tile_smem = variant == 1 ? pt_smem_bytes<32>(false) : pt_smem_bytes<48>(false);
-    const size_t tile_smem_deep = variant == 1 ? pt_smem_bytes<32>(true) : pt_smem_bytes<48>(true);
+    /* default: 48 rows, 4 CTAs / SM (64 registers, 56 KB), 256 staged segments; 1: 32 rows; 2: 48 rows, 3 CTAs / SM, 512 segments */
+    void (*k_tile)(PileArgs) = variant == 1 ? k_pileup_tile<false, 32, 4, 512> : variant == 2 ? k_pileup_tile<false, 48, 3, 512> : k_pileup_tile<false, 48, 4, 256>;
+    void (*k_tile_deep)(PileArgs) = variant == 1 ? k_pileup_tile<true, 32, 4, 512> : variant == 2 ? k_pileup_tile<true, 48, 3, 512> : k_pileup_tile<true, 48, 4, 256>;
+    const size_t tile_smem = variant == 1 ? pt_smem_bytes<32, 512>(false) : variant == 2 ? pt_smem_bytes<48, 512>(false) : pt_smem_bytes<48, 256>(false);
+    const size_t tile_smem_deep = variant == 1 ? pt_smem_bytes<32, 512>(true) : variant == 2 ? pt_smem_bytes<48, 512>(true) : pt_smem_bytes<48, 256>(true);
     TRY(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
     TRY(cudaFuncSetAttribute(k_tile_deep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_deep));
     PileArgs ka{};
@@ -1159,7 +1218,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
     ka.ref_table = ctx->d_ref_table;
     ka.tile_off = tile_off; ka.items = items;
-    ka.desc = desc; ka.segs = segs;
+    ka.desc = desc; ka.item_segs = item_segs; ka.segs = segs;
     ka.tables = ctx->d_tables;
     ka.rstate = db->rstate;
     ka.stats = db->d_stats;
@@ -1249,7 +1308,10 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaFreeAsync(slot_runs, st));
     TRY(cudaFreeAsync(tmp, st));
     TRY(cudaFreeAsync(tile_cnt, st));
-    TRY(cudaFreeAsync(tile_scan, st));
+    TRY(cudaFreeAsync(tile_off, st));
+    TRY(cudaFreeAsync(slot_segs, st));
+    TRY(cudaFreeAsync(slot_seg_off, st));
+    TRY(cudaFreeAsync(item_segs, st));
     TRY(cudaGetLastError());
     return LCR_OK;
 }
