@@ -296,7 +296,10 @@ def main():
                          "alg_bytes_per_launch": int(pile_bytes / max(args.steps, 1)), "ms_per_launch": pile_ms / max(args.steps, 1)},
             "stage_ms_per_step": {"pileup_kernel": pile_ms / args.steps, "fragments": frag_ms / args.steps, "phase": phase_ms / args.steps, "total": dev_ms / args.steps},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and len(regions) < 4:
+            # a single deep region cannot be sub-sampled by regions and takes the CPU port minutes (cfg5): not timed by default
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"skipped: {args.workload} is {len(regions)} region(s); run --impl reference --workload {args.workload} --steps 1 --warmup 0 for the CPU figure"}
+        elif not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_binding as ob
 

@@ -256,15 +256,23 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     {
         /* bins: launch shape (by number of configurations) x fragment-count class (shared memory footprint) */
         const uint32_t NF_SMALL = 1024, NF_BIG = 16384;
-        const int NBIN = 8;
+        const int NBIN = 10;
         std::vector<uint32_t> base(n_regions + 1, 0), wr[NBIN], wc[NBIN];
-        uint32_t nfmax[NBIN] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t nfmax[NBIN] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        /* regions with 5+ sites: 64 configurations per CTA when that still fills the GPU, else 16 (more, shorter CTAs) */
+        uint64_t big_cfgs = 0;
+        for (uint32_t r = 0; r < n_regions; ++r) {
+            const LcrRegionState &s = hrs[r];
+            if (s.status == 0 && s.n_cand > 4 && s.n_cand <= ctx->P.max_enum_snps && s.n_cand <= 10 && s.n_frag <= NF_BIG) big_cfgs += 1ull << s.n_cand;
+        }
+        const bool small_batch = big_cfgs / 64 < 8ull * (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
         std::vector<int> bin(n_regions, -1);
         for (uint32_t r = 0; r < n_regions; ++r) {
             const LcrRegionState &s = hrs[r];
             uint32_t chunks = 0;
             if (s.status == 0 && s.n_cand && s.n_cand <= ctx->P.max_enum_snps && s.n_cand <= 10 && s.n_frag <= NF_BIG) {
-                const int shape = lcr_enum_shape_for(s.n_cand);
+                int shape = lcr_enum_shape_for(s.n_cand);
+                if (shape == 3 && small_batch) shape = 4;
                 const uint32_t per_cta = lcr_enum_cfgs_per_cta(shape);
                 chunks = ((1u << s.n_cand) + per_cta - 1) / per_cta;
                 bin[r] = shape * 2 + (s.n_frag <= NF_SMALL ? 0 : 1);

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint
 } // namespace
 
 /* launch shapes by number of configurations: {warps per CTA, configurations per warp} */
-static const int SHAPES[4][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}};
+static const int SHAPES[5][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}, {8, 2}}; /* the last: 5+ sites when the batch is too small to fill the GPU with 64 configurations per CTA */
 
 int lcr_enum_shape_for(uint32_t n_cand) { return n_cand <= 2 ? 0 : (n_cand == 3 ? 1 : (n_cand == 4 ? 2 : 3)); }
 uint32_t lcr_enum_cfgs_per_cta(int shape) { return (uint32_t)(SHAPES[shape][0] * SHAPES[shape][1]); }
@@ -277,6 +277,7 @@ int lcr_launch_enum_search(int shape, const PhaseArgs &a, uint32_t n_work, const
         case 0: return launch_shape<1, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
         case 1: return launch_shape<2, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
         case 2: return launch_shape<4, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        default: return launch_shape<8, 8>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 3: return launch_shape<8, 8>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        default: return launch_shape<8, 2>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
     }
 }

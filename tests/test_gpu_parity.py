@@ -184,3 +184,14 @@ def test_chunked_submit_matches_single_pass(monkeypatch):
     helpers.compare_results(parts, whole, "chunked vs whole")
     want = ob.run(p, batch, refs, mode=0)
     helpers.compare_results(parts, want, "chunked vs oracle")
+
+
+@pytest.mark.parametrize("preset,platform", [("hifi-masseq", 0), ("ont-drna", 1)])
+def test_deep_tiles(preset, platform):
+    """Tiles holding more than 255 reads take the tile kernel's variant with 32-bit column counters and several row batches."""
+    syn = host.Synthetic(seed=31 + platform, contig_len=12_000, n_contigs=1, platform=platform, depth=400.0, n_het=24, n_edit=4, max_intron=300, both_strands=0, single_region=1, n_threads=4)
+    p = host.params_preset(preset, seed=5, flags=abi.LCR_FLAG_EMIT_PLANES | abi.LCR_FLAG_SKIP_PHASING)
+    regions, _ = host.find_regions(syn.reads, p)
+    got, want = run_both(p, syn.reads, syn.reference.for_reads(syn.reads), regions)
+    assert got.planes["acgt"].sum(axis=1).max() > 255
+    helpers.compare_results(got, want, preset + "/deep")
