@@ -393,9 +393,17 @@ __global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
                         if (t > last_tile) {
                             leave_tile();
                             last_tile = t;
-                            if (!FILL) { if (atomicAdd(&a.tile_count[tb + t], 1u) == 255u) *a.deep_flag = 1u; }
+                            /* reads are position-sorted, so the lanes of a warp enter the same few tiles: one atomic per tile and warp */
+                            const uint32_t key = tb + (uint32_t)t;
+                            const unsigned peers = __match_any_sync(__activemask(), key);
+                            const int leader = __ffs(peers) - 1;
+                            const uint32_t npeer = (uint32_t)__popc(peers), prank = (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+                            uint32_t first = 0;
+                            if ((int)(threadIdx.x & 31) == leader) first = atomicAdd(&a.tile_count[key], npeer);
+                            first = __shfl_sync(peers, first, leader);
+                            if (!FILL) { if (first <= 255u && first + npeer > 255u) *a.deep_flag = 1u; }
                             else {
-                                item_k = a.tile_off[tb + t] + atomicAdd(&a.tile_count[tb + t], 1u);
+                                item_k = a.tile_off[key] + first + prank;
                                 LcrItem it;
                                 it.slot = slot;
                                 it.cig = (uint32_t)(c - c0);
@@ -1051,8 +1059,8 @@ __global__ void k_iota(uint32_t *p, uint32_t n) {
     if (i < n) p[i] = i;
 }
 
-/* per region: candidate range in the sorted array + the dense-cluster filters (candidate.rs:465-526) */
-__global__ void k_cand_finalize(lcr_params P, uint32_t n_regions, const uint64_t *keys, uint32_t n_cand, lcr_candidate *cand, LcrRegionState *rstate) {
+/* per region: candidate range in the sorted array */
+__global__ void k_cand_ranges(uint32_t n_regions, const uint64_t *keys, uint32_t n_cand, LcrRegionState *rstate) {
     const uint32_t reg = blockIdx.x * blockDim.x + threadIdx.x;
     if (reg >= n_regions) return;
     uint32_t lo = 0, hi = n_cand;
@@ -1066,37 +1074,43 @@ __global__ void k_cand_finalize(lcr_params P, uint32_t n_regions, const uint64_t
     if (rstate[reg].status != 0) e = b; /* a failed region reports no candidates */
     rstate[reg].cand_begin = b;
     rstate[reg].n_cand = e - b;
-    lcr_candidate *c = cand + b;
-    const uint32_t n = e - b;
+}
+
+/* the dense-cluster filters (candidate.rs:465-526), one thread per window start i.  The windows of different starts only
+   set the same two flag bits and never read them, so they are independent of each other and of the order of the two passes. */
+__global__ void k_cand_dense(lcr_params P, const uint64_t *keys, uint32_t n_cand, lcr_candidate *cand, const LcrRegionState *rstate) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_cand) return;
+    const uint32_t reg = (uint32_t)(keys[gi] >> 32);
+    const LcrRegionState rs = rstate[reg];
+    if (gi < rs.cand_begin || gi >= rs.cand_begin + rs.n_cand) return;
+    lcr_candidate *c = cand + rs.cand_begin;
+    const uint32_t n = rs.n_cand, i = gi - rs.cand_begin;
     /* concat_idxes = homo_snps + het_snps, sorted: the candidates carrying HOM_VAR or HET_VAR */
+    if (!(c[i].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR))) return;
+    const int64_t start_pos = c[i].pos;
     for (int pass = 0; pass < 2; ++pass) {
         const int64_t win = pass == 0 ? (int64_t)P.dense_win_size : 5;
         const uint32_t min_cnt = pass == 0 ? P.min_dense_cnt : 3u;
-        for (uint32_t i = 0; i < n; ++i) {
-            if (!(c[i].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR))) continue;
-            const int64_t start_pos = c[i].pos;
-            uint32_t cnt_between = 0; /* j - i in concat_idxes terms */
-            uint32_t last_member = i;
-            bool broke = false;
-            for (uint32_t j = i; j < n; ++j) {
-                if (!(c[j].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR))) continue;
-                const int64_t diff = c[j].pos - start_pos;
-                const bool over = pass == 0 ? diff > win : diff >= win;
-                if (over) {
-                    if (cnt_between >= min_cnt)
-                        for (uint32_t tk = i; tk < j; ++tk)
-                            if (c[tk].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR)) c[tk].flags = (uint16_t)((c[tk].flags | LCR_CF_DENSE) & ~LCR_CF_FOR_PHASING);
-                    broke = true;
-                    break;
-                }
-                last_member = j;
-                cnt_between++;
+        uint32_t cnt_between = 0; /* j - i in concat_idxes terms */
+        uint32_t last_member = i, mark_end = i;
+        bool broke = false;
+        for (uint32_t j = i; j < n; ++j) {
+            if (!(c[j].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR))) continue;
+            const int64_t diff = c[j].pos - start_pos;
+            const bool over = pass == 0 ? diff > win : diff >= win;
+            if (over) {
+                if (cnt_between >= min_cnt) mark_end = j;
+                broke = true;
+                break;
             }
-            /* reached the last element inside the window: (j - i + 1) >= min_cnt marks i..j exclusive */
-            if (!broke && cnt_between >= min_cnt)
-                for (uint32_t tk = i; tk < last_member; ++tk)
-                    if (c[tk].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR)) c[tk].flags = (uint16_t)((c[tk].flags | LCR_CF_DENSE) & ~LCR_CF_FOR_PHASING);
+            last_member = j;
+            cnt_between++;
         }
+        /* reached the last element inside the window: (j - i + 1) >= min_cnt marks i..j exclusive */
+        if (!broke && cnt_between >= min_cnt) mark_end = last_member;
+        for (uint32_t tk = i; tk < mark_end; ++tk)
+            if (c[tk].flags & (LCR_CF_HOM_VAR | LCR_CF_HET_VAR)) c[tk].flags = (uint16_t)((c[tk].flags | LCR_CF_DENSE) & ~LCR_CF_FOR_PHASING);
     }
 }
 
@@ -1295,8 +1309,12 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
         TRY(cudaFreeAsync(perm_out, st));
     }
     if (db->n_regions) {
-        k_cand_finalize<<<(db->n_regions + 63) / 64, 64, 0, st>>>(ctx->P, db->n_regions, keys_sorted, n_cand, db->cand, db->rstate);
+        k_cand_ranges<<<(db->n_regions + 63) / 64, 64, 0, st>>>(db->n_regions, keys_sorted, n_cand, db->rstate);
         db->timing.kernel_launches += 1;
+        if (n_cand) {
+            k_cand_dense<<<(n_cand + 63) / 64, 64, 0, st>>>(ctx->P, keys_sorted, n_cand, db->cand, db->rstate);
+            db->timing.kernel_launches += 1;
+        }
     }
     TRY(cudaFreeAsync(keys_sorted, st));
     TRY(cudaFreeAsync(cand_raw, st));
