@@ -626,9 +626,25 @@ struct PileArgs {
 struct PtBlock { /* one 16-byte block of a segment, loads in flight */
     uint4 sv, qv;
     uint32_t s4w, q4w;
-    uint32_t z;        /* row_typ of the segment, row already relative to the batch */
-    uint32_t W0, rel, span, e;
+    uint32_t z;        /* row_typ of the segment (type, strand, transcript strand) */
+    uint32_t saddr;    /* shared-space byte address of the first column word of the block in plane X */
+    uint32_t rel, span, e;
 };
+
+/* 32-bit shared-space stores with an immediate offset (the generic-pointer form makes ptxas rebuild the shared window
+   base for every store when registers are tight) */
+template <int OFF>
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(saddr), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts8_if(uint32_t saddr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.shared.u8 [%0+%2], %1;\n\t}" ::"r"(saddr), "r"(v), "n"(OFF), "r"((uint32_t)p) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts32_if(uint32_t saddr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.shared.b32 [%0+%2], %1;\n\t}" ::"r"(saddr), "r"(v), "n"(OFF), "r"((uint32_t)p) : "memory");
+}
 
 template <int ROWS, int SEGS>
 constexpr size_t pt_smem_bytes(bool deep) {
@@ -790,6 +806,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
             }
             __syncthreads();
             /* whole column words: one lane per 16-byte block of a segment, loads issued one block ahead */
+            const uint32_t planes_s = (uint32_t)__cvta_generic_to_shared(planes);
             auto fetch = [&](uint32_t g, PtBlock &b) {
                 uint32_t k = s_tab[g >> 3];
                 while (s_choff[k + 1] <= g) ++k;
@@ -797,6 +814,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 const uint4 raw = s_seg[k];
                 const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
                 const uint32_t wlo = (col + 3u) >> 2, whi = (col + len) >> 2;
+                uint32_t W0; /* first column word of this block */
                 b.z = raw.z;
                 b.span = whi - wlo;
                 if ((raw.z & 3u) == SEG_M) {
@@ -804,48 +822,60 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                     const uint32_t al = (uint32_t)spos & 15u;
                     const uint64_t blk = (spos & ~(uint64_t)15) + 16ull * c;
                     b.e = al & 3u;
-                    b.W0 = wlo + 4u * c - (al >> 2);
+                    W0 = wlo + 4u * c - (al >> 2);
                     b.sv = __ldg(reinterpret_cast<const uint4 *>(seqp + blk));
                     b.qv = __ldg(reinterpret_cast<const uint4 *>(qualp + blk));
                     b.s4w = __ldg(reinterpret_cast<const uint32_t *>(seqp + blk + 16));
                     b.q4w = __ldg(reinterpret_cast<const uint32_t *>(qualp + blk + 16));
                 } else {
                     b.e = 0;
-                    b.W0 = (wlo & ~3u) + 4u * c;
+                    W0 = (wlo & ~3u) + 4u * c;
                 }
-                b.rel = b.W0 - wlo; /* word W0 + t is whole iff rel + t < span (unsigned) */
+                b.rel = W0 - wlo; /* word W0 + t is whole iff rel + t < span (unsigned) */
+                b.saddr = planes_s + (((raw.z >> 8) * PT_WORDS + W0) << 2);
             };
-            PtBlock cur, nxt;
-            if (tid < total) fetch(tid, cur);
-            for (uint32_t g = tid; g < total; g += PT_THREADS) {
-                const bool more = g + PT_THREADS < total;
-                if (more) fetch(g + PT_THREADS, nxt);
-                {
-                    const uint32_t typ = cur.z & 3u;
-                    uint32_t *rx = planes + (cur.z >> 8) * PT_WORDS + cur.W0, *ry = rx + ROWS * PT_WORDS;
-                    uint32_t x[4], y[4];
-                    if (typ == SEG_M) {
-                        const uint32_t fmask = (cur.z & 4u) ? 0x0f0f0f0fu : 0u;
-                        const uint32_t tsb = ((cur.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
-                        const uint32_t rot = 0x3210u + 0x1111u * cur.e;
-                        onehot4(__byte_perm(cur.sv.x, cur.sv.y, rot), __byte_perm(cur.qv.x, cur.qv.y, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
-                        onehot4(__byte_perm(cur.sv.y, cur.sv.z, rot), __byte_perm(cur.qv.y, cur.qv.z, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
-                        onehot4(__byte_perm(cur.sv.z, cur.sv.w, rot), __byte_perm(cur.qv.z, cur.qv.w, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
-                        onehot4(__byte_perm(cur.sv.w, cur.s4w, rot), __byte_perm(cur.qv.w, cur.q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
-                    } else {
-                        const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
-                        x[0] = x[1] = x[2] = x[3] = 0;
-                        y[0] = y[1] = y[2] = y[3] = v;
-                    }
-#pragma unroll
-                    for (uint32_t t = 0; t < 4; ++t) {
-                        if (cur.rel + t < cur.span) {
-                            if (typ == SEG_M) rx[t] = x[t];
-                            ry[t] = y[t];
-                        }
-                    }
+            auto process = [&](const PtBlock &cur) {
+                constexpr int YOFF = ROWS * PT_WORDS * 4;
+                const uint32_t typ = cur.z & 3u;
+                uint32_t x[4], y[4];
+                if (typ == SEG_M) {
+                    const uint32_t fmask = (cur.z & 4u) ? 0x0f0f0f0fu : 0u;
+                    const uint32_t tsb = ((cur.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
+                    const uint32_t rot = 0x3210u + 0x1111u * cur.e;
+                    onehot4(__byte_perm(cur.sv.x, cur.sv.y, rot), __byte_perm(cur.qv.x, cur.qv.y, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
+                    onehot4(__byte_perm(cur.sv.y, cur.sv.z, rot), __byte_perm(cur.qv.y, cur.qv.z, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
+                    onehot4(__byte_perm(cur.sv.z, cur.sv.w, rot), __byte_perm(cur.qv.z, cur.qv.w, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
+                    onehot4(__byte_perm(cur.sv.w, cur.s4w, rot), __byte_perm(cur.qv.w, cur.q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                } else {
+                    const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
+                    x[0] = x[1] = x[2] = x[3] = 0;
+                    y[0] = y[1] = y[2] = y[3] = v;
                 }
-                if (more) cur = nxt;
+                const bool isM = typ == SEG_M;
+                if (cur.span >= 4u && cur.rel <= cur.span - 4u) { /* all four words whole */
+                    if (isM) { sts32<0>(cur.saddr, x[0]); sts32<4>(cur.saddr, x[1]); sts32<8>(cur.saddr, x[2]); sts32<12>(cur.saddr, x[3]); }
+                    sts32<YOFF>(cur.saddr, y[0]); sts32<YOFF + 4>(cur.saddr, y[1]); sts32<YOFF + 8>(cur.saddr, y[2]); sts32<YOFF + 12>(cur.saddr, y[3]);
+                } else {
+                    const bool p0 = cur.rel < cur.span, p1 = cur.rel + 1u < cur.span, p2 = cur.rel + 2u < cur.span, p3 = cur.rel + 3u < cur.span;
+                    sts32_if<0>(cur.saddr, x[0], p0 && isM); sts32_if<4>(cur.saddr, x[1], p1 && isM);
+                    sts32_if<8>(cur.saddr, x[2], p2 && isM); sts32_if<12>(cur.saddr, x[3], p3 && isM);
+                    sts32_if<YOFF>(cur.saddr, y[0], p0); sts32_if<YOFF + 4>(cur.saddr, y[1], p1);
+                    sts32_if<YOFF + 8>(cur.saddr, y[2], p2); sts32_if<YOFF + 12>(cur.saddr, y[3], p3);
+                }
+            };
+            { /* two blocks in flight per lane, alternating buffers */
+                PtBlock b0, b1;
+                uint32_t g = tid;
+                if (g < total) fetch(g, b0);
+                while (g < total) {
+                    if (g + PT_THREADS < total) fetch(g + PT_THREADS, b1);
+                    process(b0);
+                    g += PT_THREADS;
+                    if (g >= total) break;
+                    if (g + PT_THREADS < total) fetch(g + PT_THREADS, b0);
+                    process(b1);
+                    g += PT_THREADS;
+                }
             }
             /* the columns before and after the whole words: one lane per segment, 4-byte windows of the read */
             for (uint32_t i = tid; i < ns; i += PT_THREADS) {
@@ -853,10 +883,13 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 const uint32_t typ = raw.z & 3u, col = raw.w & 0xffffu, len = raw.w >> 16;
                 if (len == 0) continue;
                 const uint32_t end = col + len, wlo = (col + 3u) >> 2, whi = end >> 2;
-                uint8_t *bx = reinterpret_cast<uint8_t *>(planes + (raw.z >> 8) * PT_WORDS), *by = bx + ROWS * PT_WORDS * 4;
+                constexpr int YOFF = ROWS * PT_WORDS * 4;
+                const uint32_t row_s = planes_s + (raw.z >> 8) * (PT_WORDS * 4); /* shared-space address of the row in plane X */
                 const uint32_t h1 = (4u * wlo < end) ? 4u * wlo : end;            /* head columns [col, h1) */
                 const uint32_t t0 = (whi >= wlo) ? 4u * whi : end;                /* tail columns [t0, end) */
                 if (h1 == col && t0 == end) continue;
+                const uint32_t ha = row_s + col, ta = row_s + t0;
+                const bool h0p = col < h1, h1p = col + 1u < h1, h2p = col + 2u < h1, t0p = t0 < end, t1p = t0 + 1u < end, t2p = t0 + 2u < end;
                 if (typ == SEG_M) {
                     const uint64_t spos = ((uint64_t)raw.y << 32) | raw.x;
                     const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u, tsb = ((raw.z >> 3) & 3u) * 0x10101010u;
@@ -869,18 +902,14 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                     uint32_t xh, yh, xt, yt;
                     onehot4(__byte_perm(sh0, sh1, roth), __byte_perm(qh0, qh1, roth), minq4, pass_allow, fmask, tsb, xh, yh);
                     onehot4(__byte_perm(st0, st1, rott), __byte_perm(qt0, qt1, rott), minq4, pass_allow, fmask, tsb, xt, yt);
-#pragma unroll
-                    for (uint32_t j = 0; j < 3; ++j) {
-                        if (col + j < h1) { bx[col + j] = (uint8_t)(xh >> (8 * j)); by[col + j] = (uint8_t)(yh >> (8 * j)); }
-                        if (t0 + j < end) { bx[t0 + j] = (uint8_t)(xt >> (8 * j)); by[t0 + j] = (uint8_t)(yt >> (8 * j)); }
-                    }
+                    sts8_if<0>(ha, xh, h0p); sts8_if<1>(ha, xh >> 8, h1p); sts8_if<2>(ha, xh >> 16, h2p);
+                    sts8_if<YOFF>(ha, yh, h0p); sts8_if<YOFF + 1>(ha, yh >> 8, h1p); sts8_if<YOFF + 2>(ha, yh >> 16, h2p);
+                    sts8_if<0>(ta, xt, t0p); sts8_if<1>(ta, xt >> 8, t1p); sts8_if<2>(ta, xt >> 16, t2p);
+                    sts8_if<YOFF>(ta, yt, t0p); sts8_if<YOFF + 1>(ta, yt >> 8, t1p); sts8_if<YOFF + 2>(ta, yt >> 16, t2p);
                 } else {
-                    const uint8_t v = typ == SEG_D ? (uint8_t)0x40 : (uint8_t)0x80;
-#pragma unroll
-                    for (uint32_t j = 0; j < 3; ++j) {
-                        if (col + j < h1) by[col + j] = v;
-                        if (t0 + j < end) by[t0 + j] = v;
-                    }
+                    const uint32_t v = typ == SEG_D ? 0x40u : 0x80u;
+                    sts8_if<YOFF>(ha, v, h0p); sts8_if<YOFF + 1>(ha, v, h1p); sts8_if<YOFF + 2>(ha, v, h2p);
+                    sts8_if<YOFF>(ta, v, t0p); sts8_if<YOFF + 1>(ta, v, t1p); sts8_if<YOFF + 2>(ta, v, t2p);
                 }
             }
         }
