@@ -110,33 +110,55 @@ __global__ void k_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_of
 
 __global__ void k_frag_fill(FragArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= a.n_slots || !a.frag_flag[slot]) return;
-    const uint32_t reg = a.slot_region[slot];
-    const LcrRegionState rs = a.rstate[reg];
-    const uint32_t read = a.regions[reg].read_begin + (slot - a.slot_off[reg]);
-    const uint32_t f = a.frag_scan[slot];
-    const uint32_t e0 = a.elem_scan[slot];
-    a.frag_slot[f] = slot;
-    a.frag_elem_off[f] = e0;
-    if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
-    if (rs.status != 0 || !rs.n_cand) { a.frag_links[f] = 0; return; } /* a failed region reports no fragments */
-    a.is_fragment[read] = 1;
-    const lcr_candidate *c = a.cand + rs.cand_begin;
-    uint32_t k = 0, links = 0;
-    const uint32_t floc = f - rs.frag_begin;
-    walk_fragment(a, read, c, rs.n_cand, [&](uint32_t idx, uint8_t base, int8_t cell, const lcr_candidate &s) {
-        a.elem_snp[e0 + k] = idx;
-        a.elem_cell[e0 + k] = cell;
-        a.elem_base[e0 + k] = base;
-        ++k;
-        if (s.flags & LCR_CF_FOR_PHASING) links++;
-        const uint32_t g = rs.cand_begin + idx;
-        const uint32_t w = a.cover_off[g] + atomicAdd(&a.cover_cursor[g], 1u);
-        a.cover_frag[w] = floc;
-        a.cover_cell[w] = cell;
-    });
-    a.frag_links[f] = links;
-    if (links >= a.P.min_linkers && links) atomicAdd((unsigned long long *)&a.stats->nnz_phase, (unsigned long long)links);
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t e0 = 0, k = 0, cb = 0, floc = 0;
+    if (slot < a.n_slots && a.frag_flag[slot]) {
+        const uint32_t reg = a.slot_region[slot];
+        const LcrRegionState rs = a.rstate[reg];
+        const uint32_t read = a.regions[reg].read_begin + (slot - a.slot_off[reg]);
+        const uint32_t f = a.frag_scan[slot];
+        e0 = a.elem_scan[slot];
+        a.frag_slot[f] = slot;
+        a.frag_elem_off[f] = e0;
+        if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
+        if (rs.status != 0 || !rs.n_cand) a.frag_links[f] = 0; /* a failed region reports no fragments */
+        else {
+            a.is_fragment[read] = 1;
+            const lcr_candidate *c = a.cand + rs.cand_begin;
+            uint32_t links = 0;
+            cb = rs.cand_begin;
+            floc = f - rs.frag_begin;
+            walk_fragment(a, read, c, rs.n_cand, [&](uint32_t idx, uint8_t base, int8_t cell, const lcr_candidate &s) {
+                a.elem_snp[e0 + k] = idx;
+                a.elem_cell[e0 + k] = cell;
+                a.elem_base[e0 + k] = base;
+                ++k;
+                if (s.flags & LCR_CF_FOR_PHASING) links++;
+            });
+            a.frag_links[f] = links;
+            if (links >= a.P.min_linkers && links) atomicAdd((unsigned long long *)&a.stats->nnz_phase, (unsigned long long)links);
+        }
+    }
+    /* cover lists (CSC): the reads of a warp are neighbours and cover the same few candidates, so the warp merges its
+       element lists (each ascending by candidate) and takes one cursor atomic per candidate instead of one per element */
+    uint32_t next = 0;
+    for (;;) {
+        const uint32_t g = next < k ? cb + a.elem_snp[e0 + next] : 0xffffffffu;
+        const uint32_t gmin = __reduce_min_sync(0xffffffffu, g);
+        if (gmin == 0xffffffffu) break;
+        const bool mine = g == gmin;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        const int leader = __ffs(m) - 1;
+        uint32_t first = 0;
+        if ((int)lane == leader) first = atomicAdd(&a.cover_cursor[gmin], (uint32_t)__popc(m));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (mine) {
+            const uint32_t w = a.cover_off[gmin] + first + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            a.cover_frag[w] = floc;
+            a.cover_cell[w] = a.elem_cell[e0 + next];
+            ++next;
+        }
+    }
 }
 
 /* fragment.rs:207-240 restricted to the pairs candidate.rs:628-692 evaluates: cis / trans counts per SNP pair */

@@ -251,7 +251,7 @@ struct PrepArgs {
    poly-A / homopolymer mask (util.rs:737-789) are applied here by cutting M runs at masked bases.  Two passes
    around an exclusive scan: COUNT sizes the per-tile lists, FILL writes them. */
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_slot_prep(PrepArgs a) {
+__global__ void __launch_bounds__(128, 6) k_slot_prep(PrepArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n_bases = 0;
     bool live = slot < a.n_slots;
