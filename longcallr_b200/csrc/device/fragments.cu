@@ -111,7 +111,7 @@ __global__ void k_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_of
 __global__ void k_frag_fill(FragArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t e0 = 0, k = 0, cb = 0, floc = 0;
+    uint32_t e0 = 0, k = 0, cb = 0, floc = 0, nnz = 0;
     if (slot < a.n_slots && a.frag_flag[slot]) {
         const uint32_t reg = a.slot_region[slot];
         const LcrRegionState rs = a.rstate[reg];
@@ -136,9 +136,11 @@ __global__ void k_frag_fill(FragArgs a) {
                 if (s.flags & LCR_CF_FOR_PHASING) links++;
             });
             a.frag_links[f] = links;
-            if (links >= a.P.min_linkers && links) atomicAdd((unsigned long long *)&a.stats->nnz_phase, (unsigned long long)links);
+            if (links >= a.P.min_linkers) nnz = links;
         }
     }
+    nnz = __reduce_add_sync(0xffffffffu, nnz); /* one atomic per warp on the shared counter, not one per fragment */
+    if (lane == 0 && nnz) atomicAdd((unsigned long long *)&a.stats->nnz_phase, (unsigned long long)nnz);
     /* cover lists (CSC): the reads of a warp are neighbours and cover the same few candidates, so the warp merges its
        element lists (each ascending by candidate) and takes one cursor atomic per candidate instead of one per element */
     uint32_t next = 0;
