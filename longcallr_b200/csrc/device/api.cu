@@ -120,7 +120,6 @@ int exclusive_scan_u32(lcr_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n
 struct lcr_device_batch_full : lcr_device_batch {
     DbExtra extra;
     uint8_t *slot_flags = nullptr;
-    cudaEvent_t ready = nullptr; /* set by an asynchronous upload: the run waits for it */
 };
 
 static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
@@ -485,6 +484,8 @@ void lcr_destroy(lcr_ctx *ctx) {
 }
 
 int lcr_set_reference(lcr_ctx *ctx, int32_t tid, const uint8_t *seq, uint64_t len) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || tid < 0 || (!seq && len)) return LCR_ERR_INVALID_ARG;
     if (ctx->sticky) return ctx->sticky;
     TRY(cudaSetDevice(ctx->device));
@@ -500,6 +501,8 @@ int lcr_set_reference(lcr_ctx *ctx, int32_t tid, const uint8_t *seq, uint64_t le
 
 /* async: allocate and copy on the context's copy stream and record `ready` instead of waiting */
 static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out, bool async) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || !b || !out) return LCR_ERR_INVALID_ARG;
     struct StreamSwap { /* the helpers above issue work on ctx->stream */
         lcr_ctx *c; cudaStream_t saved; bool on;
@@ -512,6 +515,7 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     TRY(cudaSetDevice(ctx->device));
     lcr_device_batch_full *db = new (std::nothrow) lcr_device_batch_full();
     if (!db) return LCR_ERR_OOM;
+    db->ev_meta = nullptr; db->ev_seq = nullptr; db->seq_wait_pending = false;
     db->n_regions = b->n_regions;
     db->n_reads = b->n_reads;
     db->ran = false;
@@ -566,6 +570,11 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     UP(ts, b->ts, b->n_reads);
     UP(de, b->de, b->n_reads);
     UP(cigar, b->cigar, n_cig);
+    if (!rc && async) {
+        cudaError_t e = cudaEventCreateWithFlags(&db->ev_meta, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(db->ev_meta, ctx->stream);
+        if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
+    }
     /* seq / qual carry 32 bytes of slack: the tile kernel reads aligned 16-byte blocks plus the following word */
     if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 32, &bytes);
     if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 32, &bytes);
@@ -573,8 +582,8 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     if (!rc) {
         cudaError_t e = cudaSuccess;
         if (async) {
-            e = cudaEventCreateWithFlags(&db->ready, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventRecord(db->ready, ctx->stream);
+            e = cudaEventCreateWithFlags(&db->ev_seq, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(db->ev_seq, ctx->stream);
         } else e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
     }
@@ -595,12 +604,21 @@ static void free_results(lcr_ctx *ctx, lcr_device_batch_full *db) {
 }
 
 int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || !dbb) return LCR_ERR_INVALID_ARG;
     if (ctx->sticky) return ctx->sticky;
     lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
     TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    if (db->ready) TRY(cudaStreamWaitEvent(st, db->ready, 0));
+    db->seq_wait_pending = false;
+    if (db->ev_meta) TRY(cudaStreamWaitEvent(st, db->ev_meta, 0));
+    if (db->ev_seq) {
+        /* ONT presets: nothing before the tile kernel reads bases (the read-end trim needs no sequence), so the seq / qual
+           copies keep running under the read filter and segment build; the pileup stage waits right before the tile kernel */
+        if (ctx->P.platform == 1) db->seq_wait_pending = true;
+        else TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
+    }
     free_results(ctx, db);
     const uint64_t h2d_keep = db->h2d_bytes;
     memset(&db->timing, 0, sizeof db->timing);
@@ -657,6 +675,8 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
 }
 
 int lcr_fetch(lcr_ctx *ctx, lcr_device_batch *dbb, lcr_result **out) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || !dbb || !out) return LCR_ERR_INVALID_ARG;
     if (ctx->sticky) return ctx->sticky;
     lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
@@ -758,6 +778,8 @@ void lcr_free_result(lcr_result *res) {
 }
 
 void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || !dbb) return;
     lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
     cudaSetDevice(ctx->device);
@@ -766,7 +788,8 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); DFREE(db->qual); DFREE(db->cigar);
     DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
     cudaStreamSynchronize(ctx->stream);
-    if (db->ready) { cudaEventSynchronize(db->ready); cudaEventDestroy(db->ready); }
+    if (db->ev_seq) { cudaEventSynchronize(db->ev_seq); cudaEventDestroy(db->ev_seq); }
+    if (db->ev_meta) cudaEventDestroy(db->ev_meta);
     delete db;
 }
 
@@ -777,6 +800,8 @@ int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out) {
 }
 
 int lcr_last_submit_timing(lcr_ctx *ctx, lcr_timing *out) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || !out) return LCR_ERR_INVALID_ARG;
     *out = ctx->last_submit;
     return LCR_OK;
@@ -790,7 +815,7 @@ static void add_timing(lcr_timing &acc, const lcr_timing &t) {
 
 static int submit_one(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
     lcr_device_batch *db = nullptr;
-    int rc = lcr_upload(ctx, batch, &db);
+    int rc = upload_impl(ctx, batch, &db, true); /* copies on the copy stream; the run waits on events, not on the host */
     if (rc) return rc;
     rc = lcr_run_device(ctx, db);
     if (!rc) rc = lcr_fetch(ctx, db, out);
@@ -817,6 +842,8 @@ static size_t submit_chunk_bytes() { /* seq + qual bytes per chunk (LCR_SUBMIT_C
    consecutive regions; the host-to-device copies of chunk k+1 run on the copy stream while chunk k computes (regions are
    independent, so the result is the same as one pass over the whole batch). */
 int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
+    std::unique_lock<std::recursive_mutex> ctx_lock__;
+    if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
     if (!ctx || !batch || !out) return LCR_ERR_INVALID_ARG;
     if (ctx->sticky) return ctx->sticky;
     memset(&ctx->last_submit, 0, sizeof ctx->last_submit);

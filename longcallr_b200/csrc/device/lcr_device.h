@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -67,6 +68,7 @@ struct lcr_ctx {
     cudaStream_t side[4];      /* independent launches of one stage fork onto these and join back */
     cudaStream_t copy_stream;  /* lcr_submit: the next chunk's host-to-device copies run here while the current chunk computes */
     lcr_timing last_submit;    /* accounting of the last lcr_submit (lcr_last_submit_timing) */
+    std::recursive_mutex mu;   /* entry points serialise on the context: concurrent callers (rayon workers) are safe, not parallel */
     cudaEvent_t ev_fork, ev_join[4];
     lcr_luts luts;
     LcrDeviceTables *d_tables; /* device copy */
@@ -121,6 +123,9 @@ struct lcr_device_batch {
     uint8_t *fr_elem_base;
     bool ran;
     lcr_timing timing;
+    /* asynchronous upload (lcr_submit): the small tables are ready at ev_meta, seq / qual at ev_seq (null: synchronous upload) */
+    cudaEvent_t ev_meta, ev_seq;
+    bool seq_wait_pending; /* the run has not waited for ev_seq yet */
 };
 
 /* error plumbing */

@@ -1270,6 +1270,10 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     uint32_t n_pre = 0, n_cand = 0;
     /* tiles with more than 255 items take the variant with 32-bit column counters */
     const bool any_deep = totals[2] != 0;
+    if (db->seq_wait_pending) { /* asynchronous upload: seq / qual are first read here */
+        TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
+        db->seq_wait_pending = false;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(cudaMallocAsync(&pre, sizeof(PreCand) * (size_t)pre_cap, st));
         TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), st));

@@ -195,3 +195,32 @@ def test_deep_tiles(preset, platform):
     got, want = run_both(p, syn.reads, syn.reference.for_reads(syn.reads), regions)
     assert got.planes["acgt"].sum(axis=1).max() > 255
     helpers.compare_results(got, want, preset + "/deep")
+
+
+def test_concurrent_submit_on_one_context():
+    """SURVEY 8b threading: the worker closure runs on -t rayon threads; calls on one context serialise and stay correct."""
+    import threading
+
+    syn = host.Synthetic(seed=41, contig_len=120_000, n_contigs=1, platform=1, depth=30.0, n_het=80, n_edit=10, both_strands=1, n_threads=4)
+    p = host.params_preset("ont-cdna", seed=6)
+    regions, _ = host.find_regions(syn.reads, p)
+    refs = syn.reference.for_reads(syn.reads)
+    batch = host.BatchView(syn.reads, regions)
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
+    want = eng.submit(batch)
+    got, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            got[i] = eng.submit(batch)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    eng.close()
+    assert not errs, errs
+    for i in range(4):
+        helpers.compare_results(got[i], want, f"thread {i}")
