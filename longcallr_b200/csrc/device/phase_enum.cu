@@ -33,7 +33,7 @@ struct EnumShared {
 /* EW warps per CTA, ECFG_PER_WARP configurations per warp (strided over the chunk so that warps stay balanced);
    small regions use small CTAs so that many of them share an SM */
 template <int EW, int ECFG_PER_WARP>
-__global__ void __launch_bounds__(EW * 32) k_enum_search(PhaseArgs a, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+__global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseArgs a, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                                                          long long *out_prob, uint32_t *out_cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ EnumShared S;
