@@ -291,7 +291,7 @@ def main():
             "e2e": {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks_summary(samples),
-            "roofline": {"kernel": "k_pileup_tile", "why_this_kernel": "the HBM-streaming kernel of the path: 55-58 % of the step at cfg3 scale; at cfg2 the step is spread over latency-bound kernels (see stage_ms_per_step, profiles/)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+            "roofline": {"kernel": "k_pileup_tile", "why_this_kernel": "the HBM-streaming kernel of the path (every aligned base and quality is read here); 27 % of the cfg3 step after this round's rewrite, the rest being latency-bound walks and L2/SMEM-resident phasing (see stage_ms_per_step, profiles/)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "alg_bytes_per_launch": int(pile_bytes / max(args.steps, 1)), "ms_per_launch": pile_ms / max(args.steps, 1)},
             "stage_ms_per_step": {"pileup_kernel": pile_ms / args.steps, "fragments": frag_ms / args.steps, "phase": phase_ms / args.steps, "total": dev_ms / args.steps},
