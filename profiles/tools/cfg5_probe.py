@@ -1,5 +1,5 @@
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from longcallr_b200 import host, abi
 t = time.time()
 syn = host.Synthetic(seed=20251017, contig_len=500_000, n_contigs=1, platform=0, depth=500.0, n_het=5000, n_edit=0, max_intron=500, max_gap=600, both_strands=0, single_region=1, n_threads=8)
