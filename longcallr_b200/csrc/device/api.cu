@@ -153,7 +153,9 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     fa.frag_flag = frag_flag; fa.elem_count = elem_count; fa.frag_scan = frag_scan; fa.elem_scan = elem_scan;
     fa.cover_count = cover_count; fa.cover_off = cover_off; fa.cover_cursor = cover_cursor;
     fa.is_fragment = db->is_fragment;
-    lcr_launch_frag_count(fa, st);
+    static const int walk_mode = [] { const char *e = getenv("LCR_FRAG_WALK"); return e && *e ? atoi(e) : 0; }(); /* 1: thread per read, 2: warp per read */
+    const bool long_cigars = walk_mode == 2 || (walk_mode == 0 && db->n_cigar > 24ull * (db->n_reads ? db->n_reads : 1));
+    lcr_launch_frag_count(fa, long_cigars, st);
     int rc;
     if ((rc = exclusive_scan_u32(ctx, frag_flag, frag_scan, (size_t)n_slots + 1))) return rc;
     if ((rc = exclusive_scan_u32(ctx, elem_count, elem_scan, (size_t)n_slots + 1))) return rc;
@@ -197,7 +199,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     fa.frag_slot = frag_slot; fa.frag_elem_off = frag_elem_off; fa.frag_links = frag_links;
     fa.elem_snp = elem_snp; fa.elem_cell = elem_cell; fa.elem_base = elem_base;
     fa.cover_frag = cover_frag; fa.cover_cell = cover_cell;
-    lcr_launch_frag_fill(fa, st);
+    lcr_launch_frag_fill(fa, long_cigars, st);
     db->timing.kernel_launches += 1;
 
     /* LD graph */

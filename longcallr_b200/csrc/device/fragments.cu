@@ -163,6 +163,151 @@ __global__ void k_frag_fill(FragArgs a) {
     }
 }
 
+/* ---- the same two passes with one warp per read and one lane per CIGAR op: long CIGARs (ONT reads carry ~100 ops) ---- */
+
+/* fragment.rs:122-152 for one candidate on an aligned base: 1 = element kept, 0 = skipped, negative = the walk's error */
+__device__ __forceinline__ int eval_cand(const lcr_candidate &s, const uint8_t *seq, const uint8_t *qual, int64_t seq_len, int64_t qp, uint8_t &base, int8_t &cell) {
+    if (qp >= seq_len) return LCR_ERR_BAD_CIGAR;
+    base = seq[qp];
+    const uint32_t rq = qual[qp];
+    const uint32_t q = rq < 30u ? rq : 30u;
+    int p;
+    if (base == s.reference) p = 1;
+    else if (base == s.alleles[0] || base == s.alleles[1]) p = -1;
+    else p = 0;
+    if ((s.flags & LCR_CF_DENSE) || p == 0) return 0;
+    if (q == 0) return LCR_ERR_BASEQ_ZERO;
+    cell = (int8_t)(p * (int)(q + 1));
+    return 1;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_frag_walk_w(FragArgs a) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= a.n_slots) return;
+    const uint32_t reg = a.slot_region[slot];
+    const LcrRegionState rs = a.rstate[reg];
+    const uint32_t read = a.regions[reg].read_begin + (slot - a.slot_off[reg]);
+    const lcr_candidate *c = a.cand + rs.cand_begin;
+    uint32_t isfrag = 0, f = 0, e0 = 0;
+    bool go = false;
+    if (!FILL) {
+        if ((a.slot_flags[slot] & 1) && rs.status == 0 && rs.n_cand && !((int64_t)a.pos[read] > c[rs.n_cand - 1].pos)) { isfrag = 1; go = true; }
+    } else {
+        if (!a.frag_flag[slot]) return;
+        f = a.frag_scan[slot];
+        e0 = a.elem_scan[slot];
+        if (lane == 0) {
+            a.frag_slot[f] = slot;
+            a.frag_elem_off[f] = e0;
+            if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
+        }
+        if (rs.status != 0 || !rs.n_cand) { if (lane == 0) a.frag_links[f] = 0; return; } /* a failed region reports no fragments */
+        if (lane == 0) a.is_fragment[read] = 1;
+        go = true;
+    }
+    uint32_t kbase = 0, links = 0, elig = 0;
+    int rc = 0;
+    if (go) {
+        const uint32_t nc = rs.n_cand, floc = f - rs.frag_begin;
+        const bool ld_region = nc > a.P.max_enum_snps;
+        const uint64_t c0 = a.cig_off[read], c1 = a.cig_off[read + 1];
+        const uint64_t s0 = a.seq_off[read];
+        const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
+        const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
+        long long pr = a.pos[read];
+        long long pq = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (long long)(a.cigar[c0] >> 4) : 0;
+        for (uint64_t cbase = c0; cbase < c1; cbase += 32) {
+            const uint64_t ci = cbase + lane;
+            const uint32_t op = ci < c1 ? a.cigar[ci] : 4u; /* padding: a zero-length soft clip */
+            const uint32_t opc = op & 0xf;
+            const long long len = op >> 4;
+            const bool is_m = opc == 0 || opc == 7 || opc == 8, is_dn = opc == 2 || opc == 3, is_i = opc == 1, is_sh = opc == 4 || opc == 5;
+            const unsigned badmask = __ballot_sync(0xffffffffu, !(is_m || is_dn || is_i || is_sh));
+            const uint32_t nvalid = badmask ? (uint32_t)__ffs(badmask) - 1u : 32u; /* the walk stops at the first unknown op */
+            const bool on = lane < nvalid;
+            const long long rl = (on && (is_m || is_dn)) ? len : 0, ql = (on && (is_m || is_i)) ? len : 0;
+            long long rsum = rl, qsum = ql;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long r2 = __shfl_up_sync(0xffffffffu, rsum, o), q2 = __shfl_up_sync(0xffffffffu, qsum, o);
+                if ((int)lane >= o) { rsum += r2; qsum += q2; }
+            }
+            const long long my_pr = pr + rsum - rl, my_pq = pq + qsum - ql, op_end = my_pr + rl;
+            uint32_t lo_i = 0, hi_i = 0;
+            if (on && is_m && len > 0) { /* candidates on [my_pr, op_end) */
+                uint32_t lo = 0, hi = nc;
+                while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (c[m].pos < my_pr) lo = m + 1; else hi = m; }
+                lo_i = lo;
+                hi = nc;
+                while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (c[m].pos < op_end) lo = m + 1; else hi = m; }
+                hi_i = lo;
+            }
+            uint32_t cnt = 0;
+            int err = 0;
+            for (uint32_t idx = lo_i; idx < hi_i; ++idx) {
+                uint8_t base = 0;
+                int8_t cell = 0;
+                const lcr_candidate &sc = c[idx];
+                const int r = eval_cand(sc, seq, qual, seq_len, my_pq + (sc.pos - my_pr), base, cell);
+                if (r < 0) { err = r; break; }
+                if (r && !FILL) {
+                    atomicAdd(&a.cover_count[rs.cand_begin + idx], 1u);
+                    if (ld_region && ld_eligible(sc)) elig++;
+                }
+                cnt += (uint32_t)r;
+            }
+            const unsigned errmask = __ballot_sync(0xffffffffu, err != 0);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            if (FILL) {
+                uint32_t w = e0 + kbase + incl - cnt;
+                for (uint32_t idx = lo_i; idx < hi_i; ++idx) {
+                    uint8_t base = 0;
+                    int8_t cell = 0;
+                    const lcr_candidate &sc = c[idx];
+                    const int r = eval_cand(sc, seq, qual, seq_len, my_pq + (sc.pos - my_pr), base, cell);
+                    if (r < 0) break;
+                    if (!r) continue;
+                    a.elem_snp[w] = idx;
+                    a.elem_cell[w] = cell;
+                    a.elem_base[w] = base;
+                    ++w;
+                    if (sc.flags & LCR_CF_FOR_PHASING) links++;
+                    const uint32_t g = rs.cand_begin + idx;
+                    const uint32_t cw = a.cover_off[g] + atomicAdd(&a.cover_cursor[g], 1u);
+                    a.cover_frag[cw] = floc;
+                    a.cover_cell[cw] = cell;
+                }
+            }
+            kbase += __shfl_sync(0xffffffffu, incl, 31);
+            pr += __shfl_sync(0xffffffffu, rsum, 31);
+            pq += __shfl_sync(0xffffffffu, qsum, 31);
+            if (errmask) { rc = __shfl_sync(0xffffffffu, err, __ffs(errmask) - 1); break; }
+            if (badmask) { rc = LCR_ERR_BAD_CIGAR; break; }
+        }
+    }
+    if (!FILL) {
+        elig = __reduce_add_sync(0xffffffffu, elig);
+        if (lane == 0) {
+            if (rc) atomicMin(&a.rstate[reg].status, rc);
+            if (elig > 1) atomicAdd(&a.rstate[reg].n_ld_pairs_cap, elig * (elig - 1) / 2);
+            a.frag_flag[slot] = isfrag;
+            a.elem_count[slot] = kbase;
+        }
+    } else {
+        links = __reduce_add_sync(0xffffffffu, links);
+        if (lane == 0) {
+            a.frag_links[f] = links;
+            if (links >= a.P.min_linkers && links) atomicAdd((unsigned long long *)&a.stats->nnz_phase, (unsigned long long)links);
+        }
+    }
+}
+
 /* fragment.rs:207-240 restricted to the pairs candidate.rs:628-692 evaluates: cis / trans counts per SNP pair */
 __global__ void k_pair_count(FragArgs a, LcrPairEntry *table) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,14 +385,19 @@ __global__ void k_fill_entry_region(uint32_t n_regions, const LcrRegionState *rs
 
 } // namespace
 
-void lcr_launch_frag_count(const FragArgs &a, cudaStream_t st) {
-    if (a.n_slots) k_frag_count<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
+/* long_cigars: more than ~24 ops per read on average (ONT): one warp per read, one lane per op; else one thread per read */
+void lcr_launch_frag_count(const FragArgs &a, bool long_cigars, cudaStream_t st) {
+    if (!a.n_slots) return;
+    if (long_cigars) k_frag_walk_w<false><<<(uint32_t)(((uint64_t)a.n_slots * 32 + 127) / 128), 128, 0, st>>>(a);
+    else k_frag_count<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
 }
 void lcr_launch_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate, cudaStream_t st) {
     if (n_regions) k_region_frag_ranges<<<(n_regions + 127) / 128, 128, 0, st>>>(n_regions, slot_off, frag_scan, rstate);
 }
-void lcr_launch_frag_fill(const FragArgs &a, cudaStream_t st) {
-    if (a.n_slots) k_frag_fill<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
+void lcr_launch_frag_fill(const FragArgs &a, bool long_cigars, cudaStream_t st) {
+    if (!a.n_slots) return;
+    if (long_cigars) k_frag_walk_w<true><<<(uint32_t)(((uint64_t)a.n_slots * 32 + 127) / 128), 128, 0, st>>>(a);
+    else k_frag_fill<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
 }
 void lcr_launch_pair_count(const FragArgs &a, LcrPairEntry *table, cudaStream_t st) {
     if (a.n_frag_total) k_pair_count<<<(a.n_frag_total + 127) / 128, 128, 0, st>>>(a, table);

@@ -78,9 +78,9 @@ struct PhaseArgs {
     const uint32_t *es_cfg;
 };
 
-void lcr_launch_frag_count(const FragArgs &a, cudaStream_t st);
+void lcr_launch_frag_count(const FragArgs &a, bool long_cigars, cudaStream_t st);
 void lcr_launch_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate, cudaStream_t st);
-void lcr_launch_frag_fill(const FragArgs &a, cudaStream_t st);
+void lcr_launch_frag_fill(const FragArgs &a, bool long_cigars, cudaStream_t st);
 void lcr_launch_pair_count(const FragArgs &a, LcrPairEntry *table, cudaStream_t st);
 void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrRegionState *rstate, const LcrPairEntry *table, uint64_t table_size,
                          const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj, cudaStream_t st);
