@@ -495,6 +495,327 @@ __global__ void __launch_bounds__(128, 6) k_slot_prep(PrepArgs a) {
     }
 }
 
+/* ---- the same two passes with one warp per read and one lane per CIGAR op ----
+   The thread-per-read walk is a serial chain of ~60 instructions per op, so a batch of long-CIGAR reads (ONT: ~100 ops,
+   up to several hundred) runs as long as its longest read.  Here the start position of every op comes from warp prefix sums
+   over the op lengths; "first op of the read in a tile" (item creation), the segment slots and the open item of the read
+   are carried from lane to lane with warp scans.  Results are identical to k_slot_prep (the item and segment orders inside
+   a read are the same; rows inside a tile come from the same atomic counter). */
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_slot_prep_w(PrepArgs a) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= a.n_slots) return;
+    const uint32_t reg = a.slot_region[slot];
+    if (a.rstate[reg].status != 0) return;
+    const lcr_region R = a.regions[reg];
+    const uint32_t read = R.read_begin + (slot - a.slot_off[reg]);
+    const uint64_t c0 = a.cig_off[read], c1 = a.cig_off[read + 1];
+    const uint64_t s0 = a.seq_off[read];
+    const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
+    const uint8_t *seq = a.seq + s0;
+    const int64_t lead = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (int64_t)(a.cigar[c0] >> 4) : 0; /* leading_softclips */
+    const int64_t trail = (c1 > c0 && (a.cigar[c1 - 1] & 0xf) == 4) ? (int64_t)(a.cigar[c1 - 1] >> 4) : 0;
+    const int64_t rb = seq_len - trail;
+    const int64_t dend = (int64_t)(a.P.distance_to_read_end > 0x3fffffffu ? 0x3fffffffu : a.P.distance_to_read_end);
+    const bool ont = a.P.platform == 1;
+    uint32_t sflags;
+    uint64_t runs[LCR_SLOT_RUNS];
+#pragma unroll
+    for (int i = 0; i < LCR_SLOT_RUNS; ++i) runs[i] = 0;
+    if (!FILL) {
+        /* util.rs:652-668 */
+        const uint16_t fl = a.flag[read];
+        bool pass = !((int32_t)a.mapq[read] < a.P.min_mapq || (uint64_t)seq_len < (uint64_t)a.P.min_read_length || (fl & 0x4) || (fl & 0x100) || (fl & 0x800));
+        const float de = a.de[read];
+        if (!(de != de) && de >= a.P.divergence) pass = false;
+        /* fetch((chr, start, end)): pos < end && bam_endpos > start on the region's own numbers */
+        long long rlen = 0;
+        for (uint64_t c = c0 + lane; c < c1; c += 32) {
+            const uint32_t op = a.cigar[c];
+            if (is_ref_consuming(op & 0xf)) rlen += op >> 4;
+        }
+        for (int o = 16; o; o >>= 1) rlen += __shfl_xor_sync(0xffffffffu, rlen, o);
+        const int64_t p = a.pos[read];
+        const bool in_window = p < (int64_t)R.end && p + (rlen ? rlen : 1) > (int64_t)R.start;
+        sflags = (pass && in_window) ? 1 : 0;
+        if (sflags && !ont && dend > 0) { /* the homopolymer-run table of the read ends: lane 0 scans, as k_slot_prep does */
+            const int64_t polya = (int64_t)(a.P.polya_tail_length > 0x3fffffffu ? 0x3fffffffu : a.P.polya_tail_length);
+            if (polya < 2 || rb < lead) sflags |= 6;
+            else {
+                uint32_t nrun = 0;
+                if (lane == 0) {
+                    const int64_t centre[2] = {lead, rb};
+                    int64_t scanned_to = -1;
+                    for (int z = 0; z < 2; ++z) {
+                        int64_t lo = centre[z] - dend + 1 - polya, hi = centre[z] + dend + polya;
+                        if (lo < 0) lo = 0;
+                        if (hi > seq_len) hi = seq_len;
+                        int64_t run = 0;
+                        uint8_t prev = 0;
+                        for (int64_t i = lo; i <= hi; ++i) {
+                            const uint8_t b = i < hi ? __ldg(seq + i) : (uint8_t)0;
+                            const bool letter = b == 'A' || b == 'C' || b == 'G' || b == 'T';
+                            if (letter && b == prev) { run++; continue; }
+                            if (run >= polya && i > scanned_to) {
+                                if (nrun < LCR_SLOT_RUNS) runs[nrun] = ((uint64_t)(i - run) << 32) | ((uint64_t)(run > 0xffffff ? 0xffffff : run) << 8) | (uint64_t)prev;
+                                nrun++;
+                            }
+                            run = letter ? 1 : 0;
+                            prev = b;
+                        }
+                        if (hi > scanned_to) scanned_to = hi;
+                    }
+                }
+                nrun = __shfl_sync(0xffffffffu, nrun, 0);
+#pragma unroll
+                for (int i = 0; i < LCR_SLOT_RUNS; ++i) runs[i] = __shfl_sync(0xffffffffu, runs[i], 0);
+                if (nrun) sflags |= 2;
+                if (nrun > LCR_SLOT_RUNS) sflags |= 4;
+            }
+        }
+        if (lane == 0) {
+            a.slot_flags[slot] = (uint8_t)sflags;
+            if (sflags & 2) {
+#pragma unroll
+                for (int i = 0; i < LCR_SLOT_RUNS; ++i) a.slot_runs[(size_t)slot * LCR_SLOT_RUNS + i] = runs[i];
+            }
+        }
+    } else {
+        sflags = a.slot_flags[slot];
+        if ((sflags & 6) == 2) {
+#pragma unroll
+            for (int i = 0; i < LCR_SLOT_RUNS; ++i) runs[i] = a.slot_runs[(size_t)slot * LCR_SLOT_RUNS + i];
+        }
+    }
+    if (!(sflags & 1)) return;
+
+    const int64_t vec_size = (int64_t)R.end - (int64_t)R.start;
+    const int64_t fv_start = (int64_t)R.start - 1;
+    const uint32_t tb = a.tile_base[reg];
+    const uint8_t *ref = a.ref_table[R.tid] + fv_start;
+    uint32_t rowtyp_c;
+    {
+        const int strand = (a.flag[read] & 0x10) ? 1 : 0;
+        const int8_t ts = a.ts[read];
+        uint32_t tcode = 0;
+        if (ts == '+') tcode = strand == 0 ? 1u : 2u;
+        else if (ts == '-') tcode = strand == 0 ? 2u : 1u;
+        rowtyp_c = (strand == 0 ? 4u : 0u) | (tcode << 3);
+    }
+    int64_t zlo[2] = {lead - dend + 1, rb - dend + 1}, zhi[2] = {lead + dend - 1, rb + dend - 1};
+    if (zlo[1] < zlo[0]) { int64_t t = zlo[0]; zlo[0] = zlo[1]; zlo[1] = t; t = zhi[0]; zhi[0] = zhi[1]; zhi[1] = t; }
+    const int mask_mode = dend <= 0 ? 0 : ont ? 1 : (sflags & 4) ? 2 : (sflags & 2) ? 3 : 0;
+    const int64_t polya = (int64_t)a.P.polya_tail_length;
+
+    /* the unmasked stretches of the aligned piece [pa, pb) (read coordinates) whose first base sits on region position ts:
+       WRITE stores them from segment slot w on; returns how many there are */
+    auto piece = [&](bool write, int64_t pa, int64_t pb, int64_t ts, uint32_t colr, uint32_t w) -> uint32_t {
+        uint32_t n = 0;
+        int64_t start = pa;
+        auto emit = [&](int64_t x, int64_t y) {
+            if (y <= x) return;
+            if (write) {
+                LcrSeg s;
+                s.spos = s0 + (uint64_t)x; s.row_typ = rowtyp_c | SEG_M; s.col = (uint16_t)(colr + (uint32_t)(x - pa)); s.len = (uint16_t)(y - x);
+                a.segs[w + n] = s;
+            }
+            n++;
+        };
+        if (mask_mode == 1) {
+            for (int k = 0; k < 2; ++k) {
+                const int64_t zl = zlo[k] > start ? zlo[k] : start, zh = zhi[k] < pb - 1 ? zhi[k] : pb - 1;
+                if (zl <= zh) { emit(start, zl); start = zh + 1; }
+            }
+        } else if (mask_mode == 2) {
+            for (int k = 0; k < 2; ++k) {
+                const int64_t zl = zlo[k] > start ? zlo[k] : start, zh = zhi[k] < pb - 1 ? zhi[k] : pb - 1;
+                for (int64_t rp = zl; rp <= zh; ++rp)
+                    if (base_masked(a.P, seq, rp, seq_len, lead, trail, ref[ts + (rp - pa)])) { emit(start, rp); start = rp + 1; }
+            }
+        } else if (mask_mode == 3) {
+            int64_t from = pa;
+#pragma unroll
+            for (int j = 0; j < LCR_SLOT_RUNS; ++j) {
+                const int64_t rs = (int64_t)(runs[j] >> 32), rn = (int64_t)((runs[j] >> 8) & 0xffffffu);
+                if (rn == 0) continue;
+                const int64_t zl = rs - 1 > from ? rs - 1 : from, zh = rs + rn < pb - 1 ? rs + rn : pb - 1;
+                for (int64_t rp = zl; rp <= zh; ++rp) {
+                    const int64_t d0 = rp - lead, d1 = rp - rb;
+                    if (!((d0 < 0 ? -d0 : d0) < dend || (d1 < 0 ? -d1 : d1) < dend)) continue;
+                    const uint8_t rbase = ref[ts + (rp - pa)];
+                    const int64_t wlo = rp - polya > 0 ? rp - polya : 0, whi = rp + polya + 1 < seq_len ? rp + polya + 1 : seq_len;
+                    bool m = false;
+#pragma unroll
+                    for (int q = 0; q < LCR_SLOT_RUNS; ++q) {
+                        const int64_t qs = (int64_t)(runs[q] >> 32), qn = (int64_t)((runs[q] >> 8) & 0xffffffu), qe = qs + qn;
+                        if (qn == 0 || (uint8_t)(runs[q] & 0xffu) == rbase) continue;
+                        const bool anchored = (rp - 1 >= qs && rp - 1 < qe) || (rp + 1 >= qs && rp + 1 < qe);
+                        const int64_t ov = (qe < whi ? qe : whi) - (qs > wlo ? qs : wlo);
+                        if (anchored && ov >= polya) m = true;
+                    }
+                    if (m) { emit(start, rp); start = rp + 1; }
+                }
+                if (zh + 1 > from) from = zh + 1;
+            }
+        }
+        emit(start, pb);
+        return n;
+    };
+
+    /* carried from batch to batch (the same in every lane) */
+    long long fpos_c = (long long)a.pos[read] - fv_start, rpos_c = lead;
+    long long last_tile_c = -1;
+    uint32_t seg_c = FILL ? a.slot_seg_off[slot] : 0;  /* next segment slot of the read */
+    uint32_t open_k = 0xffffffffu, open_begin = 0;      /* FILL: the read's item that later ops may still extend */
+    uint32_t n_bases = 0;
+    bool bad = false;
+    for (uint64_t cbase = c0; cbase < c1 && !bad; cbase += 32) {
+        const uint64_t ci = cbase + lane;
+        const uint32_t op = ci < c1 ? a.cigar[ci] : 4u; /* padding: a zero-length soft clip */
+        const uint32_t opc = op & 0xf;
+        const long long len = op >> 4;
+        const bool is_m = opc == 0 || opc == 7 || opc == 8, is_dn = opc == 2 || opc == 3, is_i = opc == 1, is_sh = opc == 4 || opc == 5;
+        const unsigned badmask = __ballot_sync(0xffffffffu, !(is_m || is_dn || is_i || is_sh)); /* util.rs:943-945 panics */
+        const uint32_t nvalid = badmask ? (uint32_t)__ffs(badmask) - 1u : 32u;
+        const bool on = lane < nvalid;
+        const long long rl = (on && (is_m || is_dn)) ? len : 0, ql = (on && (is_m || is_i)) ? len : 0;
+        long long rsum = rl, qsum = ql;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long r2 = __shfl_up_sync(0xffffffffu, rsum, o), q2 = __shfl_up_sync(0xffffffffu, qsum, o);
+            if ((int)lane >= o) { rsum += r2; qsum += q2; }
+        }
+        const long long lo = fpos_c + rsum - rl, hi = lo + rl, rp0 = rpos_c + qsum - ql;
+        /* the part of the op inside the region and the tiles where it takes part in an item */
+        const long long a0 = lo < 0 ? 0 : lo, b0 = hi < vec_size ? hi : vec_size;
+        const bool inside = on && rl > 0 && hi > 0 && lo < vec_size && b0 > a0;
+        long long t0 = 0, t1 = -1; /* tiles touched */
+        if (inside) { t0 = a0 / LCR_TILE; t1 = (b0 - 1) / LCR_TILE; }
+        /* whole-tile intron covers register nothing: for an N op only a partial first / last tile counts */
+        auto tile_end_of = [&](long long t) { return (t + 1) * LCR_TILE < vec_size ? (t + 1) * LCR_TILE : vec_size; };
+        auto registers = [&](long long t) -> bool {
+            if (opc != 3) return true;
+            const long long ts = a0 > t * LCR_TILE ? a0 : t * LCR_TILE, te = b0 < tile_end_of(t) ? b0 : tile_end_of(t);
+            return !(ts == t * LCR_TILE && te == tile_end_of(t));
+        };
+        long long tl = -1; /* last tile this op registers in */
+        if (inside) {
+            if (registers(t1)) tl = t1;
+            else if (t1 > t0 && registers(t0)) tl = t0; /* N op: only the first tile is partial */
+        }
+        /* last registered tile of the ops before this one: exclusive running maximum */
+        long long lt = tl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, lt, o);
+            if ((int)lane >= o && v > lt) lt = v;
+        }
+        long long last_before = __shfl_up_sync(0xffffffffu, lt, 1);
+        if (lane == 0 || last_before < last_tile_c) last_before = last_tile_c;
+        const long long batch_last = __shfl_sync(0xffffffffu, lt, 31);
+
+        /* pass 1: segments of this op (all its registered tiles), new items, aligned bases */
+        uint32_t nseg = 0, nnew = 0;
+        bool mybad = false;
+        if (inside) {
+            for (long long t = t0; t <= t1; ++t) {
+                if (!registers(t)) continue;
+                const long long ts = a0 > t * LCR_TILE ? a0 : t * LCR_TILE, te = b0 < tile_end_of(t) ? b0 : tile_end_of(t);
+                if (t > last_before) nnew++;
+                if (!is_m) { nseg++; continue; }
+                const long long pa = rp0 + (ts - lo), pb = rp0 + (te - lo);
+                if (pb > seq_len) { mybad = true; break; }
+                n_bases += (uint32_t)(te - ts);
+                nseg += piece(false, pa, pb, ts, (uint32_t)(ts - t * LCR_TILE), 0);
+            }
+        }
+        const unsigned mybadmask = __ballot_sync(0xffffffffu, mybad);
+        uint32_t sincl = nseg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, sincl, o);
+            if ((int)lane >= o) sincl += v;
+        }
+        const uint32_t seg_first = seg_c + sincl - nseg; /* first segment slot of this op */
+        const uint32_t seg_total = __shfl_sync(0xffffffffu, sincl, 31);
+
+        if (!FILL) {
+            if (inside && !mybad)
+                for (long long t = t0; t <= t1; ++t)
+                    if (registers(t) && t > last_before && atomicAdd(&a.tile_count[tb + (uint32_t)t], 1u) == 255u) *a.deep_flag = 1u;
+        } else {
+            /* the open item of the ops before this one: last lane before me that created an item, else the carry */
+            uint32_t my_open_k = 0xffffffffu, my_open_begin = 0; /* the last item this op creates */
+            uint32_t w = seg_first;
+            uint32_t prev_k = 0xffffffffu, prev_begin = 0;        /* the item this op is currently extending / has just created */
+            const unsigned creators = __ballot_sync(0xffffffffu, nnew > 0 && !mybad);
+            /* placeholders filled after the loop below needs them: fetch the inherited open item first */
+            const unsigned before = creators & ((1u << lane) - 1u);
+            /* every creating lane publishes its last created item after the loop; the inherited one therefore needs a second
+               exchange: do the tile loop first for the lane's own items, then close the inherited item with the first new begin */
+            uint32_t first_new_begin = 0;
+            bool have_first = false;
+            if (inside && !mybad) {
+                for (long long t = t0; t <= t1; ++t) {
+                    const long long ts = a0 > t * LCR_TILE ? a0 : t * LCR_TILE, te = b0 < tile_end_of(t) ? b0 : tile_end_of(t);
+                    if (!registers(t)) { atomicAdd(&a.tile_full_n[tb + (uint32_t)t], 1u); continue; }
+                    if (t > last_before) {
+                        const uint32_t k = a.tile_off[tb + (uint32_t)t] + atomicAdd(&a.tile_count[tb + (uint32_t)t], 1u);
+                        LcrItem it;
+                        it.slot = slot;
+                        it.cig = (uint32_t)(ci - c0);
+                        it.opoff = (uint32_t)(ts - lo);
+                        it.rpos = (uint32_t)(is_m ? rp0 + (ts - lo) : rp0);
+                        it.fpos = (int32_t)ts;
+                        a.items[k] = it;
+                        if (!have_first) { have_first = true; first_new_begin = w; }
+                        else a.item_segs[prev_k] = make_uint2(prev_begin, w - prev_begin); /* my previous new item is complete */
+                        prev_k = k; prev_begin = w;
+                    }
+                    if (!is_m) {
+                        LcrSeg s;
+                        s.spos = 0; s.row_typ = rowtyp_c | (opc == 2 ? SEG_D : SEG_N); s.col = (uint16_t)(ts - t * LCR_TILE); s.len = (uint16_t)(te - ts);
+                        a.segs[w] = s;
+                        w++;
+                    } else {
+                        const long long pa = rp0 + (ts - lo), pb = rp0 + (te - lo);
+                        w += piece(true, pa, pb, ts, (uint32_t)(ts - t * LCR_TILE), w);
+                    }
+                }
+                if (have_first) { my_open_k = prev_k; my_open_begin = prev_begin; }
+            }
+            /* close the inherited open item at the first new item of this op */
+            const int src = before ? 31 - __clz(before) : 0;
+            const uint32_t inh_k = __shfl_sync(0xffffffffu, my_open_k, src), inh_begin = __shfl_sync(0xffffffffu, my_open_begin, src);
+            if (have_first) {
+                const uint32_t ok = before ? inh_k : open_k, ob = before ? inh_begin : open_begin;
+                if (ok != 0xffffffffu) a.item_segs[ok] = make_uint2(ob, first_new_begin - ob);
+            }
+            if (creators) {
+                const int lastc = 31 - __clz(creators);
+                open_k = __shfl_sync(0xffffffffu, my_open_k, lastc);
+                open_begin = __shfl_sync(0xffffffffu, my_open_begin, lastc);
+            }
+        }
+        seg_c += seg_total;
+        fpos_c += __shfl_sync(0xffffffffu, rsum, 31);
+        rpos_c += __shfl_sync(0xffffffffu, qsum, 31);
+        if (batch_last > last_tile_c) last_tile_c = batch_last;
+        if (mybadmask || badmask) bad = true;
+    }
+    if (bad) {
+        if (lane == 0) atomicMin(&a.rstate[reg].status, (int32_t)LCR_ERR_BAD_CIGAR);
+        n_bases = 0;
+    }
+    if (!FILL) {
+        if (lane == 0) a.slot_segs[slot] = seg_c;
+    } else {
+        if (lane == 0 && open_k != 0xffffffffu) a.item_segs[open_k] = make_uint2(open_begin, seg_c - open_begin);
+        n_bases = __reduce_add_sync(0xffffffffu, n_bases);
+        if (lane == 0 && n_bases) atomicAdd((unsigned long long *)&a.stats->n_aligned_bases, (unsigned long long)n_bases);
+    }
+}
+
 /* ------------------------------------------------------------------------- *
  * Tile pileup, version 3: segments -> one-hot row planes -> carry-save column sums.
  *
@@ -1191,10 +1512,14 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n; pa.deep_flag = deep_flag;
     pa.slot_segs = slot_segs; pa.slot_seg_off = slot_seg_off;
     pa.items = nullptr; pa.item_segs = nullptr; pa.segs = nullptr;
-    const uint32_t pb = 128, pg = (db->n_slots + pb - 1) / pb;
+    /* batches averaging more than 24 CIGAR ops per read (ONT) take the warp-per-read, lane-per-op form (LCR_PREP_WALK: 1 / 2 forces one) */
+    static const int prep_mode = [] { const char *e = getenv("LCR_PREP_WALK"); return e && *e ? atoi(e) : 0; }();
+    const bool warp_walk = prep_mode == 2 || (prep_mode == 0 && db->n_cigar > 24ull * (db->n_reads ? db->n_reads : 1));
+    const uint32_t pb = 128, pg = warp_walk ? (uint32_t)(((uint64_t)db->n_slots * 32 + pb - 1) / pb) : (db->n_slots + pb - 1) / pb;
     if (pg) {
-        k_slot_prep<false><<<pg, pb, 0, st>>>(pa);
-        k_count_pass<<<pg, pb, 0, st>>>(slot_flags, db->n_slots, db->d_stats);
+        if (warp_walk) k_slot_prep_w<false><<<pg, pb, 0, st>>>(pa);
+        else k_slot_prep<false><<<pg, pb, 0, st>>>(pa);
+        k_count_pass<<<(db->n_slots + pb - 1) / pb, pb, 0, st>>>(slot_flags, db->n_slots, db->d_stats);
         db->timing.kernel_launches += 2;
     }
     /* exclusive scans of the per-tile item counts and the per-read segment bounds */
@@ -1219,7 +1544,8 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaMemsetAsync(item_segs, 0, sizeof(uint2) * (size_t)(n_items ? n_items : 1), st));
     pa.items = items; pa.item_segs = item_segs; pa.segs = segs;
     if (pg) {
-        k_slot_prep<true><<<pg, pb, 0, st>>>(pa);
+        if (warp_walk) k_slot_prep_w<true><<<pg, pb, 0, st>>>(pa);
+        else k_slot_prep<true><<<pg, pb, 0, st>>>(pa);
         db->timing.kernel_launches += 1;
     }
 
