@@ -1333,47 +1333,30 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a, uint32_t n_pre) {
     const int refc = (ref_base == 'A') ? 0 : (ref_base == 'C') ? 1 : (ref_base == 'G') ? 2 : (ref_base == 'T') ? 3 : 8;
     long long ll0 = 0, ll2 = 0;
     uint32_t q0flags = 0;
+    /* one lane per read of the tile: its segments are in column order and hold exactly the unmasked aligned bases */
+    const uint32_t colr = pc.col;
     for (uint32_t idx = a.tile_off[tile] + lane; idx < a.tile_off[tile + 1]; idx += 32) {
-        const LcrItem it = a.items[idx];
-        const uint32_t read = R.read_begin + (it.slot - a.slot_off[reg]);
-        const uint64_t s0 = a.seq_off[read];
-        const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
-        const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
-        const uint64_t c0 = a.cig_off[read];
-        const uint32_t ncig = (uint32_t)(a.cig_off[read + 1] - c0);
-        const uint32_t *cig = a.cigar + c0;
-        const int64_t lead = (ncig && (cig[0] & 0xf) == 4) ? (int64_t)(cig[0] >> 4) : 0;
-        const int64_t trail = (ncig && (cig[ncig - 1] & 0xf) == 4) ? (int64_t)(cig[ncig - 1] >> 4) : 0;
-        int32_t fpos = it.fpos;
-        int64_t rpos = it.rpos;
-        uint32_t off = it.opoff;
-        for (uint32_t ci = it.cig; ci < ncig && fpos <= col; ++ci, off = 0) {
-            const uint32_t op = cig[ci], opc = op & 0xf;
-            const int32_t len = (int32_t)(op >> 4) - (int32_t)off;
-            if (opc == 4 || opc == 5) continue;
-            if (opc == 1) { rpos += len; continue; }
-            const bool is_m = opc == 0 || opc == 7 || opc == 8;
-            if (col < fpos + len) {
-                if (is_m) {
-                    const int64_t rp = rpos + (col - fpos);
-                    if (rp < seq_len) {
-                        const uint8_t b = seq[rp];
-                        const uint32_t rq = qual[rp];
-                        const uint32_t q = rq < LCR_MAX_BASE_QUALITY ? rq : LCR_MAX_BASE_QUALITY;
-                        const int bc = base_code_dev(b);
-                        if (bc >= 0 && !base_masked(a.P, seq, rp, seq_len, lead, trail, ref_base)) {
-                            const bool is_ref = bc == refc;
-                            const long long E = a.tables->gl_fx_err[q], K = a.tables->gl_fx_ok[q];
-                            ll0 += is_ref ? E : K;
-                            ll2 += is_ref ? K : E;
-                            if (q == 0) q0flags |= is_ref ? 1u : 2u;
-                        }
-                    }
+        const uint2 is = a.item_segs[idx];
+        for (uint32_t k = 0; k < is.y; ++k) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + is.x + k));
+            const uint32_t scol = raw.w & 0xffffu, slen = raw.w >> 16;
+            if (scol > colr) break;
+            if (colr >= scol + slen) continue;
+            if ((raw.z & 3u) == SEG_M) {
+                const uint64_t sp = (((uint64_t)raw.y << 32) | raw.x) + (colr - scol);
+                const uint8_t b = a.seq[sp];
+                const uint32_t rq = a.qual[sp];
+                const uint32_t q = rq < LCR_MAX_BASE_QUALITY ? rq : LCR_MAX_BASE_QUALITY;
+                const int bc = base_code_dev(b);
+                if (bc >= 0) {
+                    const bool is_ref = bc == refc;
+                    const long long E = a.tables->gl_fx_err[q], K = a.tables->gl_fx_ok[q];
+                    ll0 += is_ref ? E : K;
+                    ll2 += is_ref ? K : E;
+                    if (q == 0) q0flags |= is_ref ? 1u : 2u;
                 }
-                break;
             }
-            fpos += len;
-            if (is_m) rpos += len;
+            break;
         }
     }
     for (int o = 16; o; o >>= 1) {
