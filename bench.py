@@ -112,16 +112,37 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = units / dt
     sample = f"{n_sample} of {len(regions)} regions of {args.workload} per step ({units // max(args.steps, 1)} units), C++ port of the reference loops, {cores} threads over regions"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64",
         "data": "synthetic", "config": {"workload": args.workload, **WORKLOADS[args.workload]["synth"], "preset": w["preset"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr instead."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)  # anything printed during teardown goes to stderr again
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -315,7 +336,7 @@ def main():
             cu = r1.stats["n_aligned_bases"] + r1.stats["nnz_phase"]
             out["cpu_baseline"] = {"value": cu / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"first {n_sample} of {len(regions)} regions of {args.workload} once ({cu} units, {dt:.2f} s), C++ port of the reference loops (oracle mode 1), {cores} threads over regions"}
-        print(json.dumps(out))
+        emit_json(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
