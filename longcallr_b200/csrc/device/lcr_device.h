@@ -4,7 +4,7 @@
  * One lcr_submit / lcr_run_device call = the per-region worker body of
  * src/thread.rs:78-221 for every region of the batch:
  *
- *   slot prep        read filter + fetch window (util.rs:636-668), tile work items
+ *   slot prep        read filter + fetch window (util.rs:636-668), tile work items and segments (read-end trim / poly-A mask applied)
  *   tile pileup      util.rs:650-948 fused with the per-site filter cascade and
  *                    genotype likelihood of candidate.rs:75-463
  *   cand finalize    position sort + dense-cluster filters (candidate.rs:465-526)
@@ -28,8 +28,6 @@
 #include "lcr_contract.h"
 
 #define LCR_TILE 512        /* positions per pileup tile == threads per pileup CTA */
-#define LCR_ROWS 128        /* reads staged in shared memory per chunk (8-bit column counters: < 256) */
-#define LCR_CODE_NONE 7u    /* row byte: (q << 3) | code; code 0-3 ACGT, 4 other base, 5 deletion, 6 intron, 7 nothing */
 
 struct LcrItem {            /* part of one read inside one tile (20 B) */
     uint32_t slot;          /* (region, read) pair                                  */

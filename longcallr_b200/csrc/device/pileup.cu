@@ -2,17 +2,17 @@
  * pileup.cu — read filter, tile work items, fused pileup + site genotyping, candidate lists.
  *
  * Replaces, on the device:
- *   src/util.rs:636-668      read filter and fetch window             (k_slot_prep)
- *   src/util.rs:650-948      Profile::fill_data_into_freq_vec         (k_pileup_tile, phase 1 + 2)
+ *   src/util.rs:636-668      read filter and fetch window             (k_slot_prep / k_slot_prep_w)
+ *   src/util.rs:650-948      Profile::fill_data_into_freq_vec         (k_slot_prep: CIGAR walk + masks; k_pileup_tile: counts)
  *   src/util.rs:162-176      BaseFreq::get_two_major_alleles          (site_call)
- *   src/candidate.rs:75-463  filter cascade, genotype likelihood      (site_call)
- *   src/candidate.rs:465-526 dense-cluster filters                    (k_cand_finalize)
+ *   src/candidate.rs:75-463  filter cascade, genotype likelihood      (site_call, k_site_ll)
+ *   src/candidate.rs:465-526 dense-cluster filters                    (k_cand_ranges, k_cand_dense)
  *
- * Layout: reads are decomposed into (read, tile) items on the device; one CTA owns one
- * tile of LCR_TILE reference positions, stages LCR_ROWS reads at a time as one byte per
- * position in shared memory ((q << 3) | code), and every thread accumulates the column of
- * its own position in registers: no atomics on the counters, no per-position record in HBM.
- * Only candidate sites (and, on request, the debug planes) are written out.
+ * Layout: reads are decomposed on the device into (read, tile) items and, per item, segments (runs of unmasked aligned
+ * bases / deleted / intron positions on consecutive columns); one CTA owns one tile of LCR_TILE reference positions,
+ * stages the reads of the tile as one-hot byte planes in shared memory and sums the columns with carry-save adders:
+ * no atomics on the counters, no per-position record in HBM.  Only candidate sites (and, on request, the debug planes)
+ * are written out.
  */
 #include <cub/cub.cuh>
 
@@ -843,7 +843,7 @@ struct __align__(16) LcrTileDesc { /* 48 B, one per tile (k_tile_desc) */
     const uint8_t *ref;     /* reference base of column 0 */
     uint64_t pos_g;         /* index of column 0 in the debug planes */
     uint32_t it0, n_items;  /* items of the tile */
-    uint32_t seg_lo, n_segs; /* unused */
+    uint32_t reserved[2];
     uint32_t reg, npos;
     uint32_t full_n;        /* introns covering the whole tile */
     int32_t status;         /* of the region */
@@ -872,7 +872,7 @@ __global__ void k_tile_desc(DescArgs a) {
     d.ref = d.status == 0 ? a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start : nullptr;
     d.pos_g = a.pos_off[reg] + (uint64_t)tile_start;
     d.it0 = a.tile_off[tile]; d.n_items = a.tile_off[tile + 1] - d.it0;
-    d.seg_lo = 0; d.n_segs = 0;
+    d.reserved[0] = 0; d.reserved[1] = 0;
     d.reg = reg; d.npos = (uint32_t)(tile_end - tile_start);
     d.full_n = a.tile_full_n[tile];
     a.desc[tile] = d;
