@@ -12,7 +12,8 @@
  *   phase            phase.rs:1087-1296 + snpfrags.rs:191-733, one CTA per region
  *
  * Vocabulary: a *slot* is one (region, read) pair; a *tile* is TILE consecutive
- * positions of one region; an *item* is the part of one read that falls in one tile.
+ * positions of one region; an *item* is the part of one read that falls in one tile (a row of the
+ * tile's pileup); a *segment* is a run of unmasked aligned bases / deleted / intron positions of an item.
  */
 #ifndef LCR_DEVICE_H
 #define LCR_DEVICE_H
@@ -28,14 +29,6 @@
 #include "lcr_contract.h"
 
 #define LCR_TILE 512        /* positions per pileup tile == threads per pileup CTA */
-
-struct LcrItem {            /* part of one read inside one tile (20 B) */
-    uint32_t slot;          /* (region, read) pair                                  */
-    uint32_t cig;           /* CIGAR op index within the read where the tile is entered */
-    uint32_t opoff;         /* reference bases of that op already consumed          */
-    uint32_t rpos;          /* pos_in_read at the checkpoint                        */
-    int32_t fpos;           /* pos_in_freq_vec at the checkpoint                    */
-};
 
 /* per-region scalars produced on the device */
 struct LcrRegionState {

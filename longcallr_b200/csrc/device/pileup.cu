@@ -241,13 +241,12 @@ struct PrepArgs {
     uint32_t *deep_flag;   /* COUNT: set when some tile holds more than 255 items */
     uint32_t *slot_segs;   /* COUNT: upper bound of the read's segments (exact but for poly-A cuts) */
     const uint32_t *slot_seg_off; /* its exclusive scan: the read's segments are written there, in walk order, no atomics */
-    LcrItem *items;
-    uint2 *item_segs;      /* FILL: per item (tile order), first segment and segment count */
+    uint2 *item_segs;      /* FILL: per item (tile order; an item is the part of one read inside one tile), first segment and segment count */
     LcrSeg *segs;
 };
 
 /* Read filter (util.rs:652-668), fetch window, and the decomposition of every passing read into per-tile items
-   (CIGAR checkpoints for k_site_ll) and segments (what k_pileup_tile streams).  The read-end trim (ONT) and the
+   (a row index in the tile plus the read's segment range there) and segments (what k_pileup_tile and k_site_ll read).  The read-end trim (ONT) and the
    poly-A / homopolymer mask (util.rs:737-789) are applied here by cutting M runs at masked bases.  Two passes
    around an exclusive scan: COUNT sizes the per-tile lists, FILL writes them. */
 template <bool FILL>
@@ -404,13 +403,6 @@ __global__ void __launch_bounds__(128, 6) k_slot_prep(PrepArgs a) {
                             if (!FILL) { if (first <= 255u && first + npeer > 255u) *a.deep_flag = 1u; }
                             else {
                                 item_k = a.tile_off[key] + first + prank;
-                                LcrItem it;
-                                it.slot = slot;
-                                it.cig = (uint32_t)(c - c0);
-                                it.opoff = (uint32_t)(ts - lo);
-                                it.rpos = (uint32_t)(is_m ? rpos + (ts - lo) : rpos);
-                                it.fpos = (int32_t)ts;
-                                a.items[item_k] = it;
                             }
                         }
                         const uint32_t colr = (uint32_t)(ts - t * LCR_TILE);
@@ -761,13 +753,6 @@ __global__ void __launch_bounds__(128) k_slot_prep_w(PrepArgs a) {
                     if (!registers(t)) { atomicAdd(&a.tile_full_n[tb + (uint32_t)t], 1u); continue; }
                     if (t > last_before) {
                         const uint32_t k = a.tile_off[tb + (uint32_t)t] + atomicAdd(&a.tile_count[tb + (uint32_t)t], 1u);
-                        LcrItem it;
-                        it.slot = slot;
-                        it.cig = (uint32_t)(ci - c0);
-                        it.opoff = (uint32_t)(ts - lo);
-                        it.rpos = (uint32_t)(is_m ? rp0 + (ts - lo) : rp0);
-                        it.fpos = (int32_t)ts;
-                        a.items[k] = it;
                         if (!have_first) { have_first = true; first_new_begin = w; }
                         else a.item_segs[prev_k] = make_uint2(prev_begin, w - prev_begin); /* my previous new item is complete */
                         prev_k = k; prev_begin = w;
@@ -927,7 +912,6 @@ struct PileArgs {
     const uint32_t *cigar;
     const uint8_t *const *ref_table;
     const uint32_t *tile_off;
-    const LcrItem *items;
     const LcrTileDesc *desc;
     const uint2 *item_segs;
     const LcrSeg *segs;
@@ -1469,7 +1453,6 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     /* per-tile counters: [0] items, [1] whole-tile intron covers (+ the deep-tile flag); per-slot segment bounds; their scans */
     uint32_t *tile_cnt = nullptr, *tile_off = nullptr, *slot_segs = nullptr, *slot_seg_off = nullptr;
     uint64_t *slot_runs = nullptr;
-    LcrItem *items = nullptr;
     uint2 *item_segs = nullptr;
     LcrSeg *segs = nullptr;
     const size_t tn = (size_t)n_tiles + 1, sn = (size_t)db->n_slots + 1;
@@ -1494,7 +1477,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     pa.slot_flags = slot_flags; pa.slot_runs = slot_runs;
     pa.tile_count = tile_count; pa.tile_off = tile_off; pa.tile_full_n = tile_full_n; pa.deep_flag = deep_flag;
     pa.slot_segs = slot_segs; pa.slot_seg_off = slot_seg_off;
-    pa.items = nullptr; pa.item_segs = nullptr; pa.segs = nullptr;
+    pa.item_segs = nullptr; pa.segs = nullptr;
     /* batches averaging more than 24 CIGAR ops per read (ONT) take the warp-per-read, lane-per-op form (LCR_PREP_WALK: 1 / 2 forces one) */
     static const int prep_mode = [] { const char *e = getenv("LCR_PREP_WALK"); return e && *e ? atoi(e) : 0; }();
     const bool warp_walk = prep_mode == 2 || (prep_mode == 0 && db->n_cigar > 24ull * (db->n_reads ? db->n_reads : 1));
@@ -1520,12 +1503,11 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaMemcpyAsync(&totals[2], deep_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     const uint32_t n_items = totals[0], n_segs = totals[1];
-    TRY(cudaMallocAsync(&items, sizeof(LcrItem) * (size_t)(n_items ? n_items : 1), st));
     TRY(cudaMallocAsync(&item_segs, sizeof(uint2) * (size_t)(n_items ? n_items : 1), st));
     TRY(cudaMallocAsync(&segs, sizeof(LcrSeg) * (size_t)(n_segs ? n_segs : 1), st));
     TRY(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * tn, st));
     TRY(cudaMemsetAsync(item_segs, 0, sizeof(uint2) * (size_t)(n_items ? n_items : 1), st));
-    pa.items = items; pa.item_segs = item_segs; pa.segs = segs;
+    pa.item_segs = item_segs; pa.segs = segs;
     if (pg) {
         if (warp_walk) k_slot_prep_w<true><<<pg, pb, 0, st>>>(pa);
         else k_slot_prep<true><<<pg, pb, 0, st>>>(pa);
@@ -1569,7 +1551,7 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     ka.flag = db->flag; ka.ts = db->ts; ka.seq_off = db->seq_off; ka.cig_off = db->cig_off;
     ka.seq = db->seq; ka.qual = db->qual; ka.cigar = db->cigar;
     ka.ref_table = ctx->d_ref_table;
-    ka.tile_off = tile_off; ka.items = items;
+    ka.tile_off = tile_off;
     ka.desc = desc; ka.item_segs = item_segs; ka.segs = segs;
     ka.tables = ctx->d_tables;
     ka.rstate = db->rstate;
@@ -1662,7 +1644,6 @@ int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flag
     TRY(cudaFreeAsync(cand_raw, st));
     TRY(cudaFreeAsync(cand_key, st));
     TRY(cudaFreeAsync(cand_count, st));
-    TRY(cudaFreeAsync(items, st));
     TRY(cudaFreeAsync(segs, st));
     TRY(cudaFreeAsync(desc, st));
     TRY(cudaFreeAsync(slot_runs, st));
