@@ -200,7 +200,9 @@ void lcr_destroy(lcr_ctx *ctx);
 /* upload one contig (thread.rs:59,79: load_reference / ref_seqs.get(chr)); bytes as in the FASTA, case preserved */
 int lcr_set_reference(lcr_ctx *ctx, int32_t tid, const uint8_t *seq, uint64_t len);
 
-/* the worker body, thread.rs:78-221, for every region of the batch; blocking; host buffers */
+/* the worker body, thread.rs:78-221, for every region of the batch; blocking; host buffers (pinned memory lets the copies run
+   asynchronously: large batches are cut into chunks of consecutive regions whose uploads overlap the previous chunk's kernels).
+   Every entry point takes the context's mutex: concurrent callers on one context are safe and serialised. */
 int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out);
 void lcr_free_result(lcr_result *res);
 
@@ -208,7 +210,7 @@ void lcr_free_result(lcr_result *res);
      lcr_upload      copies a batch to HBM (returns a handle),
      lcr_run_device  runs the whole path on the resident batch and leaves results on the device,
      lcr_fetch       copies the results of the last run to the host.
-   lcr_submit == upload + run_device + fetch + release. */
+   lcr_submit == upload + run_device + fetch + release, per chunk of regions, with the results merged in batch order. */
 typedef struct lcr_device_batch lcr_device_batch;
 int lcr_upload(lcr_ctx *ctx, const lcr_batch *batch, lcr_device_batch **out);
 int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *db);
