@@ -256,10 +256,10 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     long long *es_prob = nullptr;
     {
         /* bins: launch shape (by number of configurations) x fragment-count class (shared memory footprint) */
-        const uint32_t NF_SMALL = 1024, NF_BIG = 16384;
-        const int NBIN = 10;
+        const uint32_t NF_TINY = 384, NF_SMALL = 1024, NF_BIG = 16384; /* fragment-count classes: shared-memory footprint */
+        const int NBIN = 15;
         std::vector<uint32_t> base(n_regions + 1, 0), wr[NBIN], wc[NBIN];
-        uint32_t nfmax[NBIN] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t nfmax[NBIN] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         /* regions with 5+ sites: 64 configurations per CTA when that still fills the GPU, else 16 (more, shorter CTAs) */
         uint64_t big_cfgs = 0;
         for (uint32_t r = 0; r < n_regions; ++r) {
@@ -276,7 +276,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
                 if (shape == 3 && small_batch) shape = 4;
                 const uint32_t per_cta = lcr_enum_cfgs_per_cta(shape);
                 chunks = ((1u << s.n_cand) + per_cta - 1) / per_cta;
-                bin[r] = shape * 2 + (s.n_frag <= NF_SMALL ? 0 : 1);
+                bin[r] = shape * 3 + (s.n_frag <= NF_TINY ? 0 : s.n_frag <= NF_SMALL ? 1 : 2);
             }
             base[r + 1] = base[r] + chunks;
         }
@@ -316,7 +316,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
                 if (!nw) continue;
                 cudaStream_t ss = ctx->side[used % 4];
                 TRY(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-                int e = lcr_launch_enum_search(b / 2, pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, ss);
+                int e = lcr_launch_enum_search(b / 3, b % 3 == 0, pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, ss);
                 if (e) { ctx->last_error = "k_enum_search launch failed"; ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
                 db->timing.kernel_launches += 1;
                 off += nw;

@@ -91,7 +91,7 @@ int lcr_launch_phase_grid(const PhaseArgs &a, uint32_t reg, void *bcast_scratch,
 size_t lcr_phase_bcast_bytes();
 int lcr_enum_shape_for(uint32_t n_cand);
 uint32_t lcr_enum_cfgs_per_cta(int shape);
-int lcr_launch_enum_search(int shape, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+int lcr_launch_enum_search(int shape, bool pre, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                            long long *out_prob, uint32_t *out_cfg, cudaStream_t st);
 
 #endif

@@ -32,7 +32,7 @@ struct EnumShared {
 
 /* EW warps per CTA, ECFG_PER_WARP configurations per warp (strided over the chunk so that warps stay balanced);
    small regions use small CTAs so that many of them share an SM */
-template <int EW, int ECFG_PER_WARP>
+template <int EW, int ECFG_PER_WARP, bool PRE>
 __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseArgs a, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                                                          long long *out_prob, uint32_t *out_cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
     uint32_t *rrel = reinterpret_cast<uint32_t *>(rows + nf_cap);
     uint32_t *wm = rrel + nf_cap;            /* per 32 rows: sites some phasing row of the word carries (warp-uniform skips) */
     uint32_t *sig = wm + words + warp * words;
+    /* PRE (regions with few fragments): p * W of every cell, site-major, so the sweeps load a signed term instead of decoding it */
+    long long *Tm = reinterpret_cast<long long *>(smem_raw + (((size_t)nf_cap * 12 + (size_t)(EW + 1) * words * 4 + 7) & ~(size_t)7));
     const lcr_candidate *c = a.cand + cb;
     const LcrDeviceTables &T = *a.tables;
     const uint64_t region_key = lcr_region_key(a.regions[reg].tid, a.regions[reg].start);
@@ -65,11 +67,16 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
         const uint32_t f = fb + k;
         unsigned long long row = a.frag_links[f] >= a.P.min_linkers ? (1ull << 63) : 0ull;
         uint32_t present = 0;
+        if (PRE) {
+#pragma unroll
+            for (int i = 0; i < EMAXN; ++i) Tm[(size_t)i * nf_cap + k] = 0;
+        }
         for (uint32_t e = a.frag_elem_off[f]; e < a.frag_elem_off[f + 1]; ++e) {
             const int8_t cell = a.elem_cell[e];
             const uint32_t code = cell > 0 ? (uint32_t)cell : ((uint32_t)(-cell) | 32u);
             row |= (unsigned long long)code << (6 * a.elem_snp[e]);
             if (code) present |= 1u << a.elem_snp[e];
+            if (PRE && code) Tm[(size_t)a.elem_snp[e] * nf_cap + k] = cell > 0 ? S.W[(code & 31u) - 1u] : -S.W[(code & 31u) - 1u];
         }
         rows[k] = row;
         if ((row >> 63) && present) atomicOr(&wm[k >> 5], present);
@@ -150,29 +157,52 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
                 if (k < nf) row = rows[k];
                 const bool active = row >> 63;
                 long long v = 0; /* sum_i p * delta * W over heterozygous phase sites */
+                if (PRE) {
 #pragma unroll
-                for (int i = 0; i < EMAXN; ++i) {
-                    if ((vs >> i) & 1u) {
-                        const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
-                        if (code) {
-                            const long long Wq = S.W[(code & 31u) - 1u];
-                            const bool minus = ((code >> 5) ^ (dneg >> i)) & 1u;
-                            v += minus ? -Wq : Wq;
+                    for (int i = 0; i < EMAXN; ++i) {
+                        if ((vs >> i) & 1u) {
+                            const long long t = k < nf ? Tm[(size_t)i * nf_cap + k] : 0;
+                            v += ((dneg >> i) & 1u) ? -t : t;
                         }
                     }
-                }
-                if (active && v != 0) {
-                    const bool nneg = v < 0;
-                    if (nneg != neg) { any_flip = true; neg = nneg; }
-                }
+                    if (active && v != 0) {
+                        const bool nneg = v < 0;
+                        if (nneg != neg) { any_flip = true; neg = nneg; }
+                    }
+                    if (active) {
 #pragma unroll
-                for (int i = 0; i < EMAXN; ++i) {
-                    if ((ms >> i) & 1u) {
-                        const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
-                        if (active && code) {
-                            const long long Wq = S.W[(code & 31u) - 1u];
-                            const bool minus = ((code >> 5) & 1u) ^ (neg ? 1u : 0u);
-                            M[i] += minus ? -Wq : Wq;
+                        for (int i = 0; i < EMAXN; ++i) {
+                            if ((ms >> i) & 1u) {
+                                const long long t = Tm[(size_t)i * nf_cap + k];
+                                M[i] += neg ? -t : t;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < EMAXN; ++i) {
+                        if ((vs >> i) & 1u) {
+                            const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
+                            if (code) {
+                                const long long Wq = S.W[(code & 31u) - 1u];
+                                const bool minus = ((code >> 5) ^ (dneg >> i)) & 1u;
+                                v += minus ? -Wq : Wq;
+                            }
+                        }
+                    }
+                    if (active && v != 0) {
+                        const bool nneg = v < 0;
+                        if (nneg != neg) { any_flip = true; neg = nneg; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < EMAXN; ++i) {
+                        if ((ms >> i) & 1u) {
+                            const uint32_t code = (uint32_t)(row >> (6 * i)) & 63u;
+                            if (active && code) {
+                                const long long Wq = S.W[(code & 31u) - 1u];
+                                const bool minus = ((code >> 5) & 1u) ^ (neg ? 1u : 0u);
+                                M[i] += minus ? -Wq : Wq;
+                            }
                         }
                     }
                 }
@@ -258,26 +288,29 @@ static const int SHAPES[5][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}, {8, 2}}; /* the
 
 int lcr_enum_shape_for(uint32_t n_cand) { return n_cand <= 2 ? 0 : (n_cand == 3 ? 1 : (n_cand == 4 ? 2 : 3)); }
 uint32_t lcr_enum_cfgs_per_cta(int shape) { return (uint32_t)(SHAPES[shape][0] * SHAPES[shape][1]); }
-static size_t smem_bytes(uint32_t nf_cap, int ew) { return (size_t)nf_cap * 12 + (size_t)(ew + 1) * ((nf_cap + 31) / 32) * 4 + 16; }
+static size_t smem_bytes(uint32_t nf_cap, int ew, bool pre) { return (size_t)nf_cap * 12 + (size_t)(ew + 1) * ((nf_cap + 31) / 32) * 4 + 16 + (pre ? (size_t)nf_cap * 8 * EMAXN + 8 : 0); }
 
-template <int EW, int CPW>
+template <int EW, int CPW, bool PRE>
 static int launch_shape(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                         long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
-    const size_t smem = smem_bytes(nf_cap, EW);
-    cudaError_t e = cudaFuncSetAttribute(k_enum_search<EW, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = smem_bytes(nf_cap, EW, PRE);
+    cudaError_t e = cudaFuncSetAttribute(k_enum_search<EW, CPW, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    k_enum_search<EW, CPW><<<n_work, EW * 32, smem, st>>>(a, work_region, work_chunk, nf_cap, out_prob, out_cfg);
+    k_enum_search<EW, CPW, PRE><<<n_work, EW * 32, smem, st>>>(a, work_region, work_chunk, nf_cap, out_prob, out_cfg);
     return 0;
 }
 
-int lcr_launch_enum_search(int shape, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
+/* pre: the bin holds only regions with few fragments (the signed-term table fits in shared memory); used by the 5+ site shapes */
+int lcr_launch_enum_search(int shape, bool pre, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
                            long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
     if (!n_work) return 0;
     switch (shape) {
-        case 0: return launch_shape<1, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        case 1: return launch_shape<2, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        case 2: return launch_shape<4, 4>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        case 3: return launch_shape<8, 8>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        default: return launch_shape<8, 2>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 0: return launch_shape<1, 4, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 1: return launch_shape<2, 4, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 2: return launch_shape<4, 4, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 3: return pre ? launch_shape<8, 8, true>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st)
+                           : launch_shape<8, 8, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        default: return pre ? launch_shape<8, 2, true>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st)
+                            : launch_shape<8, 2, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
     }
 }
