@@ -224,3 +224,15 @@ def test_concurrent_submit_on_one_context():
     assert not errs, errs
     for i in range(4):
         helpers.compare_results(got[i], want, f"thread {i}")
+
+
+@pytest.mark.parametrize("preset,platform,both,walk", [("hifi-masseq", 0, 0, "2"), ("ont-cdna", 1, 1, "1"), ("hifi-isoseq", 0, 1, "2"), ("ont-drna", 1, 0, "1")])
+def test_walk_variants(preset, platform, both, walk):
+    """The CIGAR walks have a thread-per-read and a warp-per-read form chosen by the batch's ops per read: force each on both platforms."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, LCR_PREP_WALK=walk, LCR_FRAG_WALK=walk, LCR_TILE_VARIANT="2" if walk == "1" else "1")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "parity_case.py"), preset, str(platform), str(both)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "parity ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
