@@ -6,6 +6,11 @@
  * `ref_seqs.get(chr)` (:59,:79), lcr_submit is the closure body, and the returned records are
  * what the three queues receive (:204-221).  There is no CPU fallback: without a device every
  * compute entry point returns LCR_ERR_NO_DEVICE.
+ *
+ * A run is one uninterrupted stream of kernels: every data-dependent size stays in a device counter
+ * block (lcr_pipeline.h), scratch comes from a per-context arena sized by capacities, and the host
+ * synchronises once, at the end, to read the counters.  A run whose counters report an overflow is
+ * repeated with larger capacities.
  */
 #include <cub/cub.cuh>
 
@@ -16,7 +21,7 @@
 
 #include "lcr_frag.h"
 
-int lcr_stage_pileup_impl(lcr_ctx *ctx, lcr_device_batch *db, uint8_t *slot_flags);
+int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounters *ctr, bool launch);
 
 namespace {
 
@@ -88,60 +93,74 @@ int h2d_padded(lcr_ctx *ctx, T **dst, const T *src, size_t n, size_t pad, uint64
     return 0;
 }
 
-/* fragment count from which an LD-path region gets the cooperative whole-GPU kernel (LCR_BIG_REGION_FRAGS overrides: tests) */
-static uint32_t big_frag_threshold() {
-    const char *e = getenv("LCR_BIG_REGION_FRAGS");
-    if (e && *e) return (uint32_t)strtoul(e, nullptr, 10);
-    return 8192;
-}
-
-__global__ void k_scatter_winners(uint32_t n, const uint32_t *slot, const long long *prob, const uint32_t *cfg, long long *out_prob, uint32_t *out_cfg) {
+/* unpack the per-read (region, value) keys: hp -1 / ps 0 = no entry */
+__global__ void k_finalize_reads(uint32_t n, const uint32_t *hp_key, const unsigned long long *ps_key, int8_t *hp, uint32_t *ps) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { out_prob[slot[i]] = prob[i]; out_cfg[slot[i]] = cfg[i]; }
+    if (i >= n) return;
+    const uint32_t h = hp_key[i];
+    hp[i] = h == 0xffffffffu ? (int8_t)-1 : (int8_t)(h & 3u);
+    const unsigned long long p = ps_key[i];
+    ps[i] = p == ~0ull ? 0u : (uint32_t)p;
 }
 
-__global__ void k_init_pairs(LcrPairEntry *t, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { t[i].key = ~0ull; t[i].cis = 0; t[i].trans = 0; }
-}
-
-int exclusive_scan_u32(lcr_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) {
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream);
-    void *tmp = nullptr;
-    TRY(cudaMallocAsync(&tmp, bytes ? bytes : 16, ctx->stream));
-    TRY(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, ctx->stream));
-    TRY(cudaFreeAsync(tmp, ctx->stream));
-    return 0;
+/* start of a run: region states from the statuses known at upload */
+__global__ void k_init_rstate(uint32_t n_regions, const int32_t *status0, LcrRegionState *rstate) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_regions) return;
+    LcrRegionState s;
+    memset(&s, 0, sizeof s);
+    s.status = status0[r];
+    rstate[r] = s;
 }
 
 } // namespace
 
 struct lcr_device_batch_full : lcr_device_batch {
     DbExtra extra;
-    uint8_t *slot_flags = nullptr;
 };
 
-static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
+/* fragment matrix, LD graph, phasing, read / SNP assignment, phase sets: carve from the arena, enqueue when `launch` */
+static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrArena &A, LcrCounters *ctr, bool launch) {
     cudaStream_t st = ctx->stream;
-    const uint32_t n_slots = db->n_slots, n_cand = db->n_cand, n_regions = db->n_regions;
-    uint32_t *frag_flag = nullptr, *elem_count = nullptr, *frag_scan = nullptr, *elem_scan = nullptr;
-    uint32_t *cover_count = nullptr, *cover_off = nullptr, *cover_cursor = nullptr, *cover_frag = nullptr;
-    int8_t *cover_cell = nullptr;
-    uint32_t *frag_slot = nullptr, *frag_elem_off = nullptr, *frag_links = nullptr, *elem_snp = nullptr;
-    int8_t *elem_cell = nullptr;
-    uint8_t *elem_base = nullptr;
-    DALLOC(frag_flag, (size_t)n_slots + 1);
-    DALLOC(elem_count, (size_t)n_slots + 1);
-    DALLOC(frag_scan, (size_t)n_slots + 1);
-    DALLOC(elem_scan, (size_t)n_slots + 1);
-    DALLOC(cover_count, (size_t)n_cand + 1);
-    DALLOC(cover_off, (size_t)n_cand + 1);
-    DALLOC(cover_cursor, (size_t)n_cand + 1);
-    TRY(cudaMemsetAsync(frag_flag, 0, sizeof(uint32_t) * ((size_t)n_slots + 1), st));
-    TRY(cudaMemsetAsync(elem_count, 0, sizeof(uint32_t) * ((size_t)n_slots + 1), st));
-    TRY(cudaMemsetAsync(cover_count, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
-    TRY(cudaMemsetAsync(cover_cursor, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
+    const uint32_t n_slots = db->n_slots, n_regions = db->n_regions, n_reads = db->n_reads;
+    const LcrCaps &C = db->caps;
+    const size_t sn = (size_t)n_slots + 1, cn = (size_t)std::min<uint64_t>(C.pre, 0xfffffff0u) + 1, rn = (size_t)n_regions + 1;
+    /* zeroed block: cover_count | cover_cursor | deg | adj_cursor (each cn), es_done (rn) */
+    uint32_t *zero_blk = A.take<uint32_t>(4 * cn + rn);
+    uint32_t *frag_flag = A.take<uint32_t>(sn), *elem_count = A.take<uint32_t>(sn), *frag_scan = A.take<uint32_t>(sn), *elem_scan = A.take<uint32_t>(sn);
+    uint32_t *cover_off = A.take<uint32_t>(cn), *adj_off = A.take<uint32_t>(cn);
+    uint32_t *frag_slot = A.take<uint32_t>(sn), *frag_elem_off = A.take<uint32_t>(sn + 1), *frag_links = A.take<uint32_t>(sn);
+    uint32_t *elem_snp = A.take<uint32_t>(C.elems), *cover_frag = A.take<uint32_t>(C.elems);
+    int8_t *elem_cell = A.take<int8_t>(C.elems), *cover_cell = A.take<int8_t>(C.elems);
+    uint8_t *elem_base = A.take<uint8_t>(C.elems);
+    LcrPairEntry *table = A.take<LcrPairEntry>(C.pairs);
+    uint32_t *entry_region = A.take<uint32_t>(C.pairs / 16 + 1);
+    uint32_t *region_cap = A.take<uint32_t>(rn), *region_cap_off = A.take<uint32_t>(rn);
+    uint32_t *adj = A.take<uint32_t>(C.adj);
+    PhaseArgs pa{};
+    pa.st = A.take<char4>(cn); pa.best_hap = A.take<int8_t>(cn); pa.best_gen = A.take<int8_t>(cn);
+    pa.label = A.take<uint32_t>(cn); pa.rank = A.take<uint32_t>(cn);
+    pa.work = A.take<uint32_t>(C.adj + cn + 1);
+    pa.blk_q = A.take<long long>(cn); pa.blk_qflip = A.take<long long>(cn);
+    pa.tag = A.take<int8_t>(sn); pa.best_tag = A.take<int8_t>(sn); pa.fp = A.take<uint8_t>(sn); pa.assign = A.take<uint8_t>(sn);
+    pa.hp_key = A.take<uint32_t>(n_reads); pa.ps_key = A.take<unsigned long long>(n_reads);
+    pa.es_base = A.take<uint32_t>(rn); pa.es_cfg = A.take<uint32_t>(C.enum_work); pa.es_prob = A.take<long long>(C.enum_work);
+    pa.work_region = A.take<uint32_t>(C.enum_work); pa.work_chunk = A.take<uint32_t>(C.enum_work);
+    void *bcast = A.take<char>(lcr_phase_bcast_bytes());
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)std::max(std::max(sn, cn), rn), st);
+    void *tmp = A.take<char>(tmp_bytes + 256);
+    /* the debug copy of the matrix is taken from these after the run */
+    db->fr_frag_off = frag_slot; db->fr_frag_read = frag_elem_off; db->fr_elem_snp = elem_snp; db->fr_elem_cell = elem_cell; db->fr_elem_base = elem_base;
+    if (!launch) return LCR_OK;
+
+    uint32_t *cover_count = zero_blk, *cover_cursor = zero_blk + cn, *deg = zero_blk + 2 * cn, *adj_cursor = zero_blk + 3 * cn;
+    pa.es_done = zero_blk + 4 * cn;
+    TRY(cudaMemsetAsync(zero_blk, 0, sizeof(uint32_t) * (4 * cn + rn), st));
+    TRY(cudaMemsetAsync(pa.hp_key, 0xff, sizeof(uint32_t) * (size_t)(n_reads ? n_reads : 1), st));
+    TRY(cudaMemsetAsync(pa.ps_key, 0xff, sizeof(unsigned long long) * (size_t)(n_reads ? n_reads : 1), st));
+    TRY(cudaMemsetAsync(frag_flag + n_slots, 0, sizeof(uint32_t), st));
+    TRY(cudaMemsetAsync(elem_count + n_slots, 0, sizeof(uint32_t), st));
 
     FragArgs fa{};
     fa.P = ctx->P;
@@ -149,94 +168,39 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     fa.regions = db->regions;
     fa.slot_off = db->slot_off; fa.slot_region = db->slot_region; fa.slot_flags = db->slot_flags;
     fa.pos = db->pos; fa.seq_off = db->seq_off; fa.cig_off = db->cig_off; fa.seq = db->seq; fa.qual = db->qual; fa.cigar = db->cigar;
-    fa.rstate = db->rstate; fa.cand = db->cand; fa.stats = db->d_stats;
+    fa.rstate = db->rstate; fa.cand = db->cand; fa.stats = db->d_stats; fa.ctr = ctr;
+    fa.elem_cap = (uint32_t)std::min<uint64_t>(C.elems, 0xfffffff0u); fa.pair_cap_total = (uint32_t)std::min<uint64_t>(C.pairs, 0xfffffff0u);
+    fa.adj_cap = (uint32_t)std::min<uint64_t>(C.adj, 0xfffffff0u);
     fa.frag_flag = frag_flag; fa.elem_count = elem_count; fa.frag_scan = frag_scan; fa.elem_scan = elem_scan;
     fa.cover_count = cover_count; fa.cover_off = cover_off; fa.cover_cursor = cover_cursor;
-    fa.is_fragment = db->is_fragment;
-    static const int walk_mode = [] { const char *e = getenv("LCR_FRAG_WALK"); return e && *e ? atoi(e) : 0; }(); /* 1: thread per read, 2: warp per read */
-    const bool long_cigars = walk_mode == 2 || (walk_mode == 0 && db->n_cigar > 24ull * (db->n_reads ? db->n_reads : 1));
-    lcr_launch_frag_count(fa, long_cigars, st);
-    int rc;
-    if ((rc = exclusive_scan_u32(ctx, frag_flag, frag_scan, (size_t)n_slots + 1))) return rc;
-    if ((rc = exclusive_scan_u32(ctx, elem_count, elem_scan, (size_t)n_slots + 1))) return rc;
-    if ((rc = exclusive_scan_u32(ctx, cover_count, cover_off, (size_t)n_cand + 1))) return rc;
-    db->timing.kernel_launches += 1; /* own kernels only; cub scans are library code */
-    lcr_launch_region_frag_ranges(n_regions, db->slot_off, frag_scan, db->rstate, st);
-    db->timing.kernel_launches += 1;
-    uint32_t n_frag_total = 0, n_elem_total = 0;
-    std::vector<LcrRegionState> hrs(n_regions);
-    TRY(cudaMemcpyAsync(&n_frag_total, frag_scan + n_slots, 4, cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(&n_elem_total, elem_scan + n_slots, 4, cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(hrs.data(), db->rstate, sizeof(LcrRegionState) * n_regions, cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));
-    /* LD pair tables: one open-addressing segment per region that takes the LD path */
-    uint64_t table_size = 0;
-    for (uint32_t r = 0; r < n_regions; ++r) {
-        LcrRegionState &s = hrs[r];
-        s.pair_begin = 0; s.pair_cap = 0;
-        if (s.status != 0 || s.n_cand <= ctx->P.max_enum_snps || !s.n_ld_pairs_cap) continue;
-        uint64_t bound = std::min<uint64_t>(s.n_ld_pairs_cap, (uint64_t)s.n_cand * (s.n_cand - 1) / 2);
-        uint64_t cap = 16;
-        while (cap < 2 * bound) cap <<= 1;
-        if (table_size + cap > 0xfffffff0ull) { ctx->last_error = "LD pair table too large"; return LCR_ERR_OOM; }
-        s.pair_begin = (uint32_t)table_size;
-        s.pair_cap = (uint32_t)cap;
-        table_size += cap;
-    }
-    TRY(cudaMemcpyAsync(db->rstate, hrs.data(), sizeof(LcrRegionState) * n_regions, cudaMemcpyHostToDevice, st));
-    db->n_frag = n_frag_total;
-    db->n_elem = n_elem_total;
-    DALLOC(frag_slot, (size_t)n_frag_total + 1);
-    DALLOC(frag_elem_off, (size_t)n_frag_total + 1);
-    DALLOC(frag_links, (size_t)n_frag_total + 1);
-    DALLOC(elem_snp, n_elem_total);
-    DALLOC(elem_cell, n_elem_total);
-    DALLOC(elem_base, n_elem_total);
-    DALLOC(cover_frag, n_elem_total);
-    DALLOC(cover_cell, n_elem_total);
-    if (!n_frag_total) TRY(cudaMemsetAsync(frag_elem_off, 0, sizeof(uint32_t), st));
-    fa.n_frag_total = n_frag_total; fa.n_elem_total = n_elem_total;
+    fa.cover_frag = cover_frag; fa.cover_cell = cover_cell;
     fa.frag_slot = frag_slot; fa.frag_elem_off = frag_elem_off; fa.frag_links = frag_links;
     fa.elem_snp = elem_snp; fa.elem_cell = elem_cell; fa.elem_base = elem_base;
-    fa.cover_frag = cover_frag; fa.cover_cell = cover_cell;
+    fa.is_fragment = db->is_fragment;
+    const int walk_mode = ctx->frag_walk_mode; /* 1: thread per read, 2: warp per read */
+    const bool long_cigars = walk_mode == 2 || (walk_mode == 0 && db->n_cigar > 24ull * (db->n_reads ? db->n_reads : 1));
+    lcr_launch_frag_count(fa, long_cigars, st);
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, frag_flag, frag_scan, (int)sn, st));
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, elem_count, elem_scan, (int)sn, st));
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cover_count, cover_off, (int)cn, st));
+    lcr_launch_region_frag_ranges(fa, n_regions, st);
     lcr_launch_frag_fill(fa, long_cigars, st);
-    db->timing.kernel_launches += 1;
+    db->timing.kernel_launches += 3; /* own kernels only; cub scans are library code */
 
-    /* LD graph */
-    LcrPairEntry *table = nullptr;
-    uint32_t *entry_region = nullptr, *deg = nullptr, *adj_off = nullptr, *adj_cursor = nullptr, *adj = nullptr;
-    DALLOC(deg, (size_t)n_cand + 1);
-    DALLOC(adj_off, (size_t)n_cand + 1);
-    DALLOC(adj_cursor, (size_t)n_cand + 1);
-    TRY(cudaMemsetAsync(deg, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
-    TRY(cudaMemsetAsync(adj_cursor, 0, sizeof(uint32_t) * ((size_t)n_cand + 1), st));
-    uint32_t adj_total = 0;
-    if (table_size) {
-        DALLOC(table, table_size);
-        DALLOC(entry_region, table_size / 16);
-        k_init_pairs<<<(uint32_t)((table_size + 255) / 256), 256, 0, st>>>(table, table_size);
-        lcr_launch_fill_entry_region(n_regions, db->rstate, entry_region, st);
-        lcr_launch_pair_count(fa, table, st);
-        lcr_launch_ld_edges(false, ctx->P.ld_weight_threshold, n_regions, db->rstate, table, table_size, entry_region, deg, nullptr, nullptr, nullptr, st);
-        db->timing.kernel_launches += 4;
-    }
-    if ((rc = exclusive_scan_u32(ctx, deg, adj_off, (size_t)n_cand + 1))) return rc;
-    if (table_size) {
-        TRY(cudaMemcpyAsync(&adj_total, adj_off + n_cand, 4, cudaMemcpyDeviceToHost, st));
-        TRY(cudaStreamSynchronize(st));
-    }
-    DALLOC(adj, adj_total);
-    if (table_size && adj_total) {
-        lcr_launch_ld_edges(true, ctx->P.ld_weight_threshold, n_regions, db->rstate, table, table_size, entry_region, deg, adj_off, adj_cursor, adj, st);
-        lcr_launch_adj_sort(n_cand, adj_off, adj, st);
-        db->timing.kernel_launches += 2;
-    }
-    cudaEvent_t ev_frag;
-    TRY(cudaEventCreate(&ev_frag));
-    TRY(cudaEventRecord(ev_frag, st));
+    /* LD graph of the regions with more than max_enum_snps candidates: pair table segments, perfect-LD edges, sorted adjacency */
+    lcr_launch_pair_plan(fa, n_regions, region_cap, region_cap_off, false, st);
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, region_cap, region_cap_off, (int)rn, st));
+    lcr_launch_pair_plan(fa, n_regions, region_cap, region_cap_off, true, st);
+    lcr_launch_pair_build(fa, n_regions, table, entry_region, ctx->sm_count, st);
+    lcr_launch_ld_edges(false, fa, table, entry_region, deg, nullptr, nullptr, nullptr, ctx->sm_count, st);
+    TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, adj_off, (int)cn, st));
+    lcr_launch_adj_finish(fa, adj_off, adj, false, ctx->sm_count, st);
+    lcr_launch_ld_edges(true, fa, table, entry_region, deg, adj_off, adj_cursor, adj, ctx->sm_count, st);
+    lcr_launch_adj_finish(fa, adj_off, adj, true, ctx->sm_count, st);
+    db->timing.kernel_launches += 9;
+    TRY(cudaEventRecord(ctx->ev_t[4], st));
 
     /* phasing state */
-    PhaseArgs pa{};
     pa.P = ctx->P;
     pa.n_regions = n_regions;
     pa.regions = db->regions; pa.slot_off = db->slot_off; pa.rstate = db->rstate; pa.cand = db->cand;
@@ -245,151 +209,50 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db) {
     pa.elem_snp = elem_snp; pa.elem_cell = elem_cell;
     pa.cover_off = cover_off; pa.cover_frag = cover_frag; pa.cover_cell = cover_cell;
     pa.adj_off = adj_off; pa.adj = adj;
-    DALLOC(pa.st, n_cand); DALLOC(pa.best_hap, n_cand); DALLOC(pa.best_gen, n_cand);
-    DALLOC(pa.label, n_cand); DALLOC(pa.rank, n_cand);
-    DALLOC(pa.work, (size_t)adj_total + n_cand + 1);
-    DALLOC(pa.blk_q, n_cand); DALLOC(pa.blk_qflip, n_cand);
-    DALLOC(pa.tag, n_frag_total); DALLOC(pa.best_tag, n_frag_total); DALLOC(pa.fp, n_frag_total); DALLOC(pa.assign, n_frag_total);
-    pa.hp = db->hp; pa.ps = db->ps;
-    /* enumeration search (regions with at most min(max_enum_snps, 10) candidates): one warp per configuration */
-    uint32_t *es_base = nullptr, *es_cfg = nullptr, *work_region = nullptr, *work_chunk = nullptr;
-    long long *es_prob = nullptr;
-    {
-        /* bins: launch shape (by number of configurations) x fragment-count class (shared memory footprint) */
-        const uint32_t NF_TINY = 384, NF_SMALL = 1024, NF_BIG = 16384; /* fragment-count classes: shared-memory footprint */
-        const int NBIN = 15;
-        std::vector<uint32_t> base(n_regions + 1, 0), wr[NBIN], wc[NBIN];
-        uint32_t nfmax[NBIN] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        /* regions with 5+ sites: 64 configurations per CTA when that still fills the GPU, else 16 (more, shorter CTAs) */
-        uint64_t big_cfgs = 0;
-        for (uint32_t r = 0; r < n_regions; ++r) {
-            const LcrRegionState &s = hrs[r];
-            if (s.status == 0 && s.n_cand > 4 && s.n_cand <= ctx->P.max_enum_snps && s.n_cand <= 10 && s.n_frag <= NF_BIG) big_cfgs += 1ull << s.n_cand;
-        }
-        const bool small_batch = big_cfgs / 64 < 8ull * (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
-        std::vector<int> bin(n_regions, -1);
-        for (uint32_t r = 0; r < n_regions; ++r) {
-            const LcrRegionState &s = hrs[r];
-            uint32_t chunks = 0;
-            if (s.status == 0 && s.n_cand && s.n_cand <= ctx->P.max_enum_snps && s.n_cand <= 10 && s.n_frag <= NF_BIG) {
-                int shape = lcr_enum_shape_for(s.n_cand);
-                if (shape == 3 && small_batch) shape = 4;
-                const uint32_t per_cta = lcr_enum_cfgs_per_cta(shape);
-                chunks = ((1u << s.n_cand) + per_cta - 1) / per_cta;
-                bin[r] = shape * 3 + (s.n_frag <= NF_TINY ? 0 : s.n_frag <= NF_SMALL ? 1 : 2);
-            }
-            base[r + 1] = base[r] + chunks;
-        }
-        const uint32_t n_work_total = base[n_regions];
-        if (n_work_total) {
-            for (uint32_t r = 0; r < n_regions; ++r)
-                if (bin[r] >= 0) {
-                    nfmax[bin[r]] = std::max(nfmax[bin[r]], hrs[r].n_frag);
-                    for (uint32_t ck = 0; ck < base[r + 1] - base[r]; ++ck) { wr[bin[r]].push_back(r); wc[bin[r]].push_back(ck); }
-                }
-            DALLOC(es_base, (size_t)n_regions + 1);
-            DALLOC(es_cfg, n_work_total);
-            DALLOC(es_prob, n_work_total);
-            DALLOC(work_region, n_work_total);
-            DALLOC(work_chunk, n_work_total);
-            TRY(cudaMemcpyAsync(es_base, base.data(), sizeof(uint32_t) * (n_regions + 1), cudaMemcpyHostToDevice, st));
-            /* each bin writes its winners in launch order; they are scattered to (region, chunk) order afterwards */
-            std::vector<uint32_t> order_region, order_chunk;
-            for (int b = 0; b < NBIN; ++b) { order_region.insert(order_region.end(), wr[b].begin(), wr[b].end()); order_chunk.insert(order_chunk.end(), wc[b].begin(), wc[b].end()); }
-            TRY(cudaMemcpyAsync(work_region, order_region.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
-            TRY(cudaMemcpyAsync(work_chunk, order_chunk.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
-            long long *tmp_prob = nullptr;
-            uint32_t *tmp_cfg = nullptr, *d_slot = nullptr;
-            DALLOC(tmp_prob, n_work_total);
-            DALLOC(tmp_cfg, n_work_total);
-            DALLOC(d_slot, n_work_total);
-            std::vector<uint32_t> slot(n_work_total);
-            for (uint32_t i = 0; i < n_work_total; ++i) slot[i] = base[order_region[i]] + order_chunk[i];
-            TRY(cudaMemcpyAsync(d_slot, slot.data(), sizeof(uint32_t) * n_work_total, cudaMemcpyHostToDevice, st));
-            TRY(cudaStreamSynchronize(st)); /* the host vectors above go out of scope */
-            /* the bins are independent: fork them onto side streams so that small and large shapes overlap */
-            uint32_t off = 0;
-            TRY(cudaEventRecord(ctx->ev_fork, st));
-            int used = 0;
-            for (int b = 0; b < NBIN; ++b) {
-                const uint32_t nw = (uint32_t)wr[b].size();
-                if (!nw) continue;
-                cudaStream_t ss = ctx->side[used % 4];
-                TRY(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-                int e = lcr_launch_enum_search(b / 3, b % 3 == 0, pa, nw, work_region + off, work_chunk + off, std::max<uint32_t>(nfmax[b], 32), tmp_prob + off, tmp_cfg + off, ss);
-                if (e) { ctx->last_error = "k_enum_search launch failed"; ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
-                db->timing.kernel_launches += 1;
-                off += nw;
-                ++used;
-            }
-            for (int i = 0; i < 4 && i < used; ++i) {
-                TRY(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
-                TRY(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
-            }
-            k_scatter_winners<<<(n_work_total + 127) / 128, 128, 0, st>>>(n_work_total, d_slot, tmp_prob, tmp_cfg, es_prob, es_cfg);
-            db->timing.kernel_launches += 1;
-            DFREE(tmp_prob); DFREE(tmp_cfg); DFREE(d_slot);
-            pa.es_base = es_base; pa.es_prob = es_prob; pa.es_cfg = es_cfg;
-        }
+    pa.ctr = ctr;
+    pa.big_frag_threshold = ctx->big_frag_threshold;
+    /* enumeration search (regions with at most min(max_enum_snps, 10) candidates): work lists on the device, one persistent launch
+       per (shape, class) bin; the bins are independent: fork them onto side streams so that small and large shapes overlap */
+    lcr_launch_enum_plan(pa, (uint32_t)std::min<uint64_t>(C.enum_work, 0xfffffff0u), ctx->sm_count, st);
+    db->timing.kernel_launches += 1;
+    TRY(cudaEventRecord(ctx->ev_fork, st));
+    for (int i = 0; i < 4; ++i) TRY(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+    for (int b = 0; b < LCR_ENUM_BINS; ++b) {
+        int e = lcr_launch_enum_search(b, pa, ctx->sm_count, ctx->side[b % 4]);
+        if (e) { ctx->last_error = std::string("k_enum_search: ") + cudaGetErrorString((cudaError_t)e); ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
+        db->timing.kernel_launches += 1;
     }
-    /* regions too large for one CTA take the whole GPU, one after the other */
-    uint8_t *big_region = nullptr;
-    void *bcast = nullptr;
-    std::vector<uint32_t> big_list;
-    {
-        std::vector<uint8_t> big(n_regions, 0);
-        for (uint32_t r = 0; r < n_regions; ++r)
-            if (hrs[r].status == 0 && hrs[r].n_cand > ctx->P.max_enum_snps && hrs[r].n_frag >= big_frag_threshold()) { big[r] = 1; big_list.push_back(r); }
-        if (!big_list.empty()) {
-            DALLOC(big_region, n_regions);
-            TRY(cudaMemcpyAsync(big_region, big.data(), n_regions, cudaMemcpyHostToDevice, st));
-            TRY(cudaStreamSynchronize(st));
-            TRY(cudaMallocAsync(&bcast, lcr_phase_bcast_bytes(), st));
-            pa.big_region = big_region;
-        }
+    for (int i = 0; i < 4; ++i) {
+        TRY(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+        TRY(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }
     lcr_launch_phase(pa, st);
     db->timing.kernel_launches += 1;
-    for (uint32_t r : big_list) {
-        int e = lcr_launch_phase_grid(pa, r, bcast, ctx->sm_count, st);
+    /* regions too large for one CTA take the whole GPU, one after the other */
+    if (db->n_big_list) {
+        int e = lcr_launch_phase_grid(pa, db->big_list, db->n_big_list, bcast, ctx->sm_count, st);
         if (e) { ctx->last_error = std::string("k_phase_grid: ") + cudaGetErrorString((cudaError_t)e); ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
         db->timing.kernel_launches += 1;
     }
-    cudaEvent_t ev_end;
-    TRY(cudaEventCreate(&ev_end));
-    TRY(cudaEventRecord(ev_end, st));
-
-    if (ctx->P.flags & LCR_FLAG_EMIT_FRAGMENTS) {
-        FragDebug &fd = db->extra.fragdbg;
-        fd.frag_slot.resize(n_frag_total); fd.frag_elem_off.resize((size_t)n_frag_total + 1);
-        fd.elem_snp.resize(n_elem_total); fd.elem_cell.resize(n_elem_total); fd.elem_base.resize(n_elem_total);
-        if (n_frag_total) TRY(cudaMemcpyAsync(fd.frag_slot.data(), frag_slot, 4ull * n_frag_total, cudaMemcpyDeviceToHost, st));
-        TRY(cudaMemcpyAsync(fd.frag_elem_off.data(), frag_elem_off, 4ull * ((size_t)n_frag_total + (n_frag_total ? 1 : 0)), cudaMemcpyDeviceToHost, st));
-        if (n_elem_total) {
-            TRY(cudaMemcpyAsync(fd.elem_snp.data(), elem_snp, 4ull * n_elem_total, cudaMemcpyDeviceToHost, st));
-            TRY(cudaMemcpyAsync(fd.elem_cell.data(), elem_cell, n_elem_total, cudaMemcpyDeviceToHost, st));
-            TRY(cudaMemcpyAsync(fd.elem_base.data(), elem_base, n_elem_total, cudaMemcpyDeviceToHost, st));
-        }
-        if (!n_frag_total) fd.frag_elem_off[0] = 0;
+    if (n_reads) {
+        k_finalize_reads<<<(n_reads + 255) / 256, 256, 0, st>>>(n_reads, pa.hp_key, pa.ps_key, db->hp, db->ps);
+        db->timing.kernel_launches += 1;
     }
-    TRY(cudaStreamSynchronize(st));
     TRY(cudaGetLastError());
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev_frag, ev_end);
-    db->timing.ms_phase = ms;
-    cudaEventDestroy(ev_frag);
-    cudaEventDestroy(ev_end);
-
-    DFREE(frag_flag); DFREE(elem_count); DFREE(frag_scan); DFREE(elem_scan);
-    DFREE(cover_count); DFREE(cover_off); DFREE(cover_cursor); DFREE(cover_frag); DFREE(cover_cell);
-    DFREE(frag_slot); DFREE(frag_elem_off); DFREE(frag_links); DFREE(elem_snp); DFREE(elem_cell); DFREE(elem_base);
-    DFREE(table); DFREE(entry_region); DFREE(deg); DFREE(adj_off); DFREE(adj_cursor); DFREE(adj);
-    DFREE(pa.st); DFREE(pa.best_hap); DFREE(pa.best_gen);
-    DFREE(pa.label); DFREE(pa.rank); DFREE(pa.work); DFREE(pa.blk_q); DFREE(pa.blk_qflip);
-    DFREE(pa.tag); DFREE(pa.best_tag); DFREE(pa.fp); DFREE(pa.assign);
-    DFREE(es_base); DFREE(es_cfg); DFREE(es_prob); DFREE(work_region); DFREE(work_chunk);
-    DFREE(big_region); DFREE(bcast);
     return LCR_OK;
+}
+
+/* sizes a run needs from the arena with the batch's current capacities */
+static int plan_or_launch(lcr_ctx *ctx, lcr_device_batch_full *db, bool launch) {
+    LcrArena &A = ctx->arena;
+    A.off = 0;
+    A.dry = !launch;
+    int rc = lcr_stage_pileup(ctx, db, A, ctx->d_ctr, launch);
+    if (rc) return rc;
+    if (launch) TRY(cudaEventRecord(ctx->ev_t[3], ctx->stream));
+    if (!(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) rc = stage_fragments_phase(ctx, db, A, ctx->d_ctr, launch);
+    else if (launch) TRY(cudaEventRecord(ctx->ev_t[4], ctx->stream));
+    return rc;
 }
 
 extern "C" {
@@ -405,7 +268,7 @@ const char *lcr_strerror(int status) {
         case LCR_ERR_OOM: return "out of memory";
         case LCR_ERR_BAD_CIGAR: return "unknown or inconsistent CIGAR operation";
         case LCR_ERR_NO_REFERENCE: return "region on a contig without reference sequence";
-        case LCR_ERR_BASEQ_ZERO: return "base quality 0 at a fragment site";
+        case LCR_ERR_BASEQ_ZERO: return "base quality 0 at a phase site";
         default: return "unknown status";
     }
 }
@@ -414,6 +277,9 @@ const char *lcr_last_error(lcr_ctx *ctx) { return ctx ? ctx->last_error.c_str() 
 
 int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     if (!p || !out) return LCR_ERR_INVALID_ARG;
+    /* `1 << n` configurations are enumerated for up to max_enum_snps candidates (phase.rs:1097-1122) */
+    if (p->max_enum_snps > 20u) return LCR_ERR_INVALID_ARG;
+    if (p->platform != 0 && p->platform != 1) return LCR_ERR_INVALID_ARG;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return LCR_ERR_NO_DEVICE;
     if (cudaSetDevice(device) != cudaSuccess) return LCR_ERR_NO_DEVICE;
@@ -426,9 +292,19 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     ctx->d_ref_len = nullptr;
     ctx->ref_table_cap = 0;
     ctx->ref_dirty = true;
+    ctx->d_ctr = nullptr; ctx->h_ctr = nullptr; ctx->h_stats = nullptr;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
+    /* experiment / test knobs, read once per context (DESIGN.md "Environment knobs") */
+    {
+        const char *e = getenv("LCR_BIG_REGION_FRAGS");
+        ctx->big_frag_threshold = (e && *e) ? (uint32_t)strtoul(e, nullptr, 10) : 8192u;
+        e = getenv("LCR_FRAG_WALK");
+        ctx->frag_walk_mode = (e && *e) ? atoi(e) : 0;
+        e = getenv("LCR_SUBMIT_CHUNK_MB");
+        ctx->submit_chunk_bytes = (e && *e) ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)256 << 20;
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LCR_ERR_CUDA; }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -437,6 +313,7 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
         cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
+    for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev_t[i]);
     /* keep freed blocks in the stream-ordered pool between runs */
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -461,9 +338,11 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
         for (uint32_t k = 0; k <= n; ++k)
             if (lcr_binom_two_tailed_lt_0p05(k, n)) t.binom_reject[n] |= 1u << k;
     }
-    if (cudaMalloc(&ctx->d_tables, sizeof t) != cudaSuccess || cudaMemcpy(ctx->d_tables, &t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
+    bool ok = cudaMalloc(&ctx->d_tables, sizeof t) == cudaSuccess && cudaMemcpy(ctx->d_tables, &t, sizeof t, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_ctr, sizeof(LcrCounters)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_ctr, sizeof(LcrCounters)) == cudaSuccess && cudaMallocHost(&ctx->h_stats, sizeof(lcr_stats)) == cudaSuccess;
+    if (!ok) {
+        lcr_destroy(ctx);
         return LCR_ERR_CUDA;
     }
     *out = ctx;
@@ -478,7 +357,12 @@ void lcr_destroy(lcr_ctx *ctx) {
     if (ctx->d_ref_table) cudaFree(ctx->d_ref_table);
     if (ctx->d_ref_len) cudaFree(ctx->d_ref_len);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
     for (int i = 0; i < 4; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev_t[i]);
     cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
@@ -514,6 +398,12 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     if (ctx->sticky) return ctx->sticky;
     if (b->n_regions && !b->regions) return LCR_ERR_INVALID_ARG;
     if (b->n_reads && (!b->pos || !b->flag || !b->mapq || !b->ts || !b->de || !b->seq_off || !b->cig_off)) return LCR_ERR_INVALID_ARG;
+    /* the kernels index the pools with these offsets: they must be non-decreasing and the pools present */
+    const uint64_t n_bases = b->n_reads ? b->seq_off[b->n_reads] : 0, n_cig = b->n_reads ? b->cig_off[b->n_reads] : 0;
+    if ((n_bases && (!b->seq || !b->qual)) || (n_cig && !b->cigar)) return LCR_ERR_INVALID_ARG;
+    if (n_bases >= (1ull << 47) || n_cig >= (1ull << 47)) return LCR_ERR_INVALID_ARG;
+    for (uint32_t i = 0; i < b->n_reads; ++i)
+        if (b->seq_off[i + 1] < b->seq_off[i] || b->cig_off[i + 1] < b->cig_off[i]) return LCR_ERR_INVALID_ARG;
     TRY(cudaSetDevice(ctx->device));
     lcr_device_batch_full *db = new (std::nothrow) lcr_device_batch_full();
     if (!db) return LCR_ERR_OOM;
@@ -522,10 +412,13 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     db->n_reads = b->n_reads;
     db->ran = false;
     memset(&db->timing, 0, sizeof db->timing);
-    /* prefix sums over region lengths and read ranges; regions that cannot run get their status here */
-    std::vector<uint32_t> slot_off(b->n_regions + 1, 0), tile_base(b->n_regions + 1, 0);
+    /* prefix sums over region lengths and read ranges (64-bit: read ranges may overlap, so slots are not bounded by the
+       read count); regions that cannot run get their status here */
+    std::vector<uint32_t> slot_off(b->n_regions + 1, 0), tile_base(b->n_regions + 1, 0), big_list;
     std::vector<uint64_t> pos_off(b->n_regions + 1, 0);
     db->extra.h_status0.assign(b->n_regions, 0);
+    uint64_t slots64 = 0, tiles64 = 0;
+    uint32_t max_slots = 0;
     for (uint32_t r = 0; r < b->n_regions; ++r) {
         const lcr_region &g = b->regions[r];
         int32_t stt = 0;
@@ -535,13 +428,20 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         db->extra.h_status0[r] = stt;
         const uint64_t len = stt ? 0 : (uint64_t)(g.end - g.start);
         const uint32_t nreads = stt ? 0 : g.read_end - g.read_begin;
-        slot_off[r + 1] = slot_off[r] + nreads;
-        tile_base[r + 1] = tile_base[r] + (uint32_t)((len + LCR_TILE - 1) / LCR_TILE);
+        slots64 += nreads;
+        tiles64 += (len + LCR_TILE - 1) / LCR_TILE;
+        if (slots64 > 0xfffffff0ull || tiles64 > 0xfffffff0ull) { delete db; return LCR_ERR_INVALID_ARG; }
+        slot_off[r + 1] = (uint32_t)slots64;
+        tile_base[r + 1] = (uint32_t)tiles64;
         pos_off[r + 1] = pos_off[r] + len;
+        max_slots = std::max(max_slots, nreads);
+        if (nreads >= ctx->big_frag_threshold) big_list.push_back(r);
     }
     db->n_slots = slot_off[b->n_regions];
     db->n_tiles = tile_base[b->n_regions];
     db->n_pos = pos_off[b->n_regions];
+    db->max_region_slots = max_slots;
+    db->n_big_list = (uint32_t)big_list.size();
     std::vector<uint32_t> slot_region(db->n_slots), tile_region(db->n_tiles);
     for (uint32_t r = 0; r < b->n_regions; ++r) {
         std::fill(slot_region.begin() + slot_off[r], slot_region.begin() + slot_off[r + 1], r);
@@ -550,9 +450,20 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     db->h_pos_off = pos_off;
     db->h_slot_off = slot_off;
     db->extra.h_regions.assign(b->regions, b->regions + b->n_regions);
-    const uint64_t n_bases = b->n_reads ? b->seq_off[b->n_reads] : 0, n_cig = b->n_reads ? b->cig_off[b->n_reads] : 0;
     db->n_bases = n_bases;
     db->n_cigar = n_cig;
+    /* first guesses of the data-dependent capacities; a run that needs more says so in its counters */
+    {
+        const uint64_t factor = std::max<uint64_t>(1, (db->n_slots + (uint64_t)std::max<uint32_t>(b->n_reads, 1) - 1) / std::max<uint32_t>(b->n_reads, 1));
+        LcrCaps &C = db->caps;
+        C.items = 3ull * db->n_slots + 4ull * db->n_tiles + 1024;
+        C.segs = n_cig * factor + 32ull * db->n_slots + 1024;
+        C.pre = db->n_pos / 64 + 65536;
+        C.elems = 16ull * db->n_slots + (1ull << 20);
+        C.pairs = 1ull << 20;
+        C.adj = 1ull << 20;
+        C.enum_work = 64ull * b->n_regions + 1024;
+    }
     uint64_t bytes = 0;
     int rc = 0;
 #define UP(field, src, n) if (!rc) rc = h2d(ctx, &db->field, src, (size_t)(n), &bytes)
@@ -563,6 +474,8 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     UP(tile_base, tile_base.data(), tile_base.size());
     UP(tile_region, tile_region.data(), tile_region.size());
     UP(pos_off, pos_off.data(), pos_off.size());
+    UP(status0, db->extra.h_status0.data(), db->extra.h_status0.size());
+    UP(big_list, big_list.data(), big_list.size());
     UP(regions, b->regions, b->n_regions);
     if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
     else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
@@ -572,14 +485,21 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     UP(ts, b->ts, b->n_reads);
     UP(de, b->de, b->n_reads);
     UP(cigar, b->cigar, n_cig);
+    /* result buffers live as long as the handle */
+    if (!rc) rc = dalloc(ctx, &db->rstate, db->n_regions);
+    if (!rc) rc = dalloc(ctx, &db->hp, db->n_reads);
+    if (!rc) rc = dalloc(ctx, &db->ps, db->n_reads);
+    if (!rc) rc = dalloc(ctx, &db->is_fragment, db->n_reads);
+    if (!rc) rc = dalloc(ctx, &db->d_stats, 1);
+    if (!rc) rc = dalloc(ctx, &db->slot_flags, db->n_slots);
     if (!rc && async) {
         cudaError_t e = cudaEventCreateWithFlags(&db->ev_meta, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(db->ev_meta, ctx->stream);
         if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
     }
-    /* seq / qual carry 32 bytes of slack: the tile kernel reads aligned 16-byte blocks plus the following word */
-    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 32, &bytes);
-    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 32, &bytes);
+    /* seq / qual carry 64 bytes of slack: bulk copies and block loads read whole 16-byte groups */
+    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 64, &bytes);
+    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 64, &bytes);
 #undef UP
     if (!rc) {
         cudaError_t e = cudaSuccess;
@@ -597,14 +517,6 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
 
 int lcr_upload(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out) { return upload_impl(ctx, b, out, false); }
 
-static void free_results(lcr_ctx *ctx, lcr_device_batch_full *db) {
-    DFREE(db->rstate); DFREE(db->cand); DFREE(db->hp); DFREE(db->ps); DFREE(db->is_fragment); DFREE(db->d_stats);
-    DFREE(db->pl_acgt); DFREE(db->pl_fwd); DFREE(db->pl_d); DFREE(db->pl_n); DFREE(db->pl_ts);
-    DFREE(db->slot_flags);
-    db->n_cand = 0;
-    db->ran = false;
-}
-
 int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     std::unique_lock<std::recursive_mutex> ctx_lock__;
     if (ctx) ctx_lock__ = std::unique_lock<std::recursive_mutex>(ctx->mu);
@@ -613,18 +525,9 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
     TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    db->seq_wait_pending = false;
     if (db->ev_meta) TRY(cudaStreamWaitEvent(st, db->ev_meta, 0));
-    if (db->ev_seq) {
-        /* ONT presets: nothing before the tile kernel reads bases (the read-end trim needs no sequence), so the seq / qual
-           copies keep running under the read filter and segment build; the pileup stage waits right before the tile kernel */
-        if (ctx->P.platform == 1) db->seq_wait_pending = true;
-        else TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
-    }
-    free_results(ctx, db);
+    db->ran = false;
     const uint64_t h2d_keep = db->h2d_bytes;
-    memset(&db->timing, 0, sizeof db->timing);
-    db->timing.h2d_bytes = h2d_keep;
     if (ctx->ref_dirty) {
         const int n = (int)ctx->d_ref.size();
         if (ctx->d_ref_table) { TRY(cudaFree(ctx->d_ref_table)); ctx->d_ref_table = nullptr; }
@@ -632,46 +535,93 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
         if (n) TRY(cudaMemcpy(ctx->d_ref_table, ctx->d_ref.data(), sizeof(uint8_t *) * n, cudaMemcpyHostToDevice));
         ctx->ref_dirty = false;
     }
-    cudaEvent_t ev0, ev1, ev2;
-    TRY(cudaEventCreate(&ev0)); TRY(cudaEventCreate(&ev1)); TRY(cudaEventCreate(&ev2));
-    TRY(cudaEventRecord(ev0, st));
-    /* result buffers */
-    DALLOC(db->rstate, db->n_regions);
-    {
-        std::vector<LcrRegionState> init(db->n_regions);
-        for (uint32_t r = 0; r < db->n_regions; ++r) { memset(&init[r], 0, sizeof init[r]); init[r].status = db->extra.h_status0[r]; }
-        if (db->n_regions) TRY(cudaMemcpyAsync(db->rstate, init.data(), sizeof(LcrRegionState) * db->n_regions, cudaMemcpyHostToDevice, st));
-        TRY(cudaStreamSynchronize(st));
-    }
-    DALLOC(db->hp, db->n_reads); DALLOC(db->ps, db->n_reads); DALLOC(db->is_fragment, db->n_reads);
-    DALLOC(db->d_stats, 1);
-    DALLOC(db->slot_flags, db->n_slots);
-    TRY(cudaMemsetAsync(db->hp, 0xff, db->n_reads ? db->n_reads : 1, st));
-    TRY(cudaMemsetAsync(db->ps, 0, sizeof(uint32_t) * (db->n_reads ? db->n_reads : 1), st));
-    TRY(cudaMemsetAsync(db->is_fragment, 0, db->n_reads ? db->n_reads : 1, st));
-    TRY(cudaMemsetAsync(db->d_stats, 0, sizeof(lcr_stats), st));
-    TRY(cudaMemsetAsync(db->slot_flags, 0, db->n_slots ? db->n_slots : 1, st));
-    if (ctx->P.flags & LCR_FLAG_EMIT_PLANES) {
+    if ((ctx->P.flags & LCR_FLAG_EMIT_PLANES) && !db->pl_acgt) {
         DALLOC(db->pl_acgt, db->n_pos * 4); DALLOC(db->pl_fwd, db->n_pos * 4); DALLOC(db->pl_d, db->n_pos); DALLOC(db->pl_n, db->n_pos); DALLOC(db->pl_ts, db->n_pos * 2);
-        const size_t np1 = db->n_pos ? db->n_pos : 1; /* regions that fail on the device keep zeroed planes */
-        TRY(cudaMemsetAsync(db->pl_acgt, 0, 16 * np1 / (db->n_pos ? 1 : 4), st)); TRY(cudaMemsetAsync(db->pl_fwd, 0, 16 * np1 / (db->n_pos ? 1 : 4), st));
-        TRY(cudaMemsetAsync(db->pl_d, 0, 4 * np1, st)); TRY(cudaMemsetAsync(db->pl_n, 0, 4 * np1, st)); TRY(cudaMemsetAsync(db->pl_ts, 0, 8 * np1 / (db->n_pos ? 1 : 2), st));
     }
-    int rc = lcr_stage_pileup_impl(ctx, db, db->slot_flags);
-    if (rc) return rc;
-    TRY(cudaEventRecord(ev1, st));
-    if (!(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) {
-        rc = stage_fragments_phase(ctx, db);
+    for (int attempt = 0;; ++attempt) {
+        /* the asynchronous upload's seq / qual copies may still be in flight: the pileup stage waits where it first reads them */
+        db->seq_wait_pending = db->ev_seq != nullptr;
+        memset(&db->timing, 0, sizeof db->timing);
+        db->timing.h2d_bytes = h2d_keep;
+        /* candidates: at most one per pre-candidate */
+        if (db->cand_alloc < db->caps.pre) {
+            DFREE(db->cand);
+            DALLOC(db->cand, db->caps.pre);
+            db->cand_alloc = db->caps.pre;
+        }
+        int rc = plan_or_launch(ctx, db, false);
         if (rc) return rc;
+        if (ctx->arena.off > ctx->arena.cap) {
+            TRY(cudaStreamSynchronize(st));
+            if (ctx->arena.base) { TRY(cudaFree(ctx->arena.base)); ctx->arena.base = nullptr; ctx->arena.cap = 0; }
+            const size_t want = ctx->arena.off + ctx->arena.off / 8;
+            TRY(cudaMalloc((void **)&ctx->arena.base, want));
+            ctx->arena.cap = want;
+        }
+        TRY(cudaEventRecord(ctx->ev_t[2], st));
+        TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(LcrCounters), st));
+        TRY(cudaMemsetAsync(db->d_stats, 0, sizeof(lcr_stats), st));
+        TRY(cudaMemsetAsync(db->hp, 0xff, db->n_reads ? db->n_reads : 1, st));
+        TRY(cudaMemsetAsync(db->ps, 0, sizeof(uint32_t) * (db->n_reads ? db->n_reads : 1), st));
+        TRY(cudaMemsetAsync(db->is_fragment, 0, db->n_reads ? db->n_reads : 1, st));
+        if (db->n_regions) k_init_rstate<<<(db->n_regions + 127) / 128, 128, 0, st>>>(db->n_regions, db->status0, db->rstate);
+        if (db->pl_acgt) {
+            const size_t np1 = db->n_pos ? db->n_pos : 1; /* regions that fail on the device keep zeroed planes */
+            TRY(cudaMemsetAsync(db->pl_acgt, 0, 16 * np1 / (db->n_pos ? 1 : 4), st)); TRY(cudaMemsetAsync(db->pl_fwd, 0, 16 * np1 / (db->n_pos ? 1 : 4), st));
+            TRY(cudaMemsetAsync(db->pl_d, 0, 4 * np1, st)); TRY(cudaMemsetAsync(db->pl_n, 0, 4 * np1, st)); TRY(cudaMemsetAsync(db->pl_ts, 0, 8 * np1 / (db->n_pos ? 1 : 2), st));
+        }
+        rc = plan_or_launch(ctx, db, true);
+        if (rc) return rc;
+        TRY(cudaEventRecord(ctx->ev_t[5], st));
+        TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(LcrCounters), cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(ctx->h_stats, db->d_stats, sizeof(lcr_stats), cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st)); /* the one host synchronisation of a run */
+        TRY(cudaGetLastError());
+        const LcrCounters &K = *ctx->h_ctr;
+        db->counters = K;
+        if (!K.overflow) break;
+        if (attempt >= 4) { ctx->last_error = "run scratch overflow after repeated growth"; return LCR_ERR_OOM; }
+        /* grow what overflowed to what the counters ask for (plus slack) and run again */
+        LcrCaps &C = db->caps;
+        auto grow = [](uint64_t &cap, uint64_t need) { cap = std::max<uint64_t>(cap * 2, need + need / 4 + 1024); };
+        if (K.overflow & LCR_OVF_ITEMS) grow(C.items, K.n_items);
+        if (K.overflow & LCR_OVF_SEGS) grow(C.segs, K.n_segs);
+        if (K.overflow & LCR_OVF_PRE) grow(C.pre, K.n_pre);
+        if (K.overflow & LCR_OVF_ELEMS) grow(C.elems, K.n_elem);
+        if (K.overflow & LCR_OVF_PAIRS) grow(C.pairs, K.pair_need);
+        if (K.overflow & LCR_OVF_ADJ) grow(C.adj, K.adj_total);
+        if (K.overflow & LCR_OVF_ENUM) grow(C.enum_work, K.enum_work);
     }
-    TRY(cudaEventRecord(ev2, st));
-    TRY(cudaStreamSynchronize(st));
-    TRY(cudaGetLastError());
+    const LcrCounters &K = db->counters;
+    db->n_cand = K.n_cand;
+    db->n_frag = (ctx->P.flags & LCR_FLAG_SKIP_PHASING) ? 0 : K.n_frag;
+    db->n_elem = (ctx->P.flags & LCR_FLAG_SKIP_PHASING) ? 0 : K.n_elem;
     float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1); db->timing.ms_pileup = ms;
-    cudaEventElapsedTime(&ms, ev1, ev2); db->timing.ms_fragments = ms - db->timing.ms_phase;
-    cudaEventElapsedTime(&ms, ev0, ev2); db->timing.ms_total = ms;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    cudaEventElapsedTime(&ms, ctx->ev_t[0], ctx->ev_t[1]); db->timing.ms_pileup_kernel = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[2], ctx->ev_t[3]); db->timing.ms_pileup = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[3], ctx->ev_t[4]); db->timing.ms_fragments = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[4], ctx->ev_t[5]); db->timing.ms_phase = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[2], ctx->ev_t[5]); db->timing.ms_total = ms;
+    /* algorithmic bytes of the tile kernel: base + qual of every aligned base, the segment and item descriptors it stages, one tile
+       descriptor and the reference bytes per processed tile, the surviving sites it writes */
+    db->timing.pileup_alg_bytes = 2ull * ctx->h_stats->n_aligned_bases + 16ull * K.n_segs_used + 16ull * K.n_items_used + 48ull * K.n_tiles_done + K.n_pos_done +
+                                  72ull * std::min<uint64_t>(K.n_pre, db->caps.pre);
+    if ((ctx->P.flags & LCR_FLAG_EMIT_FRAGMENTS) && !(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) {
+        FragDebug &fd = db->extra.fragdbg;
+        const uint32_t nf = db->n_frag;
+        const uint64_t ne = db->n_elem;
+        fd.frag_slot.resize(nf); fd.frag_elem_off.resize((size_t)nf + 1);
+        fd.elem_snp.resize(ne); fd.elem_cell.resize(ne); fd.elem_base.resize(ne);
+        if (nf) TRY(cudaMemcpyAsync(fd.frag_slot.data(), db->fr_frag_off, 4ull * nf, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(fd.frag_elem_off.data(), db->fr_frag_read, 4ull * ((size_t)nf + 1), cudaMemcpyDeviceToHost, st));
+        if (ne) {
+            TRY(cudaMemcpyAsync(fd.elem_snp.data(), db->fr_elem_snp, 4ull * ne, cudaMemcpyDeviceToHost, st));
+            TRY(cudaMemcpyAsync(fd.elem_cell.data(), db->fr_elem_cell, ne, cudaMemcpyDeviceToHost, st));
+            TRY(cudaMemcpyAsync(fd.elem_base.data(), db->fr_elem_base, ne, cudaMemcpyDeviceToHost, st));
+        }
+        TRY(cudaStreamSynchronize(st));
+        if (!nf) fd.frag_elem_off[0] = 0;
+    }
     db->ran = true;
     return LCR_OK;
 }
@@ -785,7 +735,9 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     if (!ctx || !dbb) return;
     lcr_device_batch_full *db = static_cast<lcr_device_batch_full *>(dbb);
     cudaSetDevice(ctx->device);
-    free_results(ctx, db);
+    DFREE(db->rstate); DFREE(db->cand); DFREE(db->hp); DFREE(db->ps); DFREE(db->is_fragment); DFREE(db->d_stats);
+    DFREE(db->pl_acgt); DFREE(db->pl_fwd); DFREE(db->pl_d); DFREE(db->pl_n); DFREE(db->pl_ts);
+    DFREE(db->slot_flags); DFREE(db->status0); DFREE(db->big_list);
     DFREE(db->regions); DFREE(db->pos); DFREE(db->flag); DFREE(db->mapq); DFREE(db->ts); DFREE(db->de);
     DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); DFREE(db->qual); DFREE(db->cigar);
     DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
@@ -834,12 +786,6 @@ struct SubmitChunk {
     lcr_batch view;
 };
 
-static size_t submit_chunk_bytes() { /* seq + qual bytes per chunk (LCR_SUBMIT_CHUNK_MB overrides: tests) */
-    const char *e = getenv("LCR_SUBMIT_CHUNK_MB");
-    if (e && *e) return (size_t)strtoull(e, nullptr, 10) << 20;
-    return (size_t)256 << 20;
-}
-
 /* The worker body for a batch of regions, host buffers in, host results out.  Large batches are cut into chunks of
    consecutive regions; the host-to-device copies of chunk k+1 run on the copy stream while chunk k computes (regions are
    independent, so the result is the same as one pass over the whole batch). */
@@ -849,7 +795,7 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
     if (!ctx || !batch || !out) return LCR_ERR_INVALID_ARG;
     if (ctx->sticky) return ctx->sticky;
     memset(&ctx->last_submit, 0, sizeof ctx->last_submit);
-    const size_t chunk_bytes = submit_chunk_bytes();
+    const size_t chunk_bytes = ctx->submit_chunk_bytes; /* seq + qual bytes per chunk (LCR_SUBMIT_CHUNK_MB at lcr_create: tests) */
     const uint64_t total_bases = batch->n_reads && batch->seq_off ? batch->seq_off[batch->n_reads] : 0;
     const bool debug_out = ctx->P.flags & (LCR_FLAG_EMIT_PLANES | LCR_FLAG_EMIT_FRAGMENTS);
     bool chunkable = !debug_out && batch->n_regions > 1 && 2 * total_bases > chunk_bytes + chunk_bytes / 2 && batch->regions && batch->seq_off && batch->cig_off;
@@ -935,8 +881,9 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
             }
             for (uint32_t i = 0; i < part->n_reads; ++i) {
                 const size_t g = (size_t)ck.read_lo + i;
-                if (part->hp[i] != -1) all->hp[g] = part->hp[i];
-                if (part->ps[i]) all->ps[g] = part->ps[i];
+                /* chunks are consecutive regions: the first chunk with an entry is the lowest region (same rule as on the device) */
+                if (part->hp[i] != -1 && all->hp[g] == -1) all->hp[g] = part->hp[i];
+                if (part->ps[i] && !all->ps[g]) all->ps[g] = part->ps[i];
                 if (part->is_fragment[i]) all->is_fragment[g] = 1;
             }
             st.n_reads_pass += part->stats.n_reads_pass; st.n_aligned_bases += part->stats.n_aligned_bases;

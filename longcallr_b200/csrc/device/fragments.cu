@@ -38,7 +38,7 @@ __device__ int walk_fragment(const FragArgs &a, uint32_t read, const lcr_candida
         idx = lo;
     }
     int64_t pr = pos;
-    int64_t pq = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (int64_t)(a.cigar[c0] >> 4) : 0;
+    int64_t pq = lcr_leading_softclips(a.cigar, c0, c1); /* fragment.rs:59 */
     for (uint64_t ci = c0; ci < c1; ++ci) {
         const uint32_t op = a.cigar[ci], opc = op & 0xf;
         const int64_t len = op >> 4;
@@ -58,7 +58,9 @@ __device__ int walk_fragment(const FragArgs &a, uint32_t read, const lcr_candida
                 else if (base == s.alleles[0] || base == s.alleles[1]) p = -1;
                 else p = 0;
                 if (!(s.flags & LCR_CF_DENSE) && p != 0) {
-                    if (q == 0) return LCR_ERR_BASEQ_ZERO;
+                    /* quality 0 (prob = 1.0, fragment.rs:133): log10(0) reaches the first sigma sweep only from a phase site, where
+                       the reference panics (phase.rs:307); elsewhere the element is kept and phase.cu restates the IEEE outcomes */
+                    if (q == 0 && (s.flags & LCR_CF_FOR_PHASING)) return LCR_ERR_BASEQ_ZERO;
                     emit(idx, base, (int8_t)(p * (int)(q + 1)), s);
                 }
                 ++idx;
@@ -100,18 +102,26 @@ __global__ void k_frag_count(FragArgs a) {
     a.elem_count[slot] = nelem;
 }
 
-__global__ void k_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate) {
+__global__ void k_region_frag_ranges(FragArgs a, uint32_t n_regions) {
     const uint32_t reg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (reg == 0) { /* the totals stay on the device; the host reads them with the counter block at the end of the run */
+        a.ctr->n_frag = a.frag_scan[a.n_slots];
+        a.ctr->n_elem = a.elem_scan[a.n_slots];
+        if (a.elem_scan[a.n_slots] > a.elem_cap) atomicOr(&a.ctr->overflow, LCR_OVF_ELEMS);
+        if (a.frag_scan[a.n_slots] == 0) a.frag_elem_off[0] = 0;
+    }
     if (reg >= n_regions) return;
-    const uint32_t b = frag_scan[slot_off[reg]], e = frag_scan[slot_off[reg + 1]];
-    rstate[reg].frag_begin = b;
-    rstate[reg].n_frag = e - b;
+    const uint32_t b = a.frag_scan[a.slot_off[reg]], e = a.frag_scan[a.slot_off[reg + 1]];
+    a.rstate[reg].frag_begin = b;
+    a.rstate[reg].n_frag = e - b;
 }
 
 __global__ void k_frag_fill(FragArgs a) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     uint32_t e0 = 0, k = 0, cb = 0, floc = 0, nnz = 0;
+    const uint32_t n_frag_total = a.frag_scan[a.n_slots], n_elem_total = a.elem_scan[a.n_slots];
+    if (n_elem_total > a.elem_cap) return; /* the run is repeated with larger element arrays */
     if (slot < a.n_slots && a.frag_flag[slot]) {
         const uint32_t reg = a.slot_region[slot];
         const LcrRegionState rs = a.rstate[reg];
@@ -120,7 +130,7 @@ __global__ void k_frag_fill(FragArgs a) {
         e0 = a.elem_scan[slot];
         a.frag_slot[f] = slot;
         a.frag_elem_off[f] = e0;
-        if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
+        if (f + 1 == n_frag_total) a.frag_elem_off[f + 1] = n_elem_total;
         if (rs.status != 0 || !rs.n_cand) a.frag_links[f] = 0; /* a failed region reports no fragments */
         else {
             a.is_fragment[read] = 1;
@@ -176,7 +186,7 @@ __device__ __forceinline__ int eval_cand(const lcr_candidate &s, const uint8_t *
     else if (base == s.alleles[0] || base == s.alleles[1]) p = -1;
     else p = 0;
     if ((s.flags & LCR_CF_DENSE) || p == 0) return 0;
-    if (q == 0) return LCR_ERR_BASEQ_ZERO;
+    if (q == 0 && (s.flags & LCR_CF_FOR_PHASING)) return LCR_ERR_BASEQ_ZERO;
     cell = (int8_t)(p * (int)(q + 1));
     return 1;
 }
@@ -195,12 +205,13 @@ __global__ void __launch_bounds__(128) k_frag_walk_w(FragArgs a) {
         if ((a.slot_flags[slot] & 1) && rs.status == 0 && rs.n_cand && !((int64_t)a.pos[read] > c[rs.n_cand - 1].pos)) { isfrag = 1; go = true; }
     } else {
         if (!a.frag_flag[slot]) return;
+        if (a.elem_scan[a.n_slots] > a.elem_cap) return; /* the run is repeated with larger element arrays */
         f = a.frag_scan[slot];
         e0 = a.elem_scan[slot];
         if (lane == 0) {
             a.frag_slot[f] = slot;
             a.frag_elem_off[f] = e0;
-            if (f + 1 == a.n_frag_total) a.frag_elem_off[f + 1] = a.n_elem_total;
+            if (f + 1 == a.frag_scan[a.n_slots]) a.frag_elem_off[f + 1] = a.elem_scan[a.n_slots];
         }
         if (rs.status != 0 || !rs.n_cand) { if (lane == 0) a.frag_links[f] = 0; return; } /* a failed region reports no fragments */
         if (lane == 0) a.is_fragment[read] = 1;
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(128) k_frag_walk_w(FragArgs a) {
         const int64_t seq_len = (int64_t)(a.seq_off[read + 1] - s0);
         const uint8_t *seq = a.seq + s0, *qual = a.qual + s0;
         long long pr = a.pos[read];
-        long long pq = (c1 > c0 && (a.cigar[c0] & 0xf) == 4) ? (long long)(a.cigar[c0] >> 4) : 0;
+        long long pq = lcr_leading_softclips(a.cigar, c0, c1);
         for (uint64_t cbase = c0; cbase < c1; cbase += 32) {
             const uint64_t ci = cbase + lane;
             const uint32_t op = ci < c1 ? a.cigar[ci] : 4u; /* padding: a zero-length soft clip */
@@ -310,12 +321,13 @@ __global__ void __launch_bounds__(128) k_frag_walk_w(FragArgs a) {
 
 /* fragment.rs:207-240 restricted to the pairs candidate.rs:628-692 evaluates: cis / trans counts per SNP pair */
 __global__ void k_pair_count(FragArgs a, LcrPairEntry *table) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.n_frag_total) return;
+    if (a.ctr->pair_total == 0 || (a.ctr->overflow & (LCR_OVF_ELEMS | LCR_OVF_PAIRS))) return;
+    const uint32_t n_frag_total = a.frag_scan[a.n_slots];
+  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frag_total; f += gridDim.x * blockDim.x) {
     const uint32_t slot = a.frag_slot[f];
     const uint32_t reg = a.slot_region[slot];
     const LcrRegionState rs = a.rstate[reg];
-    if (rs.status != 0 || rs.n_cand <= a.P.max_enum_snps || !rs.pair_cap) return;
+    if (rs.status != 0 || rs.n_cand <= a.P.max_enum_snps || !rs.pair_cap) continue;
     const lcr_candidate *c = a.cand + rs.cand_begin;
     const uint32_t e0 = a.frag_elem_off[f], e1 = a.frag_elem_off[f + 1];
     LcrPairEntry *tab = table + rs.pair_begin;
@@ -338,18 +350,21 @@ __global__ void k_pair_count(FragArgs a, LcrPairEntry *table) {
             atomicAdd(pi * pj > 0 ? &tab[h].cis : &tab[h].trans, 1u);
         }
     }
+  }
 }
 
 /* candidate.rs:679-713 + snp.rs:158-188: perfect-LD pairs (min(cis, trans) == 0, |weight| >= threshold) become edges */
 template <bool FILL>
-__global__ void k_ld_edges(uint32_t ld_weight_threshold, uint32_t n_regions, const LcrRegionState *rstate, const LcrPairEntry *table, uint64_t table_size,
-                           const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= table_size) return;
+__global__ void k_ld_edges(FragArgs a, const LcrPairEntry *table, const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj) {
+    const uint32_t ld_weight_threshold = a.P.ld_weight_threshold;
+    const LcrRegionState *rstate = a.rstate;
+    if (a.ctr->overflow & (LCR_OVF_ELEMS | LCR_OVF_PAIRS | LCR_OVF_ADJ)) return;
+    const uint32_t table_size = a.ctr->pair_total;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < table_size; t += gridDim.x * blockDim.x) {
     const LcrPairEntry e = table[t];
-    if (e.key == ~0ull) return;
+    if (e.key == ~0ull) continue;
     const uint32_t c1 = e.cis < e.trans ? e.cis : e.trans, c2 = e.cis < e.trans ? e.trans : e.cis;
-    if (c1 != 0 || c2 < ld_weight_threshold || c2 == 0) return;
+    if (c1 != 0 || c2 < ld_weight_threshold || c2 == 0) continue;
     const uint32_t reg = entry_region[t >> 4]; /* region of every 16-entry group (capacities are multiples of 16) */
     const uint32_t cb = rstate[reg].cand_begin;
     const uint32_t i = (uint32_t)(e.key >> 32), j = (uint32_t)e.key;
@@ -361,13 +376,15 @@ __global__ void k_ld_edges(uint32_t ld_weight_threshold, uint32_t n_regions, con
         adj[adj_off[cb + i] + atomicAdd(&adj_cursor[cb + i], 1u)] = j | sign;
         adj[adj_off[cb + j] + atomicAdd(&adj_cursor[cb + j], 1u)] = i | sign;
     }
+  }
 }
 
 /* GraphMap adjacency order: edges are inserted in lexicographic (i, j) order, so every node's
    neighbour list ends up ascending by neighbour index */
-__global__ void k_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cand) return;
+__global__ void k_adj_sort(FragArgs a, const uint32_t *adj_off, uint32_t *adj) {
+    if (a.ctr->overflow & (LCR_OVF_ELEMS | LCR_OVF_PAIRS | LCR_OVF_ADJ)) return;
+    const uint32_t n_cand = a.ctr->n_cand;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += gridDim.x * blockDim.x) {
     const uint32_t b = adj_off[i], e = adj_off[i + 1];
     for (uint32_t x = b + 1; x < e; ++x) {
         const uint32_t v = adj[x];
@@ -375,12 +392,58 @@ __global__ void k_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *a
         while (y > b && (adj[y - 1] & 0x7fffffffu) > (v & 0x7fffffffu)) { adj[y] = adj[y - 1]; --y; }
         adj[y] = v;
     }
+  }
+}
+
+/* adjacency size check between the two k_ld_edges passes */
+__global__ void k_adj_total(FragArgs a, const uint32_t *adj_off) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t t = adj_off[a.ctr->n_cand];
+        a.ctr->adj_total = t;
+        if (t > a.adj_cap) atomicOr(&a.ctr->overflow, LCR_OVF_ADJ);
+    }
+}
+
+/* LD pair tables: one open-addressing segment per region that takes the LD path (more than max_enum_snps candidates) */
+__global__ void k_pair_cap(FragArgs a, uint32_t n_regions, uint32_t *region_cap) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_regions) return;
+    uint32_t cap = 0;
+    if (r < n_regions) {
+        const LcrRegionState s = a.rstate[r];
+        if (s.status == 0 && s.n_cand > a.P.max_enum_snps && s.n_ld_pairs_cap) {
+            const unsigned long long all = (unsigned long long)s.n_cand * (s.n_cand - 1) / 2;
+            const unsigned long long bound = s.n_ld_pairs_cap < all ? s.n_ld_pairs_cap : all;
+            unsigned long long c = 16;
+            while (c < 2 * bound) c <<= 1;
+            cap = c > 0x40000000ull ? 0x40000000u : (uint32_t)c;
+        }
+    }
+    region_cap[r] = cap;
+}
+__global__ void k_pair_assign(FragArgs a, uint32_t n_regions, const uint32_t *region_cap, const uint32_t *region_cap_off) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = region_cap_off[n_regions];
+    const bool ovf = total > a.pair_cap_total;
+    if (r == 0) {
+        a.ctr->pair_total = ovf ? 0u : total;
+        a.ctr->pair_need = total;
+        if (ovf) atomicOr(&a.ctr->overflow, LCR_OVF_PAIRS);
+    }
+    if (r >= n_regions) return;
+    a.rstate[r].pair_begin = ovf ? 0u : region_cap_off[r];
+    a.rstate[r].pair_cap = ovf ? 0u : region_cap[r];
+}
+__global__ void k_init_pairs(FragArgs a, LcrPairEntry *t) {
+    const uint32_t n = a.ctr->pair_total;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { t[i].key = ~0ull; t[i].cis = 0; t[i].trans = 0; }
 }
 
 __global__ void k_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region) {
-    const uint32_t reg = blockIdx.x;
-    const LcrRegionState rs = rstate[reg];
-    for (uint32_t g = threadIdx.x; g < rs.pair_cap / 16; g += blockDim.x) entry_region[rs.pair_begin / 16 + g] = reg;
+    for (uint32_t reg = blockIdx.x; reg < n_regions; reg += gridDim.x) {
+        const LcrRegionState rs = rstate[reg];
+        for (uint32_t g = threadIdx.x; g < rs.pair_cap / 16; g += blockDim.x) entry_region[rs.pair_begin / 16 + g] = reg;
+    }
 }
 
 } // namespace
@@ -391,27 +454,33 @@ void lcr_launch_frag_count(const FragArgs &a, bool long_cigars, cudaStream_t st)
     if (long_cigars) k_frag_walk_w<false><<<(uint32_t)(((uint64_t)a.n_slots * 32 + 127) / 128), 128, 0, st>>>(a);
     else k_frag_count<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
 }
-void lcr_launch_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate, cudaStream_t st) {
-    if (n_regions) k_region_frag_ranges<<<(n_regions + 127) / 128, 128, 0, st>>>(n_regions, slot_off, frag_scan, rstate);
+void lcr_launch_region_frag_ranges(const FragArgs &a, uint32_t n_regions, cudaStream_t st) {
+    k_region_frag_ranges<<<(n_regions + 128) / 128, 128, 0, st>>>(a, n_regions);
 }
 void lcr_launch_frag_fill(const FragArgs &a, bool long_cigars, cudaStream_t st) {
     if (!a.n_slots) return;
     if (long_cigars) k_frag_walk_w<true><<<(uint32_t)(((uint64_t)a.n_slots * 32 + 127) / 128), 128, 0, st>>>(a);
     else k_frag_fill<<<(a.n_slots + 127) / 128, 128, 0, st>>>(a);
 }
-void lcr_launch_pair_count(const FragArgs &a, LcrPairEntry *table, cudaStream_t st) {
-    if (a.n_frag_total) k_pair_count<<<(a.n_frag_total + 127) / 128, 128, 0, st>>>(a, table);
+void lcr_launch_pair_plan(const FragArgs &a, uint32_t n_regions, uint32_t *region_cap, const uint32_t *region_cap_off, bool assign, cudaStream_t st) {
+    const uint32_t g = (n_regions + 128) / 128;
+    if (assign) k_pair_assign<<<g, 128, 0, st>>>(a, n_regions, region_cap, region_cap_off);
+    else k_pair_cap<<<g, 128, 0, st>>>(a, n_regions, region_cap);
 }
-void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrRegionState *rstate, const LcrPairEntry *table, uint64_t table_size,
-                         const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj, cudaStream_t st) {
-    if (!table_size) return;
-    const uint32_t g = (uint32_t)((table_size + 255) / 256);
-    if (fill) k_ld_edges<true><<<g, 256, 0, st>>>(thr, n_regions, rstate, table, table_size, entry_region, deg, adj_off, adj_cursor, adj);
-    else k_ld_edges<false><<<g, 256, 0, st>>>(thr, n_regions, rstate, table, table_size, entry_region, deg, adj_off, adj_cursor, adj);
+void lcr_launch_pair_build(const FragArgs &a, uint32_t n_regions, LcrPairEntry *table, uint32_t *entry_region, int sm_count, cudaStream_t st) {
+    const int sms = sm_count > 0 ? sm_count : 148;
+    k_init_pairs<<<sms * 4, 256, 0, st>>>(a, table);
+    k_fill_entry_region<<<sms * 4, 128, 0, st>>>(n_regions, a.rstate, entry_region);
+    k_pair_count<<<sms * 8, 128, 0, st>>>(a, table);
 }
-void lcr_launch_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj, cudaStream_t st) {
-    if (n_cand) k_adj_sort<<<(n_cand + 127) / 128, 128, 0, st>>>(n_cand, adj_off, adj);
+void lcr_launch_ld_edges(bool fill, const FragArgs &a, const LcrPairEntry *table, const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor,
+                         uint32_t *adj, int sm_count, cudaStream_t st) {
+    const int sms = sm_count > 0 ? sm_count : 148;
+    if (fill) k_ld_edges<true><<<sms * 4, 256, 0, st>>>(a, table, entry_region, deg, adj_off, adj_cursor, adj);
+    else k_ld_edges<false><<<sms * 4, 256, 0, st>>>(a, table, entry_region, deg, adj_off, adj_cursor, adj);
 }
-void lcr_launch_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region, cudaStream_t st) {
-    if (n_regions) k_fill_entry_region<<<n_regions, 128, 0, st>>>(n_regions, rstate, entry_region);
+void lcr_launch_adj_finish(const FragArgs &a, const uint32_t *adj_off, uint32_t *adj, bool sort, int sm_count, cudaStream_t st) {
+    const int sms = sm_count > 0 ? sm_count : 148;
+    if (sort) k_adj_sort<<<sms * 2, 128, 0, st>>>(a, adj_off, adj);
+    else k_adj_total<<<1, 32, 0, st>>>(a, adj_off);
 }

@@ -27,6 +27,7 @@
 
 #include "longcallr_b200.h"
 #include "lcr_contract.h"
+#include "lcr_pipeline.h"
 
 #define LCR_TILE 512        /* positions per pileup tile == threads per pileup CTA */
 
@@ -72,6 +73,16 @@ struct lcr_ctx {
     std::string last_error;
     int sticky;
     int sm_count;
+    /* one device run at a time per context (the entry points serialise on `mu`): its scratch, counters and timing events */
+    LcrArena arena;
+    LcrCounters *d_ctr;        /* device counter block of the current run */
+    LcrCounters *h_ctr;        /* pinned host copies read once at the end of a run */
+    lcr_stats *h_stats;
+    cudaEvent_t ev_t[6];       /* tile kernel begin / end, run begin, pileup stage end, fragment build end, run end */
+    /* experiment / test knobs read from the environment when the context is created */
+    uint32_t big_frag_threshold; /* LCR_BIG_REGION_FRAGS: fragments from which an LD-path region takes the cooperative kernel */
+    int frag_walk_mode;          /* LCR_FRAG_WALK: 0 by ops per read, 1 thread per read, 2 warp per read */
+    size_t submit_chunk_bytes;   /* LCR_SUBMIT_CHUNK_MB: seq + qual bytes per chunk of lcr_submit */
 };
 
 struct lcr_device_batch {
@@ -114,10 +125,44 @@ struct lcr_device_batch {
     uint8_t *fr_elem_base;
     bool ran;
     lcr_timing timing;
+    /* capacities of the data-dependent scratch of a run (grown when a run reports an overflow) and of the result buffers */
+    LcrCaps caps;
+    uint64_t cand_alloc;       /* candidates `cand` can hold */
+    uint8_t *slot_flags;       /* [n_slots] bit 0: read passes the filter and overlaps its region's window */
+    int32_t *status0;          /* [n_regions] region statuses known at upload */
+    uint32_t max_region_slots; /* largest read range of a region */
+    uint32_t *big_list;        /* regions with enough reads to need the cooperative phasing kernel */
+    uint32_t n_big_list;
+    LcrCounters counters;      /* host copy of the last run's counter block */
     /* asynchronous upload (lcr_submit): the small tables are ready at ev_meta, seq / qual at ev_seq (null: synchronous upload) */
     cudaEvent_t ev_meta, ev_seq;
     bool seq_wait_pending; /* the run has not waited for ev_seq yet */
 };
+
+/* rust-htslib CigarStringView::leading_softclips / trailing_softclips (util.rs:682-690, fragment.rs:59): the soft clip at that
+   end of the alignment, looking through one hard clip (`5H10S...` has 10 leading soft clips) */
+#if defined(__CUDACC__)
+__device__ __forceinline__ int64_t lcr_leading_softclips(const uint32_t *cigar, uint64_t c0, uint64_t c1) {
+    if (c1 <= c0) return 0;
+    const uint32_t o0 = cigar[c0];
+    if ((o0 & 0xf) == 4) return (int64_t)(o0 >> 4);
+    if ((o0 & 0xf) == 5 && c0 + 1 < c1) {
+        const uint32_t o1 = cigar[c0 + 1];
+        if ((o1 & 0xf) == 4) return (int64_t)(o1 >> 4);
+    }
+    return 0;
+}
+__device__ __forceinline__ int64_t lcr_trailing_softclips(const uint32_t *cigar, uint64_t c0, uint64_t c1) {
+    if (c1 <= c0) return 0;
+    const uint32_t o0 = cigar[c1 - 1];
+    if ((o0 & 0xf) == 4) return (int64_t)(o0 >> 4);
+    if ((o0 & 0xf) == 5 && c1 - c0 >= 2) {
+        const uint32_t o1 = cigar[c1 - 2];
+        if ((o1 & 0xf) == 4) return (int64_t)(o1 >> 4);
+    }
+    return 0;
+}
+#endif
 
 /* error plumbing */
 #define LCR_CUDA_TRY(ctx, expr)                                                         \

@@ -3,6 +3,7 @@
 #define LCR_FRAG_H
 
 #include "lcr_device.h"
+#include "lcr_pipeline.h"
 
 struct LcrPairEntry { /* open-addressing table of co-observed SNP pairs of one region */
     unsigned long long key; /* (i << 32) | j, i < j; ~0 = empty */
@@ -23,6 +24,8 @@ struct FragArgs {
     LcrRegionState *rstate;
     const lcr_candidate *cand;
     lcr_stats *stats;
+    struct LcrCounters *ctr;
+    uint32_t elem_cap, pair_cap_total, adj_cap; /* capacities of the element arrays, the pair table and the adjacency */
     /* per slot */
     uint32_t *frag_flag, *elem_count; /* count pass outputs (u32 so they can be scanned in place) */
     const uint32_t *frag_scan, *elem_scan;
@@ -32,8 +35,7 @@ struct FragArgs {
     uint32_t *cover_cursor;
     uint32_t *cover_frag; /* fragment index within the region */
     int8_t *cover_cell;
-    /* per fragment (global index) */
-    uint32_t n_frag_total, n_elem_total;
+    /* per fragment (global index); the totals are frag_scan[n_slots] and elem_scan[n_slots], known on the device only */
     uint32_t *frag_slot, *frag_elem_off, *frag_links;
     /* per element */
     uint32_t *elem_snp;
@@ -68,30 +70,32 @@ struct PhaseArgs {
     /* state, per fragment (global index) */
     int8_t *tag, *best_tag;
     uint8_t *fp, *assign;
-    /* outputs per read */
-    int8_t *hp;
-    uint32_t *ps;
-    /* winners of the warp-per-configuration enumeration search (phase_enum.cu), per (region, chunk) */
-    const uint8_t *big_region; /* [n_regions] 1: handled by the cooperative whole-GPU kernel, or null */
-    const uint32_t *es_base; /* [n_regions+1] or null */
-    const long long *es_prob;
-    const uint32_t *es_cfg;
+    /* outputs per read: (region << 2 | HP) and (region << 32 | PS) under atomicMin, so that a read shared by several regions
+       keeps the entry of the lowest region whatever the CTA order; unpacked by k_finalize_reads */
+    uint32_t *hp_key;
+    unsigned long long *ps_key;
+    /* the warp-per-configuration enumeration search (phase_enum.cu): work lists and winners per (region, chunk) */
+    struct LcrCounters *ctr;
+    uint32_t big_frag_threshold; /* LD-path regions with at least this many fragments run on the whole GPU (k_phase_grid) */
+    uint32_t *es_base;       /* [n_regions+1] first result slot of every region */
+    long long *es_prob;
+    uint32_t *es_cfg;
+    uint32_t *es_done;       /* [n_regions] chunks finished; 0x80000000: the winner's final state is in best_hap / best_gen / best_tag */
+    uint32_t *work_region, *work_chunk;
 };
 
 void lcr_launch_frag_count(const FragArgs &a, bool long_cigars, cudaStream_t st);
-void lcr_launch_region_frag_ranges(uint32_t n_regions, const uint32_t *slot_off, const uint32_t *frag_scan, LcrRegionState *rstate, cudaStream_t st);
+void lcr_launch_region_frag_ranges(const FragArgs &a, uint32_t n_regions, cudaStream_t st);
 void lcr_launch_frag_fill(const FragArgs &a, bool long_cigars, cudaStream_t st);
-void lcr_launch_pair_count(const FragArgs &a, LcrPairEntry *table, cudaStream_t st);
-void lcr_launch_ld_edges(bool fill, uint32_t thr, uint32_t n_regions, const LcrRegionState *rstate, const LcrPairEntry *table, uint64_t table_size,
-                         const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor, uint32_t *adj, cudaStream_t st);
-void lcr_launch_adj_sort(uint32_t n_cand, const uint32_t *adj_off, uint32_t *adj, cudaStream_t st);
-void lcr_launch_fill_entry_region(uint32_t n_regions, const LcrRegionState *rstate, uint32_t *entry_region, cudaStream_t st);
+void lcr_launch_pair_plan(const FragArgs &a, uint32_t n_regions, uint32_t *region_cap, const uint32_t *region_cap_off, bool assign, cudaStream_t st);
+void lcr_launch_pair_build(const FragArgs &a, uint32_t n_regions, LcrPairEntry *table, uint32_t *entry_region, int sm_count, cudaStream_t st);
+void lcr_launch_ld_edges(bool fill, const FragArgs &a, const LcrPairEntry *table, const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor,
+                         uint32_t *adj, int sm_count, cudaStream_t st);
+void lcr_launch_adj_finish(const FragArgs &a, const uint32_t *adj_off, uint32_t *adj, bool sort, int sm_count, cudaStream_t st);
 void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st);
-int lcr_launch_phase_grid(const PhaseArgs &a, uint32_t reg, void *bcast_scratch, int sm_count, cudaStream_t st);
+int lcr_launch_phase_grid(const PhaseArgs &a, const uint32_t *big_list, uint32_t n_big_list, void *bcast_scratch, int sm_count, cudaStream_t st);
 size_t lcr_phase_bcast_bytes();
-int lcr_enum_shape_for(uint32_t n_cand);
-uint32_t lcr_enum_cfgs_per_cta(int shape);
-int lcr_launch_enum_search(int shape, bool pre, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
-                           long long *out_prob, uint32_t *out_cfg, cudaStream_t st);
+void lcr_launch_enum_plan(const PhaseArgs &a, uint32_t work_cap, int sm_count, cudaStream_t st);
+int lcr_launch_enum_search(int bin, const PhaseArgs &a, int sm_count, cudaStream_t st);
 
 #endif

@@ -261,20 +261,9 @@ __device__ void init_assignment(Ctx &x, uint32_t call) { /* phase.rs:673-680 */
 
 /* phase.rs:1097-1122: all 2^n starting haplotypes */
 __device__ bool phase_enum(Ctx &x) {
-    /* the search kernel already ran every configuration: replay the winner only */
-    if (x.a.es_base && x.a.es_base[x.reg + 1] > x.a.es_base[x.reg]) {
-        long long bp = 0;
-        uint32_t cfg = NONE32;
-        for (uint32_t w = x.a.es_base[x.reg]; w < x.a.es_base[x.reg + 1]; ++w) {
-            const uint32_t cw = x.a.es_cfg[w];
-            if (cw == NONE32) continue;
-            if (cfg == NONE32 || x.a.es_prob[w] > bp || (x.a.es_prob[w] == bp && cw < cfg)) { bp = x.a.es_prob[w]; cfg = cw; }
-        }
-        for (uint32_t i = x.tid; i < x.n; i += x.nthreads) x.st[i].x = ((cfg >> i) & 1u) ? -1 : 1;
-        init_assignment(x, cfg);
-        init_genotype(x);
-        tsync(x);
-        cross_optimize(x, false, true);
+    /* the search kernel (phase_enum.cu) already ran every configuration and left the winner's final state in the best_* arrays */
+    if (x.a.es_done && x.a.es_done[x.reg] == 0x80000000u) {
+        load_best(x);
         return true;
     }
     long long best = 0;
@@ -446,16 +435,21 @@ __device__ void assign_reads(Ctx &x, bool record) {
         const int sg = x.tag[k];
         long long A = 0, B = 0;
         uint32_t cnt = 0;
+        bool q0_used = false;
         for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
             const lcr_candidate &s = x.c[x.a.elem_snp[e]];
             if (!(s.flags & LCR_CF_FOR_PHASING) || s.haplotype == 0 || s.genotype != 0) continue;
             const int8_t cell = x.a.elem_cell[e];
+            cnt++;
+            if (cell_q(cell) == 0) { q0_used = true; continue; } /* only at a rescued site: see below */
             A += aki_fx(x, sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
             B += aki_fx(x, -sg, s.haplotype, 0, cell_p(cell), cell_q(cell));
-            cnt++;
         }
         int asg = 0;
         if (sg == 0 || cnt == 0) { x.tag[k] = 0; }
+        /* a quality-0 element has prob = 1.0: one of the two sums holds log10(0) = -inf, one of q, qn is NaN, and
+           `(q - qn).abs() >= cutoff` sends the read to the unknown group (snpfrags.rs:580-618) */
+        else if (q0_used) { x.tag[k] = 0; }
         else {
             const double den = lcr_fx_to_f64(A + B);
             const double q = 1.0 - lcr_fx_to_f64(A) / den;
@@ -467,8 +461,9 @@ __device__ void assign_reads(Ctx &x, bool record) {
         }
         x.assign[k] = (uint8_t)asg;
         if (record) {
+            /* a read shared by several regions keeps the entry of the lowest region (thread.rs:308-314 keeps the first per qname) */
             const uint32_t read = x.a.regions[x.reg].read_begin + read_rel(x, k);
-            x.a.hp[read] = (int8_t)asg;
+            atomicMin(&x.a.hp_key[read], (x.reg << 2) | (uint32_t)asg);
         }
     }
     tsync(x);
@@ -538,23 +533,31 @@ __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
         if (!(s.flags & list_flag)) continue;
         if (x.cover_off[ti + 1] == x.cover_off[ti]) { if (x.tid == 0) s.flags |= LCR_CF_SINGLE; tsync(x); continue; }
         if (s.variant_type != 1) { if (x.tid == 0) s.flags |= LCR_CF_NON_SELECTED; tsync(x); continue; }
-        long long Lp = 0, Lm = 0, h1 = 0, h2 = 0, cnt = 0;
+        long long Lp = 0, Lm = 0, h1 = 0, h2 = 0, cnt = 0, zz = 0;
         for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += x.nthreads) {
             const uint32_t k = x.a.cover_frag[w];
             if (!x.fp[k] || x.assign[k] == 0 || x.frag_links[k] < x.a.P.min_linkers) continue;
             if (x.assign[k] == 1) h1++; else if (x.assign[k] == 2) h2++;
             const int8_t cell = x.a.cover_cell[w];
             const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
+            cnt++;
+            if (q == 0) { zz += (p == sg) ? 1ll : (1ll << 32); continue; } /* aki = 0 for delta = +1 (low half) / delta = -1 (high half) */
             Lp += aki_fx(x, sg, 1, 0, p, q);
             Lm += aki_fx(x, sg, -1, 0, p, q);
-            cnt++;
         }
-        Lp = tsum(x, Lp); Lm = tsum(x, Lm); h1 = tsum(x, h1); h2 = tsum(x, h2); cnt = tsum(x, cnt);
+        Lp = tsum(x, Lp); Lm = tsum(x, Lm); h1 = tsum(x, h1); h2 = tsum(x, h2); cnt = tsum(x, cnt); zz = tsum(x, zz);
         if (x.tid == 0) {
             int decision = 0;
             if (cnt == 0 || h1 < 2 || h2 < 2) s.flags |= LCR_CF_SINGLE;
             else {
-                const double s1 = phase_score_from(Lp, Lp, Lm), s2 = phase_score_from(Lm, Lp, Lm);
+                double s1, s2;
+                if (zz) {
+                    /* quality-0 elements: log_q2 and / or log_q3 of cal_phase_score_log (phase.rs:238-255) is -inf; the score of the delta
+                       whose own sum is infinite is NaN (inf / inf), the other one is -10 log10(1 - 1) = +inf */
+                    const double qnan = lcr_u2d(0x7ff8000000000000ULL), pinf = lcr_u2d(0x7ff0000000000000ULL);
+                    s1 = (zz & 0xffffffffll) ? qnan : pinf;
+                    s2 = (zz >> 32) ? qnan : pinf;
+                } else { s1 = phase_score_from(Lp, Lp, Lm); s2 = phase_score_from(Lm, Lp, Lm); }
                 s.flags &= ~LCR_CF_SINGLE;
                 const double best = fmax(s1, s2);
                 if (best >= (double)mps) {
@@ -646,7 +649,7 @@ __device__ void phase_sets(Ctx &x) {
         }
         if (best != NONE32) {
             const uint32_t read = x.a.regions[x.reg].read_begin + read_rel(x, k);
-            x.a.ps[read] = (uint32_t)(x.c[best].pos + 1);
+            atomicMin(&x.a.ps_key[read], ((unsigned long long)x.reg << 32) | (unsigned long long)(uint32_t)(x.c[best].pos + 1));
         }
     }
     tsync(x);
@@ -723,7 +726,8 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     __shared__ TeamBcast bc;
     const uint32_t reg = blockIdx.x;
     const LcrRegionState rs = a.rstate[reg];
-    if (rs.status != 0 || rs.n_cand == 0 || (a.big_region && a.big_region[reg])) return;
+    if (rs.status != 0 || rs.n_cand == 0) return;
+    if (rs.n_cand > a.P.max_enum_snps && rs.n_frag >= a.big_frag_threshold) return; /* k_phase_grid takes it */
     Ctx x{a, *a.tables};
     x.reg = reg; x.tid = threadIdx.x; x.nthreads = PB; x.grid = false; x.bc = &bc; x.sh = sh;
     load_tables(a, tabs);
@@ -733,14 +737,25 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
 
 /* the whole GPU on one large region: every sweep is a grid-wide pass over the fragment matrix in L2,
    grid.sync() between passes, no host round trips (SURVEY.md section 7 "ragged work", BASELINE config 5) */
-__global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, uint32_t reg, TeamBcast *gbc) {
+__global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, const uint32_t *big_list, uint32_t n_big_list, TeamBcast *gbc) {
     __shared__ long long sh[32];
     __shared__ long long tabs[3][32];
     Ctx x{a, *a.tables};
     load_tables(a, tabs);
     x.OK = tabs[0]; x.ERR = tabs[1]; x.W = tabs[2];
-    x.reg = reg; x.tid = blockIdx.x * blockDim.x + threadIdx.x; x.nthreads = gridDim.x * blockDim.x; x.grid = true; x.bc = gbc; x.sh = sh;
-    run_region(x);
+    x.tid = blockIdx.x * blockDim.x + threadIdx.x; x.nthreads = gridDim.x * blockDim.x; x.grid = true; x.bc = gbc; x.sh = sh;
+    /* the regions that can be this large are known from their read counts at upload; whether one is decided here, by
+       the same test k_phase uses to leave it alone */
+    for (uint32_t bi = 0; bi < n_big_list; ++bi) {
+        const uint32_t reg = big_list[bi];
+        const LcrRegionState rs = a.rstate[reg];
+        if (rs.status != 0 || rs.n_cand <= a.P.max_enum_snps || rs.n_frag < a.big_frag_threshold) continue;
+        if (x.tid == 0) { TeamBcast z{}; *gbc = z; }
+        cg::this_grid().sync();
+        x.reg = reg;
+        run_region(x);
+        cg::this_grid().sync();
+    }
 }
 
 } // namespace
@@ -749,17 +764,20 @@ void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st) {
     if (a.n_regions) k_phase<<<a.n_regions, PB, 0, st>>>(a);
 }
 
-int lcr_launch_phase_grid(const PhaseArgs &a, uint32_t reg, void *bcast_scratch, int sm_count, cudaStream_t st) {
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_phase_grid, PBG, 0);
-    if (e != cudaSuccess) return (int)e;
-    if (occ < 1) occ = 1;
-    if (occ > 2) occ = 2;
-    e = cudaMemsetAsync(bcast_scratch, 0, sizeof(TeamBcast), st);
-    if (e != cudaSuccess) return (int)e;
+int lcr_launch_phase_grid(const PhaseArgs &a, const uint32_t *big_list, uint32_t n_big_list, void *bcast_scratch, int sm_count, cudaStream_t st) {
+    static int occ_cached = 0;
+    int occ = occ_cached;
+    cudaError_t e = cudaSuccess;
+    if (!occ) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_phase_grid, PBG, 0);
+        if (e != cudaSuccess) return (int)e;
+        if (occ < 1) occ = 1;
+        if (occ > 2) occ = 2;
+        occ_cached = occ;
+    }
     PhaseArgs args = a;
     TeamBcast *gbc = reinterpret_cast<TeamBcast *>(bcast_scratch);
-    void *params[] = {&args, &reg, &gbc};
+    void *params[] = {&args, &big_list, &n_big_list, &gbc};
     e = cudaLaunchCooperativeKernel((void *)k_phase_grid, dim3((unsigned)(sm_count * occ)), dim3(PBG), params, 0, st);
     return (int)e;
 }

@@ -15,11 +15,14 @@
  * where W = log10(1 - eps) - log10(eps) in fixed point and C, R, V are per-column constants.
  */
 #include "lcr_frag.h"
+#include "lcr_pipeline.h"
 
 #define EMAXN 10
 #define EW_MAX 8
 
 namespace {
+
+__device__ __forceinline__ int lcr_enum_shape_for_dev(uint32_t n_cand) { return n_cand <= 2 ? 0 : (n_cand == 3 ? 1 : (n_cand == 4 ? 2 : 3)); }
 
 struct EnumShared {
     long long W[32], OK[32], ERR[32];
@@ -28,17 +31,24 @@ struct EnumShared {
     long long best_prob[EW_MAX];
     uint32_t best_cfg[EW_MAX];
     unsigned long long iters[EW_MAX];
+    uint32_t work, last, win_cfg;
 };
 
 /* EW warps per CTA, ECFG_PER_WARP configurations per warp (strided over the chunk so that warps stay balanced);
    small regions use small CTAs so that many of them share an SM */
 template <int EW, int ECFG_PER_WARP, bool PRE>
-__global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseArgs a, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
-                                                         long long *out_prob, uint32_t *out_cfg) {
+__global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseArgs a, int bin, uint32_t nf_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ EnumShared S;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t reg = work_region[blockIdx.x], chunk = work_chunk[blockIdx.x];
+    /* the bin's work list is built on the device (k_enum_plan): CTAs draw (region, chunk) items from its ticket counter */
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.work = atomicAdd(&a.ctr->enum_ticket[bin], 1u);
+    __syncthreads();
+    if (S.work >= a.ctr->enum_cnt[bin]) return;
+    const uint32_t witem = a.ctr->enum_off[bin] + S.work;
+    const uint32_t reg = a.work_region[witem], chunk = a.work_chunk[witem];
     const LcrRegionState rs = a.rstate[reg];
     const uint32_t n = rs.n_cand, nf = rs.n_frag, cb = rs.cand_begin, fb = rs.frag_begin;
     const uint32_t words = (nf_cap + 31) / 32;
@@ -124,11 +134,12 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
     uint32_t best_cfg = 0xffffffffu;
     unsigned long long iters = 0;
     const uint32_t nwords = (nf + 31) / 32;
-    for (uint32_t j = 0; j < ECFG_PER_WARP; ++j) {
-        const uint32_t cfg = chunk * (EW * ECFG_PER_WARP) + j * EW + warp;
-        if (cfg >= n_cfg) break;
-        uint32_t dneg = cfg; /* bit i set: delta_i = -1 */
-        uint32_t eta_het = het0, eta_pos = pos0; /* bit i: eta_i == 0 / eta_i == +1 (neither: -1) */
+    /* one cross_optimize run (phase.rs:810-976) from configuration cfg by this warp; leaves the final haplotags in sig[] and
+       the final site state in (dneg, eta_het, eta_pos) */
+    uint32_t dneg = 0, eta_het = 0, eta_pos = 0;
+    auto run_cfg = [&](uint32_t cfg) -> long long {
+        dneg = cfg; /* bit i set: delta_i = -1 */
+        eta_het = het0; eta_pos = pos0; /* bit i: eta_i == 0 / eta_i == +1 (neither: -1) */
         /* init_assignment (phase.rs:673-680) */
         for (uint32_t w = 0; w < nwords; ++w) {
             const uint32_t k = w * 32 + lane;
@@ -257,11 +268,17 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
             prob2 = ((eta_het >> lane) & 1u) ? (S.C[lane] + dM) : (((eta_pos >> lane) & 1u) ? 2 * S.R[lane] : 2 * S.V[lane]);
         }
         for (int o = 16; o; o >>= 1) prob2 += __shfl_xor_sync(0xffffffffu, prob2, o);
-        const long long prob = prob2 / 2;
+        return prob2 / 2;
+    };
+    for (uint32_t j = 0; j < ECFG_PER_WARP; ++j) {
+        const uint32_t cfg = chunk * (EW * ECFG_PER_WARP) + j * EW + warp;
+        if (cfg >= n_cfg) break;
+        const long long prob = run_cfg(cfg);
         if (best_cfg == 0xffffffffu || prob > best_prob) { best_prob = prob; best_cfg = cfg; }
     }
     if (lane == 0) { S.best_prob[warp] = best_prob; S.best_cfg[warp] = best_cfg; S.iters[warp] = iters; }
     __syncthreads();
+    const uint32_t es0 = a.es_base[reg], n_chunks = a.es_base[reg + 1] - es0;
     if (tid == 0) {
         long long bp = 0;
         uint32_t bc = 0xffffffffu;
@@ -274,43 +291,156 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
         }
         const uint32_t first = chunk * (EW * ECFG_PER_WARP);
         ncfg_done = n_cfg > first ? (n_cfg - first < EW * ECFG_PER_WARP ? n_cfg - first : EW * ECFG_PER_WARP) : 0;
-        out_prob[blockIdx.x] = bp;
-        out_cfg[blockIdx.x] = bc;
+        a.es_prob[es0 + chunk] = bp;
+        a.es_cfg[es0 + chunk] = bc;
         atomicAdd((unsigned long long *)&a.stats->n_sweep_iters, it);
         atomicAdd((unsigned long long *)&a.stats->n_cross_optimize, (unsigned long long)ncfg_done);
+        /* the CTA that finishes the region's last chunk materialises the winner: its rows are already staged here */
+        __threadfence();
+        S.last = atomicAdd(&a.es_done[reg], 1u) + 1u == n_chunks ? 1u : 0u;
+        if (S.last) {
+            __threadfence();
+            long long wp = 0;
+            uint32_t wc = 0xffffffffu;
+            for (uint32_t w = 0; w < n_chunks; ++w) { /* strict `>` in enumeration order (phase.rs:1108-1122): highest objective, lowest index on ties */
+                const uint32_t cw = *(volatile uint32_t *)&a.es_cfg[es0 + w];
+                const long long pw = *(volatile long long *)&a.es_prob[es0 + w];
+                if (cw == 0xffffffffu) continue;
+                if (wc == 0xffffffffu || pw > wp || (pw == wp && cw < wc)) { wp = pw; wc = cw; }
+            }
+            S.win_cfg = wc;
+        }
+    }
+    __syncthreads();
+    if (S.last && warp == 0 && S.win_cfg != 0xffffffffu) {
+        run_cfg(S.win_cfg);
+        /* final state of the winning run: what phase() leaves in the candidates and fragments before thread.rs:168 */
+        if (lane < n) {
+            a.best_hap[cb + lane] = ((dneg >> lane) & 1u) ? -1 : 1;
+            a.best_gen[cb + lane] = ((eta_het >> lane) & 1u) ? 0 : (((eta_pos >> lane) & 1u) ? 1 : -1);
+        }
+        __syncwarp();
+        for (uint32_t w = 0; w < nwords; ++w) {
+            const uint32_t k = w * 32 + lane;
+            if (k < nf) a.best_tag[fb + k] = (rows[k] >> 63) ? (((sig[w] >> lane) & 1u) ? -1 : 1) : 0;
+        }
+        if (lane == 0) a.es_done[reg] = 0x80000000u; /* replayed: k_phase loads the state instead of running the configuration again */
+    }
+  }
+}
+
+/* ---- work lists of the enumeration search, built on the device ----
+   One CTA walks the regions: every region with at most min(max_enum_snps, 10) candidates and at most 16384 fragments gets a
+   launch shape by its number of configurations and a class by its fragment count (shared-memory footprint); its 2^n
+   configurations are cut into chunks of one CTA each.  Output: es_base (first result slot of every region), the
+   per-bin (region, chunk) lists and their sizes in the counter block. */
+#define EP_THREADS 1024
+__global__ void __launch_bounds__(EP_THREADS) k_enum_plan(PhaseArgs a, uint32_t work_cap, int sm_count) {
+    __shared__ unsigned long long s_big;
+    __shared__ uint32_t s_cnt[LCR_ENUM_BINS], s_off[LCR_ENUM_BINS], s_cur[LCR_ENUM_BINS];
+    __shared__ uint32_t s_scan[EP_THREADS / 32], s_carry, s_ovf;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_regions = a.n_regions;
+    if (tid == 0) { s_big = 0; s_carry = 0; s_ovf = 0; }
+    if (tid < LCR_ENUM_BINS) { s_cnt[tid] = 0; s_cur[tid] = 0; }
+    __syncthreads();
+    auto eligible = [&](const LcrRegionState &rs) {
+        return rs.status == 0 && rs.n_cand && rs.n_cand <= a.P.max_enum_snps && rs.n_cand <= 10u && rs.n_frag <= 16384u;
+    };
+    /* regions with 5+ sites: 64 configurations per CTA when that still fills the GPU, else 16 (more, shorter CTAs) */
+    unsigned long long big = 0;
+    for (uint32_t r = tid; r < n_regions; r += EP_THREADS) {
+        const LcrRegionState rs = a.rstate[r];
+        if (eligible(rs) && rs.n_cand > 4) big += 1ull << rs.n_cand;
+    }
+    if (big) atomicAdd(&s_big, big);
+    __syncthreads();
+    const bool small_batch = s_big / 64 < 8ull * (unsigned long long)(sm_count > 0 ? sm_count : 148);
+    auto plan = [&](const LcrRegionState &rs, int &bin) -> uint32_t {
+        bin = -1;
+        if (!eligible(rs)) return 0;
+        int shape = lcr_enum_shape_for_dev(rs.n_cand);
+        if (shape == 3 && small_batch) shape = 4;
+        const uint32_t per_cta = shape == 0 ? 4u : shape == 1 ? 8u : shape == 2 ? 16u : shape == 3 ? 64u : 16u;
+        const int cls = rs.n_frag <= 384u ? 0 : rs.n_frag <= 1024u ? 1 : rs.n_frag <= 4096u ? 2 : 3;
+        bin = shape * LCR_ENUM_CLASSES + cls;
+        return ((1u << rs.n_cand) + per_cta - 1) / per_cta;
+    };
+    /* pass 1: chunks per region -> es_base (exclusive scan in region order) and the bin sizes */
+    for (uint32_t base = 0; base < n_regions; base += EP_THREADS) {
+        const uint32_t r = base + tid;
+        uint32_t chunks = 0;
+        int bin = -1;
+        if (r < n_regions) chunks = plan(a.rstate[r], bin);
+        if (bin >= 0) atomicAdd(&s_cnt[bin], chunks);
+        uint32_t incl = chunks;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t wb = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) wb += s_scan[w];
+        if (r < n_regions) a.es_base[r] = wb + incl - chunks;
+        __syncthreads();
+        if (tid == EP_THREADS - 1) s_carry = wb + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.es_base[n_regions] = s_carry;
+        uint32_t off = 0;
+        for (int b = 0; b < LCR_ENUM_BINS; ++b) { s_off[b] = off; off += s_cnt[b]; }
+        a.ctr->enum_work = off;
+        if (off > work_cap) { atomicOr(&a.ctr->overflow, LCR_OVF_ENUM); s_ovf = 1; }
+        for (int b = 0; b < LCR_ENUM_BINS; ++b) { a.ctr->enum_off[b] = s_off[b]; a.ctr->enum_cnt[b] = s_ovf ? 0u : s_cnt[b]; a.ctr->enum_ticket[b] = 0; }
+    }
+    __syncthreads();
+    if (s_ovf) return;
+    /* pass 2: the (region, chunk) items of every bin */
+    for (uint32_t r = tid; r < n_regions; r += EP_THREADS) {
+        int bin;
+        const uint32_t chunks = plan(a.rstate[r], bin);
+        if (bin < 0) continue;
+        const uint32_t p0 = s_off[bin] + atomicAdd(&s_cur[bin], chunks);
+        for (uint32_t ck = 0; ck < chunks; ++ck) { a.work_region[p0 + ck] = r; a.work_chunk[p0 + ck] = ck; }
     }
 }
 
 } // namespace
 
 /* launch shapes by number of configurations: {warps per CTA, configurations per warp} */
-static const int SHAPES[5][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}, {8, 2}}; /* the last: 5+ sites when the batch is too small to fill the GPU with 64 configurations per CTA */
+static const int SHAPES[LCR_ENUM_SHAPES][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}, {8, 2}}; /* the last: 5+ sites when the batch is too small to fill the GPU with 64 configurations per CTA */
+static const uint32_t CLASS_ROWS[LCR_ENUM_CLASSES] = {384, 1024, 4096, 16384};            /* fragment-count classes: rows staged in shared memory */
 
-int lcr_enum_shape_for(uint32_t n_cand) { return n_cand <= 2 ? 0 : (n_cand == 3 ? 1 : (n_cand == 4 ? 2 : 3)); }
-uint32_t lcr_enum_cfgs_per_cta(int shape) { return (uint32_t)(SHAPES[shape][0] * SHAPES[shape][1]); }
 static size_t smem_bytes(uint32_t nf_cap, int ew, bool pre) { return (size_t)nf_cap * 12 + (size_t)(ew + 1) * ((nf_cap + 31) / 32) * 4 + 16 + (pre ? (size_t)nf_cap * 8 * EMAXN + 8 : 0); }
 
 template <int EW, int CPW, bool PRE>
-static int launch_shape(const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
-                        long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
+static int launch_shape(const PhaseArgs &a, int bin, uint32_t nf_cap, int grid, cudaStream_t st) {
     const size_t smem = smem_bytes(nf_cap, EW, PRE);
     cudaError_t e = cudaFuncSetAttribute(k_enum_search<EW, CPW, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    k_enum_search<EW, CPW, PRE><<<n_work, EW * 32, smem, st>>>(a, work_region, work_chunk, nf_cap, out_prob, out_cfg);
-    return 0;
+    k_enum_search<EW, CPW, PRE><<<grid, EW * 32, smem, st>>>(a, bin, nf_cap);
+    return (int)cudaGetLastError();
 }
 
-/* pre: the bin holds only regions with few fragments (the signed-term table fits in shared memory); used by the 5+ site shapes */
-int lcr_launch_enum_search(int shape, bool pre, const PhaseArgs &a, uint32_t n_work, const uint32_t *work_region, const uint32_t *work_chunk, uint32_t nf_cap,
-                           long long *out_prob, uint32_t *out_cfg, cudaStream_t st) {
-    if (!n_work) return 0;
+void lcr_launch_enum_plan(const PhaseArgs &a, uint32_t work_cap, int sm_count, cudaStream_t st) {
+    k_enum_plan<<<1, EP_THREADS, 0, st>>>(a, work_cap, sm_count);
+}
+
+/* one persistent launch per (shape, class) bin; bins without work cost one ticket per CTA.  pre: regions with few fragments
+   (class 0) of the 5+ site shapes keep the signed-term table in shared memory */
+int lcr_launch_enum_search(int bin, const PhaseArgs &a, int sm_count, cudaStream_t st) {
+    const int shape = bin / LCR_ENUM_CLASSES, cls = bin % LCR_ENUM_CLASSES;
+    const uint32_t nf_cap = CLASS_ROWS[cls];
+    const bool pre = cls == 0;
+    const int sms = sm_count > 0 ? sm_count : 148;
     switch (shape) {
-        case 0: return launch_shape<1, 4, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        case 1: return launch_shape<2, 4, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        case 2: return launch_shape<4, 4, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        case 3: return pre ? launch_shape<8, 8, true>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st)
-                           : launch_shape<8, 8, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
-        default: return pre ? launch_shape<8, 2, true>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st)
-                            : launch_shape<8, 2, false>(a, n_work, work_region, work_chunk, nf_cap, out_prob, out_cfg, st);
+        case 0: return launch_shape<1, 4, false>(a, bin, nf_cap, sms * 16, st);
+        case 1: return launch_shape<2, 4, false>(a, bin, nf_cap, sms * 16, st);
+        case 2: return launch_shape<4, 4, false>(a, bin, nf_cap, sms * 8, st);
+        case 3: return pre ? launch_shape<8, 8, true>(a, bin, nf_cap, sms * 4, st) : launch_shape<8, 8, false>(a, bin, nf_cap, sms * 4, st);
+        default: return pre ? launch_shape<8, 2, true>(a, bin, nf_cap, sms * 4, st) : launch_shape<8, 2, false>(a, bin, nf_cap, sms * 4, st);
     }
 }

@@ -26,7 +26,7 @@
  * Third-party behaviour restated from the published algorithms (not in /root/reference):
  *   petgraph 0.6.4 GraphMap / kosaraju_scc / Dfs / DfsPostOrder / Bfs  (ordering only)
  *   rust-htslib 0.46 CigarStringView::leading_softclips / trailing_softclips
- *       (first / last op only), Record::seq_len, htslib bam_endpos + fetch overlap test
+ *       (first / last op, looking through one hard clip), Record::seq_len, htslib bam_endpos + fetch overlap test
  *   statrs 0.16 Binomial::cdf: replaced by the exact integer evaluation
  *       lcr_binom_two_tailed_lt_0p05 (include/lcr_contract.h)
  *   rand 0.8.5 thread_rng: replaced by lcr_uniform (include/lcr_contract.h)
@@ -275,15 +275,22 @@ struct Worker {
         int64_t endpos = pos + (rlen ? rlen : 1);
         return pos < (int64_t)reg.end && endpos > (int64_t)reg.start;
     }
+    /* rust-htslib CigarStringView::leading_softclips / trailing_softclips: the soft clip at the end of the
+       alignment, looking through one hard clip (`5H10S...` has 10 leading soft clips, `...7S3H` 7 trailing ones);
+       util.rs:682-690 and fragment.rs:59 start pos_in_read there */
     int64_t leading_softclips(uint32_t i) const {
         uint64_t a = B.cig_off[i], b = B.cig_off[i + 1];
         if (a == b) return 0;
-        return ((B.cigar[a] & 0xf) == 4) ? (int64_t)(B.cigar[a] >> 4) : 0;
+        if ((B.cigar[a] & 0xf) == 4) return (int64_t)(B.cigar[a] >> 4);
+        if ((B.cigar[a] & 0xf) == 5 && a + 1 < b && (B.cigar[a + 1] & 0xf) == 4) return (int64_t)(B.cigar[a + 1] >> 4);
+        return 0;
     }
     int64_t trailing_softclips(uint32_t i) const {
         uint64_t a = B.cig_off[i], b = B.cig_off[i + 1];
         if (a == b) return 0;
-        return ((B.cigar[b - 1] & 0xf) == 4) ? (int64_t)(B.cigar[b - 1] >> 4) : 0;
+        if ((B.cigar[b - 1] & 0xf) == 4) return (int64_t)(B.cigar[b - 1] >> 4);
+        if ((B.cigar[b - 1] & 0xf) == 5 && b - a >= 2 && (B.cigar[b - 2] & 0xf) == 4) return (int64_t)(B.cigar[b - 2] >> 4);
+        return 0;
     }
 
     /* ---- P1: Profile::fill_data_into_freq_vec (util.rs:621-949) */
@@ -683,7 +690,11 @@ struct Worker {
                 }
             uint32_t hete_links = 0;
             for (const FragElem &fe : fragment.list) {
-                if (fe.baseq == 0) return LCR_ERR_BASEQ_ZERO; /* contract: reference panics later on NaN (phase.rs:307) */
+                /* a base of quality 0 has prob = 1.0 (fragment.rs:133): at a phase site log10(0) reaches the first sigma
+                   sweep and the reference panics on the NaN compare (phase.rs:307) -> status.  At the other sites (edit /
+                   low-fraction candidates) the reference carries on: the IEEE outcomes are restated in eval_rescue and
+                   assign_reads_haplotype below (mode 1 simply computes them) */
+                if (fe.baseq == 0 && fe.phase_site) return LCR_ERR_BASEQ_ZERO;
                 if (fe.phase_site) hete_links++;
             }
             fragment.num_hete_links = hete_links;
@@ -1255,19 +1266,27 @@ struct Worker {
             const int sigma_k = f.haplotag;
             delta.clear(); eta.clear(); ps.clear(); qs.clear();
             int64_t A = 0, Bs = 0;
+            bool q0_used = false; /* contract: a quality-0 element (only possible at a rescued site) */
             for (FragElem &fe : f.list) {
                 const Cand &c = cands[fe.snp_idx];
                 if (!fe.phase_site && c.for_phasing) fe.phase_site = true;
                 if (!c.for_phasing || c.haplotype == 0 || c.genotype != 0) continue;
                 ps.push_back(fe.p); qs.push_back(fe.baseq); delta.push_back(c.haplotype); eta.push_back(c.genotype);
-                if (FX) { A += aki_fx(sigma_k, c.haplotype, c.genotype, fe.p, fe.baseq); Bs += aki_fx(-sigma_k, c.haplotype, c.genotype, fe.p, fe.baseq); }
+                if (FX) {
+                    if (fe.baseq == 0) { q0_used = true; continue; }
+                    A += aki_fx(sigma_k, c.haplotype, c.genotype, fe.p, fe.baseq); Bs += aki_fx(-sigma_k, c.haplotype, c.genotype, fe.p, fe.baseq);
+                }
             }
             int assign = 0;
             if (sigma_k == 0 || delta.empty()) {
                 f.assignment = 0; f.haplotag = 0; f.assignment_score = 0.0;
             } else {
                 double q, qn;
-                if (FX) {
+                if (FX && q0_used) {
+                    /* exactly one of the two sums holds log10(0) = -inf (both when two such elements disagree): one of q, qn
+                       is NaN, `(q - qn).abs() >= cutoff` is false and the read goes to the unknown group (snpfrags.rs:611-618) */
+                    q = qn = std::nan("");
+                } else if (FX) {
                     /* both denominators are the same pair of sums in either order: integer add, one conversion */
                     const double den = lcr_fx_to_f64(A + Bs);
                     q = 1.0 - lcr_fx_to_f64(A) / den;
@@ -1301,6 +1320,16 @@ struct Worker {
     /* phase score from a column (snpfrags.rs:245-246,483): -10 log10(1 - cal_phase_score_log) */
     double phase_score_of(int delta_i, const ColData &cd) const {
         if (FX) {
+            /* quality-0 elements: aki(sigma, delta, 0, p, 1.0) is 0 when p == sigma * delta, so log_q2 (delta = +1) or log_q3
+               (delta = -1) of phase.rs:238-255 is -inf.  log_q1 / (log_q2 + log_q3) is then NaN when log_q1 is the infinite
+               one and +-0 otherwise, i.e. the score is NaN or -10 log10(1 - 1) = +inf */
+            bool z1 = false, z2 = false;
+            for (size_t k = 0; k < cd.sigma.size(); ++k)
+                if (cd.qs[k] == 0) { if (cd.ps[k] == cd.sigma[k]) z1 = true; else z2 = true; }
+            if (z1 || z2) {
+                const bool mine_inf = delta_i == 1 ? z1 : z2;
+                return mine_inf ? std::nan("") : HUGE_VAL;
+            }
             int64_t L1 = 0, L2 = 0, L3 = 0;
             for (size_t k = 0; k < cd.sigma.size(); ++k) {
                 L1 += aki_fx(cd.sigma[k], delta_i, 0, cd.ps[k], cd.qs[k]);
@@ -1564,8 +1593,10 @@ int lcr_oracle_run(const lcr_params *params, const lcr_batch *batch, const uint8
             box->cand.push_back(o);
         }
         box->cand_off[r + 1] = (uint32_t)box->cand.size();
-        for (auto &h : ro.hp) box->hp[h.first] = (int8_t)h.second;
-        for (auto &p : ro.ps) box->ps[p.first] = p.second;
+        /* a read shared by several regions keeps the entry of the lowest region (thread.rs:308-325 keeps the first entry
+           per qname in queue order, which is completion order there; the contract fixes it to region order) */
+        for (auto &h : ro.hp) if (box->hp[h.first] == -1) box->hp[h.first] = (int8_t)h.second;
+        for (auto &p : ro.ps) if (box->ps[p.first] == 0) box->ps[p.first] = p.second;
         for (const Fragment &f : ro.frags) box->is_fragment[f.read] = 1;
         if (planes) {
             for (const BaseFreq &bf : ro.pileup) {

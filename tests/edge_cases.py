@@ -117,6 +117,53 @@ def cases():
         r["seq"] = s.decode()
     out["polya_tail"] = (p, helpers.make_reads(L, recs), [ref], helpers.one_region(701, 1901, 12), [0])
 
+    # hard clip then soft clip: rust-htslib's leading/trailing_softclips look through the H (util.rs:682-690, fragment.rs:59)
+    recs = []
+    for k in range(14):
+        body = bytearray(ref[700:1900].tobytes())
+        if k % 2:
+            for pos, b in alts.items():
+                body[pos - 700] = b
+        if k % 3 == 0:
+            seq, cig = b"T" * 10 + bytes(body) + b"G" * 7, "5H10S1200M7S3H"
+        elif k % 3 == 1:
+            seq, cig = b"T" * 4 + bytes(body), "2H4S1200M9H"
+        else:
+            seq, cig = bytes(body) + b"AAAAAA", "8H1200M6S"
+        recs.append(dict(pos=700, cigar=cig, seq=seq.decode(), qual=[12 + (i * 5 + k) % 30 for i in range(len(seq))], flag=16 if k % 4 < 2 else 0))
+    out["hard_then_soft_clips"] = (p, helpers.make_reads(L, recs), [ref], helpers.one_region(701, 1901, 14), [0])
+    po2 = host.params_preset("ont-drna", seed=3, flags=p.flags)
+    out["hard_then_soft_clips_ont"] = (po2, helpers.make_reads(L, recs), [ref], helpers.one_region(701, 1901, 14), [0])
+
+    # quality 0 on an RNA-edit candidate (A>G, not a phase site): the reference does not panic there; its IEEE outcomes
+    # (NaN / +inf phase scores in the rescue pass, snpfrags.rs:191-281, NaN read scores afterwards, :580-618) are part of the contract
+    a_sites = [int(x) for x in np.nonzero(ref[1100:1800] == ord("A"))[0][:3] + 1100]
+    hets = {1000: alt_of(ref, 1000), 1300: alt_of(ref, 1300), 1850: alt_of(ref, 1850)}
+    for name, zeros in (("baseq_zero_edit_site_one", [(1, 0)]), ("baseq_zero_edit_site_both", [(1, 0), (4, 0)]),
+                        ("baseq_zero_edit_site_discordant", [(1, 0), (6, 1)]), ("baseq_zero_edit_site_unused_read", [(3, 0)])):
+        recs = _reads_over(ref, 700, 16, 1200, alts=hets)
+        for k, r in enumerate(recs):
+            sq = bytearray(r["seq"].encode())
+            for j, apos in enumerate(a_sites):
+                if k % 2:
+                    sq[apos - 700] = ord("G")
+            r["qual"] = [30] * 1200
+            r["seq"] = sq.decode()
+        for k, flip in zeros:
+            sq = bytearray(recs[k]["seq"].encode())
+            if flip:  # this read carries the other haplotype's allele at the edit site
+                sq[a_sites[0] - 700] = ord("G") if sq[a_sites[0] - 700] == ord("A") else ord("A")
+            recs[k]["seq"] = sq.decode()
+            recs[k]["qual"][a_sites[0] - 700] = 0
+        out[name] = (p, helpers.make_reads(L, recs), [ref], helpers.one_region(701, 1901, 16), [0])
+
+    # two regions whose read ranges overlap: reads that fall into both windows keep the HP / PS entry of the lower region
+    recs = _reads_over(ref, 700, 12, 1200, alts=alts) + _reads_over(ref, 1250, 12, 1400, alts={1300: alt_of(ref, 1300), 1600: alt_of(ref, 1600), 2000: alt_of(ref, 2000), 2400: alt_of(ref, 2400)})
+    regs = np.zeros(2, dtype=abi.REGION_DTYPE)
+    regs[0] = (0, 701, 1501, 0, 24)
+    regs[1] = (0, 1501, 2651, 0, 24)
+    out["shared_reads_two_regions"] = (p, helpers.make_reads(L, recs), [ref], regs, [0, 0])
+
     # maximum depth: sites above max_depth are skipped (candidate.rs:90-94)
     pm = host.params_preset("hifi-masseq", seed=3, max_depth=20, flags=p.flags)
     out["above_max_depth"] = (pm, helpers.make_reads(L, _reads_over(ref, 700, 40, 1200, alts=alts)), [ref], helpers.one_region(701, 1901, 40), [0])

@@ -89,7 +89,8 @@ def compare_results(a, b, what=""):
     np.testing.assert_array_equal(a.ps, b.ps, err_msg=what + " ps")
     np.testing.assert_array_equal(a.is_fragment, b.is_fragment, err_msg=what + " is_fragment")
     if (a.region_status == 0).all():  # a failed region stops the reference mid-way; its partial counts are not defined
-        for k in ("n_reads_pass", "n_aligned_bases", "n_positions", "n_candidates"):
+        # the metric's numerator is n_aligned_bases + nnz_phase; the sweep counters pin the iteration-for-iteration equality of the phasing
+        for k in ("n_reads_pass", "n_aligned_bases", "n_positions", "n_candidates", "n_fragments", "nnz_phase", "n_cross_optimize", "n_sweep_iters"):
             assert a.stats[k] == b.stats[k], f"{what} stats.{k}: {a.stats[k]} != {b.stats[k]}"
     if a.planes is not None and b.planes is not None:
         for k in ("pos_off", "acgt", "fwd", "d", "n", "ts"):

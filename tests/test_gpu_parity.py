@@ -171,12 +171,16 @@ def test_chunked_submit_matches_single_pass(monkeypatch):
     regions, _ = host.find_regions(syn.reads, p)
     refs = syn.reference.for_reads(syn.reads)
     batch = host.BatchView(syn.reads, regions)
+    # the chunk size is read from the environment when a context is created
+    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", "100000")
     eng = host.Engine(p, device=0)
     eng.set_references(refs)
-    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", "100000")
     whole = eng.submit(batch)
     n_launch_whole = eng.last_submit_timing()["kernel_launches"]
+    eng.close()
     monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", "1")
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
     parts = eng.submit(batch)
     t = eng.last_submit_timing()
     eng.close()
@@ -228,11 +232,54 @@ def test_concurrent_submit_on_one_context():
 
 @pytest.mark.parametrize("preset,platform,both,walk", [("hifi-masseq", 0, 0, "2"), ("ont-cdna", 1, 1, "1"), ("hifi-isoseq", 0, 1, "2"), ("ont-drna", 1, 0, "1")])
 def test_walk_variants(preset, platform, both, walk):
-    """The CIGAR walks have a thread-per-read and a warp-per-read form chosen by the batch's ops per read: force each on both platforms."""
+    """The fragment walk has a thread-per-read and a warp-per-read form chosen by the batch's ops per read: force each on both platforms."""
     import subprocess
     import sys
 
-    env = dict(os.environ, LCR_PREP_WALK=walk, LCR_FRAG_WALK=walk, LCR_TILE_VARIANT="2" if walk == "1" else "1")
+    env = dict(os.environ, LCR_FRAG_WALK=walk)
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "parity_case.py"), preset, str(platform), str(both)],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "parity ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_full_size_cfg3_against_oracle():
+    """BASELINE config 3 at full size (64 Mb, 30x HiFi MAS-Seq, 1.2 M reads, 16 k regions): every candidate field, HP and PS
+    of the CUDA path against the oracle (contract mode on all host cores), plus the size-independent properties."""
+    import bench
+
+    w, syn, p, regions = bench.make_workload("cfg3", 0)
+    batch = host.BatchView(syn.reads, regions)
+    refs = syn.reference.for_reads(syn.reads)
+    eng = host.Engine(p)
+    eng.set_references(refs)
+    got = eng.submit(batch)
+    eng.close()
+    assert got.stats["n_aligned_bases"] > 1.4e9 and got.n_cand > 40000 and (got.region_status == 0).all()
+    c = got.cand
+    key = c["region"].astype(np.int64) * (1 << 40) + c["pos"]
+    assert (np.diff(key) > 0).all()
+    assert set(int(x) for x in c["phase_set"] if x) <= set(int(x) + 1 for x in c["pos"])
+    assert ((got.ps > 0) <= (got.hp > 0)).all()
+    truth = set(int(x) for x in syn.het_pos)
+    called = set(int(x) for x in c["pos"][c["variant_type"] == 1])
+    assert len(called & truth) >= 0.8 * len(truth)
+    want = ob.run(p, batch, refs, mode=0, threads=os.cpu_count() or 1)
+    helpers.compare_results(got, want, "cfg3 full size")
+    rescued = (c["flags"] & abi.CF_EDIT_LIST != 0) & (c["flags"] & abi.CF_FOR_PHASING != 0) & (c["flags"] & abi.CF_RNA_EDITING == 0)
+    assert rescued.sum() > 100, "the rescue pass (snpfrags.rs:191-281) promoted no editing site"
+
+
+@pytest.mark.parametrize("name", ["shared_reads_two_regions"])
+def test_shared_reads_are_deterministic(name):
+    """A read that lies in two regions keeps the HP / PS entry of the lower region on every run (no cross-CTA write race)."""
+    p, reads, refs, regions, status = EDGE[name]
+    batch = host.BatchView(reads, regions)
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
+    runs = [eng.submit(batch) for _ in range(5)]
+    eng.close()
+    want = ob.run(p, batch, refs, mode=0)
+    for r in runs:
+        helpers.compare_results(r, want, name)
+    shared = np.nonzero((reads.pos < 1500) & (reads.pos + 1200 > 1500))[0]
+    assert len(shared) > 0
