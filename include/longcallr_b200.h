@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LCR_ABI_VERSION 1
+#define LCR_ABI_VERSION 2
 
 typedef enum lcr_status {
     LCR_OK = 0,
@@ -217,6 +217,17 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *db);
 int lcr_fetch(lcr_ctx *ctx, lcr_device_batch *db, lcr_result **out);
 void lcr_release(lcr_ctx *ctx, lcr_device_batch *db);
 
+/* device-resident results of the last lcr_run_device on this batch (valid until the next run or lcr_release): what a
+   caller that keeps results on the GPU reads instead of lcr_fetch, e.g. the per-rank gather of VCF records over NCCL */
+typedef struct lcr_device_view {
+    const lcr_candidate *cand; /* [n_cand] device pointer, sorted by (region, pos) */
+    const int8_t *hp;          /* [n_reads] device pointer                          */
+    const uint32_t *ps;        /* [n_reads] device pointer                          */
+    uint32_t n_cand;
+    uint32_t n_reads;
+} lcr_device_view;
+int lcr_device_results(lcr_ctx *ctx, lcr_device_batch *db, lcr_device_view *out);
+
 /* timing / accounting of the last lcr_run_device on this batch */
 typedef struct lcr_timing {
     float ms_total;           /* CUDA-event time of the whole run on the context stream   */
@@ -229,6 +240,15 @@ typedef struct lcr_timing {
     uint64_t pileup_alg_bytes; /* algorithmic bytes of the tile pileup kernel  */
     uint64_t h2d_bytes;        /* bytes lcr_upload copied                                  */
     uint64_t d2h_bytes;        /* bytes lcr_fetch copied                                   */
+    /* ABI 2: finer stage times (CUDA events on the context stream) and the counts behind the roofline figures */
+    float ms_prep;            /* read filter / span pass, scans, CIGAR walk, tile descriptors      */
+    float ms_enum;            /* enumeration work lists + search kernels (regions of <= 10 sites)  */
+    float ms_phase_kernel;    /* k_phase / k_phase_grid: LD path, read / SNP assignment, phase sets */
+    uint32_t run_attempts;    /* 1, or more when a capacity overflow made the run repeat           */
+    uint64_t n_segments;      /* segments the walk emitted                                         */
+    uint64_t n_items;         /* (read, tile) rows                                                 */
+    uint64_t n_tiles;         /* tiles the pileup kernel processed                                 */
+    uint64_t phase_alg_bytes; /* algorithmic bytes of the phasing sweeps: B_sweep x sweep iterations */
 } lcr_timing;
 int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out);
 /* accounting of the last lcr_submit on this context, summed over the chunks it was cut into */

@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-LCR_ABI_VERSION = 1
+LCR_ABI_VERSION = 2
 
 LCR_OK = 0
 LCR_ERR_INVALID_ARG = -1
@@ -210,7 +210,19 @@ class Timing(C.Structure):
         ("pileup_alg_bytes", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("ms_prep", C.c_float),
+        ("ms_enum", C.c_float),
+        ("ms_phase_kernel", C.c_float),
+        ("run_attempts", C.c_uint32),
+        ("n_segments", C.c_uint64),
+        ("n_items", C.c_uint64),
+        ("n_tiles", C.c_uint64),
+        ("phase_alg_bytes", C.c_uint64),
     ]
+
+
+class DeviceView(C.Structure):
+    _fields_ = [("cand", C.c_void_p), ("hp", C.c_void_p), ("ps", C.c_void_p), ("n_cand", C.c_uint32), ("n_reads", C.c_uint32)]
 
 
 # ---- csrc/host/lcr_host.h ----

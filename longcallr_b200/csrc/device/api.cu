@@ -179,25 +179,33 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     fa.is_fragment = db->is_fragment;
     const int walk_mode = ctx->frag_walk_mode; /* 1: thread per read, 2: warp per read */
     const bool long_cigars = walk_mode == 2 || (walk_mode == 0 && db->n_cigar > 24ull * (db->n_reads ? db->n_reads : 1));
+    LCR_DEBUG_CHECK(ctx, "fragment stage memsets");
     lcr_launch_frag_count(fa, long_cigars, st);
+    LCR_DEBUG_CHECK(ctx, "frag_count");
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, frag_flag, frag_scan, (int)sn, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, elem_count, elem_scan, (int)sn, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cover_count, cover_off, (int)cn, st));
+    LCR_DEBUG_CHECK(ctx, "fragment scans");
     lcr_launch_region_frag_ranges(fa, n_regions, st);
+    LCR_DEBUG_CHECK(ctx, "region_frag_ranges");
     lcr_launch_frag_fill(fa, long_cigars, st);
+    LCR_DEBUG_CHECK(ctx, "frag_fill");
     db->timing.kernel_launches += 3; /* own kernels only; cub scans are library code */
 
     /* LD graph of the regions with more than max_enum_snps candidates: pair table segments, perfect-LD edges, sorted adjacency */
     lcr_launch_pair_plan(fa, n_regions, region_cap, region_cap_off, false, st);
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, region_cap, region_cap_off, (int)rn, st));
     lcr_launch_pair_plan(fa, n_regions, region_cap, region_cap_off, true, st);
+    LCR_DEBUG_CHECK(ctx, "pair_plan");
     lcr_launch_pair_build(fa, n_regions, table, entry_region, ctx->sm_count, st);
+    LCR_DEBUG_CHECK(ctx, "pair_build");
     lcr_launch_ld_edges(false, fa, table, entry_region, deg, nullptr, nullptr, nullptr, ctx->sm_count, st);
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, adj_off, (int)cn, st));
     lcr_launch_adj_finish(fa, adj_off, adj, false, ctx->sm_count, st);
     lcr_launch_ld_edges(true, fa, table, entry_region, deg, adj_off, adj_cursor, adj, ctx->sm_count, st);
     lcr_launch_adj_finish(fa, adj_off, adj, true, ctx->sm_count, st);
     db->timing.kernel_launches += 9;
+    LCR_DEBUG_CHECK(ctx, "ld graph");
     TRY(cudaEventRecord(ctx->ev_t[4], st));
 
     /* phasing state */
@@ -215,6 +223,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
        per (shape, class) bin; the bins are independent: fork them onto side streams so that small and large shapes overlap */
     lcr_launch_enum_plan(pa, (uint32_t)std::min<uint64_t>(C.enum_work, 0xfffffff0u), ctx->sm_count, st);
     db->timing.kernel_launches += 1;
+    LCR_DEBUG_CHECK(ctx, "enum_plan");
     TRY(cudaEventRecord(ctx->ev_fork, st));
     for (int i = 0; i < 4; ++i) TRY(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
     for (int b = 0; b < LCR_ENUM_BINS; ++b) {
@@ -226,14 +235,18 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
         TRY(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
         TRY(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }
+    LCR_DEBUG_CHECK(ctx, "enum_search");
+    TRY(cudaEventRecord(ctx->ev_t[6], st));
     lcr_launch_phase(pa, st);
     db->timing.kernel_launches += 1;
+    LCR_DEBUG_CHECK(ctx, "k_phase");
     /* regions too large for one CTA take the whole GPU, one after the other */
     if (db->n_big_list) {
         int e = lcr_launch_phase_grid(pa, db->big_list, db->n_big_list, bcast, ctx->sm_count, st);
         if (e) { ctx->last_error = std::string("k_phase_grid: ") + cudaGetErrorString((cudaError_t)e); ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
         db->timing.kernel_launches += 1;
     }
+    TRY(cudaEventRecord(ctx->ev_t[7], st));
     if (n_reads) {
         k_finalize_reads<<<(n_reads + 255) / 256, 256, 0, st>>>(n_reads, pa.hp_key, pa.ps_key, db->hp, db->ps);
         db->timing.kernel_launches += 1;
@@ -251,7 +264,7 @@ static int plan_or_launch(lcr_ctx *ctx, lcr_device_batch_full *db, bool launch) 
     if (rc) return rc;
     if (launch) TRY(cudaEventRecord(ctx->ev_t[3], ctx->stream));
     if (!(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) rc = stage_fragments_phase(ctx, db, A, ctx->d_ctr, launch);
-    else if (launch) TRY(cudaEventRecord(ctx->ev_t[4], ctx->stream));
+    else if (launch) { TRY(cudaEventRecord(ctx->ev_t[4], ctx->stream)); TRY(cudaEventRecord(ctx->ev_t[6], ctx->stream)); TRY(cudaEventRecord(ctx->ev_t[7], ctx->stream)); }
     return rc;
 }
 
@@ -304,6 +317,8 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
         ctx->frag_walk_mode = (e && *e) ? atoi(e) : 0;
         e = getenv("LCR_SUBMIT_CHUNK_MB");
         ctx->submit_chunk_bytes = (e && *e) ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)256 << 20;
+        e = getenv("LCR_DEBUG_SYNC");
+        ctx->debug_sync = (e && *e) ? atoi(e) : 0;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LCR_ERR_CUDA; }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -313,7 +328,7 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
         cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
-    for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev_t[i]);
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev_t[i]);
     /* keep freed blocks in the stream-ordered pool between runs */
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -362,7 +377,7 @@ void lcr_destroy(lcr_ctx *ctx) {
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     for (int i = 0; i < 4; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-    for (int i = 0; i < 6; ++i) cudaEventDestroy(ctx->ev_t[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev_t[i]);
     cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
@@ -538,7 +553,9 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     if ((ctx->P.flags & LCR_FLAG_EMIT_PLANES) && !db->pl_acgt) {
         DALLOC(db->pl_acgt, db->n_pos * 4); DALLOC(db->pl_fwd, db->n_pos * 4); DALLOC(db->pl_d, db->n_pos); DALLOC(db->pl_n, db->n_pos); DALLOC(db->pl_ts, db->n_pos * 2);
     }
+    uint32_t attempts = 0;
     for (int attempt = 0;; ++attempt) {
+        ++attempts;
         /* the asynchronous upload's seq / qual copies may still be in flight: the pileup stage waits where it first reads them */
         db->seq_wait_pending = db->ev_seq != nullptr;
         memset(&db->timing, 0, sizeof db->timing);
@@ -602,6 +619,14 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     cudaEventElapsedTime(&ms, ctx->ev_t[3], ctx->ev_t[4]); db->timing.ms_fragments = ms;
     cudaEventElapsedTime(&ms, ctx->ev_t[4], ctx->ev_t[5]); db->timing.ms_phase = ms;
     cudaEventElapsedTime(&ms, ctx->ev_t[2], ctx->ev_t[5]); db->timing.ms_total = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[2], ctx->ev_t[0]); db->timing.ms_prep = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[4], ctx->ev_t[6]); db->timing.ms_enum = ms;
+    cudaEventElapsedTime(&ms, ctx->ev_t[6], ctx->ev_t[7]); db->timing.ms_phase_kernel = ms;
+    db->timing.run_attempts = attempts;
+    db->timing.n_segments = K.n_segs_used; db->timing.n_items = K.n_items_used; db->timing.n_tiles = K.n_tiles_done;
+    /* one sweep iteration (sigma pass + delta / eta pass) touches every phase-site cell twice (1 B cell + 4 B index), every fragment's row
+       pointer and haplotag, every site's column pointer and state: B_sweep of SURVEY 8(d), times the iterations executed */
+    db->timing.phase_alg_bytes = (10ull * ctx->h_stats->nnz_phase + 6ull * db->n_frag + 8ull * K.n_cand) * (ctx->h_stats->n_cross_optimize ? ctx->h_stats->n_sweep_iters / std::max<uint64_t>(1, ctx->h_stats->n_cross_optimize) : 0) ;
     /* algorithmic bytes of the tile kernel: base + qual of every aligned base, the segment and item descriptors it stages, one tile
        descriptor and the reference bytes per processed tile, the surviving sites it writes */
     db->timing.pileup_alg_bytes = 2ull * ctx->h_stats->n_aligned_bases + 16ull * K.n_segs_used + 16ull * K.n_items_used + 48ull * K.n_tiles_done + K.n_pos_done +
@@ -745,6 +770,13 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     if (db->ev_seq) { cudaEventSynchronize(db->ev_seq); cudaEventDestroy(db->ev_seq); }
     if (db->ev_meta) cudaEventDestroy(db->ev_meta);
     delete db;
+}
+
+int lcr_device_results(lcr_ctx *ctx, lcr_device_batch *db, lcr_device_view *out) {
+    if (!ctx || !db || !out || !db->ran) return LCR_ERR_INVALID_ARG;
+    out->cand = db->cand; out->hp = db->hp; out->ps = db->ps;
+    out->n_cand = db->n_cand; out->n_reads = db->n_reads;
+    return LCR_OK;
 }
 
 int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out) {

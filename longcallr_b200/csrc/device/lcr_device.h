@@ -78,11 +78,12 @@ struct lcr_ctx {
     LcrCounters *d_ctr;        /* device counter block of the current run */
     LcrCounters *h_ctr;        /* pinned host copies read once at the end of a run */
     lcr_stats *h_stats;
-    cudaEvent_t ev_t[6];       /* tile kernel begin / end, run begin, pileup stage end, fragment build end, run end */
+    cudaEvent_t ev_t[8];       /* tile kernel begin / end, run begin, pileup stage end, fragment build end, run end, enumeration end, phase kernels end */
     /* experiment / test knobs read from the environment when the context is created */
     uint32_t big_frag_threshold; /* LCR_BIG_REGION_FRAGS: fragments from which an LD-path region takes the cooperative kernel */
     int frag_walk_mode;          /* LCR_FRAG_WALK: 0 by ops per read, 1 thread per read, 2 warp per read */
     size_t submit_chunk_bytes;   /* LCR_SUBMIT_CHUNK_MB: seq + qual bytes per chunk of lcr_submit */
+    int debug_sync;              /* LCR_DEBUG_SYNC: synchronise and check after every launch group (bring-up only) */
 };
 
 struct lcr_device_batch {
@@ -163,6 +164,20 @@ __device__ __forceinline__ int64_t lcr_trailing_softclips(const uint32_t *cigar,
     return 0;
 }
 #endif
+
+/* bring-up aid: with LCR_DEBUG_SYNC set, wait for the stream after a launch group and attribute a failure to it */
+#define LCR_DEBUG_CHECK(ctx, what)                                                      \
+    do {                                                                                \
+        if ((ctx)->debug_sync) {                                                        \
+            cudaError_t e__ = cudaStreamSynchronize((ctx)->stream);                     \
+            if (e__ == cudaSuccess) e__ = cudaGetLastError();                           \
+            if (e__ != cudaSuccess) {                                                   \
+                (ctx)->last_error = std::string(what) + ": " + cudaGetErrorString(e__); \
+                (ctx)->sticky = LCR_ERR_CUDA;                                           \
+                return (ctx)->sticky;                                                   \
+            }                                                                           \
+        }                                                                               \
+    } while (0)
 
 /* error plumbing */
 #define LCR_CUDA_TRY(ctx, expr)                                                         \

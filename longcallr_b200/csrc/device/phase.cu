@@ -726,7 +726,14 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     __shared__ TeamBcast bc;
     const uint32_t reg = blockIdx.x;
     const LcrRegionState rs = a.rstate[reg];
-    if (rs.status != 0 || rs.n_cand == 0) return;
+    if (rs.status != 0) return;
+    if (rs.n_cand == 0) { /* phase() still runs its single (empty) configuration: one cross_optimize call of one iteration (phase.rs:1097-1122) */
+        if (threadIdx.x == 0) {
+            atomicAdd((unsigned long long *)&a.stats->n_cross_optimize, 1ull);
+            atomicAdd((unsigned long long *)&a.stats->n_sweep_iters, 1ull);
+        }
+        return;
+    }
     if (rs.n_cand > a.P.max_enum_snps && rs.n_frag >= a.big_frag_threshold) return; /* k_phase_grid takes it */
     Ctx x{a, *a.tables};
     x.reg = reg; x.tid = threadIdx.x; x.nthreads = PB; x.grid = false; x.bc = &bc; x.sh = sh;

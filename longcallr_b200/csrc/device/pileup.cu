@@ -1356,7 +1356,7 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     const uint32_t n_tiles = db->n_tiles, n_slots = db->n_slots, n_regions = db->n_regions;
     const LcrCaps &C = db->caps;
     const size_t tn = (size_t)n_tiles + 1, sn = (size_t)n_slots + 1;
-    /* one zeroed block: tile_diff [tn] | tile_cursor [tn] | tile_full_n [tn] | tile_pre [2 tn] */
+    /* one zeroed block: tile_pre [2 tn] | tile_diff [tn] | tile_cursor [tn] | tile_full_n [tn] */
     uint32_t *zero_blk = A.take<uint32_t>(5 * tn);
     uint32_t *tile_off = A.take<uint32_t>(tn);
     uint32_t *slot_seg_ub = A.take<uint32_t>(sn);
@@ -1380,8 +1380,8 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     void *tmp = A.take<char>(tmp_bytes + 256);
     if (!launch) return LCR_OK;
 
-    uint32_t *tile_diff = zero_blk, *tile_cursor = zero_blk + tn, *tile_full_n = zero_blk + 2 * tn;
-    uint2 *tile_pre = reinterpret_cast<uint2 *>(zero_blk + 3 * tn);
+    uint2 *tile_pre = reinterpret_cast<uint2 *>(zero_blk);
+    uint32_t *tile_diff = zero_blk + 2 * tn, *tile_cursor = zero_blk + 3 * tn, *tile_full_n = zero_blk + 4 * tn;
     TRY(cudaMemsetAsync(zero_blk, 0, sizeof(uint32_t) * 5 * tn, st));
     TRY(cudaMemsetAsync(slot_seg_ub + n_slots, 0, sizeof(uint32_t), st));
 
@@ -1404,17 +1404,21 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
         TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
         db->seq_wait_pending = false;
     }
+    LCR_DEBUG_CHECK(ctx, "pileup stage memsets");
     if (pg) {
         k_read_span<<<pg, pb, 0, st>>>(pa);
         db->timing.kernel_launches += 1;
     }
+    LCR_DEBUG_CHECK(ctx, "k_read_span");
     /* item slots per tile (running sum of the difference array, then its exclusive scan) and segment slots per read */
     TRY(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, tile_diff, tile_diff, (int)tn, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_diff, tile_off, (int)tn, st));
     TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, slot_seg_ub, slot_seg_off, (int)sn, st));
     k_fix_totals<<<1, 32, 0, st>>>(tile_off, n_tiles, slot_seg_off, n_slots, C.items, C.segs, ctr);
+    LCR_DEBUG_CHECK(ctx, "prep scans");
     if (pg) k_read_walk<<<pg, pb, 0, st>>>(pa);
     db->timing.kernel_launches += 2;
+    LCR_DEBUG_CHECK(ctx, "k_read_walk");
 
     DescArgs da{};
     da.n_tiles = n_tiles; da.regions = db->regions;
@@ -1443,6 +1447,7 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
         TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
         db->seq_wait_pending = false;
     }
+    LCR_DEBUG_CHECK(ctx, "k_tile_desc");
     TRY(cudaEventRecord(ctx->ev_t[0], st));
     if (n_tiles) {
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
@@ -1458,9 +1463,11 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
         }
     }
     TRY(cudaEventRecord(ctx->ev_t[1], st));
+    LCR_DEBUG_CHECK(ctx, "k_pileup_tile");
     {
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
         k_site_ll<<<sms * 8, 256, 0, st>>>(ka);
+        LCR_DEBUG_CHECK(ctx, "k_site_ll");
         k_tile_cand_count<<<(uint32_t)((tn + 127) / 128), 128, 0, st>>>(n_tiles, tile_pre, keep, ka.pre_cap, tile_cand_cnt);
         TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, tile_cand_cnt, tile_cand_off, (int)tn, st));
         if (n_tiles) k_tile_cand_gather<<<(n_tiles + 127) / 128, 128, 0, st>>>(n_tiles, tile_pre, keep, ka.pre_cap, tile_cand_off, cand_raw, db->cand, ctr);
@@ -1471,6 +1478,7 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
             db->timing.kernel_launches += 2;
         }
     }
+    LCR_DEBUG_CHECK(ctx, "candidate compaction");
     TRY(cudaGetLastError());
     return LCR_OK;
 }
