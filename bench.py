@@ -1,24 +1,25 @@
 #!/usr/bin/env python
 """bench.py — aligned bases piled-up + het-SNP fragment alleles phased per second (BASELINE.json metric).
 
-One step = one pass of the whole hot path (read filter, tile pileup + site genotyping, fragment
+One step = one pass of the whole hot path (read filter, CIGAR walk, tile pileup + site genotyping, fragment
 matrix, phasing, read/SNP assignment, phase sets) over one synthetic batch.
 
   value   device-resident: inputs already in HBM, lcr_run_device timed with CUDA events on the
-          library's own stream (lcr_get_timing), L2 flushed between steps
+          library's own stream (lcr_get_timing), L2 flushed between steps; at N > 1 every step also
+          gathers the candidate records and the per-read (HP, PS) arrays to rank 0 over NCCL
   e2e     the same pass through lcr_submit with pinned HOST buffers: H2D of the decoded reads,
-          the run, D2H of candidates / HP / PS, timed by wall clock around the call
+          the run, D2H of candidates / HP / PS (and the NCCL gather at N > 1), wall clock around the call
   --impl reference   the reference's CPU algorithm (the line-faithful C++ port in oracle/, mode 1;
           the Rust crate cannot be built here) on all host cores, same workload and metric
 
-Multi-GPU (torchrun): contigs shard across ranks (weak scaling, one synthetic contig per rank);
-rank 0 broadcasts the packed reference over NCCL and gathers the per-region candidate records.
+Default workload: cfg3 (BASELINE configs[2], the largest 30x single-GPU configuration).  Multi-GPU (torchrun):
+contigs are dealt to ranks by longcallr_b200.shard.plan_shards (longest-processing-time on their aligned-base
+estimate; weak scaling: the job holds `contigs_per_rank` x N contigs), rank 0 broadcasts the packed reference once.
 """
 import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -30,46 +31,90 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[1]: synthetic 1 Mb contig, 30x ONT-cDNA, ~1k het SNPs
-    "cfg2": dict(preset="ont-cdna", synth=dict(contig_len=1_000_000, n_contigs=1, platform=1, depth=30.0, n_het=1000, n_edit=200, max_intron=300, max_gap=600, both_strands=1)),
+    "cfg2": dict(preset="ont-cdna", contigs_per_rank=1, synth=dict(contig_len=1_000_000, platform=1, depth=30.0, n_het=1000, n_edit=200, max_intron=300, max_gap=600, both_strands=1)),
     # configs[2]: synthetic chr20 (64 Mb), 30x HiFi MAS-Seq, ~50k candidate sites
-    "cfg3": dict(preset="hifi-masseq", synth=dict(contig_len=64_000_000, n_contigs=1, platform=0, depth=30.0, n_het=40000, n_edit=10000, max_intron=300, max_gap=600, both_strands=0)),
+    "cfg3": dict(preset="hifi-masseq", contigs_per_rank=1, synth=dict(contig_len=64_000_000, platform=0, depth=30.0, n_het=40000, n_edit=10000, max_intron=300, max_gap=600, both_strands=0)),
+    # configs[3] scaled to what 8 ranks of one box can generate and hold on the host: 3 contigs x 10 Mb per rank at 20x ONT-dRNA, 1 het / 1.3 kb
+    # (the full configuration is 300 x 10 Mb, i.e. 37.5 contigs per GPU; the per-contig shape is the same)
+    "cfg4": dict(preset="ont-drna", contigs_per_rank=3, synth=dict(contig_len=10_000_000, platform=1, depth=20.0, n_het=7700, n_edit=1500, max_intron=300, max_gap=600, both_strands=0)),
     # configs[4]: phasing stress, 500 kb gene-dense block at 500x, 5k het SNPs
-    "cfg5": dict(preset="hifi-masseq", synth=dict(contig_len=500_000, n_contigs=1, platform=0, depth=500.0, n_het=5000, n_edit=0, max_intron=500, max_gap=600, both_strands=0, single_region=1)),
+    "cfg5": dict(preset="hifi-masseq", contigs_per_rank=1, synth=dict(contig_len=500_000, platform=0, depth=500.0, n_het=5000, n_edit=0, max_intron=500, max_gap=600, both_strands=0, single_region=1)),
     # small case for quick checks
-    "tiny": dict(preset="hifi-masseq", synth=dict(contig_len=100_000, n_contigs=1, platform=0, depth=30.0, n_het=100, n_edit=20, max_intron=300, max_gap=600, both_strands=0)),
+    "tiny": dict(preset="hifi-masseq", contigs_per_rank=1, synth=dict(contig_len=100_000, platform=0, depth=30.0, n_het=100, n_edit=20, max_intron=300, max_gap=600, both_strands=0)),
 }
 METRIC = "aligned bases piled-up + het-SNP fragments phased /sec (synthetic 30x)"
 UNIT = "bases+alleles/s"
 SEED = 20251017
 
 
-def sample_clocks(stop, out, gpu_index):
-    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
+class ClockSampler:
+    """SM clocks and throttle reasons of the job's GPUs through NVML, sampled by rank 0 during the timed region."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_indices):
+        self.samples, self.stop = [], threading.Event()
+        self.thread = None
         try:
-            r = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-            f = [x.strip() for x in r.stdout.strip().split(",")]
-            if len(f) >= 6:
-                out.append(f)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in gpu_indices]
         except Exception:
-            pass
-        stop.wait(0.2)
+            self.nv, self.handles = None, []
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            for h in self.handles:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append((sm, mx, int(rs)))
+                except Exception:
+                    pass
+            self.stop.wait(0.1)
+
+    def start(self):
+        if self.handles:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def finish(self):
+        self.stop.set()
+        if self.thread:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": [n for b, n in self.REASONS.items() if bits & b], "samples": len(self.samples), "source": "nvml"}
 
 
-def clocks_summary(samples):
-    if not samples:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": reasons}
+def deal_contigs(name, world):
+    """Contigs of the job and the ranks they go to: LPT on the aligned-base estimate (contig length x depth)."""
+    from longcallr_b200 import shard
+
+    w = WORKLOADS[name]
+    n = w["contigs_per_rank"] * world
+    weights = [int(w["synth"]["contig_len"] * w["synth"]["depth"])] * n
+    return shard.plan_shards(weights, world)
 
 
-def make_workload(name, rank):
+def make_workload(name, rank, world=1):
     from longcallr_b200 import host
 
     w = WORKLOADS[name]
-    syn = host.Synthetic(seed=SEED + 7919 * rank, **w["synth"])
+    mine = deal_contigs(name, world)[rank]
+    # every contig of the job has its own seed; a rank generates only the contigs it was dealt
+    syn = host.Synthetic(seed=SEED + 7919 * int(mine[0]), n_contigs=len(mine), **w["synth"])
     p = host.params_preset(w["preset"], seed=SEED)
     regions, _ = host.find_regions(syn.reads, p)
     return w, syn, p, regions
@@ -79,9 +124,8 @@ def bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s):
     """How many leading regions the CPU port can process in about budget_s seconds (probe on 16 regions)."""
     probe_n = max(1, min(len(regions), 16))
     t0 = time.perf_counter()
-    r = ob.run(p, host.BatchView(syn.reads, regions[:probe_n]), refs, mode=1, threads=cores)
+    ob.run(p, host.BatchView(syn.reads, regions[:probe_n]), refs, mode=1, threads=cores)
     dt = max(time.perf_counter() - t0, 1e-9)
-    units = max(r.stats["n_aligned_bases"] + r.stats["nnz_phase"], 1)
     est_total_s = dt * len(regions) / probe_n
     if est_total_s <= budget_s:
         return len(regions)
@@ -96,25 +140,26 @@ def run_reference(args, rank, world):
     import oracle_binding as ob
     from longcallr_b200 import host
 
-    w, syn, p, regions = make_workload(args.workload, 0)
-    batch = host.BatchView(syn.reads, regions)
+    w, syn, p, regions = make_workload(args.workload, 0, 1)
     refs = syn.reference.for_reads(syn.reads)
     cores = os.cpu_count() or 1
-    n_sample = bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s=8.0)
+    single = len(regions) < 4  # one deep region (cfg5) cannot be sub-sampled by regions: it is timed whole, once
+    n_sample = len(regions) if single else bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s=10.0)
     sb = host.BatchView(syn.reads, regions[:n_sample])
-    for _ in range(args.warmup):
+    steps, warm = (1, 0) if single else (args.steps, args.warmup)
+    for _ in range(warm):
         ob.run(p, sb, refs, mode=1, threads=cores)
     t0 = time.perf_counter()
     units = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         r = ob.run(p, sb, refs, mode=1, threads=cores)
         units += r.stats["n_aligned_bases"] + r.stats["nnz_phase"]
     dt = time.perf_counter() - t0
     value = units / dt
-    sample = f"{n_sample} of {len(regions)} regions of {args.workload} per step ({units // max(args.steps, 1)} units), C++ port of the reference loops, {cores} threads over regions"
+    sample = f"{n_sample} of {len(regions)} regions of {args.workload} per step ({units // max(steps, 1)} units), C++ port of the reference loops (oracle mode 1, -O3 -march=native), {cores} threads over regions"
     emit_json({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt / max(steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64",
         "data": "synthetic", "config": {"workload": args.workload, **WORKLOADS[args.workload]["synth"], "preset": w["preset"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -141,6 +186,13 @@ def emit_json(obj):
         os.dup2(2, 1)  # anything printed during teardown goes to stderr again
 
 
+class _DevBuf:
+    """Device memory owned by the library, exposed to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 def main():
     guard_stdout()
     ap = argparse.ArgumentParser()
@@ -148,7 +200,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -167,35 +219,42 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/INFO; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("LCR_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
-    w, syn, p, regions = make_workload(args.workload, rank)
+    w, syn, p, regions = make_workload(args.workload, rank, world)
     refs = syn.reference.for_reads(syn.reads)
 
-    # reference slice: rank 0 packs every rank's contig and broadcasts it once over NCCL (north_star);
-    # each rank keeps its own contig.  Contig lengths are equal by construction (weak scaling).
-    ref_np = np.ascontiguousarray(refs[0])
+    # reference slices: rank 0 packs every rank's contigs and broadcasts them once over NCCL (north_star: "a single NCCL
+    # broadcast of the reference slice"); each rank keeps its own.  Contig sets are equal-sized by construction (weak scaling).
+    ref_np = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.uint8) for r in refs]))
+    bcast_ms = 0.0
     if world > 1:
         L = int(ref_np.size)
-        packed = torch.empty(world * L, dtype=torch.uint8, device="cuda")
-        mine = torch.from_numpy(ref_np).cuda()
-        parts = [torch.empty(L, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        mine = torch.from_numpy(ref_np).to(dev)
+        parts = [torch.empty(L, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
-        if rank == 0:
-            packed.copy_(torch.cat(parts))
+        packed = torch.cat(parts) if rank == 0 else torch.empty(world * L, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         dist.broadcast(packed, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
         got = packed[rank * L:(rank + 1) * L].cpu().numpy()
         assert np.array_equal(got, ref_np), "reference broadcast mismatch"
         ref_np = got
-        del packed, parts
+        del packed, parts, mine
 
     eng = host.Engine(p, device=local_rank)
-    eng.set_reference(0, ref_np)
+    off = 0
+    for tid, r in enumerate(refs):
+        eng.set_reference(tid, ref_np[off:off + len(r)])
+        off += len(r)
 
     # pinned staging buffers for the end-to-end path
     pinned_keep = []
@@ -208,7 +267,7 @@ def main():
     pinned_reads = host.ArrayReadSet.like(syn.reads, alloc_pinned)
     batch = host.BatchView(pinned_reads, regions)
 
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def flush_l2():
         flush.add_(1)
@@ -220,31 +279,56 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_results(cand_u8, hp_u8, ps_u8):
+        """The per-rank VCF records and (read, HP, PS) arrays go to rank 0 (device tensors in, padded to the largest rank)."""
+        n = torch.tensor([cand_u8.numel(), hp_u8.numel(), ps_u8.numel()], device=dev, dtype=torch.int64)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        mx = max(int(s.sum().item()) for s in sizes)
+        buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
+        payload = torch.cat([cand_u8, hp_u8, ps_u8])
+        buf[: payload.numel()] = payload
+        outl = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, outl, dst=0)
+        return sizes, outl
+
     # ---- device-resident timing ----
     handle = eng.upload(batch)
     for _ in range(args.warmup):
         eng.run_device(handle)
-    stop, samples = threading.Event(), []
-    th = threading.Thread(target=sample_clocks, args=(stop, samples, local_rank), daemon=True)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])
     barrier()
-    th.start()
-    dev_ms, pile_ms, pile_bytes, launches = 0.0, 0.0, 0, 0
-    phase_ms, frag_ms = 0.0, 0.0
-    wall0 = time.perf_counter()
+    sampler.start()
+    acc = dict(ms_total=0.0, ms_pileup=0.0, ms_pileup_kernel=0.0, ms_fragments=0.0, ms_phase=0.0, ms_prep=0.0, ms_enum=0.0, ms_phase_kernel=0.0)
+    pile_bytes = phase_bytes = launches = attempts = 0
+    gather_ms = 0.0
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gathered_cands = 0
     for _ in range(args.steps):
         flush_l2()
         eng.run_device(handle)
         t = eng.timing(handle)
-        dev_ms += t["ms_total"]
-        pile_ms += t["ms_pileup_kernel"]
-        phase_ms += t["ms_phase"]
-        frag_ms += t["ms_fragments"]
+        for k in acc:
+            acc[k] += t[k]
         pile_bytes += t["pileup_alg_bytes"]
+        phase_bytes += t["phase_alg_bytes"]
         launches += t["kernel_launches"]
+        attempts += t["run_attempts"]
+        if world > 1:
+            v = eng.device_view(handle)
+            g0.record()
+            cand_u8 = torch.as_tensor(_DevBuf(v.cand, v.n_cand * abi.CANDIDATE_DTYPE.itemsize), device=dev) if v.n_cand else torch.zeros(0, dtype=torch.uint8, device=dev)
+            hp_u8 = torch.as_tensor(_DevBuf(v.hp, v.n_reads), device=dev) if v.n_reads else torch.zeros(0, dtype=torch.uint8, device=dev)
+            ps_u8 = torch.as_tensor(_DevBuf(v.ps, 4 * v.n_reads), device=dev) if v.n_reads else torch.zeros(0, dtype=torch.uint8, device=dev)
+            sizes, outl = gather_results(cand_u8, hp_u8, ps_u8)
+            g1.record()
+            torch.cuda.synchronize()
+            gather_ms += g0.elapsed_time(g1)
+            if rank == 0:
+                gathered_cands = sum(int(s[0].item()) for s in sizes) // abi.CANDIDATE_DTYPE.itemsize
     barrier()
-    wall_ms = (time.perf_counter() - wall0) * 1e3
-    stop.set()
-    th.join()
+    clocks = sampler.finish()
+    dev_ms = acc["ms_total"] + gather_ms
     res = eng.fetch(handle)
     eng.release(handle)
     units = res.stats["n_aligned_bases"] + res.stats["nnz_phase"]
@@ -260,34 +344,32 @@ def main():
         flush_l2()
         raw = eng.submit_raw(batch)  # the reference-facing call: host buffers in, host results out
         rr = host.ResultView(raw)
+        if world > 1:
+            cand_u8 = torch.from_numpy(np.frombuffer(rr.cand.tobytes(), dtype=np.uint8).copy()).to(dev)
+            hp_u8 = torch.from_numpy(rr.hp.view(np.uint8).copy()).to(dev)
+            ps_u8 = torch.from_numpy(rr.ps.view(np.uint8).copy()).to(dev)
+            sizes, outl = gather_results(cand_u8, hp_u8, ps_u8)
+            if rank == 0:
+                _ = [o.cpu() for o in outl]  # rank 0 writes the VCF / tags the BAM from host memory
+            torch.cuda.synchronize()
+        n_cand_last = rr.n_cand
         eng.free_result(raw)
         tt = eng.last_submit_timing()
         h2d, d2h = tt["h2d_bytes"], tt["d2h_bytes"]
     barrier()
     e2e_ms = (time.perf_counter() - e2e_t0) * 1e3
-    n_cand_total = rr.n_cand
-    if world > 1:
-        # gather of per-region VCF records to rank 0 (fixed 88-byte candidate records, padded to the max count)
-        cnt = torch.tensor([rr.n_cand], device="cuda", dtype=torch.int64)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        mx = int(max(int(c.item()) for c in cnts))
-        rec = torch.zeros(mx * abi.CANDIDATE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        raw = torch.from_numpy(np.frombuffer(rr.cand.tobytes(), dtype=np.uint8).copy()).cuda()
-        rec[: raw.numel()] = raw
-        outl = [torch.empty_like(rec) for _ in range(world)] if rank == 0 else None
-        dist.gather(rec, outl, dst=0)
-        n_cand_total = int(sum(int(c.item()) for c in cnts))
 
     # max over ranks
-    tvals = torch.tensor([dev_ms, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
+    tvals = torch.tensor([dev_ms, e2e_ms, gather_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(tvals[0]), float(tvals[1])
-    uvals = torch.tensor([units], device="cuda", dtype=torch.float64)
+    dev_ms_max, e2e_ms_max, gather_ms_max = float(tvals[0]), float(tvals[1]), float(tvals[2])
+    uvals = torch.tensor([units, res.n_cand], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(uvals, op=dist.ReduceOp.SUM)
-    total_units = float(uvals[0])
+    total_units, total_cands = float(uvals[0]), int(uvals[1])
+    if world > 1 and rank == 0:
+        assert gathered_cands == total_cands, "the gather lost candidate records"
 
     if rank == 0:
         peaks = {}
@@ -296,33 +378,57 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = (pile_bytes / 1e9) / (pile_ms / 1e3) if pile_ms > 0 else 0.0
+        steps = max(args.steps, 1)
+
+        def gbs(nbytes, ms):
+            return (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0
+
+        # the kernels / kernel groups of one step with their measured time (CUDA events on the library stream) and algorithmic bytes
+        kernels = {
+            "k_pileup_tile": dict(ms=acc["ms_pileup_kernel"] / steps, bytes=pile_bytes / steps, what="tile pileup + count filters: 2 B per aligned base + 16 B per segment and item + 48 B and the reference bytes per tile"),
+            "k_read_span+k_read_walk": dict(ms=acc["ms_prep"] / steps, bytes=None, what="read filter, reference spans, CIGAR walk into items / segments (latency-bound walks)"),
+            "k_enum_search": dict(ms=acc["ms_enum"] / steps, bytes=None, what="2^n enumeration of regions with <= 10 sites (shared-memory resident)"),
+            "k_phase": dict(ms=acc["ms_phase_kernel"] / steps, bytes=phase_bytes / steps, what="LD path, read / SNP assignment, rescue, phase sets (L2 resident): B_sweep x iterations"),
+            "fragments+ld": dict(ms=acc["ms_fragments"] / steps, bytes=None, what="fragment matrix (CSR + CSC), LD pair tables and graph"),
+        }
+        dominant = max(kernels, key=lambda k: kernels[k]["ms"])
+        # the roofline object describes the dominant kernel when its bytes are defined, else the HBM-streaming kernel of the path
+        rk = dominant if kernels[dominant]["bytes"] else "k_pileup_tile"
+        achieved = gbs(kernels[rk]["bytes"], kernels[rk]["ms"])
         traffic = None
-        try:  # DRAM bytes of one launch of the same kernel from the committed ncu --set full capture of this workload
-            t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))).get(args.workload)
+        try:  # DRAM bytes of one launch of that kernel from the committed ncu --set full capture of this workload (profiles/)
+            t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))).get(args.workload, {}).get(rk)
             if t:
                 traffic = int(t["dram_read_bytes"] + t["dram_write_bytes"])
         except Exception:
             pass
+        stage_bytes = 2 * res.stats["n_aligned_bases"] + 4 * int(syn.reads.cig_off[-1]) + 32 * int(syn.reads.n_reads) + int(res.stats["n_positions"])
         out = {
             "metric": METRIC, "value": total_units * args.steps / (dev_ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64 fixed-point (f64 for QUAL)",
             "data": "synthetic",
-            "config": {"workload": args.workload, "preset": w["preset"], **w["synth"], "regions_per_gpu": int(len(regions)), "reads_per_gpu": int(syn.reads.n_reads),
-                       "aligned_bases_per_gpu": int(res.stats["n_aligned_bases"]), "phase_alleles_per_gpu": int(res.stats["nnz_phase"]),
-                       "candidates": int(n_cand_total), "cross_optimize_calls": int(res.stats["n_cross_optimize"]), "sweep_iters": int(res.stats["n_sweep_iters"]),
-                       "l2": "flushed between steps (512 MiB write)", "sharding": "one contig per rank, no data-path collective"},
+            "config": {"workload": args.workload, "preset": w["preset"], **w["synth"], "contigs_per_gpu": int(w["contigs_per_rank"]), "regions_per_gpu": int(len(regions)),
+                       "reads_per_gpu": int(syn.reads.n_reads), "aligned_bases_per_gpu": int(res.stats["n_aligned_bases"]), "phase_alleles_per_gpu": int(res.stats["nnz_phase"]),
+                       "candidates": int(total_cands), "cross_optimize_calls": int(res.stats["n_cross_optimize"]), "sweep_iters": int(res.stats["n_sweep_iters"]),
+                       "l2": "flushed between steps (512 MiB write)",
+                       "sharding": "contigs dealt by LPT (shard.plan_shards); per step one NCCL gather of candidate records + per-read HP/PS to rank 0 inside the timed region" if world > 1 else "single GPU",
+                       "reference_broadcast_ms": bcast_ms, "gather_ms_per_step": gather_ms_max / args.steps, "run_attempts_per_step": attempts / steps},
             "e2e": {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
-            "clocks": clocks_summary(samples),
-            "roofline": {"kernel": "k_pileup_tile", "why_this_kernel": "the HBM-streaming kernel of the path (every aligned base and quality is read here); 27 % of the cfg3 step after this round's rewrite, the rest being latency-bound walks and L2/SMEM-resident phasing (see stage_ms_per_step, profiles/)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+            "clocks": clocks,
+            "roofline": {"kernel": rk, "dominant_kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "alg_bytes_per_launch": int(pile_bytes / max(args.steps, 1)), "ms_per_launch": pile_ms / max(args.steps, 1)},
-            "stage_ms_per_step": {"pileup_kernel": pile_ms / args.steps, "fragments": frag_ms / args.steps, "phase": phase_ms / args.steps, "total": dev_ms / args.steps},
+                         "alg_bytes_per_launch": int(kernels[rk]["bytes"]), "ms_per_launch": kernels[rk]["ms"], "what": kernels[rk]["what"]},
+            "roofline_stage": {"stage": "pileup + genotype (P0-P7): span pass, walk, tile kernel, site likelihood, candidate compaction", "ms": acc["ms_pileup"] / steps,
+                               "alg_bytes": int(stage_bytes), "achieved": gbs(stage_bytes, acc["ms_pileup"] / steps), "frac": gbs(stage_bytes, acc["ms_pileup"] / steps) / peak,
+                               "formula": "2 N_al + 4 N_cigar + 32 N_reads + N_pos (SURVEY 8d without the per-position record this build never writes)"},
+            "kernel_ms_per_step": {k: v["ms"] for k, v in kernels.items()},
+            "stage_ms_per_step": {"pileup": acc["ms_pileup"] / steps, "fragments": acc["ms_fragments"] / steps, "phase": acc["ms_phase"] / steps, "total": acc["ms_total"] / steps,
+                                  "gather": gather_ms / steps},
         }
         if not args.no_cpu_baseline and len(regions) < 4:
-            # a single deep region cannot be sub-sampled by regions and takes the CPU port minutes (cfg5): not timed by default
-            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"skipped: {args.workload} is {len(regions)} region(s); run --impl reference --workload {args.workload} --steps 1 --warmup 0 for the CPU figure"}
+            # a single deep region cannot be sub-sampled by regions and takes the CPU port minutes (cfg5): timed by --impl reference
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"skipped: {args.workload} is {len(regions)} region(s); bench.py --impl reference --workload {args.workload} times it whole (profiles/)"}
         elif not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_binding as ob
@@ -335,7 +441,7 @@ def main():
             dt = time.perf_counter() - t0
             cu = r1.stats["n_aligned_bases"] + r1.stats["nnz_phase"]
             out["cpu_baseline"] = {"value": cu / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"first {n_sample} of {len(regions)} regions of {args.workload} once ({cu} units, {dt:.2f} s), C++ port of the reference loops (oracle mode 1), {cores} threads over regions"}
+                                   "sample": f"first {n_sample} of {len(regions)} regions of {args.workload} once ({cu} units, {dt:.2f} s), C++ port of the reference loops (oracle mode 1, -O3 -march=native), {cores} threads over regions"}
         emit_json(out)
     eng.close()
     if world > 1:

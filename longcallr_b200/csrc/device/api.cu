@@ -317,6 +317,8 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
         ctx->frag_walk_mode = (e && *e) ? atoi(e) : 0;
         e = getenv("LCR_SUBMIT_CHUNK_MB");
         ctx->submit_chunk_bytes = (e && *e) ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)256 << 20;
+        e = getenv("LCR_TILE_VARIANT");
+        ctx->tile_variant = (e && *e) ? atoi(e) : 0;
         e = getenv("LCR_DEBUG_SYNC");
         ctx->debug_sync = (e && *e) ? atoi(e) : 0;
     }

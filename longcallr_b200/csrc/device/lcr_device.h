@@ -83,6 +83,7 @@ struct lcr_ctx {
     uint32_t big_frag_threshold; /* LCR_BIG_REGION_FRAGS: fragments from which an LD-path region takes the cooperative kernel */
     int frag_walk_mode;          /* LCR_FRAG_WALK: 0 by ops per read, 1 thread per read, 2 warp per read */
     size_t submit_chunk_bytes;   /* LCR_SUBMIT_CHUNK_MB: seq + qual bytes per chunk of lcr_submit */
+    int tile_variant;            /* LCR_TILE_VARIANT: launch shape of the tile pileup kernel (pileup.cu) */
     int debug_sync;              /* LCR_DEBUG_SYNC: synchronise and check after every launch group (bring-up only) */
 };
 

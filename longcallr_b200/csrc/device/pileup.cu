@@ -581,9 +581,9 @@ __global__ void __launch_bounds__(128, 6) k_read_walk(PrepArgs a) {
  * surviving sites are appended in column order to the tile's range of the pre-candidate list.
  * ------------------------------------------------------------------------- */
 #define PT_CONS 256                       /* consumer threads */
-#define PT_THREADS (PT_CONS + 32)         /* + the producer warp */
+#define PT_PROD_WARPS 3                   /* producer warps: one per copied stream (seq bytes, qual bytes, segment descriptors) */
+#define PT_THREADS (PT_CONS + 32 * PT_PROD_WARPS)
 #define PT_WORDS (LCR_TILE / 4)
-#define PT_STAGES 2
 #define PT_ROW_BYTES_MAX 2048u            /* largest item span staged as one row (larger ones are cut into pieces by the producer) */
 #define PT_FLAG_FIRST 1u
 #define PT_FLAG_LAST 2u
@@ -662,7 +662,8 @@ __device__ __forceinline__ uint32_t prmt_sign(uint32_t x) {
     return r;
 }
 
-/* 4 read bases + 4 qualities (column order) -> plane bytes */
+/* 4 read bases + 4 qualities (column order) -> plane bytes; ALLPASS: the caller has checked that every quality of the block is >= min_baseq */
+template <bool ALLPASS>
 __device__ __forceinline__ void onehot4(uint32_t s, uint32_t q, uint32_t minq4, uint32_t pass_allow, uint32_t fmask, uint32_t tsb, uint32_t &x, uint32_t &y) {
     /* PRMT as an 8-entry table on the low three bits of each letter: A=..001 C=..011 T=..100 G=..111 */
     const uint32_t t = s & 0x07070707u;
@@ -673,9 +674,12 @@ __device__ __forceinline__ void onehot4(uint32_t s, uint32_t q, uint32_t minq4, 
     const uint32_t d = (s & 0xdfdfdfdfu) ^ canon;                       /* non-zero byte: not exactly that letter (either case) */
     const uint32_t nz = ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d;
     oh &= ~prmt_sign(nz);
-    const uint32_t ge = ((((q & 0x7f7f7f7fu) | 0x80808080u) - minq4) | q);
-    const uint32_t pm = prmt_sign(ge) & pass_allow;
-    x = oh | ((oh << 4) & pm);
+    if (ALLPASS) x = oh * 17u; /* oh | oh << 4 */
+    else {
+        const uint32_t ge = ((((q & 0x7f7f7f7fu) | 0x80808080u) - minq4) | q);
+        const uint32_t pm = prmt_sign(ge) & pass_allow;
+        x = oh | ((oh << 4) & pm);
+    }
     y = (oh & fmask) | tsb;
 }
 
@@ -715,19 +719,30 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    /* try_wait suspends the thread in hardware up to the hint (ns) before it reports false: waiting warps issue almost nothing */
     asm volatile(
         "{\n\t.reg .pred p;\n"
         "LCR_MBAR_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra LCR_MBAR_DONE_%=;\n\t"
         "bra LCR_MBAR_WAIT_%=;\n"
-        "LCR_MBAR_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "LCR_MBAR_DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
+}
+/* the producers' wait for a free stage: they run ahead of the consumers, so they back off between probes instead of taking issue slots */
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(256);
+    }
 }
 /* 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier; 16-byte aligned addresses and size */
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PT_CONS) : "memory"); }
+__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, %0;" ::"n"(32 * PT_PROD_WARPS) : "memory"); }
 __device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
@@ -739,9 +754,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 __device__ __forceinline__ void sts32a(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-template <int ROWS>
+template <int ROWS, int STAGES>
 struct PtLayout { /* dynamic shared memory of k_pileup_tile, byte offsets */
-    static constexpr uint32_t STAGE_BYTES = ROWS == 32 ? 13312u : 16384u;   /* per stream (seq, qual) and stage */
+    static constexpr uint32_t STAGE_BYTES = STAGES == 1 ? (ROWS == 32 ? 12288u : 16384u) : (ROWS == 32 ? 13312u : 8192u);   /* per stream (seq, qual) and stage */
     static constexpr uint32_t SEG_CAP = 512u;                                /* segments per batch */
     static constexpr uint32_t ROW_SEG_MAX = 256u;                            /* segments of one row */
     static constexpr uint32_t BLK_CAP = ROWS * (LCR_TILE / 16) + SEG_CAP;    /* 16-column blocks per batch */
@@ -756,14 +771,14 @@ struct PtLayout { /* dynamic shared memory of k_pileup_tile, byte offsets */
     static constexpr uint32_t st_rowdelta = st_rowseg + (ROWS + 1u) * 4u;    /* [ROWS] staged byte offset minus pool offset (mod 2^32) */
     static constexpr uint32_t st_hdr = (st_rowdelta + ROWS * 4u + 15u) & ~15u; /* tile, rows, segments, flags */
     static constexpr uint32_t stage_size = (st_hdr + 16u + 127u) & ~127u;
-    static constexpr uint32_t blk = stage0 + PT_STAGES * stage_size;         /* [BLK_CAP] u32: segment | block in segment << 10 | row << 16 */
+    static constexpr uint32_t blk = stage0 + STAGES * stage_size;         /* [BLK_CAP] u32: segment | block in segment << 10 | row << 16 */
     static constexpr uint32_t out32 = (blk + BLK_CAP * 4u + 15u) & ~15u;     /* DEEP: [16][LCR_TILE] */
     static constexpr uint32_t bytes(bool deep) { return out32 + (deep ? 16u * LCR_TILE * 4u : 0u); }
 };
 
-template <bool DEEP, int ROWS>
-__global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileArgs a) {
-    using L = PtLayout<ROWS>;
+template <bool DEEP, int ROWS, int PT_STAGES, int MINB>
+__global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
+    using L = PtLayout<ROWS, PT_STAGES>;
     static_assert(ROWS % 16 == 0 && ROWS >= 16 && ROWS <= 64, "the column sums read whole blocks of 16 rows; row ids take 6 bits");
     static_assert(L::SEG_CAP % PT_CONS == 0 && L::SEG_CAP <= 1024, "whole segments per consumer thread; segment ids take 10 bits");
     static_assert(PT_ROW_BYTES_MAX + 32 <= L::STAGE_BYTES && L::ROW_SEG_MAX <= L::SEG_CAP, "one row always fits an empty batch");
@@ -771,24 +786,34 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
     __shared__ __align__(8) unsigned long long s_bar[2 * PT_STAGES]; /* full[stage], empty[stage] */
     __shared__ uint32_t s_wsum[PT_CONS / 32];
     __shared__ uint32_t s_pcnt[2 * PT_CONS / 32 + 2];
+    __shared__ uint32_t s_ticket[2];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t smem0 = smem_u32(pt_smem);
     const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[PT_STAGES]);
     if (tid == 0) {
-        for (int s = 0; s < PT_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < PT_STAGES; ++s) { mbar_init(bar_full + 8 * s, PT_PROD_WARPS); mbar_init(bar_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    { /* the planes start zeroed; from then on whoever reads a word clears it */
+        uint4 *p4 = reinterpret_cast<uint4 *>(pt_smem + L::planes);
+        for (uint32_t i = tid; i < 2u * ROWS * PT_WORDS / 4u; i += PT_THREADS) p4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
 
-    if (warp == PT_CONS / 32) {
-        /* ================= producer warp ================= */
+    if (warp >= PT_CONS / 32) {
+        /* ================= producer warps =================
+           The three warps run the same control flow over the same tiles and batches; warp 0 copies the seq bytes, warp 1 the
+           qual bytes, warp 2 the segment descriptors and writes the row tables and the batch header.  (A bulk copy takes its
+           operands from uniform registers, so a warp issues its lanes' copies one after the other: three warps triple the rate.) */
+        const uint32_t role = warp - PT_CONS / 32;
         uint32_t stage = 0, empty_par = (1u << PT_STAGES) - 1u; /* bit s: parity to wait for; a fresh barrier passes a wait on the opposite parity, so both stages start empty */
         uint32_t rows = 0, bytes = 0, nsegs = 0, tx = 0, cur_tile = 0, flags = PT_FLAG_FIRST;
         bool open = false;
         auto stage_base = [&](uint32_t s) { return smem0 + L::stage0 + s * L::stage_size; };
+        uint32_t tile_seq = 0;
         auto open_batch = [&]() { /* all lanes; lane 0 waits for the consumers to release the stage */
-            if (lane == 0) mbar_wait(bar_empty + 8 * stage, (empty_par >> stage) & 1u);
+            if (lane == 0) mbar_wait_relaxed(bar_empty + 8 * stage, (empty_par >> stage) & 1u);
             empty_par ^= 1u << stage;
             __syncwarp();
             rows = 0; bytes = 0; nsegs = 0; tx = 0;
@@ -799,8 +824,10 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
             __syncwarp();
             if (lane == 0) {
                 const uint32_t sb = stage_base(stage);
-                sts32a(sb + L::st_rowseg + rows * 4u, nsegs);
-                sts128(sb + L::st_hdr, cur_tile, rows, nsegs, fl);
+                if (role == 2) {
+                    sts32a(sb + L::st_rowseg + rows * 4u, nsegs);
+                    sts128(sb + L::st_hdr, cur_tile, rows, nsegs, fl);
+                }
                 mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
             }
             __syncwarp();
@@ -810,18 +837,22 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
         /* one row: bulk copies of [src_lo, src_lo + nbytes) of both pools and of segments [seg_first, seg_first + ns) */
         auto issue_row = [&](uint32_t row, uint32_t byte_off, uint32_t seg_off, uint64_t src_lo, uint32_t nbytes, uint32_t seg_first, uint32_t ns) {
             const uint32_t sb = stage_base(stage), bar = bar_full + 8 * stage;
-            if (nbytes) {
-                bulk_g2s(sb + L::st_seq + L::PAD + byte_off, a.seq + src_lo, nbytes, bar);
-                bulk_g2s(sb + L::st_qual + L::PAD + byte_off, a.qual + src_lo, nbytes, bar);
+            if (role == 0) { if (nbytes) bulk_g2s(sb + L::st_seq + L::PAD + byte_off, a.seq + src_lo, nbytes, bar); }
+            else if (role == 1) { if (nbytes) bulk_g2s(sb + L::st_qual + L::PAD + byte_off, a.qual + src_lo, nbytes, bar); }
+            else {
+                if (ns) bulk_g2s(sb + L::st_segs + seg_off * 16u, a.segs + seg_first, ns * 16u, bar);
+                sts32a(sb + L::st_rowseg + row * 4u, seg_off);
+                sts32a(sb + L::st_rowdelta + row * 4u, (L::PAD + byte_off) - (uint32_t)src_lo);
             }
-            if (ns) bulk_g2s(sb + L::st_segs + seg_off * 16u, a.segs + seg_first, ns * 16u, bar);
-            sts32a(sb + L::st_rowseg + row * 4u, seg_off);
-            sts32a(sb + L::st_rowdelta + row * 4u, (L::PAD + byte_off) - (uint32_t)src_lo);
         };
+        /* bytes this warp's copies of a batch bring in */
+        auto tx_of = [&](uint32_t nbytes, uint32_t ns) { return role == 2 ? 16u * ns : nbytes; };
         for (;;) {
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&a.ctr->ticket[a.list_id], 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
+            /* warp 0 draws the next tile, the other two read it (slots alternate, so one barrier per tile is enough) */
+            if (role == 0 && lane == 0) s_ticket[tile_seq & 1u] = atomicAdd(&a.ctr->ticket[a.list_id], 1u);
+            prod_bar();
+            const uint32_t t = s_ticket[tile_seq & 1u];
+            ++tile_seq;
             if (t >= a.ctr->n_list[a.list_id]) break;
             cur_tile = a.tile_list[t];
             const LcrTileDesc *dp = a.desc + cur_tile;
@@ -860,7 +891,7 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
                         if (fits) issue_row(rows + (lane - first), bytes + (pb - base_b) - nb, nsegs + (ps - base_s) - ns, src_lo, nb, seg0, ns);
                         const uint32_t lastl = first + nfit - 1;
                         const uint32_t eb = __shfl_sync(0xffffffffu, pb, lastl), es = __shfl_sync(0xffffffffu, ps, lastl);
-                        rows += nfit; bytes += eb - base_b; nsegs += es - base_s; tx += 2u * (eb - base_b) + 16u * (es - base_s);
+                        rows += nfit; bytes += eb - base_b; nsegs += es - base_s; tx += tx_of(eb - base_b, es - base_s);
                         base_b = eb; base_s = es; first += nfit;
                     }
                 } else {
@@ -888,7 +919,7 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
                             if (open && !(rows < (uint32_t)ROWS && bytes + pbytes <= L::STAGE_BYTES && nsegs + cnt <= L::SEG_CAP)) { close_batch(flags); flags = 0; }
                             if (!open) open_batch();
                             if (lane == 0) issue_row(rows, bytes, nsegs, lo_g, pbytes, i_seg0 + s, cnt);
-                            rows += 1; bytes += pbytes; nsegs += cnt; tx += 2u * pbytes + 16u * cnt;
+                            rows += 1; bytes += pbytes; nsegs += cnt; tx += tx_of(pbytes, cnt);
                             s += cnt;
                         } while (s < i_ns);
                     }
@@ -941,6 +972,9 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
             for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
     };
 
+    LcrTileDesc D;
+    memset(&D, 0, sizeof D);
+    uint8_t refb[2] = {0, 0};
     uint32_t stage = 0, full_par = 0; /* bit s: parity to wait for */
     for (;;) {
         mbar_wait(bar_full + 8 * stage, (full_par >> stage) & 1u);
@@ -953,6 +987,14 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
         if (bflags & PT_FLAG_FIRST) {
             ones = twos = fours = eights = s4 = s5 = s6 = s7 = 0;
             acc_rows = 0;
+            /* the tile's descriptor and this thread's two reference bytes are fetched now, long before the epilogue needs them */
+            {
+                const uint4 *dp = reinterpret_cast<const uint4 *>(a.desc + tile);
+                uint4 *dd = reinterpret_cast<uint4 *>(&D);
+                dd[0] = __ldg(dp); dd[1] = __ldg(dp + 1); dd[2] = __ldg(dp + 2);
+            }
+            refb[0] = tid < D.npos ? __ldg(D.ref + tid) : (uint8_t)0;
+            refb[1] = tid + PT_CONS < D.npos ? __ldg(D.ref + tid + PT_CONS) : (uint8_t)0;
             if (DEEP) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -961,12 +1003,6 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
             }
         }
         if (DEEP && acc_rows + nrow > 255u) flush_deep();
-        const uint32_t nrow16 = (nrow + 15u) & ~15u;
-        /* zero this thread's column word in every row of the batch (the thread that sums a word is the one that clears it) */
-        {
-            uint32_t *pl = planes + my_plane * (ROWS * PT_WORDS) + my_word;
-            for (uint32_t r = 0; r < nrow16; ++r) pl[r * PT_WORDS] = 0;
-        }
         /* the batch's segments: row of each, number of 16-column blocks, block list */
         const uint4 *s_seg = reinterpret_cast<const uint4 *>(stg + L::st_segs);
         const uint32_t *s_rowseg = reinterpret_cast<const uint32_t *>(stg + L::st_rowseg);
@@ -996,7 +1032,7 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
             if ((int)lane >= o) incl += v;
         }
         if (lane == 31) s_wsum[warp] = incl;
-        cons_bar(); /* also: planes zeroed, previous batch's block list consumed */
+        cons_bar(); /* also: the previous batch's block list is consumed and the plane words it used are cleared again */
         uint32_t wbase = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < PT_CONS / 32; ++w) {
@@ -1036,10 +1072,22 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
                 const uint32_t q0 = lds32(qa), q1 = lds32(qa + 4), q2 = lds32(qa + 8), q3 = lds32(qa + 12), q4w = lds32(qa + 16);
                 const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u;
                 const uint32_t tsb = ((raw.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
-                onehot4(__byte_perm(s0, s1, rot), __byte_perm(q0, q1, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
-                onehot4(__byte_perm(s1, s2, rot), __byte_perm(q1, q2, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
-                onehot4(__byte_perm(s2, s3, rot), __byte_perm(q2, q3, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
-                onehot4(__byte_perm(s3, s4w, rot), __byte_perm(q3, q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                /* every quality of the five loaded words at least min_baseq (bit 7 of (q | 0x80) - minq stays set, or q >= 128): the
+                   common case on HiFi; the pass bits are then a copy of the base bits */
+                const uint32_t H = 0x80808080u;
+                const uint32_t allge = (((q0 & ~H) | H) - minq4 | q0) & (((q1 & ~H) | H) - minq4 | q1) & (((q2 & ~H) | H) - minq4 | q2) & (((q3 & ~H) | H) - minq4 | q3) &
+                                       (((q4w & ~H) | H) - minq4 | q4w) & H;
+                if (allge == H && pass_allow) {
+                    onehot4<true>(__byte_perm(s0, s1, rot), 0, minq4, pass_allow, fmask, tsb, x[0], y[0]);
+                    onehot4<true>(__byte_perm(s1, s2, rot), 0, minq4, pass_allow, fmask, tsb, x[1], y[1]);
+                    onehot4<true>(__byte_perm(s2, s3, rot), 0, minq4, pass_allow, fmask, tsb, x[2], y[2]);
+                    onehot4<true>(__byte_perm(s3, s4w, rot), 0, minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                } else {
+                    onehot4<false>(__byte_perm(s0, s1, rot), __byte_perm(q0, q1, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
+                    onehot4<false>(__byte_perm(s1, s2, rot), __byte_perm(q1, q2, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
+                    onehot4<false>(__byte_perm(s2, s3, rot), __byte_perm(q2, q3, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
+                    onehot4<false>(__byte_perm(s3, s4w, rot), __byte_perm(q3, q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
+                }
             } else {
                 const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
                 x[0] = x[1] = x[2] = x[3] = 0;
@@ -1071,11 +1119,13 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
         stage = (stage + 1) % PT_STAGES;
         /* column sums of this batch: Harley-Seal blocks of 16 rows (rows up to the next multiple of 16 are zero) */
         {
-            const uint32_t *pl = planes + my_plane * (ROWS * PT_WORDS) + my_word;
+            uint32_t *pl = planes + my_plane * (ROWS * PT_WORDS) + my_word;
             for (uint32_t r0 = 0; r0 < nrow; r0 += 16) {
                 uint32_t w[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) w[j] = pl[(r0 + j) * PT_WORDS];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pl[(r0 + j) * PT_WORDS] = 0; /* the thread that sums a word is the one that clears it for the next batch */
                 uint32_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
                 CSA(t2a, ones, ones, w[0], w[1]);
                 CSA(t2b, ones, ones, w[2], w[3]);
@@ -1113,14 +1163,7 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
             for (int i = 0; i < 8; ++i) planes[(my_plane * ROWS + i) * PT_WORDS + my_word] = cnt8[i];
         }
         cons_bar();
-        LcrTileDesc D;
-        {
-            const uint4 *dp = reinterpret_cast<const uint4 *>(a.desc + tile);
-            uint4 *dd = reinterpret_cast<uint4 *>(&D);
-            dd[0] = __ldg(dp); dd[1] = __ldg(dp + 1); dd[2] = __ldg(dp + 2);
-        }
         const uint32_t npos = D.npos;
-        const uint8_t *ref = D.ref;
         auto load_site = [&](uint32_t colr, SiteCounters &sc) {
             uint32_t v[16];
             if (DEEP) {
@@ -1140,7 +1183,36 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint32_t colr = tid + h * PT_CONS;
-            if (colr < npos) {
+            /* most columns hold nothing but the reference base (or too few reads): settle those from the four base counters alone */
+            bool maybe = colr < npos;
+            if (maybe && !a.pl_acgt) {
+                uint32_t c4[4];
+                if (DEEP) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c4[i] = s_out32[i * LCR_TILE + colr];
+                } else {
+                    const uint8_t *o8 = reinterpret_cast<const uint8_t *>(planes);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c4[i] = o8[i * LCR_TILE + colr];
+                }
+                const uint32_t total = c4[0] + c4[1] + c4[2] + c4[3];
+                const uint8_t rb = refb[h];
+                const uint32_t rc = rb == 'A' ? c4[0] : rb == 'C' ? c4[1] : rb == 'G' ? c4[2] : rb == 'T' ? c4[3] : 0xffffffffu;
+                maybe = !(total < a.P.min_depth || total > a.P.max_depth || rc == 0xffffffffu || rc == total); /* candidate.rs:90-94,132,165 */
+                if (maybe) {
+                    /* the reference base strictly ahead of the three others: it is allele 1, the largest other count is the only alternative
+                       allele, and a stray mismatch fails the low-fraction / low-count test (candidate.rs:142-155) */
+                    const uint32_t mx = max(max(c4[0], c4[1]), max(c4[2], c4[3]));
+                    if (rc == mx) {
+                        const uint32_t alt = max(max(rb == 'A' ? 0u : c4[0], rb == 'C' ? 0u : c4[1]), max(rb == 'G' ? 0u : c4[2], rb == 'T' ? 0u : c4[3]));
+                        if (alt < rc) {
+                            if (total < 200u) { if ((float)alt / (float)total < a.P.low_allele_frac_cutoff) maybe = false; }
+                            else if (alt < a.P.low_allele_cnt_cutoff) maybe = false;
+                        }
+                    }
+                }
+            }
+            if (maybe) {
                 SiteCounters sc;
                 load_site(colr, sc);
                 if (a.pl_acgt) {
@@ -1150,7 +1222,7 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
                     a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
                 }
                 lcr_candidate dummy;
-                okc[h] = site_call<true>(a.P, *a.tables, sc, ref[colr], dummy);
+                okc[h] = site_call<true>(a.P, *a.tables, sc, refb[h], dummy);
             }
             const unsigned m = __ballot_sync(0xffffffffu, okc[h]);
             if (lane == 0) s_pcnt[h * (PT_CONS / 32) + warp] = __popc(m);
@@ -1186,7 +1258,11 @@ __global__ void __launch_bounds__(PT_THREADS, DEEP ? 1 : 2) k_pileup_tile(PileAr
                 }
             }
         }
-        cons_bar(); /* the counters in the planes are read: the next batch may clear them */
+        cons_bar(); /* the counters in the planes are read */
+        if (!DEEP) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) planes[(my_plane * ROWS + i) * PT_WORDS + my_word] = 0; /* ... and cleared by their writer: the planes are all zero again */
+        }
     }
 }
 
@@ -1340,12 +1416,13 @@ __global__ void k_cand_dense(lcr_params P, const LcrCounters *ctr, lcr_candidate
 
 #define TRY(expr) LCR_CUDA_TRY(ctx, expr)
 
-template <bool DEEP, int ROWS>
-static cudaError_t launch_tile(const PileArgs &ka, int grid, cudaStream_t st) {
-    const size_t smem = PtLayout<ROWS>::bytes(DEEP);
-    cudaError_t e = cudaFuncSetAttribute(k_pileup_tile<DEEP, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool DEEP, int ROWS, int STAGES, int MINB>
+static cudaError_t launch_tile(const PileArgs &ka, int sms, uint32_t n_tiles, cudaStream_t st) {
+    const size_t smem = PtLayout<ROWS, STAGES>::bytes(DEEP);
+    cudaError_t e = cudaFuncSetAttribute(k_pileup_tile<DEEP, ROWS, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_pileup_tile<DEEP, ROWS><<<grid, PT_THREADS, smem, st>>>(ka);
+    const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)(MINB * sms));
+    k_pileup_tile<DEEP, ROWS, STAGES, MINB><<<grid, PT_THREADS, smem, st>>>(ka);
     return cudaGetLastError();
 }
 
@@ -1452,13 +1529,16 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     if (n_tiles) {
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
         ka.tile_list = list0; ka.list_id = 0;
-        const int grid0 = (int)std::min<uint32_t>(n_tiles, (uint32_t)(2 * sms));
-        TRY((launch_tile<false, 32>(ka, grid0, st)));
+        /* LCR_TILE_VARIANT (experiments): 0 = 48 rows, one 16 KB stage, 2 CTAs / SM; 1 = 32 rows, two 13 KB stages, 2 CTAs / SM;
+           2 = 48 rows, two 8 KB stages, 2 CTAs / SM; 3 = 32 rows, one 12 KB stage, 3 CTAs / SM */
+        if (ctx->tile_variant == 1) TRY((launch_tile<false, 32, 2, 2>(ka, sms, n_tiles, st)));
+        else if (ctx->tile_variant == 2) TRY((launch_tile<false, 48, 2, 2>(ka, sms, n_tiles, st)));
+        else if (ctx->tile_variant == 3) TRY((launch_tile<false, 32, 1, 3>(ka, sms, n_tiles, st)));
+        else TRY((launch_tile<false, 48, 1, 2>(ka, sms, n_tiles, st)));
         db->timing.kernel_launches += 1;
         if (db->max_region_slots > 255u) { /* only a region with more than 255 reads can hold a deep tile */
             ka.tile_list = list1; ka.list_id = 1;
-            const int grid1 = (int)std::min<uint32_t>(n_tiles, (uint32_t)sms);
-            TRY((launch_tile<true, 32>(ka, grid1, st)));
+            TRY((launch_tile<true, 32, 1, 1>(ka, sms, n_tiles, st)));
             db->timing.kernel_launches += 1;
         }
     }

@@ -76,6 +76,7 @@ def cuda_lib():
         L.lcr_release.argtypes = [C.c_void_p, C.c_void_p]
         L.lcr_release.restype = None
         L.lcr_get_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Timing)]
+        L.lcr_device_results.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.DeviceView)]
         L.lcr_last_submit_timing.argtypes = [C.c_void_p, C.POINTER(abi.Timing)]
         L.lcr_strerror.argtypes = [C.c_int]
         L.lcr_strerror.restype = C.c_char_p
@@ -405,6 +406,12 @@ class Engine:
 
     def release(self, handle):
         self.L.lcr_release(self.ctx, handle)
+
+    def device_view(self, handle):
+        """Device pointers of the last run's results on this handle (lcr_device_results): candidates, HP, PS."""
+        v = abi.DeviceView()
+        self._check(self.L.lcr_device_results(self.ctx, handle, C.byref(v)), "lcr_device_results")
+        return v
 
     def timing(self, handle):
         t = abi.Timing()
