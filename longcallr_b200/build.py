@@ -19,7 +19,8 @@ OBJ = os.path.join(HERE, "build")
 HOST_SRC = ["lcr_host.cpp", "vcf.cpp", "synth.cpp"]
 DEV_SRC = ["api.cu", "pileup.cu", "fragments.cu", "phase.cu", "phase_enum.cu", "params.cpp"]
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+EXTRA = os.environ.get("LCR_NVCC_EXTRA", "").split()
+NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v", "--expt-relaxed-constexpr", "--extended-lambda"]
 
 

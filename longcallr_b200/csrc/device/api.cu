@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -394,7 +395,7 @@ int lcr_set_reference(lcr_ctx *ctx, int32_t tid, const uint8_t *seq, uint64_t le
     TRY(cudaSetDevice(ctx->device));
     if ((size_t)tid >= ctx->d_ref.size()) { ctx->d_ref.resize(tid + 1, nullptr); ctx->ref_len.resize(tid + 1, 0); }
     if (ctx->d_ref[tid]) { TRY(cudaFree(ctx->d_ref[tid])); ctx->d_ref[tid] = nullptr; }
-    TRY(cudaMalloc(&ctx->d_ref[tid], len ? len : 1));
+    TRY(cudaMalloc(&ctx->d_ref[tid], len + 64)); /* slack: the tile kernel copies whole 16-byte groups */
     if (len) TRY(cudaMemcpyAsync(ctx->d_ref[tid], seq, len, cudaMemcpyHostToDevice, ctx->stream));
     TRY(cudaStreamSynchronize(ctx->stream));
     ctx->ref_len[tid] = len;
@@ -612,6 +613,11 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
         if (K.overflow & LCR_OVF_ENUM) grow(C.enum_work, K.enum_work);
     }
     const LcrCounters &K = db->counters;
+    if (getenv("LCR_TILE_PROF")) {
+        fprintf(stderr, "tile prof (cycles, consumer warp 0 / producer warp 0, summed over CTAs):");
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " [%d]=%llu", i, K.prof[i]);
+        fprintf(stderr, " tiles=%u\n", K.n_tiles_done);
+    }
     db->n_cand = K.n_cand;
     db->n_frag = (ctx->P.flags & LCR_FLAG_SKIP_PHASING) ? 0 : K.n_frag;
     db->n_elem = (ctx->P.flags & LCR_FLAG_SKIP_PHASING) ? 0 : K.n_elem;

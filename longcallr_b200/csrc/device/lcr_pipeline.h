@@ -52,6 +52,7 @@ struct LcrCounters {
     uint32_t enum_cnt[LCR_ENUM_BINS], enum_off[LCR_ENUM_BINS], enum_ticket[LCR_ENUM_BINS];
     uint32_t n_big;          /* LD-path regions handed to the cooperative kernel */
     uint32_t pair_need;      /* LD pair table entries the batch asks for */
+    unsigned long long prof[16]; /* LCR_TILE_PROF builds: cycles per phase of the tile kernel */
 };
 
 /* bump allocator over one device block */

@@ -129,8 +129,12 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     if (s.d >= alt_cnt[0]) return false;
     const uint32_t depth_incl = total + s.d + s.n;
     if ((float)(allele1_cnt + allele2_cnt) / (float)depth_incl < P.min_allele_freq_include_intron) return false;
-    if (allele1 != ref_base) { if (allele1_cnt > 0 && pick(s.pass, i1) < 2) return false; }
-    else if (allele2 != ref_base) { if (allele2_cnt > 0 && pick(s.pass, i2) < 2) return false; }
+    /* candidate.rs:177-194 needs base qualities: the tile kernel (PRE) never reads them, k_site_ll counts them at the surviving sites
+       (every test of the cascade only rejects, so the order of the tests does not change the outcome) */
+    if (!PRE) {
+        if (allele1 != ref_base) { if (allele1_cnt > 0 && pick(s.pass, i1) < 2) return false; }
+        else if (allele2 != ref_base) { if (allele2_cnt > 0 && pick(s.pass, i2) < 2) return false; }
+    }
     if (P.use_strand_bias) {
         const int32_t rf = (int32_t)pick(s.fwd, ref_code), rr = (int32_t)(pick(s.cnt, ref_code) - pick(s.fwd, ref_code));
         const int32_t af = (int32_t)pick(s.fwd, alt_i[0]), ar = (int32_t)(pick(s.cnt, alt_i[0]) - pick(s.fwd, alt_i[0]));
@@ -563,31 +567,48 @@ __global__ void __launch_bounds__(128, 6) k_read_walk(PrepArgs a) {
 }
 
 /* ------------------------------------------------------------------------- *
- * Tile pileup, version 4: persistent, warp-specialised, bulk-async.
+ * Tile pileup, version 6: persistent, warp-specialised, bulk-async, reference-differential.
  *
- * k_pileup_tile runs one CTA of 8 consumer warps + 1 producer warp per resident slot (2 per SM) over a dynamic list of
- * tiles.  The producer warp turns the items of a tile into batches of at most ROWS rows: for every item it issues 1-D
- * bulk copies (cp.async.bulk.shared::cluster.global, completion on an mbarrier) of the item's contiguous seq and qual
- * bytes and of its segment descriptors into one of two shared-memory stages, so the bases of batch t+1 land while the
- * consumers work on batch t and no consumer ever waits on a global load.  The consumers expand the staged bytes into
- * two one-hot byte planes per (row, column):
- *     plane X   bit 0-3  base is A,C,G,T          bit 4-7  ... and base quality >= min_baseq
- *     plane Y   bit 0-3  A,C,G,T on a forward read; bit 4 / 5 transcript strand forward / reverse
- *               (util.rs:803-819, any base letter); bit 6 deletion; bit 7 intron
- * one lane per 16-column block of a segment (conflict-free 128-bit plane stores for whole blocks, masked OR for the
- * partial blocks at segment ends), then every thread sums one 32-bit column word (4 columns x 8 indicators) over the
- * rows with a Harley-Seal carry-save adder tree: ~2.4 logic instructions per row for 32 counters.  Counters are
- * unpacked once per tile (once per 255 rows on deep tiles), the count-based site filters run on the columns, and the
- * surviving sites are appended in column order to the tile's range of the pre-candidate list.
+ * k_pileup_tile runs CTAs of 8 consumer warps + 3 producer warps (2 CTAs per SM) over a dynamic list of tiles.
+ *
+ * Producers turn the items of a tile into batches of rows: for every item they issue 1-D bulk copies
+ * (cp.async.bulk.shared::cluster.global, completion counted in bytes on an mbarrier) of the item's contiguous seq and
+ * qual bytes and of its segment descriptors into a shared-memory stage, plus the tile's reference bytes with the first
+ * batch, so no consumer ever waits on a global load.
+ *
+ * Consumers count by difference from the reference.  Almost every aligned base equals the reference base, so a base
+ * is not expanded into counters at all:
+ *   - coverage of every (strand, transcript-strand) class, deletions and introns are range updates: +1 / -1 on a
+ *     per-class difference array at the ends of each segment, prefix-summed once per tile;
+ *   - one lane takes a 16-column block of an aligned segment and XORs the 16 read bytes with the 16 reference bytes
+ *     of its columns with word-wide logic; blocks holding a byte that differs are appended (with a 16-bit mask of
+ *     those bytes) to a short list;
+ *   - a second pass takes the listed bytes (mismatches, lower-case and non-ACGT bytes: ~1 % of the bases) to
+ *     per-column event counters with shared-memory atomics.
+ * Base qualities are not read here: the only count filter that needs them (candidate.rs:177-194) is evaluated by
+ * k_site_ll, which reads the qualities of the surviving sites anyway.
+ * At the end of the tile the per-column counters of util.rs:100-127 follow exactly from coverage minus events
+ * (all integers), the count-based site filters run on the columns with a mismatch, and the surviving sites are
+ * appended in column order to the tile's range of the pre-candidate list.  32-bit counters: any depth.
  * ------------------------------------------------------------------------- */
+#ifdef LCR_TILE_PROF
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, t0, t1) do { if (lane == 0 && (warp == 0 || warp == PT_CONS / 32)) atomicAdd(&a.ctr->prof[slot], (unsigned long long)((t1) - (t0))); } while (0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, t0, t1)
+#endif
+#ifndef PT_CONS
 #define PT_CONS 256                       /* consumer threads */
-#define PT_PROD_WARPS 3                   /* producer warps: one per copied stream (seq bytes, qual bytes, segment descriptors) */
+#endif
+#define PT_PROD_WARPS 2                   /* producer warps: one per copied stream (seq bytes; segment descriptors + reference + row tables) */
 #define PT_THREADS (PT_CONS + 32 * PT_PROD_WARPS)
 #define PT_WORDS (LCR_TILE / 4)
 #define PT_ROW_BYTES_MAX 2048u            /* largest item span staged as one row (larger ones are cut into pieces by the producer) */
 #define PT_FLAG_FIRST 1u
 #define PT_FLAG_LAST 2u
 #define PT_FLAG_QUIT 4u
+#define PT_PRE_CHUNK 64u                  /* pre-candidate slots a CTA reserves at a time */
 
 struct PreCand { /* a site that passed every count-based filter; its likelihood is computed by k_site_ll */
     uint32_t tile, col;
@@ -615,6 +636,7 @@ struct DescArgs {
     uint32_t *list[2];      /* work lists: tiles of at most / more than 255 items */
     LcrCounters *ctr;
     int all_tiles;          /* debug planes requested: empty tiles are processed too */
+    uint32_t big_rows;      /* tiles with more rows than this take the 32-bit event counters */
 };
 
 __global__ void k_tile_desc(DescArgs a) {
@@ -634,10 +656,23 @@ __global__ void k_tile_desc(DescArgs a) {
     d.reg = reg; d.npos = (uint32_t)(tile_end - tile_start);
     d.full_n = a.tile_full_n[tile];
     a.desc[tile] = d;
-    if (d.status == 0 && d.n_items) atomicAdd(&a.ctr->n_items_used, d.n_items);
-    if (d.status == 0 && (d.n_items || a.all_tiles)) {
-        const int deep = d.n_items > 255u;
-        a.list[deep][atomicAdd(&a.ctr->n_list[deep], 1u)] = tile;
+    {
+        uint32_t ni = d.status == 0 ? d.n_items : 0u;
+        ni = __reduce_add_sync(__activemask(), ni);
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(__activemask()) - 1) && ni) atomicAdd(&a.ctr->n_items_used, ni);
+    }
+    /* work lists of the tile kernel (tiles of more than 65535 rows take its 32-bit flavour): one atomic per warp */
+    const bool want = d.status == 0 && (d.n_items || a.all_tiles);
+    if (want && d.n_items > a.big_rows) a.list[1][atomicAdd(&a.ctr->n_list[1], 1u)] = tile;
+    const bool want0 = want && d.n_items <= a.big_rows;
+    const unsigned m = __ballot_sync(__activemask(), want0);
+    if (want0) {
+        const unsigned lane = threadIdx.x & 31u;
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&a.ctr->n_list[0], (uint32_t)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        a.list[0][base + __popc(m & ((1u << lane) - 1u))] = tile;
     }
 }
 
@@ -734,8 +769,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
-        __nanosleep(256);
+        __nanosleep(64);
     }
+}
+/* 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); its completion is tied to an mbarrier by cp_async_arrive */
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+/* one pending arrival of the barrier is delivered when all earlier cp.async of this thread have landed */
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 /* 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier; 16-byte aligned addresses and size */
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -753,59 +796,86 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void sts32a(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8a(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-template <int ROWS, int STAGES>
+#define PT_NDIFF 8                        /* difference arrays: coverage of the 6 (strand, transcript strand) classes, deletions, introns */
+#define PT_DIFF_LEN (LCR_TILE + 4)        /* one entry past the last column, padded to whole uint4 */
+#define PT_NEV 10                         /* event counters per column */
+#define EV_MIS 0                          /* [4] bases of letter L that differ from the reference base */
+#define EV_MISFWD 4                       /* [4] ... on forward reads */
+#define EV_NONACGT 8                      /* aligned bytes that are no A/C/G/T letter */
+#define EV_NONACGT_FWD 9                  /* ... on forward reads */
+
+template <bool BIG, int STAGES>
 struct PtLayout { /* dynamic shared memory of k_pileup_tile, byte offsets */
-    static constexpr uint32_t STAGE_BYTES = STAGES == 1 ? (ROWS == 32 ? 12288u : 16384u) : (ROWS == 32 ? 13312u : 8192u);   /* per stream (seq, qual) and stage */
-    static constexpr uint32_t SEG_CAP = 512u;                                /* segments per batch */
-    static constexpr uint32_t ROW_SEG_MAX = 256u;                            /* segments of one row */
+    static constexpr uint32_t ROWS = 32u;                                    /* rows per batch */
+    static constexpr uint32_t STAGE_BYTES = STAGES == 1 ? 12288u : 8192u;    /* seq bytes per stage */
+    static constexpr uint32_t SEG_CAP = 256u;                                /* segments per batch */
+    static constexpr uint32_t ROW_SEG_MAX = 128u;                            /* segments of one row */
     static constexpr uint32_t BLK_CAP = ROWS * (LCR_TILE / 16) + SEG_CAP;    /* 16-column blocks per batch */
     static constexpr uint32_t PAD = 32u;                                     /* slack before / after the staged bytes (block loads start up to 15 B early, read 20 B) */
-    static constexpr uint32_t planes = 0;
-    static constexpr uint32_t stage0 = planes + 2u * ROWS * PT_WORDS * 4u;
+    static constexpr uint32_t diff = 0;                                      /* int32 [PT_NDIFF][PT_DIFF_LEN] */
+    static constexpr uint32_t ev = diff + PT_NDIFF * PT_DIFF_LEN * 4u;       /* event counters: uint32 [PT_NEV][LCR_TILE] (BIG) or 16-bit pairs */
+    static constexpr uint32_t cnt_end = ev + PT_NEV * LCR_TILE * (BIG ? 4u : 2u); /* everything before is cleared between tiles */
+    static constexpr uint32_t ref = cnt_end;                                 /* [LCR_TILE] compare byte of every column */
+    static constexpr uint32_t stage0 = ref + LCR_TILE;
     /* one stage */
     static constexpr uint32_t st_seq = 0;
-    static constexpr uint32_t st_qual = st_seq + PAD + STAGE_BYTES + PAD;
-    static constexpr uint32_t st_segs = st_qual + PAD + STAGE_BYTES + PAD;
-    static constexpr uint32_t st_rowseg = st_segs + SEG_CAP * 16u;           /* [ROWS + 1] first staged segment of every row */
+    static constexpr uint32_t st_segs = st_seq + PAD + STAGE_BYTES + PAD;
+    static constexpr uint32_t st_ref = st_segs + SEG_CAP * 16u;              /* the tile's reference bytes from the 16-byte boundary below column 0 */
+    static constexpr uint32_t st_segrow = st_ref + LCR_TILE + 32u;           /* [SEG_CAP] row of every staged segment */
+    static constexpr uint32_t st_rowseg = st_segrow + SEG_CAP;               /* [ROWS + 1] first staged segment of every row */
     static constexpr uint32_t st_rowdelta = st_rowseg + (ROWS + 1u) * 4u;    /* [ROWS] staged byte offset minus pool offset (mod 2^32) */
     static constexpr uint32_t st_hdr = (st_rowdelta + ROWS * 4u + 15u) & ~15u; /* tile, rows, segments, flags */
     static constexpr uint32_t stage_size = (st_hdr + 16u + 127u) & ~127u;
-    static constexpr uint32_t blk = stage0 + STAGES * stage_size;         /* [BLK_CAP] u32: segment | block in segment << 10 | row << 16 */
-    static constexpr uint32_t out32 = (blk + BLK_CAP * 4u + 15u) & ~15u;     /* DEEP: [16][LCR_TILE] */
-    static constexpr uint32_t bytes(bool deep) { return out32 + (deep ? 16u * LCR_TILE * 4u : 0u); }
+    static constexpr uint32_t blk = stage0 + STAGES * stage_size;            /* [BLK_CAP] u32 per 16-column block: staged byte of its first column | block << 14 | first byte << 19 | last byte << 23 | forward << 27 */
+    static constexpr uint32_t evl = blk + BLK_CAP * 4u;                      /* [BLK_CAP] u32: blocks with exceptional bytes: block list index | byte mask << 16 */
+    static constexpr uint32_t bytes() { return evl + BLK_CAP * 4u; }
 };
 
-template <bool DEEP, int ROWS, int PT_STAGES, int MINB>
+/* BIG: tiles of more than 65535 rows (32-bit event counters); the others pack two 16-bit event counters per word */
+template <bool BIG, int PT_STAGES, int MINB>
 __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
-    using L = PtLayout<ROWS, PT_STAGES>;
-    static_assert(ROWS % 16 == 0 && ROWS >= 16 && ROWS <= 64, "the column sums read whole blocks of 16 rows; row ids take 6 bits");
-    static_assert(L::SEG_CAP % PT_CONS == 0 && L::SEG_CAP <= 1024, "whole segments per consumer thread; segment ids take 10 bits");
+    using L = PtLayout<BIG, PT_STAGES>;
+    constexpr uint32_t ROWS = L::ROWS;
+    static_assert(ROWS <= 64 && L::SEG_CAP <= 1024, "row ids take 6 bits, segment ids 10");
+    static_assert(LCR_TILE % PT_CONS == 0, "whole columns per consumer thread");
+    static_assert(L::PAD + L::STAGE_BYTES + 16 <= (1u << 14) && LCR_TILE / 16 <= 32, "block entries: 14 bits of staged offset, 5 bits of block index");
+    static_assert(L::BLK_CAP <= 65536, "block list indices take 16 bits");
     static_assert(PT_ROW_BYTES_MAX + 32 <= L::STAGE_BYTES && L::ROW_SEG_MAX <= L::SEG_CAP, "one row always fits an empty batch");
     extern __shared__ __align__(128) unsigned char pt_smem[];
     __shared__ __align__(8) unsigned long long s_bar[2 * PT_STAGES]; /* full[stage], empty[stage] */
-    __shared__ uint32_t s_wsum[PT_CONS / 32];
-    __shared__ uint32_t s_pcnt[2 * PT_CONS / 32 + 2];
+    __shared__ uint32_t s_pcnt[2];
     __shared__ uint32_t s_ticket[2];
+    __shared__ uint32_t s_nev, s_nblk, s_nsurv;
+    __shared__ uint32_t s_bitmap[LCR_TILE / 32];  /* columns that passed the count filters */
+    __shared__ uint32_t s_chunk[2];               /* next free slot and slots left of the CTA's chunk of the pre-candidate list */
+    __shared__ uint16_t s_surv[LCR_TILE];         /* columns that need the full cascade */
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t smem0 = smem_u32(pt_smem);
     const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[PT_STAGES]);
+    if (tid < LCR_TILE / 32) s_bitmap[tid] = 0;
     if (tid == 0) {
-        for (int s = 0; s < PT_STAGES; ++s) { mbar_init(bar_full + 8 * s, PT_PROD_WARPS); mbar_init(bar_empty + 8 * s, 1); }
+        s_nblk = 0; s_nsurv = 0; s_chunk[0] = 0; s_chunk[1] = 0;
+        /* a batch is full when every producer lane's asynchronous copies have landed (one deferred arrival per lane), the header is
+           written and the bulk copy of the reference window has delivered its bytes (one arrival with the expected byte count) */
+        for (int s = 0; s < PT_STAGES; ++s) { mbar_init(bar_full + 8 * s, 32 * PT_PROD_WARPS + 1); mbar_init(bar_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    { /* the planes start zeroed; from then on whoever reads a word clears it */
-        uint4 *p4 = reinterpret_cast<uint4 *>(pt_smem + L::planes);
-        for (uint32_t i = tid; i < 2u * ROWS * PT_WORDS / 4u; i += PT_THREADS) p4[i] = make_uint4(0, 0, 0, 0);
+    { /* the counters start zeroed; every tile's epilogue clears them again */
+        uint4 *p4 = reinterpret_cast<uint4 *>(pt_smem + L::diff);
+        for (uint32_t i = tid; i < L::cnt_end / 16u; i += PT_THREADS) p4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
 
     if (warp >= PT_CONS / 32) {
         /* ================= producer warps =================
-           The three warps run the same control flow over the same tiles and batches; warp 0 copies the seq bytes, warp 1 the
-           qual bytes, warp 2 the segment descriptors and writes the row tables and the batch header.  (A bulk copy takes its
-           operands from uniform registers, so a warp issues its lanes' copies one after the other: three warps triple the rate.) */
+           The two warps run the same control flow over the same tiles and batches.  Rows are a few hundred bytes each, too small
+           for one bulk copy apiece (a bulk copy takes uniform operands, so a warp issues its lanes' copies one after the other):
+           every lane streams its own row with 16-byte asynchronous copies (LDGSTS), 32 rows in flight per instruction.
+           Warp 0 copies the seq bytes; warp 1 the segment descriptors, writes the row tables and the batch header and, with the
+           first batch of a tile, fetches the tile's reference window with one bulk copy. */
         const uint32_t role = warp - PT_CONS / 32;
         uint32_t stage = 0, empty_par = (1u << PT_STAGES) - 1u; /* bit s: parity to wait for; a fresh barrier passes a wait on the opposite parity, so both stages start empty */
         uint32_t rows = 0, bytes = 0, nsegs = 0, tx = 0, cur_tile = 0, flags = PT_FLAG_FIRST;
@@ -813,42 +883,68 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
         auto stage_base = [&](uint32_t s) { return smem0 + L::stage0 + s * L::stage_size; };
         uint32_t tile_seq = 0;
         auto open_batch = [&]() { /* all lanes; lane 0 waits for the consumers to release the stage */
+            PROF_T(pp0);
             if (lane == 0) mbar_wait_relaxed(bar_empty + 8 * stage, (empty_par >> stage) & 1u);
             empty_par ^= 1u << stage;
             __syncwarp();
+            PROF_T(pp1);
+            PROF_ADD(8, pp0, pp1);
             rows = 0; bytes = 0; nsegs = 0; tx = 0;
             open = true;
         };
-        auto close_batch = [&](uint32_t fl) { /* all lanes: publish the header, arm the barrier with the batch's bytes */
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t sb = stage_base(stage);
-                if (role == 2) {
+        auto close_batch = [&](uint32_t fl) { /* all lanes: tie the copies to the barrier, publish the header */
+            cp_async_arrive(bar_full + 8 * stage);
+            if (role == 1) {
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t sb = stage_base(stage);
                     sts32a(sb + L::st_rowseg + rows * 4u, nsegs);
                     sts128(sb + L::st_hdr, cur_tile, rows, nsegs, fl);
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
                 }
-                mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
             }
             __syncwarp();
             stage = (stage + 1) % PT_STAGES;
             open = false;
         };
-        /* one row: bulk copies of [src_lo, src_lo + nbytes) of both pools and of segments [seg_first, seg_first + ns) */
+        /* one row by one lane: [src_lo, src_lo + nbytes) of the seq pool, segments [seg_first, seg_first + ns) */
         auto issue_row = [&](uint32_t row, uint32_t byte_off, uint32_t seg_off, uint64_t src_lo, uint32_t nbytes, uint32_t seg_first, uint32_t ns) {
-            const uint32_t sb = stage_base(stage), bar = bar_full + 8 * stage;
-            if (role == 0) { if (nbytes) bulk_g2s(sb + L::st_seq + L::PAD + byte_off, a.seq + src_lo, nbytes, bar); }
-            else if (role == 1) { if (nbytes) bulk_g2s(sb + L::st_qual + L::PAD + byte_off, a.qual + src_lo, nbytes, bar); }
-            else {
-                if (ns) bulk_g2s(sb + L::st_segs + seg_off * 16u, a.segs + seg_first, ns * 16u, bar);
+            const uint32_t sb = stage_base(stage);
+            if (role == 0) {
+                const uint32_t dst = sb + L::st_seq + L::PAD + byte_off;
+                const uint8_t *src = a.seq + src_lo;
+                for (uint32_t o = 0; o < nbytes; o += 16) cp_async16(dst + o, src + o);
+            } else {
+                const uint32_t dst = sb + L::st_segs + seg_off * 16u;
+                const LcrSeg *src = a.segs + seg_first;
+                for (uint32_t o = 0; o < ns; ++o) {
+                    cp_async16(dst + o * 16u, src + o);
+                    sts8a(sb + L::st_segrow + seg_off + o, row);
+                }
                 sts32a(sb + L::st_rowseg + row * 4u, seg_off);
                 sts32a(sb + L::st_rowdelta + row * 4u, (L::PAD + byte_off) - (uint32_t)src_lo);
             }
         };
-        /* bytes this warp's copies of a batch bring in */
-        auto tx_of = [&](uint32_t nbytes, uint32_t ns) { return role == 2 ? 16u * ns : nbytes; };
+        /* the same by the whole warp (rows cut from oversized items) */
+        auto issue_row_warp = [&](uint32_t row, uint32_t byte_off, uint32_t seg_off, uint64_t src_lo, uint32_t nbytes, uint32_t seg_first, uint32_t ns) {
+            const uint32_t sb = stage_base(stage);
+            if (role == 0) {
+                for (uint32_t o = lane * 16u; o < nbytes; o += 512u) cp_async16(sb + L::st_seq + L::PAD + byte_off + o, a.seq + src_lo + o);
+            } else {
+                for (uint32_t o = lane; o < ns; o += 32u) {
+                    cp_async16(sb + L::st_segs + (seg_off + o) * 16u, a.segs + seg_first + o);
+                    sts8a(sb + L::st_segrow + seg_off + o, row);
+                }
+                if (lane == 0) {
+                    sts32a(sb + L::st_rowseg + row * 4u, seg_off);
+                    sts32a(sb + L::st_rowdelta + row * 4u, (L::PAD + byte_off) - (uint32_t)src_lo);
+                }
+            }
+        };
         for (;;) {
-            /* warp 0 draws the next tile, the other two read it (slots alternate, so one barrier per tile is enough) */
+            /* warp 0 draws the next tile, the other reads it (slots alternate, so one barrier per tile is enough) */
+            PROF_T(pq0);
             if (role == 0 && lane == 0) s_ticket[tile_seq & 1u] = atomicAdd(&a.ctr->ticket[a.list_id], 1u);
             prod_bar();
             const uint32_t t = s_ticket[tile_seq & 1u];
@@ -858,13 +954,29 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
             const LcrTileDesc *dp = a.desc + cur_tile;
             const uint32_t it0 = dp->it0, n_items = dp->n_items;
             flags = PT_FLAG_FIRST;
+            uint4 nxt = make_uint4(0, 0, 0, 0); /* the items of a round are loaded one round ahead */
+            if (lane < n_items) nxt = __ldg(reinterpret_cast<const uint4 *>(a.items + it0 + lane));
+#ifdef LCR_TILE_PROF
+            if (nxt.x == 0xdeadbeefu) flags |= 8u; /* make the timer below wait for the load */
+#endif
+            PROF_T(pq1);
+            PROF_ADD(9, pq0, pq1);
+            /* the tile's reference bytes travel with its first batch */
+            if (!open) open_batch();
+            if (role == 1) {
+                const uint8_t *rp = dp->ref;
+                const uint32_t roff = (uint32_t)((uintptr_t)rp & 15u), rbytes = (roff + dp->npos + 15u) & ~15u;
+                if (lane == 0) bulk_g2s(stage_base(stage) + L::st_ref, rp - roff, rbytes, bar_full + 8 * stage);
+                tx += rbytes;
+            }
             for (uint32_t done = 0; done < n_items; done += 32) {
                 const uint32_t it = done + lane;
                 const bool valid = it < n_items;
+                const uint4 raw = nxt;
+                if (it + 32 < n_items) nxt = __ldg(reinterpret_cast<const uint4 *>(a.items + it0 + it + 32));
                 uint64_t spos0 = 0;
                 uint32_t ns = 0, seg0 = 0, span = 0;
                 if (valid) {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.items + it0 + it));
                     spos0 = (((uint64_t)raw.y << 32) | raw.x) & 0xffffffffffffull;
                     ns = raw.y >> 16; seg0 = raw.z; span = raw.w;
                 }
@@ -889,14 +1001,15 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                         const uint32_t nfit = __popc(__ballot_sync(0xffffffffu, fits)); /* prefix sums are monotone: the fitting lanes are the first nfit pending ones */
                         if (nfit == 0) { close_batch(flags); flags = 0; continue; }
                         if (fits) issue_row(rows + (lane - first), bytes + (pb - base_b) - nb, nsegs + (ps - base_s) - ns, src_lo, nb, seg0, ns);
+                        __syncwarp();
                         const uint32_t lastl = first + nfit - 1;
                         const uint32_t eb = __shfl_sync(0xffffffffu, pb, lastl), es = __shfl_sync(0xffffffffu, ps, lastl);
-                        rows += nfit; bytes += eb - base_b; nsegs += es - base_s; tx += tx_of(eb - base_b, es - base_s);
+                        rows += nfit; bytes += eb - base_b; nsegs += es - base_s;
                         base_b = eb; base_s = es; first += nfit;
                     }
                 } else {
                     /* rare: an item with hundreds of segments or a long insertion inside.  All lanes walk the round's items one by one with
-                       the same control flow (the segment loads are warp-uniform); the item is cut into pieces that fit a row, lane 0 issues them */
+                       the same control flow (the segment loads are warp-uniform); the item is cut into pieces that fit a row */
                     const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
                     for (uint32_t l = 0; l < nvalid; ++l) {
                         const uint32_t i_ns = __shfl_sync(0xffffffffu, ns, l), i_seg0 = __shfl_sync(0xffffffffu, seg0, l);
@@ -918,8 +1031,8 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                             const uint32_t pbytes = have_m ? (uint32_t)(hi_g - lo_g) : 0u;
                             if (open && !(rows < (uint32_t)ROWS && bytes + pbytes <= L::STAGE_BYTES && nsegs + cnt <= L::SEG_CAP)) { close_batch(flags); flags = 0; }
                             if (!open) open_batch();
-                            if (lane == 0) issue_row(rows, bytes, nsegs, lo_g, pbytes, i_seg0 + s, cnt);
-                            rows += 1; bytes += pbytes; nsegs += cnt; tx += tx_of(pbytes, cnt);
+                            issue_row_warp(rows, bytes, nsegs, lo_g, pbytes, i_seg0 + s, cnt);
+                            rows += 1; bytes += pbytes; nsegs += cnt;
                             s += cnt;
                         } while (s < i_ns);
                     }
@@ -935,320 +1048,312 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
     }
 
     /* ================= consumer warps ================= */
-    uint32_t *planes = reinterpret_cast<uint32_t *>(pt_smem + L::planes);   /* [2][ROWS][PT_WORDS] */
-    const uint32_t planes_s = smem0 + L::planes;
+    int32_t *s_diff = reinterpret_cast<int32_t *>(pt_smem + L::diff);     /* [PT_NDIFF][PT_DIFF_LEN] */
+    uint32_t *s_ev = reinterpret_cast<uint32_t *>(pt_smem + L::ev);       /* [PT_NEV][LCR_TILE] counters (BIG) or [PT_NEV][LCR_TILE / 2] pairs of 16-bit counters */
+    uint8_t *s_ref = pt_smem + L::ref;                                    /* compare byte per column: the reference byte if it is an upper-case A/C/G/T, else 0x80 */
     uint32_t *s_blk = reinterpret_cast<uint32_t *>(pt_smem + L::blk);
-    uint32_t *s_out32 = reinterpret_cast<uint32_t *>(pt_smem + L::out32);
-    const uint32_t minq = (uint32_t)a.P.min_baseq;
-    const uint32_t minq4 = (minq > 30u ? 0u : minq) * 0x01010101u;
-    const uint32_t pass_allow = minq > 30u ? 0u : 0xffffffffu;
-
-    /* carry-save state of this thread's column word: plane (tid / PT_WORDS), word (tid % PT_WORDS) */
-    uint32_t ones = 0, twos = 0, fours = 0, eights = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
-    uint32_t acc_rows = 0;
-    const uint32_t my_plane = tid / PT_WORDS, my_word = tid % PT_WORDS;
-    uint32_t cnt8[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cnt8[i] = 0;
-    auto flush = [&]() { /* bit-sliced counters -> 4 x 8-bit fields per indicator */
-        const uint32_t lv[8] = {ones, twos, fours, eights, s4, s5, s6, s7};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cnt8[i] = 0;
-#pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            if ((acc_rows >> l) != 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cnt8[i] |= (i >= l ? lv[l] >> (i - l) : lv[l] << (l - i)) & (0x01010101u << l); /* bit l of 4 counters */
-            }
-        }
-        ones = twos = fours = eights = s4 = s5 = s6 = s7 = 0;
-        acc_rows = 0;
+    uint32_t *s_evl = reinterpret_cast<uint32_t *>(pt_smem + L::evl);
+    auto ev_add = [&](uint32_t arr, uint32_t colx) {
+        if (BIG) atomicAdd(&s_ev[arr * LCR_TILE + colx], 1u);
+        else atomicAdd(&s_ev[arr * (LCR_TILE / 2) + (colx >> 1)], 1u << (16u * (colx & 1u))); /* at most 65535 rows per tile: no carry into the neighbour */
     };
-    auto flush_deep = [&]() {
-        flush();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] += (cnt8[i] >> (8 * j)) & 0xffu;
+    auto ev_get = [&](uint32_t arr, uint32_t colx) -> uint32_t {
+        if (BIG) return s_ev[arr * LCR_TILE + colx];
+        return (s_ev[arr * (LCR_TILE / 2) + (colx >> 1)] >> (16u * (colx & 1u))) & 0xffffu;
     };
+    constexpr int NCW = PT_CONS / 32;          /* consumer warps */
+    constexpr int CPT = LCR_TILE / PT_CONS;    /* columns per consumer thread in the epilogue */
 
     LcrTileDesc D;
     memset(&D, 0, sizeof D);
-    uint8_t refb[2] = {0, 0};
     uint32_t stage = 0, full_par = 0; /* bit s: parity to wait for */
     for (;;) {
+        PROF_T(tp0);
         mbar_wait(bar_full + 8 * stage, (full_par >> stage) & 1u);
         full_par ^= 1u << stage;
+        PROF_T(tp1);
+        PROF_ADD(0, tp0, tp1);
         const unsigned char *stg = pt_smem + L::stage0 + stage * L::stage_size;
         const uint32_t stg_s = smem0 + L::stage0 + stage * L::stage_size;
         const uint4 hdr = *reinterpret_cast<const uint4 *>(stg + L::st_hdr);
         const uint32_t tile = hdr.x, nrow = hdr.y, nseg = hdr.z, bflags = hdr.w;
-        if (bflags & PT_FLAG_QUIT) break;
+        if (bflags & PT_FLAG_QUIT) {
+            for (uint32_t k = tid; k < s_chunk[1]; k += PT_CONS)
+                if (s_chunk[0] + k < a.pre_cap) a.pre[s_chunk[0] + k].tile = 0xffffffffu; /* unused tail of the last chunk */
+            break;
+        }
         if (bflags & PT_FLAG_FIRST) {
-            ones = twos = fours = eights = s4 = s5 = s6 = s7 = 0;
-            acc_rows = 0;
-            /* the tile's descriptor and this thread's two reference bytes are fetched now, long before the epilogue needs them */
             {
                 const uint4 *dp = reinterpret_cast<const uint4 *>(a.desc + tile);
                 uint4 *dd = reinterpret_cast<uint4 *>(&D);
                 dd[0] = __ldg(dp); dd[1] = __ldg(dp + 1); dd[2] = __ldg(dp + 2);
             }
-            refb[0] = tid < D.npos ? __ldg(D.ref + tid) : (uint8_t)0;
-            refb[1] = tid + PT_CONS < D.npos ? __ldg(D.ref + tid + PT_CONS) : (uint8_t)0;
-            if (DEEP) {
+            /* column-aligned compare bytes from the staged reference window */
+            const uint32_t roff = (uint32_t)((uintptr_t)D.ref & 15u);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) s_out32[(my_plane * 8 + i) * LCR_TILE + my_word * 4 + j] = 0; /* this thread's own counters */
+            for (int h = 0; h < CPT; ++h) {
+                const uint32_t colr = tid + h * PT_CONS;
+                uint8_t b = 0x80;
+                if (colr < D.npos) {
+                    b = stg[L::st_ref + roff + colr];
+                    if (!(b == 'A' || b == 'C' || b == 'G' || b == 'T')) b = 0x80;
+                }
+                s_ref[colr] = b;
             }
         }
-        if (DEEP && acc_rows + nrow > 255u) flush_deep();
-        /* the batch's segments: row of each, number of 16-column blocks, block list */
+        /* the batch's segments: range updates of the coverage / deletion / intron arrays, and the 16-column blocks of the aligned ones
+           (listed in any order: a warp reserves its lanes' entries with one atomic) */
         const uint4 *s_seg = reinterpret_cast<const uint4 *>(stg + L::st_segs);
-        const uint32_t *s_rowseg = reinterpret_cast<const uint32_t *>(stg + L::st_rowseg);
+        const uint8_t *s_segrow = stg + L::st_segrow;
         const uint32_t *s_rowdelta = reinterpret_cast<const uint32_t *>(stg + L::st_rowdelta);
-        constexpr int SPT = L::SEG_CAP / PT_CONS;
-        uint32_t nch[SPT], srow[SPT], mysum = 0;
-#pragma unroll
-        for (int qd = 0; qd < SPT; ++qd) {
-            const uint32_t i = tid * SPT + qd;
-            uint32_t n = 0, j = 0;
+        if (tid == 0) s_nev = 0;
+        for (uint32_t i0 = 0; i0 < nseg; i0 += PT_CONS) {
+            const uint32_t i = i0 + tid;
+            uint32_t n = 0, ent0 = 0, lo0 = 0, hi1 = 0;
             if (i < nseg) {
-                /* row of staged segment i: last j with s_rowseg[j] <= i */
-#pragma unroll
-                for (uint32_t step = 32; step; step >>= 1)
-                    if (j + step < nrow && s_rowseg[j + step] <= i) j += step;
-                const uint32_t w = s_seg[i].w;
-                const uint32_t col = w & 0xffffu, len = w >> 16;
-                if (len) n = ((col + len + 15u) >> 4) - (col >> 4);
+                const uint4 sg = s_seg[i];
+                const uint32_t col = sg.w & 0xffffu, len = sg.w >> 16, typ = sg.z & 3u;
+                if (len) {
+                    uint32_t arr;
+                    if (typ == SEG_M) {
+                        n = ((col + len + 15u) >> 4) - (col >> 4);
+                        arr = ((sg.z & 4u) ? 3u : 0u) + ((sg.z >> 3) & 3u); /* class: forward strand x transcript-strand code */
+                        /* staged byte of the first column of the segment's first block (mod 2^32 arithmetic on the pool offset) */
+                        const uint32_t src0 = s_rowdelta[s_segrow[i]] + sg.x - (col & 15u);
+                        ent0 = src0 | ((col >> 4) << 14) | ((sg.z & 4u) << 25);
+                        lo0 = col & 15u; hi1 = (col + len - 1u) & 15u;
+                    } else arr = typ == SEG_D ? 6u : 7u;
+                    atomicAdd(&s_diff[arr * PT_DIFF_LEN + col], 1);
+                    atomicAdd(&s_diff[arr * PT_DIFF_LEN + col + len], -1);
+                }
             }
-            nch[qd] = n; srow[qd] = j;
-            mysum += n;
-        }
-        uint32_t incl = mysum;
+            uint32_t incl = n;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += v;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        cons_bar(); /* also: the previous batch's block list is consumed and the plane words it used are cleared again */
-        uint32_t wbase = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < PT_CONS / 32; ++w) {
-            const uint32_t v = s_wsum[w];
-            if (w < (int)warp) wbase += v;
-            total += v;
-        }
-        {
-            uint32_t run = wbase + incl - mysum;
-#pragma unroll
-            for (int qd = 0; qd < SPT; ++qd) {
-                const uint32_t i = tid * SPT + qd;
-                for (uint32_t k = 0; k < nch[qd]; ++k) s_blk[run + k] = i | (k << 10) | (srow[qd] << 16);
-                run += nch[qd];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
             }
+            uint32_t base = 0;
+            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtot) {
+                if (lane == 31) base = atomicAdd(&s_nblk, wtot);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                const uint32_t run = base + incl - n;
+                for (uint32_t k = 0; k < n; ++k) /* next block: 16 staged bytes and one block further; only the first / last block are partial */
+                    s_blk[run + k] = (ent0 + k * (16u + (1u << 14))) | ((k == 0 ? lo0 : 0u) << 19) | ((k + 1 == n ? hi1 : 15u) << 23);
+            }
+        }
+        cons_bar(); /* also: the compare bytes are in place */
+        PROF_T(tp2);
+        PROF_ADD(1, tp1, tp2);
+        const uint32_t total = s_nblk;
+        /* aligned bases, pass 1: one lane per 16-column block, read bytes from the stage against the compare bytes of the columns;
+           blocks with a differing byte go to the event list with a mask of those bytes */
+        const uint32_t seq_s = stg_s + L::st_seq;
+        auto detect = [&](uint32_t g) -> uint32_t { /* bit i of the result: byte i of block g differs from its compare byte */
+            const uint32_t e = s_blk[g];
+            const uint32_t src = e & 0x3fffu, c0 = ((e >> 14) & 31u) << 4, lo = (e >> 19) & 15u, hi = ((e >> 23) & 15u) + 1u;
+            const uint32_t al = src & ~3u, rot = 0x3210u + 0x1111u * (src & 3u);
+            const uint32_t sa = seq_s + al;
+            const uint32_t s0 = lds32(sa), s1 = lds32(sa + 4), s2 = lds32(sa + 8), s3 = lds32(sa + 12), s4w = lds32(sa + 16);
+            const uint4 rf = *reinterpret_cast<const uint4 *>(s_ref + c0);
+            const uint32_t d0 = __byte_perm(s0, s1, rot) ^ rf.x, d1 = __byte_perm(s1, s2, rot) ^ rf.y, d2 = __byte_perm(s2, s3, rot) ^ rf.z, d3 = __byte_perm(s3, s4w, rot) ^ rf.w;
+            if ((d0 | d1 | d2 | d3) == 0u) return 0u;
+            auto nzbits = [](uint32_t d) -> uint32_t {
+                const uint32_t nz = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d) & 0x80808080u; /* bit 7 of every non-zero byte */
+                return ((nz >> 7) * 0x10204080u) >> 28;                                      /* gathered into 4 bits: byte i -> bit 28 + i */
+            };
+            const uint32_t m16 = nzbits(d0) | (nzbits(d1) << 4) | (nzbits(d2) << 8) | (nzbits(d3) << 12);
+            return m16 & (0xffffu >> (16u - hi)) & (0xffffu << lo); /* only the bytes of the block that belong to the segment */
+        };
+        auto append = [&](uint32_t g, uint32_t m16) { /* all lanes of the warp */
+            const unsigned vote = __ballot_sync(0xffffffffu, m16 != 0u);
+            if (vote) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_nev, (uint32_t)__popc(vote));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (m16) s_evl[base + __popc(vote & ((1u << lane) - 1u))] = g | (m16 << 16);
+            }
+        };
+        for (uint32_t g0 = 0; g0 < total; g0 += 2 * PT_CONS) { /* warp-uniform trip count; two independent blocks per lane in flight */
+            const uint32_t ga = g0 + tid, gb = g0 + PT_CONS + tid;
+            const uint32_t ma = ga < total ? detect(ga) : 0u;
+            const uint32_t mb = gb < total ? detect(gb) : 0u;
+            append(ga, ma);
+            append(gb, mb);
         }
         cons_bar();
-        /* expansion: one lane per 16-column block of a segment, source bytes from the stage */
-        const uint32_t seq_s = stg_s + L::st_seq, qual_s = stg_s + L::st_qual;
-        for (uint32_t g = tid; g < total; g += PT_CONS) {
-            const uint32_t e = s_blk[g];
-            const uint4 raw = s_seg[e & 1023u];
-            const uint32_t k = (e >> 10) & 63u, row = e >> 16;
-            const uint32_t col = raw.w & 0xffffu, len = raw.w >> 16;
-            const uint32_t B = (col >> 4) + k, c0 = B << 4;
-            const uint32_t lo = col > c0 ? col - c0 : 0u;
-            const uint32_t hi = col + len < c0 + 16u ? col + len - c0 : 16u;
-            const uint32_t typ = raw.z & 3u;
-            const uint32_t dst = planes_s + ((row * PT_WORDS + B * 4u) << 2);
-            constexpr uint32_t YOFF = ROWS * PT_WORDS * 4;
-            uint32_t x[4], y[4];
-            if (typ == SEG_M) {
-                const uint32_t src = s_rowdelta[row] + raw.x + c0 - col; /* staged byte of column c0 (mod 2^32 arithmetic on the pool offset) */
-                const uint32_t al = src & ~3u, rot = 0x3210u + 0x1111u * (src & 3u);
-                const uint32_t sa = seq_s + al, qa = qual_s + al;
-                const uint32_t s0 = lds32(sa), s1 = lds32(sa + 4), s2 = lds32(sa + 8), s3 = lds32(sa + 12), s4w = lds32(sa + 16);
-                const uint32_t q0 = lds32(qa), q1 = lds32(qa + 4), q2 = lds32(qa + 8), q3 = lds32(qa + 12), q4w = lds32(qa + 16);
-                const uint32_t fmask = (raw.z & 4u) ? 0x0f0f0f0fu : 0u;
-                const uint32_t tsb = ((raw.z >> 3) & 3u) * 0x10101010u; /* code 1 -> bit 4, code 2 -> bit 5 */
-                /* every quality of the five loaded words at least min_baseq (bit 7 of (q | 0x80) - minq stays set, or q >= 128): the
-                   common case on HiFi; the pass bits are then a copy of the base bits */
-                const uint32_t H = 0x80808080u;
-                const uint32_t allge = (((q0 & ~H) | H) - minq4 | q0) & (((q1 & ~H) | H) - minq4 | q1) & (((q2 & ~H) | H) - minq4 | q2) & (((q3 & ~H) | H) - minq4 | q3) &
-                                       (((q4w & ~H) | H) - minq4 | q4w) & H;
-                if (allge == H && pass_allow) {
-                    onehot4<true>(__byte_perm(s0, s1, rot), 0, minq4, pass_allow, fmask, tsb, x[0], y[0]);
-                    onehot4<true>(__byte_perm(s1, s2, rot), 0, minq4, pass_allow, fmask, tsb, x[1], y[1]);
-                    onehot4<true>(__byte_perm(s2, s3, rot), 0, minq4, pass_allow, fmask, tsb, x[2], y[2]);
-                    onehot4<true>(__byte_perm(s3, s4w, rot), 0, minq4, pass_allow, fmask, tsb, x[3], y[3]);
-                } else {
-                    onehot4<false>(__byte_perm(s0, s1, rot), __byte_perm(q0, q1, rot), minq4, pass_allow, fmask, tsb, x[0], y[0]);
-                    onehot4<false>(__byte_perm(s1, s2, rot), __byte_perm(q1, q2, rot), minq4, pass_allow, fmask, tsb, x[1], y[1]);
-                    onehot4<false>(__byte_perm(s2, s3, rot), __byte_perm(q2, q3, rot), minq4, pass_allow, fmask, tsb, x[2], y[2]);
-                    onehot4<false>(__byte_perm(s3, s4w, rot), __byte_perm(q3, q4w, rot), minq4, pass_allow, fmask, tsb, x[3], y[3]);
-                }
-            } else {
-                const uint32_t v = typ == SEG_D ? 0x40404040u : 0x80808080u;
-                x[0] = x[1] = x[2] = x[3] = 0;
-                y[0] = y[1] = y[2] = y[3] = v;
-            }
-            if (lo == 0u && hi == 16u) {
-                if (typ == SEG_M) sts128(dst, x[0], x[1], x[2], x[3]);
-                sts128(dst + YOFF, y[0], y[1], y[2], y[3]);
-            } else {
-                /* partial block: a neighbouring segment of the same row may own the other bytes of a word */
-                const uint32_t m16 = (0xffffu >> (16u - hi)) & (0xffffu << lo);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t nib = (m16 >> (4 * j)) & 15u;
-                    if (nib == 0u) continue;
-                    const uint32_t mask = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
-                    if (nib == 15u) {
-                        if (typ == SEG_M) sts32a(dst + 4 * j, x[j]);
-                        sts32a(dst + YOFF + 4 * j, y[j]);
-                    } else {
-                        if (typ == SEG_M) red_or_shared(dst + 4 * j, x[j] & mask);
-                        red_or_shared(dst + YOFF + 4 * j, y[j] & mask);
+        PROF_T(tp3);
+        PROF_ADD(2, tp2, tp3);
+        if (tid == 0) s_nblk = 0; /* everybody has read it; the next batch's reservations come after the barriers below */
+        /* pass 2: the exceptional bytes (mismatches, lower-case letters, non-ACGT bytes), one listed block per lane */
+        {
+            const uint32_t nev = s_nev;
+            const unsigned char *seq_b = stg + L::st_seq;
+            for (uint32_t x = tid; x < nev; x += PT_CONS) {
+                const uint32_t ent = s_evl[x];
+                const uint32_t e = s_blk[ent & 0xffffu];
+                uint32_t m16 = ent >> 16;
+                const uint32_t src = e & 0x3fffu, c0 = ((e >> 14) & 31u) << 4;
+                const bool fwd = (e >> 27) & 1u;
+                while (m16) {
+                    const uint32_t t = (uint32_t)__ffs((int)m16) - 1u;
+                    m16 &= m16 - 1u;
+                    const uint32_t colx = c0 + t;
+                    const uint32_t b = seq_b[src + t], rb = s_ref[colx];
+                    const int lc = base_code_dev((uint8_t)b);
+                    if (lc < 0) {
+                        ev_add(EV_NONACGT, colx);
+                        if (fwd) ev_add(EV_NONACGT_FWD, colx);
+                    } else if ((b & 0xdfu) != rb) { /* not the reference letter in lower case */
+                        ev_add(EV_MIS + lc, colx);
+                        if (fwd) ev_add(EV_MISFWD + lc, colx);
                     }
                 }
             }
         }
         cons_bar();
+        PROF_T(tp4);
+        PROF_ADD(3, tp3, tp4);
         if (tid == 0) mbar_arrive(bar_empty + 8 * stage); /* the stage's bytes and segments are consumed */
         stage = (stage + 1) % PT_STAGES;
-        /* column sums of this batch: Harley-Seal blocks of 16 rows (rows up to the next multiple of 16 are zero) */
-        {
-            uint32_t *pl = planes + my_plane * (ROWS * PT_WORDS) + my_word;
-            for (uint32_t r0 = 0; r0 < nrow; r0 += 16) {
-                uint32_t w[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] = pl[(r0 + j) * PT_WORDS];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) pl[(r0 + j) * PT_WORDS] = 0; /* the thread that sums a word is the one that clears it for the next batch */
-                uint32_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
-                CSA(t2a, ones, ones, w[0], w[1]);
-                CSA(t2b, ones, ones, w[2], w[3]);
-                CSA(t4a, twos, twos, t2a, t2b);
-                CSA(t2a, ones, ones, w[4], w[5]);
-                CSA(t2b, ones, ones, w[6], w[7]);
-                CSA(t4b, twos, twos, t2a, t2b);
-                CSA(t8a, fours, fours, t4a, t4b);
-                CSA(t2a, ones, ones, w[8], w[9]);
-                CSA(t2b, ones, ones, w[10], w[11]);
-                CSA(t4a, twos, twos, t2a, t2b);
-                CSA(t2a, ones, ones, w[12], w[13]);
-                CSA(t2b, ones, ones, w[14], w[15]);
-                CSA(t4b, twos, twos, t2a, t2b);
-                CSA(t8b, fours, fours, t4a, t4b);
-                CSA(t16, eights, eights, t8a, t8b);
-                /* ripple the sixteens into the upper bit slices */
-                uint32_t cy = t16, tt;
-                tt = s4 & cy; s4 ^= cy; cy = tt;
-                tt = s5 & cy; s5 ^= cy; cy = tt;
-                tt = s6 & cy; s6 ^= cy; cy = tt;
-                s7 ^= cy;
-            }
-            acc_rows += nrow;
-        }
         if (!(bflags & PT_FLAG_LAST)) continue;
 
-        /* ---- end of the tile: counters, count-based site filters, pre-candidates in column order ---- */
-        if (DEEP) flush_deep();
-        else {
-            flush();
-            /* counter exchange: 8-bit counters go to rows 0-7 of the thread's own plane, at its own word (only this thread ever
-               touches that word during the column sums, so no barrier is needed before the write) */
+        /* ---- end of the tile: coverage from the difference arrays, exact counters, count-based site filters, pre-candidates in column order ---- */
+        for (int ai = warp; ai < PT_NDIFF; ai += NCW) { /* a warp turns a difference array into running sums: 16 consecutive entries per lane, then a warp scan of the lane totals */
+            int32_t *arr = s_diff + ai * PT_DIFF_LEN + lane * 16;
+            int4 v[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) planes[(my_plane * ROWS + i) * PT_WORDS + my_word] = cnt8[i];
+            for (int j = 0; j < 4; ++j) v[j] = reinterpret_cast<const int4 *>(arr)[j];
+            int32_t x[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+#pragma unroll
+            for (int j = 1; j < 16; ++j) x[j] += x[j - 1];
+            int32_t tot = x[15], incl2 = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t u = __shfl_up_sync(0xffffffffu, incl2, o);
+                if ((int)lane >= o) incl2 += u;
+            }
+            const int32_t base = incl2 - tot;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<int4 *>(arr)[j] = make_int4(x[4 * j] + base, x[4 * j + 1] + base, x[4 * j + 2] + base, x[4 * j + 3] + base);
         }
         cons_bar();
+        PROF_T(tp5);
+        PROF_ADD(4, tp4, tp5);
         const uint32_t npos = D.npos;
-        auto load_site = [&](uint32_t colr, SiteCounters &sc) {
-            uint32_t v[16];
-            if (DEEP) {
+        auto load_site = [&](uint32_t colr, SiteCounters &sc, uint8_t &ref_byte) {
+            uint32_t cov[6], evv[PT_NEV];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = s_out32[i * LCR_TILE + colr];
-            } else {
-                const uint8_t *o8 = reinterpret_cast<const uint8_t *>(planes);
+            for (int c = 0; c < 6; ++c) cov[c] = (uint32_t)s_diff[c * PT_DIFF_LEN + colr];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { v[i] = o8[i * LCR_TILE + colr]; v[8 + i] = o8[(ROWS + i) * LCR_TILE + colr]; }
+            for (int i = 0; i < PT_NEV; ++i) evv[i] = ev_get(i, colr);
+            const uint8_t rb = s_ref[colr];
+            const int refc = rb == 'A' ? 0 : rb == 'C' ? 1 : rb == 'G' ? 2 : rb == 'T' ? 3 : -1;
+            const uint32_t cov_all = cov[0] + cov[1] + cov[2] + cov[3] + cov[4] + cov[5], cov_fwd = cov[3] + cov[4] + cov[5];
+            const uint32_t acgt = cov_all - evv[EV_NONACGT], acgt_fwd = cov_fwd - evv[EV_NONACGT_FWD];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sc.cnt[i] = evv[EV_MIS + i]; sc.pass[i] = 0; sc.fwd[i] = evv[EV_MISFWD + i]; } /* pass: counted by k_site_ll */
+            if (refc >= 0) { /* the bases that are not events are the reference letter */
+                const uint32_t mis = evv[EV_MIS] + evv[EV_MIS + 1] + evv[EV_MIS + 2] + evv[EV_MIS + 3];
+                const uint32_t misf = evv[EV_MISFWD] + evv[EV_MISFWD + 1] + evv[EV_MISFWD + 2] + evv[EV_MISFWD + 3];
+                const uint32_t rc = acgt - mis;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i == refc) { sc.cnt[i] = rc; sc.fwd[i] = acgt_fwd - misf; }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { sc.cnt[i] = v[i]; sc.pass[i] = v[4 + i]; sc.fwd[i] = v[8 + i]; }
-            sc.ts[0] = v[12]; sc.ts[1] = v[13]; sc.d = v[14]; sc.n = v[15] + D.full_n;
+            sc.ts[0] = cov[1] + cov[4]; sc.ts[1] = cov[2] + cov[5]; /* transcript-strand code 1 / 2 on either read strand (util.rs:803-819) */
+            sc.d = (uint32_t)s_diff[6 * PT_DIFF_LEN + colr]; sc.n = (uint32_t)s_diff[7 * PT_DIFF_LEN + colr] + D.full_n;
             sc.ll0 = 0; sc.ll2 = 0; sc.q0flags = 0;
+            ref_byte = rb == 0x80 ? (uint8_t)'N' : rb; /* any byte that is no upper-case A/C/G/T ends the cascade the same way (candidate.rs:132) */
         };
-        bool okc[2] = {false, false};
+        /* (a) columns that can still be candidates: a base that differs from an upper-case A/C/G/T reference byte, enough depth,
+           and not the everyday case of a stray mismatch under the low-fraction / low-count cut-off (candidate.rs:90-94,132,142-155,165) */
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < CPT; ++h) {
             const uint32_t colr = tid + h * PT_CONS;
-            /* most columns hold nothing but the reference base (or too few reads): settle those from the four base counters alone */
             bool maybe = colr < npos;
-            if (maybe && !a.pl_acgt) {
-                uint32_t c4[4];
-                if (DEEP) {
+            if (maybe && a.pl_acgt) { /* debug planes: every column is written */
+                SiteCounters sc;
+                uint8_t rb;
+                load_site(colr, sc, rb);
+                const uint64_t g = D.pos_g + colr;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c4[i] = s_out32[i * LCR_TILE + colr];
-                } else {
-                    const uint8_t *o8 = reinterpret_cast<const uint8_t *>(planes);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) c4[i] = o8[i * LCR_TILE + colr];
-                }
-                const uint32_t total = c4[0] + c4[1] + c4[2] + c4[3];
-                const uint8_t rb = refb[h];
-                const uint32_t rc = rb == 'A' ? c4[0] : rb == 'C' ? c4[1] : rb == 'G' ? c4[2] : rb == 'T' ? c4[3] : 0xffffffffu;
-                maybe = !(total < a.P.min_depth || total > a.P.max_depth || rc == 0xffffffffu || rc == total); /* candidate.rs:90-94,132,165 */
+                for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = sc.cnt[i]; a.pl_fwd[g * 4 + i] = sc.fwd[i]; }
+                a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
+            }
+            if (maybe) {
+                const uint32_t m0 = ev_get(EV_MIS, colr), m1 = ev_get(EV_MIS + 1, colr), m2 = ev_get(EV_MIS + 2, colr), m3 = ev_get(EV_MIS + 3, colr);
+                maybe = (m0 | m1 | m2 | m3) != 0u && s_ref[colr] != 0x80;
                 if (maybe) {
-                    /* the reference base strictly ahead of the three others: it is allele 1, the largest other count is the only alternative
-                       allele, and a stray mismatch fails the low-fraction / low-count test (candidate.rs:142-155) */
-                    const uint32_t mx = max(max(c4[0], c4[1]), max(c4[2], c4[3]));
-                    if (rc == mx) {
-                        const uint32_t alt = max(max(rb == 'A' ? 0u : c4[0], rb == 'C' ? 0u : c4[1]), max(rb == 'G' ? 0u : c4[2], rb == 'T' ? 0u : c4[3]));
-                        if (alt < rc) {
-                            if (total < 200u) { if ((float)alt / (float)total < a.P.low_allele_frac_cutoff) maybe = false; }
-                            else if (alt < a.P.low_allele_cnt_cutoff) maybe = false;
-                        }
+                    uint32_t cov_all = 0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) cov_all += (uint32_t)s_diff[c * PT_DIFF_LEN + colr];
+                    const uint32_t total = cov_all - ev_get(EV_NONACGT, colr);
+                    const uint32_t rc = total - (m0 + m1 + m2 + m3), alt = max(max(m0, m1), max(m2, m3));
+                    if (total < a.P.min_depth || total > a.P.max_depth) maybe = false;
+                    else if (rc > alt) { /* the reference base strictly ahead: it is allele 1 and the largest other count the only alternative allele */
+                        if (total < 200u) { if ((float)alt / (float)total < a.P.low_allele_frac_cutoff) maybe = false; }
+                        else if (alt < a.P.low_allele_cnt_cutoff) maybe = false;
                     }
                 }
             }
-            if (maybe) {
-                SiteCounters sc;
-                load_site(colr, sc);
-                if (a.pl_acgt) {
-                    const uint64_t g = D.pos_g + colr;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = sc.cnt[i]; a.pl_fwd[g * 4 + i] = sc.fwd[i]; }
-                    a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
-                }
-                lcr_candidate dummy;
-                okc[h] = site_call<true>(a.P, *a.tables, sc, refb[h], dummy);
+            const unsigned m = __ballot_sync(0xffffffffu, maybe);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_nsurv, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (maybe) s_surv[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)colr;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, okc[h]);
-            if (lane == 0) s_pcnt[h * (PT_CONS / 32) + warp] = __popc(m);
         }
         cons_bar();
+        PROF_T(tp6);
+        PROF_ADD(5, tp5, tp6);
+        /* (b) the full count-based cascade on the survivors, one per thread; the ones that pass set their bit in the column bitmap */
+        const uint32_t nsurv = s_nsurv;
+        for (uint32_t x = tid; x < nsurv; x += PT_CONS) {
+            const uint32_t colr = s_surv[x];
+            SiteCounters sc;
+            uint8_t rb;
+            load_site(colr, sc, rb);
+            lcr_candidate dummy;
+            if (site_call<true>(a.P, *a.tables, sc, rb, dummy)) atomicOr(&s_bitmap[colr >> 5], 1u << (colr & 31u));
+        }
+        cons_bar();
+        /* (c) a contiguous range of the pre-candidate list for the tile, sub-allocated from a chunk the CTA reserves with one global atomic */
         if (tid == 0) {
             uint32_t tot = 0;
-            for (int i = 0; i < 2 * PT_CONS / 32; ++i) { const uint32_t c = s_pcnt[i]; s_pcnt[i] = tot; tot += c; }
-            const uint32_t base = tot ? atomicAdd(&a.ctr->n_pre, tot) : 0u;
-            s_pcnt[2 * PT_CONS / 32] = base;
+            for (int i = 0; i < LCR_TILE / 32; ++i) tot += __popc(s_bitmap[i]);
+            uint32_t base = 0;
+            if (tot) {
+                if (tot > s_chunk[1]) { /* the unused tail of the old chunk stays marked invalid (k_site_ll skips it) */
+                    for (uint32_t k = 0; k < s_chunk[1]; ++k)
+                        if (s_chunk[0] + k < a.pre_cap) a.pre[s_chunk[0] + k].tile = 0xffffffffu;
+                    const uint32_t want = tot > PT_PRE_CHUNK ? tot : PT_PRE_CHUNK;
+                    s_chunk[0] = atomicAdd(&a.ctr->n_pre, want);
+                    s_chunk[1] = want;
+                }
+                base = s_chunk[0];
+                s_chunk[0] += tot; s_chunk[1] -= tot;
+            }
+            s_pcnt[0] = base;
             a.tile_pre[tile] = make_uint2(base, tot);
             atomicAdd(&a.ctr->n_tiles_done, 1u);
             atomicAdd(&a.ctr->n_pos_done, (unsigned long long)npos);
         }
         cons_bar();
         {
-            const uint32_t base = s_pcnt[2 * PT_CONS / 32];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned m = __ballot_sync(0xffffffffu, okc[h]);
-                if (!okc[h]) continue;
-                const uint32_t k = base + s_pcnt[h * (PT_CONS / 32) + warp] + __popc(m & ((1u << lane) - 1u));
+            const uint32_t base = s_pcnt[0];
+            for (uint32_t x = tid; x < nsurv; x += PT_CONS) {
+                const uint32_t colr = s_surv[x];
+                if (!((s_bitmap[colr >> 5] >> (colr & 31u)) & 1u)) continue;
+                uint32_t rank = __popc(s_bitmap[colr >> 5] & ((1u << (colr & 31u)) - 1u)); /* passing columns before this one: column order */
+                for (uint32_t w = 0; w < (colr >> 5); ++w) rank += __popc(s_bitmap[w]);
+                const uint32_t k = base + rank;
                 if (k < a.pre_cap) {
-                    const uint32_t colr = tid + h * PT_CONS;
                     SiteCounters sc;
-                    load_site(colr, sc);
+                    uint8_t rb;
+                    load_site(colr, sc, rb);
                     PreCand pc;
                     pc.tile = tile; pc.col = colr;
 #pragma unroll
@@ -1258,11 +1363,18 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 }
             }
         }
-        cons_bar(); /* the counters in the planes are read */
-        if (!DEEP) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) planes[(my_plane * ROWS + i) * PT_WORDS + my_word] = 0; /* ... and cleared by their writer: the planes are all zero again */
+        cons_bar(); /* the counters are read: clear them for the next tile */
+        PROF_T(tp7);
+        PROF_ADD(6, tp6, tp7);
+        {
+            uint4 *p4 = reinterpret_cast<uint4 *>(pt_smem + L::diff);
+            for (uint32_t i = tid; i < L::cnt_end / 16u; i += PT_CONS) p4[i] = make_uint4(0, 0, 0, 0);
+            if (tid < LCR_TILE / 32) s_bitmap[tid] = 0;
+            if (tid == 0) s_nsurv = 0;
         }
+        cons_bar();
+        PROF_T(tp8);
+        PROF_ADD(7, tp7, tp8);
     }
 }
 
@@ -1276,6 +1388,7 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_pre; w += nwarps) {
         const PreCand pc = a.pre[w];
         const uint32_t tile = pc.tile;
+        if (tile == 0xffffffffu) { if (lane == 0) a.cand_keep[w] = 0; continue; } /* unused slot at the end of a CTA's chunk */
         const uint32_t reg = a.tile_region[tile];
         const lcr_region R = a.regions[reg];
         const int32_t tile_start = (int32_t)((tile - a.tile_base[reg]) * LCR_TILE);
@@ -1284,6 +1397,7 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
         const int refc = (ref_base == 'A') ? 0 : (ref_base == 'C') ? 1 : (ref_base == 'G') ? 2 : (ref_base == 'T') ? 3 : 8;
         long long ll0 = 0, ll2 = 0;
         uint32_t q0flags = 0;
+        uint32_t npass[4] = {0, 0, 0, 0}; /* bases of each letter with (capped) quality >= min_baseq (candidate.rs:177-194) */
         /* one lane per read of the tile: its segments are in column order and hold exactly the unmasked aligned bases */
         const uint32_t colr = pc.col;
         const LcrTileDesc *dp = a.desc + tile;
@@ -1308,6 +1422,10 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
                         ll0 += is_ref ? E : K;
                         ll2 += is_ref ? K : E;
                         if (q == 0) q0flags |= is_ref ? 1u : 2u;
+                        if ((int32_t)q >= a.P.min_baseq) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) npass[i] += bc == i ? 1u : 0u;
+                        }
                     }
                 }
                 break;
@@ -1317,11 +1435,13 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, o);
             ll2 += __shfl_xor_sync(0xffffffffu, ll2, o);
             q0flags |= __shfl_xor_sync(0xffffffffu, q0flags, o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) npass[i] += __shfl_xor_sync(0xffffffffu, npass[i], o);
         }
         if (lane != 0) continue;
         SiteCounters sc;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { sc.cnt[i] = pc.cnt[i]; sc.pass[i] = pc.pass[i]; sc.fwd[i] = pc.fwd[i]; }
+        for (int i = 0; i < 4; ++i) { sc.cnt[i] = pc.cnt[i]; sc.pass[i] = npass[i]; sc.fwd[i] = pc.fwd[i]; }
         sc.ts[0] = pc.ts[0]; sc.ts[1] = pc.ts[1]; sc.d = pc.d; sc.n = pc.n; sc.ll0 = ll0; sc.ll2 = ll2; sc.q0flags = q0flags;
         lcr_candidate o;
         const bool keep = site_call<false>(a.P, *a.tables, sc, ref_base, o);
@@ -1416,13 +1536,13 @@ __global__ void k_cand_dense(lcr_params P, const LcrCounters *ctr, lcr_candidate
 
 #define TRY(expr) LCR_CUDA_TRY(ctx, expr)
 
-template <bool DEEP, int ROWS, int STAGES, int MINB>
+template <bool BIG, int STAGES, int MINB>
 static cudaError_t launch_tile(const PileArgs &ka, int sms, uint32_t n_tiles, cudaStream_t st) {
-    const size_t smem = PtLayout<ROWS, STAGES>::bytes(DEEP);
-    cudaError_t e = cudaFuncSetAttribute(k_pileup_tile<DEEP, ROWS, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = PtLayout<BIG, STAGES>::bytes();
+    cudaError_t e = cudaFuncSetAttribute(k_pileup_tile<BIG, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)(MINB * sms));
-    k_pileup_tile<DEEP, ROWS, STAGES, MINB><<<grid, PT_THREADS, smem, st>>>(ka);
+    k_pileup_tile<BIG, STAGES, MINB><<<grid, PT_THREADS, smem, st>>>(ka);
     return cudaGetLastError();
 }
 
@@ -1503,6 +1623,8 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     da.pos_off = db->pos_off; da.ref_table = ctx->d_ref_table; da.rstate = db->rstate; da.desc = desc;
     da.list[0] = list0; da.list[1] = list1; da.ctr = ctr;
     da.all_tiles = db->pl_acgt != nullptr;
+    const bool force_big = ctx->tile_variant == 3; /* tests: every non-empty tile through the 32-bit flavour */
+    da.big_rows = force_big ? 0u : 65535u;
     if (n_tiles) {
         k_tile_desc<<<(n_tiles + 255) / 256, 256, 0, st>>>(da);
         db->timing.kernel_launches += 1;
@@ -1529,16 +1651,14 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     if (n_tiles) {
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
         ka.tile_list = list0; ka.list_id = 0;
-        /* LCR_TILE_VARIANT (experiments): 0 = 48 rows, one 16 KB stage, 2 CTAs / SM; 1 = 32 rows, two 13 KB stages, 2 CTAs / SM;
-           2 = 48 rows, two 8 KB stages, 2 CTAs / SM; 3 = 32 rows, one 12 KB stage, 3 CTAs / SM */
-        if (ctx->tile_variant == 1) TRY((launch_tile<false, 32, 2, 2>(ka, sms, n_tiles, st)));
-        else if (ctx->tile_variant == 2) TRY((launch_tile<false, 48, 2, 2>(ka, sms, n_tiles, st)));
-        else if (ctx->tile_variant == 3) TRY((launch_tile<false, 32, 1, 3>(ka, sms, n_tiles, st)));
-        else TRY((launch_tile<false, 48, 1, 2>(ka, sms, n_tiles, st)));
+        /* LCR_TILE_VARIANT (experiments): 0 = one 12 KB stage, 4 CTAs / SM; 1 = two 8 KB stages, 3 CTAs / SM; 2 = one stage, 3 CTAs / SM */
+        if (ctx->tile_variant == 1) TRY((launch_tile<false, 2, 3>(ka, sms, n_tiles, st)));
+        else if (ctx->tile_variant == 2) TRY((launch_tile<false, 1, 3>(ka, sms, n_tiles, st)));
+        else TRY((launch_tile<false, 1, 4>(ka, sms, n_tiles, st)));
         db->timing.kernel_launches += 1;
-        if (db->max_region_slots > 255u) { /* only a region with more than 255 reads can hold a deep tile */
+        if (db->max_region_slots > 65535u || force_big) { /* only a region with more reads than that can hold a tile whose 16-bit event counters would overflow */
             ka.tile_list = list1; ka.list_id = 1;
-            TRY((launch_tile<true, 32, 1, 1>(ka, sms, n_tiles, st)));
+            TRY((launch_tile<true, 1, 2>(ka, sms, n_tiles, st)));
             db->timing.kernel_launches += 1;
         }
     }
