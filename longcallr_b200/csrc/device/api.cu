@@ -307,6 +307,7 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     ctx->ref_table_cap = 0;
     ctx->ref_dirty = true;
     ctx->d_ctr = nullptr; ctx->h_ctr = nullptr; ctx->h_stats = nullptr;
+    memset(&ctx->caps_hint, 0, sizeof ctx->caps_hint);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
@@ -481,6 +482,10 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         C.pairs = 1ull << 20;
         C.adj = 1ull << 20;
         C.enum_work = 64ull * b->n_regions + 1024;
+        /* what earlier batches of this context needed (lcr_submit cuts a run into similar chunks; callers resubmit similar regions) */
+        const LcrCaps &Hc = ctx->caps_hint;
+        C.items = std::max(C.items, Hc.items); C.segs = std::max(C.segs, Hc.segs); C.pre = std::max(C.pre, Hc.pre); C.elems = std::max(C.elems, Hc.elems);
+        C.pairs = std::max(C.pairs, Hc.pairs); C.adj = std::max(C.adj, Hc.adj);
     }
     uint64_t bytes = 0;
     int rc = 0;
@@ -611,6 +616,9 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
         if (K.overflow & LCR_OVF_PAIRS) grow(C.pairs, K.pair_need);
         if (K.overflow & LCR_OVF_ADJ) grow(C.adj, K.adj_total);
         if (K.overflow & LCR_OVF_ENUM) grow(C.enum_work, K.enum_work);
+        /* only the capacities that depend on the data's depth and variant density are remembered, not the ones that scale with the batch */
+        ctx->caps_hint.pairs = std::max(ctx->caps_hint.pairs, C.pairs);
+        ctx->caps_hint.adj = std::max(ctx->caps_hint.adj, C.adj);
     }
     const LcrCounters &K = db->counters;
     if (getenv("LCR_TILE_PROF")) {

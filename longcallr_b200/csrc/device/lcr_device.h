@@ -84,6 +84,7 @@ struct lcr_ctx {
     int frag_walk_mode;          /* LCR_FRAG_WALK: 0 by ops per read, 1 thread per read, 2 warp per read */
     size_t submit_chunk_bytes;   /* LCR_SUBMIT_CHUNK_MB: seq + qual bytes per chunk of lcr_submit */
     int tile_variant;            /* LCR_TILE_VARIANT: launch shape of the tile pileup kernel (pileup.cu) */
+    LcrCaps caps_hint;           /* largest capacities any batch of this context has needed: first guess for the next upload */
     int debug_sync;              /* LCR_DEBUG_SYNC: synchronise and check after every launch group (bring-up only) */
 };
 

@@ -725,6 +725,7 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     __shared__ long long tabs[3][32];
     __shared__ TeamBcast bc;
     const uint32_t reg = blockIdx.x;
+    if (a.ctr->overflow) return; /* a capacity was exceeded: the run is repeated with larger buffers */
     const LcrRegionState rs = a.rstate[reg];
     if (rs.status != 0) return;
     if (rs.n_cand == 0) { /* phase() still runs its single (empty) configuration: one cross_optimize call of one iteration (phase.rs:1097-1122) */
@@ -751,6 +752,7 @@ __global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, const uint32_t 
     load_tables(a, tabs);
     x.OK = tabs[0]; x.ERR = tabs[1]; x.W = tabs[2];
     x.tid = blockIdx.x * blockDim.x + threadIdx.x; x.nthreads = gridDim.x * blockDim.x; x.grid = true; x.bc = gbc; x.sh = sh;
+    if (a.ctr->overflow) return; /* uniform over the grid: a capacity was exceeded, the run is repeated with larger buffers */
     /* the regions that can be this large are known from their read counts at upload; whether one is decided here, by
        the same test k_phase uses to leave it alone */
     for (uint32_t bi = 0; bi < n_big_list; ++bi) {

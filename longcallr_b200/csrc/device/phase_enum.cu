@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
     __syncthreads();
     if (tid == 0) S.work = atomicAdd(&a.ctr->enum_ticket[bin], 1u);
     __syncthreads();
-    if (S.work >= a.ctr->enum_cnt[bin]) return;
+    if (S.work >= a.ctr->enum_cnt[bin] || a.ctr->overflow) return;
     const uint32_t witem = a.ctr->enum_off[bin] + S.work;
     const uint32_t reg = a.work_region[witem], chunk = a.work_chunk[witem];
     const LcrRegionState rs = a.rstate[reg];

@@ -134,6 +134,9 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     if (!PRE) {
         if (allele1 != ref_base) { if (allele1_cnt > 0 && pick(s.pass, i1) < 2) return false; }
         else if (allele2 != ref_base) { if (allele2_cnt > 0 && pick(s.pass, i2) < 2) return false; }
+    } else { /* fewer than two bases of that allele cannot hold two passing ones */
+        if (allele1 != ref_base) { if (allele1_cnt == 1) return false; }
+        else if (allele2 != ref_base) { if (allele2_cnt == 1) return false; }
     }
     if (P.use_strand_bias) {
         const int32_t rf = (int32_t)pick(s.fwd, ref_code), rr = (int32_t)(pick(s.cnt, ref_code) - pick(s.fwd, ref_code));

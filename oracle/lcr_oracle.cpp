@@ -57,6 +57,9 @@
 #include "longcallr_b200.h"
 #include "lcr_contract.h"
 
+/* oracle-only test hook (tests/test_oracle_crosscheck.py): stop after phase() and report its state */
+#define LCR_ORACLE_FLAG_STOP_AFTER_PHASE 0x40000000u
+
 namespace {
 
 /* ---------------------------------------------------------------- types -- */
@@ -1494,6 +1497,10 @@ struct Worker {
         st = get_fragments();
         if (st) { out.status = st; frags.clear(); for (Cand &c : cands) c.cover.clear(); return; }
         phase();
+        if (P.flags & LCR_ORACLE_FLAG_STOP_AFTER_PHASE) { /* test hook: the state phase() leaves (haplotags as HP 1 / 2) */
+            for (const Fragment &f : frags) out.hp.emplace_back(f.read, f.haplotag == 1 ? 1 : (f.haplotag == -1 ? 2 : 0));
+            return;
+        }
         assign_reads_haplotype(nullptr);
         assign_snp_haplotype_genotype();
         assign_reads_haplotype(nullptr);

@@ -283,3 +283,41 @@ def test_shared_reads_are_deterministic(name):
         helpers.compare_results(r, want, name)
     shared = np.nonzero((reads.pos < 1500) & (reads.pos + 1200 > 1500))[0]
     assert len(shared) > 0
+
+
+def test_full_size_cfg5_against_golden():
+    """BASELINE config 5 at full size (one 500 kb region at 500x, 4,661 candidates, 2,333 cross_optimize calls on the LD path, cooperative
+    whole-GPU phasing kernel) against the oracle's committed output (tests/golden/cfg5_oracle.npz, written by make_cfg5_golden.py: the
+    oracle needs ~8 minutes for this region on one thread)."""
+    import bench
+
+    z = np.load(os.path.join(helpers.GOLDEN, "cfg5_oracle.npz"))
+    w, syn, p, regions = bench.make_workload("cfg5", 0)
+    batch = host.BatchView(syn.reads, regions)
+    eng = host.Engine(p)
+    eng.set_references(syn.reference.for_reads(syn.reads))
+    got = eng.submit(batch)
+    eng.close()
+    assert list(got.region_status) == [0] and got.n_cand == len(z["cand"]) == 4661
+    for f in helpers.INT_FIELDS:
+        np.testing.assert_array_equal(got.cand[f], z["cand"][f], err_msg=f"cfg5 cand.{f}")
+    for f in helpers.FP_FIELDS:
+        x, y = got.cand[f].astype(np.float64), z["cand"][f].astype(np.float64)
+        ok = (np.abs(x - y) <= helpers.FP_TOL) | (np.isinf(x) & np.isinf(y) & (np.sign(x) == np.sign(y))) | (np.isnan(x) & np.isnan(y))
+        assert ok.all(), f
+    np.testing.assert_array_equal(got.hp, z["hp"])
+    np.testing.assert_array_equal(got.ps, z["ps"])
+    np.testing.assert_array_equal(got.is_fragment, z["is_fragment"])
+    want_stats = dict(zip([str(k) for k in z["stats_keys"]], [int(v) for v in z["stats"]]))
+    for k in ("n_reads_pass", "n_aligned_bases", "n_candidates", "n_fragments", "nnz_phase", "n_cross_optimize", "n_sweep_iters"):
+        assert got.stats[k] == want_stats[k], (k, got.stats[k], want_stats[k])
+    # planted truth: within the phase sets HP follows the planted read haplotype
+    agree = total = 0
+    for ps in np.unique(got.ps):
+        m = (got.ps == ps) & (got.hp > 0)
+        if ps == 0 or m.sum() < 10:
+            continue
+        a = ((got.hp[m] == 1) == (syn.read_hap[m] == 0)).sum()
+        agree += max(a, m.sum() - a)
+        total += m.sum()
+    assert total > 50000 and agree / total > 0.95
