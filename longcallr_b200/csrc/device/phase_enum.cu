@@ -16,9 +16,18 @@
  */
 #include "lcr_frag.h"
 #include "lcr_pipeline.h"
+#include "lcr_async.h"
 
 #define EMAXN 10
 #define EW_MAX 8
+#define NF_PRE 384 /* rows of the signed-term table (PRE bins: regions of at most that many fragments) */
+/* PRE bins: the region's tile of the fragment matrix (CSR slice: row offsets, site indices, cells) is staged in shared memory by
+   the TMA engine (1-D bulk copies, completion on an mbarrier) before the rows are built from it */
+#define TILE_ELEMS (NF_PRE * EMAXN)
+#define TILE_OFF_BYTES ((((NF_PRE + 1) * 4 + 32) + 15) & ~15)
+#define TILE_SNP_BYTES (TILE_ELEMS * 4 + 32)
+#define TILE_CELL_BYTES (TILE_ELEMS + 32)
+#define TILE_BYTES (TILE_OFF_BYTES + TILE_SNP_BYTES + TILE_CELL_BYTES)
 
 namespace {
 
@@ -32,15 +41,22 @@ struct EnumShared {
     uint32_t best_cfg[EW_MAX];
     unsigned long long iters[EW_MAX];
     uint32_t work, last, win_cfg;
+    uint32_t t_off, t_snp, t_cell; /* staged tile: byte offsets of the region's first row offset / site index / cell inside the staged windows */
 };
 
 /* EW warps per CTA, ECFG_PER_WARP configurations per warp (strided over the chunk so that warps stay balanced);
    small regions use small CTAs so that many of them share an SM */
 template <int EW, int ECFG_PER_WARP, bool PRE>
-__global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseArgs a, int bin, uint32_t nf_cap) {
+__global__ void __launch_bounds__(EW * 32, EW == 8 ? 3 : 1) k_enum_search(PhaseArgs a, int bin, uint32_t nf_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ EnumShared S;
+    __shared__ __align__(8) unsigned long long s_tile_bar;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t tile_par = 0;
+    if (PRE) {
+        if (tid == 0) { mbar_init(smem_u32(&s_tile_bar), 1); mbar_fence_init(); }
+        __syncthreads();
+    }
     /* the bin's work list is built on the device (k_enum_plan): CTAs draw (region, chunk) items from its ticket counter */
   for (;;) {
     __syncthreads();
@@ -58,6 +74,7 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
     uint32_t *sig = wm + words + warp * words;
     /* PRE (regions with few fragments): p * W of every cell, site-major, so the sweeps load a signed term instead of decoding it */
     long long *Tm = reinterpret_cast<long long *>(smem_raw + (((size_t)nf_cap * 12 + (size_t)(EW + 1) * words * 4 + 7) & ~(size_t)7));
+    unsigned char *tile = smem_raw + (((size_t)(reinterpret_cast<unsigned char *>(Tm + (size_t)NF_PRE * EMAXN) - smem_raw) + 15) & ~(size_t)15); /* PRE: 16-byte aligned */
     const lcr_candidate *c = a.cand + cb;
     const LcrDeviceTables &T = *a.tables;
     const uint64_t region_key = lcr_region_key(a.regions[reg].tid, a.regions[reg].start);
@@ -71,7 +88,33 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
     }
     if (tid < EMAXN) { S.C[tid] = 0; S.R[tid] = 0; S.V[tid] = 0; S.cov[tid] = 0; }
     for (uint32_t w = tid; w < words; w += EW * 32) wm[w] = 0;
+    if (PRE) {
+        if (tid == 0) { /* windows from the 16-byte boundary below the region's first row offset / element to the one above its last */
+            const uint32_t e0 = a.frag_elem_off[fb], e1 = a.frag_elem_off[fb + nf];
+            const uint32_t bar = smem_u32(&s_tile_bar), dst = smem_u32(tile);
+            const unsigned char *g_off = reinterpret_cast<const unsigned char *>(a.frag_elem_off + fb);
+            const unsigned char *g_snp = reinterpret_cast<const unsigned char *>(a.elem_snp + e0);
+            const unsigned char *g_cell = reinterpret_cast<const unsigned char *>(a.elem_cell + e0);
+            const uint32_t o_off = (uint32_t)((uintptr_t)g_off & 15u), o_snp = (uint32_t)((uintptr_t)g_snp & 15u), o_cell = (uint32_t)((uintptr_t)g_cell & 15u);
+            const uint32_t b_off = (o_off + 4u * (nf + 1u) + 15u) & ~15u, b_snp = (o_snp + 4u * (e1 - e0) + 15u) & ~15u, b_cell = (o_cell + (e1 - e0) + 15u) & ~15u;
+            S.t_off = o_off; S.t_snp = TILE_OFF_BYTES + o_snp; S.t_cell = TILE_OFF_BYTES + TILE_SNP_BYTES + o_cell;
+            bulk_g2s(dst, g_off - o_off, b_off, bar);
+            if (e1 > e0) {
+                bulk_g2s(dst + TILE_OFF_BYTES, g_snp - o_snp, b_snp, bar);
+                bulk_g2s(dst + TILE_OFF_BYTES + TILE_SNP_BYTES, g_cell - o_cell, b_cell, bar);
+            }
+            mbar_arrive_expect_tx(bar, b_off + (e1 > e0 ? b_snp + b_cell : 0u));
+        }
+    }
     __syncthreads();
+    if (PRE) {
+        mbar_wait(smem_u32(&s_tile_bar), tile_par);
+        tile_par ^= 1u;
+    }
+    const uint32_t *t_off = reinterpret_cast<const uint32_t *>(tile + S.t_off);
+    const uint32_t *t_snp = reinterpret_cast<const uint32_t *>(tile + S.t_snp);
+    const int8_t *t_cell = reinterpret_cast<const int8_t *>(tile + S.t_cell);
+    const uint32_t t_e0 = PRE ? t_off[0] : 0u;
     /* stage the rows: bit 63 = fragment used for phasing, 6 bits per site: (q + 1) | 32 when p < 0 */
     for (uint32_t k = tid; k < nf; k += EW * 32) {
         const uint32_t f = fb + k;
@@ -79,18 +122,26 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
         uint32_t present = 0;
         if (PRE) {
 #pragma unroll
-            for (int i = 0; i < EMAXN; ++i) Tm[(size_t)i * nf_cap + k] = 0;
+            for (int i = 0; i < EMAXN; ++i) Tm[i * NF_PRE + k] = 0;
         }
-        for (uint32_t e = a.frag_elem_off[f]; e < a.frag_elem_off[f + 1]; ++e) {
-            const int8_t cell = a.elem_cell[e];
+        const uint32_t ea = PRE ? t_off[k] - t_e0 : a.frag_elem_off[f], eb = PRE ? t_off[k + 1] - t_e0 : a.frag_elem_off[f + 1];
+        for (uint32_t e = ea; e < eb; ++e) {
+            const int8_t cell = PRE ? t_cell[e] : a.elem_cell[e];
+            const uint32_t snp = PRE ? t_snp[e] : a.elem_snp[e];
             const uint32_t code = cell > 0 ? (uint32_t)cell : ((uint32_t)(-cell) | 32u);
-            row |= (unsigned long long)code << (6 * a.elem_snp[e]);
-            if (code) present |= 1u << a.elem_snp[e];
-            if (PRE && code) Tm[(size_t)a.elem_snp[e] * nf_cap + k] = cell > 0 ? S.W[(code & 31u) - 1u] : -S.W[(code & 31u) - 1u];
+            row |= (unsigned long long)code << (6 * snp);
+            if (code) present |= 1u << snp;
+            if (PRE && code) Tm[snp * NF_PRE + k] = cell > 0 ? S.W[(code & 31u) - 1u] : -S.W[(code & 31u) - 1u];
         }
         rows[k] = row;
         if ((row >> 63) && present) atomicOr(&wm[k >> 5], present);
         rrel[k] = a.frag_slot[f] - slot0;
+    }
+    if (PRE) { /* the table is read in whole words of 32 rows: rows past the last fragment hold zeros */
+        for (uint32_t k = nf + tid; k < ((nf + 31u) & ~31u); k += EW * 32) {
+#pragma unroll
+            for (int i = 0; i < EMAXN; ++i) Tm[i * NF_PRE + k] = 0;
+        }
     }
     uint32_t phase0 = 0; /* for_phasing mask */
     uint32_t het0 = 0, pos0 = 0xffffffffu; /* init_genotype, phase.rs:682-691: type 0 -> eta 1, type 1 -> 0, else -1 */
@@ -169,25 +220,22 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 4 : 1) k_enum_search(PhaseA
                 const bool active = row >> 63;
                 long long v = 0; /* sum_i p * delta * W over heterozygous phase sites */
                 if (PRE) {
+                    /* one load per (site of the word, row): the signed term p * W feeds the read's decision and the site's column sum */
+                    const long long *Tk = Tm + k;
+                    long long tv[EMAXN];
 #pragma unroll
-                    for (int i = 0; i < EMAXN; ++i) {
-                        if ((vs >> i) & 1u) {
-                            const long long t = k < nf ? Tm[(size_t)i * nf_cap + k] : 0;
-                            v += ((dneg >> i) & 1u) ? -t : t;
-                        }
-                    }
+                    for (int i = 0; i < EMAXN; ++i) tv[i] = ((ms >> i) & 1u) ? Tk[i * NF_PRE] : 0ll;
+#pragma unroll
+                    for (int i = 0; i < EMAXN; ++i)
+                        if ((vs >> i) & 1u) v += ((dneg >> i) & 1u) ? -tv[i] : tv[i];
                     if (active && v != 0) {
                         const bool nneg = v < 0;
                         if (nneg != neg) { any_flip = true; neg = nneg; }
                     }
                     if (active) {
 #pragma unroll
-                        for (int i = 0; i < EMAXN; ++i) {
-                            if ((ms >> i) & 1u) {
-                                const long long t = Tm[(size_t)i * nf_cap + k];
-                                M[i] += neg ? -t : t;
-                            }
-                        }
+                        for (int i = 0; i < EMAXN; ++i)
+                            if ((ms >> i) & 1u) M[i] += neg ? -tv[i] : tv[i];
                     }
                 } else {
 #pragma unroll
@@ -412,9 +460,9 @@ __global__ void __launch_bounds__(EP_THREADS) k_enum_plan(PhaseArgs a, uint32_t 
 
 /* launch shapes by number of configurations: {warps per CTA, configurations per warp} */
 static const int SHAPES[LCR_ENUM_SHAPES][2] = {{1, 4}, {2, 4}, {4, 4}, {8, 8}, {8, 2}}; /* the last: 5+ sites when the batch is too small to fill the GPU with 64 configurations per CTA */
-static const uint32_t CLASS_ROWS[LCR_ENUM_CLASSES] = {384, 1024, 4096, 16384};            /* fragment-count classes: rows staged in shared memory */
+static const uint32_t CLASS_ROWS[LCR_ENUM_CLASSES] = {NF_PRE, 1024, 4096, 16384};            /* fragment-count classes: rows staged in shared memory */
 
-static size_t smem_bytes(uint32_t nf_cap, int ew, bool pre) { return (size_t)nf_cap * 12 + (size_t)(ew + 1) * ((nf_cap + 31) / 32) * 4 + 16 + (pre ? (size_t)nf_cap * 8 * EMAXN + 8 : 0); }
+static size_t smem_bytes(uint32_t nf_cap, int ew, bool pre) { return (size_t)nf_cap * 12 + (size_t)(ew + 1) * ((nf_cap + 31) / 32) * 4 + 16 + (pre ? (size_t)NF_PRE * 8 * EMAXN + 32 + TILE_BYTES : 0); }
 
 template <int EW, int CPW, bool PRE>
 static int launch_shape(const PhaseArgs &a, int bin, uint32_t nf_cap, int grid, cudaStream_t st) {

@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "lcr_device.h"
+#include "lcr_async.h"
 
 namespace {
 
@@ -745,48 +746,6 @@ struct PileArgs {
     uint8_t *cand_keep;
 };
 
-/* ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ---- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    /* try_wait suspends the thread in hardware up to the hint (ns) before it reports false: waiting warps issue almost nothing */
-    asm volatile(
-        "{\n\t.reg .pred p;\n"
-        "LCR_MBAR_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra LCR_MBAR_DONE_%=;\n\t"
-        "bra LCR_MBAR_WAIT_%=;\n"
-        "LCR_MBAR_DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
-}
-/* the producers' wait for a free stage: they run ahead of the consumers, so they back off between probes instead of taking issue slots */
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    for (;;) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) break;
-        __nanosleep(64);
-    }
-}
-/* 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); its completion is tied to an mbarrier by cp_async_arrive */
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-/* one pending arrival of the barrier is delivered when all earlier cp.async of this thread have landed */
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-/* 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier; 16-byte aligned addresses and size */
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PT_CONS) : "memory"); }
 __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, %0;" ::"n"(32 * PT_PROD_WARPS) : "memory"); }
 __device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
@@ -864,7 +823,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
         /* a batch is full when every producer lane's asynchronous copies have landed (one deferred arrival per lane), the header is
            written and the bulk copy of the reference window has delivered its bytes (one arrival with the expected byte count) */
         for (int s = 0; s < PT_STAGES; ++s) { mbar_init(bar_full + 8 * s, 32 * PT_PROD_WARPS + 1); mbar_init(bar_empty + 8 * s, 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     { /* the counters start zeroed; every tile's epilogue clears them again */
         uint4 *p4 = reinterpret_cast<uint4 *>(pt_smem + L::diff);
