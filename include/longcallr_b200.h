@@ -35,7 +35,8 @@ typedef enum lcr_status {
     LCR_ERR_OOM = -4,
     LCR_ERR_BAD_CIGAR = -5,     /* reference: panic "unknown cigar operation" util.rs:944, fragment.rs:191 */
     LCR_ERR_NO_REFERENCE = -6,  /* region on a contig never given to lcr_set_reference (thread.rs:79 unwrap) */
-    LCR_ERR_BASEQ_ZERO = -7     /* base quality 0 at a phase site: reference panics on NaN, phase.rs:307 */
+    LCR_ERR_BASEQ_ZERO = -7,    /* base quality 0 at a phase site: reference panics on NaN, phase.rs:307 */
+    LCR_ERR_INTERNAL = -8       /* a device-side invariant did not hold (a bug here, not in the input) */
 } lcr_status;
 
 /* Scalar parameters of the worker, src/thread.rs:17-51; defaults per preset in
@@ -227,6 +228,29 @@ typedef struct lcr_device_view {
     uint32_t n_reads;
 } lcr_device_view;
 int lcr_device_results(lcr_ctx *ctx, lcr_device_batch *db, lcr_device_view *out);
+
+/* Isolated-region discovery on the device: replaces find_isolated_regions_with_depth (util.rs:236-332, called per contig
+   from util.rs:558-602), i.e. the reference's first BAM pass.  Input is the per-read columns that pass reads (no bases, no
+   qualities); reads in BAM order (tid, pos).  The read filter uses the context's min_mapq / min_read_length / divergence
+   (util.rs:262-279).  Output: regions sorted by (tid, start) with read_begin / read_end filled (ready for lcr_batch) and
+   Region.max_coverage of each; both arrays are malloc'ed and released with lcr_free_regions.  ms (optional) receives the
+   CUDA-event time of the device work, host-to-device copies excluded. */
+typedef struct lcr_align_index {
+    uint32_t n_reads;
+    uint32_t n_contigs;
+    const uint64_t *contig_lens; /* [n_contigs] */
+    const int32_t *tid;          /* [n_reads] */
+    const int32_t *pos;
+    const uint16_t *flag;
+    const uint8_t *mapq;
+    const float *de;
+    const uint64_t *seq_off;     /* [n_reads+1] only the differences (l_seq) are used */
+    const uint64_t *cig_off;     /* [n_reads+1] */
+    const uint32_t *cigar;
+} lcr_align_index;
+int lcr_discover_regions(lcr_ctx *ctx, const lcr_align_index *in, int truncation, uint32_t truncation_coverage,
+                         lcr_region **regions, uint32_t **max_coverage, uint32_t *n_regions, float *ms);
+void lcr_free_regions(lcr_region *regions, uint32_t *max_coverage);
 
 /* timing / accounting of the last lcr_run_device on this batch */
 typedef struct lcr_timing {

@@ -17,6 +17,7 @@ LCR_ERR_OOM = -4
 LCR_ERR_BAD_CIGAR = -5
 LCR_ERR_NO_REFERENCE = -6
 LCR_ERR_BASEQ_ZERO = -7
+LCR_ERR_INTERNAL = -8
 
 LCR_FLAG_EMIT_PLANES = 1
 LCR_FLAG_SKIP_PHASING = 2
@@ -223,6 +224,13 @@ class Timing(C.Structure):
 
 class DeviceView(C.Structure):
     _fields_ = [("cand", C.c_void_p), ("hp", C.c_void_p), ("ps", C.c_void_p), ("n_cand", C.c_uint32), ("n_reads", C.c_uint32)]
+
+
+class AlignIndex(C.Structure):
+    """lcr_align_index: the per-read columns region discovery reads."""
+
+    _fields_ = [("n_reads", C.c_uint32), ("n_contigs", C.c_uint32), ("contig_lens", C.c_void_p), ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p),
+                ("mapq", C.c_void_p), ("de", C.c_void_p), ("seq_off", C.c_void_p), ("cig_off", C.c_void_p), ("cigar", C.c_void_p)]
 
 
 # ---- csrc/host/lcr_host.h ----

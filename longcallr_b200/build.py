@@ -17,7 +17,7 @@ INC = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "lib")
 OBJ = os.path.join(HERE, "build")
 HOST_SRC = ["lcr_host.cpp", "vcf.cpp", "synth.cpp"]
-DEV_SRC = ["api.cu", "pileup.cu", "fragments.cu", "phase.cu", "phase_enum.cu", "params.cpp"]
+DEV_SRC = ["api.cu", "pileup.cu", "fragments.cu", "phase.cu", "phase_enum.cu", "regions.cu", "params.cpp"]
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 EXTRA = os.environ.get("LCR_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -283,6 +283,7 @@ const char *lcr_strerror(int status) {
         case LCR_ERR_BAD_CIGAR: return "unknown or inconsistent CIGAR operation";
         case LCR_ERR_NO_REFERENCE: return "region on a contig without reference sequence";
         case LCR_ERR_BASEQ_ZERO: return "base quality 0 at a phase site";
+        case LCR_ERR_INTERNAL: return "internal invariant violated";
         default: return "unknown status";
     }
 }

@@ -77,6 +77,10 @@ def cuda_lib():
         L.lcr_release.restype = None
         L.lcr_get_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Timing)]
         L.lcr_device_results.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.DeviceView)]
+        L.lcr_discover_regions.argtypes = [C.c_void_p, C.POINTER(abi.AlignIndex), C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                           C.POINTER(C.c_float)]
+        L.lcr_free_regions.argtypes = [C.c_void_p, C.c_void_p]
+        L.lcr_free_regions.restype = None
         L.lcr_last_submit_timing.argtypes = [C.c_void_p, C.POINTER(abi.Timing)]
         L.lcr_strerror.argtypes = [C.c_int]
         L.lcr_strerror.restype = C.c_char_p
@@ -406,6 +410,24 @@ class Engine:
 
     def release(self, handle):
         self.L.lcr_release(self.ctx, handle)
+
+    def discover_regions(self, reads, truncation=False, truncation_coverage=200000, with_time=False):
+        """Isolated regions found on the device (lcr_discover_regions; reference util.rs:236-332): the same (regions, max_coverage)
+        pair find_regions() returns from the host implementation."""
+        keep = [np.ascontiguousarray(getattr(reads, f)) for f in ("tid", "pos", "flag", "mapq", "de", "seq_off", "cig_off", "cigar")]
+        lens = np.ascontiguousarray(reads.contig_lens, dtype="<u8")
+        a = abi.AlignIndex()
+        a.n_reads, a.n_contigs, a.contig_lens = reads.n_reads, len(lens), lens.ctypes.data
+        for name, arr in zip(("tid", "pos", "flag", "mapq", "de", "seq_off", "cig_off", "cigar"), keep):
+            setattr(a, name, arr.ctypes.data)
+        pr, pm, n, ms = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_float()
+        self._check(self.L.lcr_discover_regions(self.ctx, C.byref(a), int(truncation), truncation_coverage, C.byref(pr), C.byref(pm), C.byref(n), C.byref(ms)), "lcr_discover_regions")
+        try:
+            regions = abi.as_array(pr.value, abi.REGION_DTYPE, n.value).copy() if n.value else np.zeros(0, abi.REGION_DTYPE)
+            maxcov = abi.as_array(pm.value, "<u4", n.value).copy() if n.value else np.zeros(0, "<u4")
+        finally:
+            self.L.lcr_free_regions(pr, pm)
+        return (regions, maxcov, ms.value) if with_time else (regions, maxcov)
 
     def device_view(self, handle):
         """Device pointers of the last run's results on this handle (lcr_device_results): candidates, HP, PS."""

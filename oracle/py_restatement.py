@@ -7,6 +7,7 @@ the reference's order.  A transcription error in either restatement shows up as 
 the two; an error of the numerical contract (fixed point, lcr_log10 ...) shows up against this file's libm
 arithmetic.  What it covers:
 
+    R0  isolated regions               util.rs:236-332
     P0  read filter + fetch window     util.rs:636-668
     P1  pileup                         util.rs:669-949
     P2  two major alleles              util.rs:158-176
@@ -610,3 +611,39 @@ def phase_enum(P, region, cands, frags, reads_in_region_index):
     for f, t in zip(frags, best[2]):
         f["haplotag"] = t
     return counters
+
+
+# ---------------------------------------------------------------- R0 isolated regions   util.rs:236-332
+def find_isolated_regions(ref_len, reads, min_mapq, min_read_length, divergence, truncation=False, truncation_coverage=200000):
+    """One contig.  reads: iterable of dicts {mapq, l_seq, flag, de (float or None), pos, end} with [pos, end) the
+    reference span of the alignment (record.reference_start() / reference_end()).  Returns [(start, end, max_coverage)],
+    start 1-based inclusive, end 1-based exclusive, exactly as the per-position loop of util.rs:282-330 produces them,
+    including its two quirks: a covered run of one position is not pushed and not forgotten (it becomes the start of the
+    region that the next run closes), and max_coverage is taken before the push test."""
+    depth = [0] * ref_len
+    for r in reads:
+        if r["mapq"] < min_mapq or r["l_seq"] < min_read_length or (r["flag"] & 0x4) or (r["flag"] & 0x100) or (r["flag"] & 0x800):  # util.rs:262-270
+            continue
+        if r["de"] is not None and f32(r["de"]) >= f32(divergence):  # util.rs:272-279
+            continue
+        for i in range(max(r["pos"], 0), min(r["end"], ref_len)):  # util.rs:281-285
+            depth[i] += 1
+    out = []
+    region_start = region_end = -1
+    max_coverage = 0
+    for i in range(ref_len):  # util.rs:290-318
+        if depth[i] > max_coverage:
+            max_coverage = depth[i]
+        if depth[i] == 0 or (truncation and depth[i] > truncation_coverage):
+            if region_end > region_start:
+                out.append((region_start + 1, region_end + 2, max_coverage))
+                region_start = region_end = -1
+                max_coverage = 0
+        else:
+            if region_start == -1:
+                region_start = region_end = i
+            else:
+                region_end = i
+    if region_end > region_start:  # util.rs:319-329
+        out.append((region_start + 1, region_end + 2, max_coverage))
+    return out
