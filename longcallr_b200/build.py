@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 INC = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "lib")
 OBJ = os.path.join(HERE, "build")
-HOST_SRC = ["lcr_host.cpp", "vcf.cpp", "synth.cpp"]
+HOST_SRC = ["lcr_host.cpp", "vcf.cpp", "synth.cpp", "bam_io.cpp"]
 DEV_SRC = ["api.cu", "pileup.cu", "fragments.cu", "phase.cu", "phase_enum.cu", "regions.cu", "params.cpp"]
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 EXTRA = os.environ.get("LCR_NVCC_EXTRA", "").split()

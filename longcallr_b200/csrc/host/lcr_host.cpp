@@ -20,7 +20,7 @@
 
 namespace lcrhost {
 
-static bool read_file(const char *path, std::vector<uint8_t> &buf) {
+bool read_file(const char *path, std::vector<uint8_t> &buf) {
     FILE *f = fopen(path, "rb");
     if (!f) return false;
     fseek(f, 0, SEEK_END);
@@ -69,7 +69,7 @@ static bool bgzf_index(const std::vector<uint8_t> &file, std::vector<BgzfBlock> 
     return p == file.size();
 }
 
-static bool bgzf_inflate(const std::vector<uint8_t> &file, std::vector<uint8_t> &out, int n_threads) {
+bool bgzf_inflate(const std::vector<uint8_t> &file, std::vector<uint8_t> &out, int n_threads) {
     std::vector<BgzfBlock> blocks;
     size_t total;
     if (!bgzf_index(file, blocks, total)) return false;

@@ -78,6 +78,30 @@ int lcr_host_format_vcf_header(const char *const *contig_names, const uint64_t *
                                char **out, uint64_t *out_len);
 void lcr_host_free_text(char *t);
 
+/* ---- BAM output ---- */
+
+/* A BAM file (BGZF, no index) holding `reads` as records: what tests and the bench use to put synthetic alignments
+   through the real decode path.  header_text may be NULL (a minimal @HD/@SQ header is written).  Records carry
+   qname, flag, mapq, CIGAR, 4-bit bases, qualities, ts:A (when not '*') and de:f (when not NaN); mate fields are unset. */
+int lcr_host_write_bam(const char *path, const lcr_reads *reads, const char *header_text, int n_threads);
+
+/* The phased BAM of thread.rs:307-361.  Records of in_bam are copied byte for byte, region by region in `regions`
+   order, with the aux fields the reference pushes:
+     - a record is written for a region when htslib's fetch((chr, start, end)) returns it (pos < end && endpos > start),
+       it is mapped, primary and not supplementary (thread.rs:336-338), and lies fully inside the region:
+       reference_start + 1 >= start && reference_end + 1 <= end (thread.rs:339-345); everything else is dropped;
+     - HP:i (int32) when the read's assignment is 1 or 2, PS:I (uint32) when the read has a phase set
+       (thread.rs:346-357); rust-htslib's push_aux refuses a tag that is already present and the reference ignores
+       that error, so a record that already carries HP / PS keeps its old value;
+     - assignments are looked up by QNAME with the first entry winning (thread.rs:308-325).  hp / ps are per record of
+       in_bam (record i == read i of lcr_host_read_bam); for records sharing a QNAME the first record in file order that
+       has an entry (has_entry[i] != 0; NULL: hp[i] != 0 resp. ps[i] != 0) provides the value for all of them - the
+       deterministic stand-in for the reference's thread-order-dependent queue.
+   n_written receives the number of records written. */
+int lcr_host_write_phased_bam(const char *in_bam, const char *out_bam, const lcr_region *regions, uint32_t n_regions,
+                              const int8_t *hp, const uint32_t *ps, const uint8_t *has_entry, uint32_t n_reads,
+                              int n_threads, uint64_t *n_written);
+
 /* ---- synthetic long-read RNA alignments ---- */
 typedef struct lcr_synth_config {
     uint64_t seed;

@@ -43,6 +43,8 @@ struct Regions {
     std::vector<uint32_t> max_coverage;
 };
 
+bool read_file(const char *path, std::vector<uint8_t> &buf);
+bool bgzf_inflate(const std::vector<uint8_t> &file, std::vector<uint8_t> &out, int n_threads);
 int read_bam(const char *path, int n_threads, Reads &R);
 int read_fasta(const char *path, Fasta &F);
 int find_regions(const lcr_reads &R, const lcr_params &P, bool truncation, uint32_t trunc_cov, Regions &out);

@@ -254,6 +254,32 @@ def reads_struct(reads):
     return C.pointer(r)
 
 
+def write_bam(path, reads, header_text=None, threads=4):
+    """Write a read set as a BAM file (lcr_host_write_bam); ReadSet keeps its QNAMEs, an ArrayReadSet gets r<index>."""
+    L = host_lib()
+    L.lcr_host_write_bam.argtypes = [C.c_char_p, C.POINTER(abi.Reads), C.c_char_p, C.c_int]
+    rs = reads_struct(reads)
+    rc = L.lcr_host_write_bam(os.fsencode(path), rs, header_text.encode() if header_text is not None else None, threads)
+    if rc:
+        raise LcrError(rc, f"lcr_host_write_bam({path})")
+
+
+def write_phased_bam(in_bam, out_bam, regions, hp, ps, has_entry=None, threads=4):
+    """The phased BAM of thread.rs:307-361 (lcr_host_write_phased_bam): returns the number of records written."""
+    L = host_lib()
+    L.lcr_host_write_phased_bam.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    regions = np.ascontiguousarray(regions, dtype=abi.REGION_DTYPE)
+    hp = np.ascontiguousarray(hp, dtype="i1")
+    ps = np.ascontiguousarray(ps, dtype="<u4")
+    he = None if has_entry is None else np.ascontiguousarray(has_entry, dtype="u1")
+    n = C.c_uint64()
+    rc = L.lcr_host_write_phased_bam(os.fsencode(in_bam), os.fsencode(out_bam), regions.ctypes.data, len(regions), hp.ctypes.data, ps.ctypes.data,
+                                     he.ctypes.data if he is not None else None, len(hp), threads, C.byref(n))
+    if rc:
+        raise LcrError(rc, f"lcr_host_write_phased_bam({in_bam})")
+    return n.value
+
+
 def find_regions(reads, params, truncation=False, truncation_coverage=200000):
     """Isolated regions (src/util.rs:236-332) with the read range of each; numpy REGION_DTYPE array."""
     out = C.POINTER(abi.RegionList)()

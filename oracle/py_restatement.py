@@ -647,3 +647,35 @@ def find_isolated_regions(ref_len, reads, min_mapq, min_read_length, divergence,
     if region_end > region_start:  # util.rs:319-329
         out.append((region_start + 1, region_end + 2, max_coverage))
     return out
+
+
+# ---------------------------------------------------------------- B0 phased BAM   thread.rs:307-361
+def phased_bam(records, regions, haplotag_queue, phaseset_queue):
+    """records: BAM-ordered dicts {qname, tid, pos, end, flag, tags: {tag: value}} (end = htslib bam_endpos);
+    regions: [(tid, start, end)] in output order; the two queues are the (qname, value) pairs in the order the region
+    workers pushed them.  Returns [(record index, HP or None, PS or None)] in the order the writer emits them; None
+    means no aux field is pushed (or rust-htslib refused it because the tag was already there and the error was ignored)."""
+    read_assignments = {}
+    for q, v in haplotag_queue:  # thread.rs:308-316
+        if q not in read_assignments:
+            read_assignments[q] = v
+    read_phasesets = {}
+    for q, v in phaseset_queue:  # thread.rs:317-325
+        if q not in read_phasesets:
+            read_phasesets[q] = v
+    out = []
+    for tid, start, end in regions:  # thread.rs:330-358
+        for i, r in enumerate(records):
+            if r["tid"] != tid or not (r["pos"] < end and r["end"] > start):  # fetch((chr, start, end))
+                continue
+            if r["flag"] & 0x4 or r["flag"] & 0x100 or r["flag"] & 0x800:
+                continue
+            if r["pos"] + 1 < start or r["end"] + 1 > end:
+                continue
+            hp = ps = None
+            if r["qname"] in read_assignments and read_assignments[r["qname"]] != 0 and "HP" not in r["tags"]:
+                hp = read_assignments[r["qname"]]
+            if r["qname"] in read_phasesets and "PS" not in r["tags"]:
+                ps = read_phasesets[r["qname"]]
+            out.append((i, hp, ps))
+    return out
