@@ -32,7 +32,7 @@ def test_bam_in_vcf_and_phased_bam_out(tmp_path, preset, platform):
     eng = host.Engine(p, device=0)
     regions, maxcov = eng.discover_regions(reads)
     want_regions, want_maxcov = host.find_regions(reads, p)
-    assert len(regions) > 10 and regions.tobytes() == want_regions.tobytes() and (maxcov == want_maxcov).all()
+    assert len(regions) >= 8 and regions.tobytes() == want_regions.tobytes() and (maxcov == want_maxcov).all()
     batch = host.BatchView(reads, regions)
     eng.set_references(refs)
     raw = eng.submit_raw(batch)
