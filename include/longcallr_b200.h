@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LCR_ABI_VERSION 2
+#define LCR_ABI_VERSION 3
 
 typedef enum lcr_status {
     LCR_OK = 0,
@@ -71,6 +71,10 @@ typedef struct lcr_params {
 #define LCR_FLAG_EMIT_PLANES 1u  /* also return the per-position pileup counters (debug / parity) */
 #define LCR_FLAG_SKIP_PHASING 2u /* stop after candidate calling (lcr_pileup_genotype semantics)  */
 #define LCR_FLAG_EMIT_FRAGMENTS 4u /* also return the read x SNP fragment matrix (debug / parity)  */
+/* Base qualities are read at candidate sites only (genotype likelihood, fragment elements): with this flag a `qual` array that
+   lies in page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister, lcr_pin_host) is not copied; the kernels
+   fetch the bytes they need over the bus.  A pageable `qual` is copied as usual.  Results are identical either way. */
+#define LCR_FLAG_QUAL_ON_DEMAND 8u
 
 enum { LCR_PRESET_ONT_CDNA = 0, LCR_PRESET_ONT_DRNA = 1, LCR_PRESET_HIFI_ISOSEQ = 2, LCR_PRESET_HIFI_MASSEQ = 3 };
 
@@ -102,6 +106,11 @@ typedef struct lcr_batch {
     const uint8_t *seq;      /* ASCII as rust-htslib decodes nibbles: "=ACMGRSVTWYHKDBN"            */
     const uint8_t *qual;     /* raw phred, uncapped                                                 */
     const uint32_t *cigar;   /* BAM encoding: len<<4 | op, op in MIDNSHP=X                          */
+    /* ABI 3: bases as the BAM record stores them (what record.seq() wraps before rust-htslib decodes it, util.rs:693): two bases
+       per byte, high nibble first, read i at seq4[seq4_off[i] .. seq4_off[i] + (l_seq + 1) / 2).  When seq4 is not NULL it is
+       used instead of seq (which may then be NULL) and expanded to the same ASCII letters on the device: half the bytes over the bus. */
+    const uint8_t *seq4;
+    const uint64_t *seq4_off; /* [n_reads+1] */
 } lcr_batch;
 
 /* candidate flags (snp.rs:66-84) */
@@ -277,6 +286,11 @@ typedef struct lcr_timing {
 int lcr_get_timing(lcr_ctx *ctx, lcr_device_batch *db, lcr_timing *out);
 /* accounting of the last lcr_submit on this context, summed over the chunks it was cut into */
 int lcr_last_submit_timing(lcr_ctx *ctx, lcr_timing *out);
+
+/* page-lock (and map for the device) a host buffer the caller will hand over repeatedly: faster copies, and what
+   LCR_FLAG_QUAL_ON_DEMAND needs for `qual` */
+int lcr_pin_host(void *ptr, size_t bytes);
+int lcr_unpin_host(void *ptr);
 
 const char *lcr_strerror(int status);
 const char *lcr_last_error(lcr_ctx *ctx);

@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-LCR_ABI_VERSION = 2
+LCR_ABI_VERSION = 3
 
 LCR_OK = 0
 LCR_ERR_INVALID_ARG = -1
@@ -22,6 +22,7 @@ LCR_ERR_INTERNAL = -8
 LCR_FLAG_EMIT_PLANES = 1
 LCR_FLAG_SKIP_PHASING = 2
 LCR_FLAG_EMIT_FRAGMENTS = 4
+LCR_FLAG_QUAL_ON_DEMAND = 8
 
 PRESETS = {"ont-cdna": 0, "ont-drna": 1, "hifi-isoseq": 2, "hifi-masseq": 3}
 
@@ -96,6 +97,8 @@ class Batch(C.Structure):
         ("seq", C.c_void_p),
         ("qual", C.c_void_p),
         ("cigar", C.c_void_p),
+        ("seq4", C.c_void_p),
+        ("seq4_off", C.c_void_p),
     ]
 
 

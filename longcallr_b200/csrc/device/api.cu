@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -51,6 +52,8 @@ struct FragDebug {
 
 struct DbExtra {
     FragDebug fragdbg;
+    char *stage = nullptr; /* page-locked staging block of this upload (returned to the context at release) */
+    size_t stage_cap = 0, stage_off = 0;
     std::vector<lcr_region> h_regions;
     std::vector<int32_t> h_status0;
 };
@@ -94,6 +97,56 @@ int h2d_padded(lcr_ctx *ctx, T **dst, const T *src, size_t n, size_t pad, uint64
     return 0;
 }
 
+/* page-locked staging: take a block of at least `need` bytes from the context's free list (or allocate one) */
+static bool stage_take(lcr_ctx *ctx, DbExtra &x, size_t need) {
+    for (size_t i = 0; i < ctx->stage_free.size(); ++i)
+        if (ctx->stage_free[i].second >= need) {
+            x.stage = ctx->stage_free[i].first; x.stage_cap = ctx->stage_free[i].second; x.stage_off = 0;
+            ctx->stage_free.erase(ctx->stage_free.begin() + i);
+            return true;
+        }
+    const size_t cap = need + need / 4 + (1u << 20);
+    void *p = nullptr;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return false; }
+    x.stage = static_cast<char *>(p); x.stage_cap = cap; x.stage_off = 0;
+    return true;
+}
+static void stage_give_back(lcr_ctx *ctx, DbExtra &x) {
+    if (!x.stage) return;
+    if (ctx->stage_free.size() < 16) ctx->stage_free.emplace_back(x.stage, x.stage_cap);
+    else cudaFreeHost(x.stage);
+    x.stage = nullptr; x.stage_cap = 0;
+}
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+/* a copy of [src, src + bytes) inside the staging block, or src itself when the block is absent or full */
+static const void *stage_copy(DbExtra &x, const void *src, size_t bytes) {
+    const size_t a = (x.stage_off + 63) & ~(size_t)63;
+    if (!x.stage || !bytes || a + bytes > x.stage_cap) return src;
+    memcpy(x.stage + a, src, bytes);
+    x.stage_off = a + bytes;
+    return x.stage + a;
+}
+
+/* lcr_batch.seq4 -> the ASCII letters rust-htslib's Seq::as_bytes() yields (util.rs:693): one warp per read, one packed byte per lane and step */
+__global__ void __launch_bounds__(256) k_unpack_seq4(uint32_t n_reads, const uint64_t *seq_off, const uint64_t *seq4_off, const uint8_t *seq4, uint8_t *seq) {
+    const unsigned long long LO = 0x565352474d43413dull, HI = 0x4e42444b48595754ull; /* "=ACMGRSV" "TWYHKDBN", first letter in the low byte */
+    const uint32_t lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += nwarps) {
+        const uint64_t s0 = seq_off[r], l = seq_off[r + 1] - s0;
+        const uint8_t *src = seq4 + seq4_off[r];
+        uint8_t *dst = seq + s0;
+        for (uint64_t k = lane; 2 * k < l; k += 32) {
+            const uint32_t b = src[k], hi = b >> 4, lo = b & 15u;
+            dst[2 * k] = (uint8_t)((hi < 8 ? LO : HI) >> (8 * (hi & 7)));
+            if (2 * k + 1 < l) dst[2 * k + 1] = (uint8_t)((lo < 8 ? LO : HI) >> (8 * (lo & 7)));
+        }
+    }
+}
+
 /* unpack the per-read (region, value) keys: hp -1 / ps 0 = no entry */
 __global__ void k_finalize_reads(uint32_t n, const uint32_t *hp_key, const unsigned long long *ps_key, int8_t *hp, uint32_t *ps) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,6 +168,18 @@ __global__ void k_init_rstate(uint32_t n_regions, const int32_t *status0, LcrReg
 }
 
 } // namespace
+
+int lcr_unpack_seq4(lcr_ctx *ctx, lcr_device_batch *db, cudaStream_t st) {
+    if (!db->seq4_pending) return LCR_OK;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(((uint64_t)db->n_reads + 7) / 8, (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 8);
+    if (db->n_reads) k_unpack_seq4<<<grid, 256, 0, st>>>(db->n_reads, db->seq_off, db->seq4_off, db->seq4, db->seq);
+    LCR_CUDA_TRY(ctx, cudaGetLastError());
+    cudaFreeAsync(db->seq4, st); db->seq4 = nullptr;
+    cudaFreeAsync(db->seq4_off, st); db->seq4_off = nullptr;
+    db->seq4_pending = false;
+    return LCR_OK;
+}
+
 
 struct lcr_device_batch_full : lcr_device_batch {
     DbExtra extra;
@@ -273,6 +338,18 @@ extern "C" {
 
 int lcr_abi_version(void) { return LCR_ABI_VERSION; }
 
+int lcr_pin_host(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return LCR_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? LCR_ERR_OOM : LCR_ERR_CUDA; }
+    return LCR_OK;
+}
+int lcr_unpin_host(void *ptr) {
+    if (!ptr) return LCR_ERR_INVALID_ARG;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return LCR_ERR_CUDA; }
+    return LCR_OK;
+}
+
 const char *lcr_strerror(int status) {
     switch (status) {
         case LCR_OK: return "ok";
@@ -319,7 +396,7 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
         e = getenv("LCR_FRAG_WALK");
         ctx->frag_walk_mode = (e && *e) ? atoi(e) : 0;
         e = getenv("LCR_SUBMIT_CHUNK_MB");
-        ctx->submit_chunk_bytes = (e && *e) ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)256 << 20;
+        ctx->submit_chunk_bytes = (e && *e) ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)512 << 20;
         e = getenv("LCR_TILE_VARIANT");
         ctx->tile_variant = (e && *e) ? atoi(e) : 0;
         e = getenv("LCR_DEBUG_SYNC");
@@ -381,6 +458,8 @@ void lcr_destroy(lcr_ctx *ctx) {
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
+    for (auto &sb : ctx->stage_free) cudaFreeHost(sb.first);
+    ctx->stage_free.clear();
     for (int i = 0; i < 4; ++i) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev_t[i]);
     cudaEventDestroy(ctx->ev_fork);
@@ -420,14 +499,21 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     if (b->n_reads && (!b->pos || !b->flag || !b->mapq || !b->ts || !b->de || !b->seq_off || !b->cig_off)) return LCR_ERR_INVALID_ARG;
     /* the kernels index the pools with these offsets: they must be non-decreasing and the pools present */
     const uint64_t n_bases = b->n_reads ? b->seq_off[b->n_reads] : 0, n_cig = b->n_reads ? b->cig_off[b->n_reads] : 0;
-    if ((n_bases && (!b->seq || !b->qual)) || (n_cig && !b->cigar)) return LCR_ERR_INVALID_ARG;
+    if ((n_bases && ((!b->seq && !b->seq4) || !b->qual)) || (n_cig && !b->cigar)) return LCR_ERR_INVALID_ARG;
     if (n_bases >= (1ull << 47) || n_cig >= (1ull << 47)) return LCR_ERR_INVALID_ARG;
     for (uint32_t i = 0; i < b->n_reads; ++i)
         if (b->seq_off[i + 1] < b->seq_off[i] || b->cig_off[i + 1] < b->cig_off[i]) return LCR_ERR_INVALID_ARG;
+    const bool packed = n_bases && b->seq4;
+    if (packed) { /* every read's packed bytes must lie inside its own span of the pool */
+        if (!b->seq4_off) return LCR_ERR_INVALID_ARG;
+        for (uint32_t i = 0; i < b->n_reads; ++i)
+            if (b->seq4_off[i + 1] < b->seq4_off[i] || b->seq4_off[i + 1] - b->seq4_off[i] < (b->seq_off[i + 1] - b->seq_off[i] + 1) / 2) return LCR_ERR_INVALID_ARG;
+    }
     TRY(cudaSetDevice(ctx->device));
     lcr_device_batch_full *db = new (std::nothrow) lcr_device_batch_full();
     if (!db) return LCR_ERR_OOM;
     db->ev_meta = nullptr; db->ev_seq = nullptr; db->seq_wait_pending = false;
+    db->seq4 = nullptr; db->seq4_off = nullptr; db->seq4_pending = false;
     db->n_regions = b->n_regions;
     db->n_reads = b->n_reads;
     db->ran = false;
@@ -490,25 +576,42 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     }
     uint64_t bytes = 0;
     int rc = 0;
+    /* the tables built above and any pageable per-read array go through a page-locked staging block: a pageable source would make
+       cudaMemcpyAsync wait for everything queued on the stream before it, i.e. for the previous chunk's bases and qualities */
+    const bool pin_soff = !b->n_reads || host_is_pinned(b->seq_off), pin_coff = !b->n_reads || host_is_pinned(b->cig_off), pin_pos = !b->n_reads || host_is_pinned(b->pos),
+               pin_flag = !b->n_reads || host_is_pinned(b->flag), pin_mapq = !b->n_reads || host_is_pinned(b->mapq), pin_ts = !b->n_reads || host_is_pinned(b->ts),
+               pin_de = !b->n_reads || host_is_pinned(b->de), pin_cig = !n_cig || host_is_pinned(b->cigar), pin_s4off = !packed || (host_is_pinned(b->seq4_off) && b->seq4_off[0] == 0);
+    {
+        size_t need = 4 * (slot_off.size() + slot_region.size() + tile_base.size() + tile_region.size() + big_list.size() + db->extra.h_status0.size()) + 8 * pos_off.size() +
+                      sizeof(lcr_region) * (size_t)b->n_regions + 64 * 16;
+        const size_t nr = b->n_reads;
+        need += (pin_soff ? 0 : 8 * (nr + 1)) + (pin_coff ? 0 : 8 * (nr + 1)) + (pin_pos ? 0 : 4 * nr) + (pin_flag ? 0 : 2 * nr) + (pin_mapq ? 0 : nr) + (pin_ts ? 0 : nr) + (pin_de ? 0 : 4 * nr) +
+                (pin_s4off ? 0 : 8 * (nr + 1)) + ((pin_cig || n_cig * 4 > (64ull << 20)) ? 0 : 4 * (size_t)n_cig);
+        if (need <= (512ull << 20)) stage_take(ctx, db->extra, need);
+    }
+    DbExtra &X = db->extra;
 #define UP(field, src, n) if (!rc) rc = h2d(ctx, &db->field, src, (size_t)(n), &bytes)
+#define UPS(field, src, n) if (!rc) rc = h2d(ctx, &db->field, static_cast<decltype(src)>(stage_copy(X, src, sizeof(*(src)) * (size_t)(n))), (size_t)(n), &bytes)
     /* the small host-side tables first (pageable sources: those copies wait for the stream), the caller's large arrays last,
        so that an asynchronous upload returns while seq / qual are still in flight */
-    UP(slot_off, slot_off.data(), slot_off.size());
-    UP(slot_region, slot_region.data(), slot_region.size());
-    UP(tile_base, tile_base.data(), tile_base.size());
-    UP(tile_region, tile_region.data(), tile_region.size());
-    UP(pos_off, pos_off.data(), pos_off.size());
-    UP(status0, db->extra.h_status0.data(), db->extra.h_status0.size());
-    UP(big_list, big_list.data(), big_list.size());
-    UP(regions, b->regions, b->n_regions);
-    if (b->n_reads) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
-    else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
-    UP(pos, b->pos, b->n_reads);
-    UP(flag, b->flag, b->n_reads);
-    UP(mapq, b->mapq, b->n_reads);
-    UP(ts, b->ts, b->n_reads);
-    UP(de, b->de, b->n_reads);
-    UP(cigar, b->cigar, n_cig);
+    UPS(slot_off, (const uint32_t *)slot_off.data(), slot_off.size());
+    UPS(slot_region, (const uint32_t *)slot_region.data(), slot_region.size());
+    UPS(tile_base, (const uint32_t *)tile_base.data(), tile_base.size());
+    UPS(tile_region, (const uint32_t *)tile_region.data(), tile_region.size());
+    UPS(pos_off, (const uint64_t *)pos_off.data(), pos_off.size());
+    UPS(status0, (const int32_t *)db->extra.h_status0.data(), db->extra.h_status0.size());
+    UPS(big_list, (const uint32_t *)big_list.data(), big_list.size());
+    UPS(regions, b->regions, b->n_regions);
+    if (b->n_reads) {
+        if (pin_soff) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); } else { UPS(seq_off, b->seq_off, (size_t)b->n_reads + 1); }
+        if (pin_coff) { UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); } else { UPS(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
+    } else { static const uint64_t zero = 0; UP(seq_off, &zero, 1); UP(cig_off, &zero, 1); }
+    if (pin_pos) { UP(pos, b->pos, b->n_reads); } else { UPS(pos, b->pos, b->n_reads); }
+    if (pin_flag) { UP(flag, b->flag, b->n_reads); } else { UPS(flag, b->flag, b->n_reads); }
+    if (pin_mapq) { UP(mapq, b->mapq, b->n_reads); } else { UPS(mapq, b->mapq, b->n_reads); }
+    if (pin_ts) { UP(ts, b->ts, b->n_reads); } else { UPS(ts, b->ts, b->n_reads); }
+    if (pin_de) { UP(de, b->de, b->n_reads); } else { UPS(de, b->de, b->n_reads); }
+    if (pin_cig) { UP(cigar, b->cigar, n_cig); } else { UPS(cigar, b->cigar, n_cig); }
     /* result buffers live as long as the handle */
     if (!rc) rc = dalloc(ctx, &db->rstate, db->n_regions);
     if (!rc) rc = dalloc(ctx, &db->hp, db->n_reads);
@@ -522,9 +625,38 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
     }
     /* seq / qual carry 64 bytes of slack: bulk copies and block loads read whole 16-byte groups */
-    if (!rc) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 64, &bytes);
-    if (!rc) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 64, &bytes);
+    if (!rc && !packed) rc = h2d_padded(ctx, &db->seq, b->seq, (size_t)n_bases, 64, &bytes);
+    if (!rc && packed) {
+        /* bases in the BAM record's 4-bit form: half the bytes over the bus, expanded here to the letters the kernels compare */
+        const uint64_t o0 = b->seq4_off[0], n4 = b->seq4_off[b->n_reads] - o0;
+        std::vector<uint64_t> rel;
+        const uint64_t *offs = b->seq4_off;
+        if (o0) { rel.resize((size_t)b->n_reads + 1); for (uint32_t i = 0; i <= b->n_reads; ++i) rel[i] = b->seq4_off[i] - o0; offs = rel.data(); }
+        /* a pageable `rel` may die at the end of this block: cudaMemcpyAsync returns once a pageable source has been staged */
+        if (pin_s4off) rc = h2d(ctx, &db->seq4_off, offs, (size_t)b->n_reads + 1, &bytes);
+        else rc = h2d(ctx, &db->seq4_off, static_cast<const uint64_t *>(stage_copy(X, offs, 8 * ((size_t)b->n_reads + 1))), (size_t)b->n_reads + 1, &bytes);
+        if (!rc) rc = h2d(ctx, &db->seq4, b->seq4 + o0, (size_t)n4, &bytes);
+        if (!rc) rc = dalloc(ctx, &db->seq, (size_t)n_bases + 64);
+        if (!rc) {
+            const cudaError_t e = cudaMemsetAsync(db->seq + n_bases, 0, 64, ctx->stream);
+            if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); ctx->sticky = LCR_ERR_CUDA; rc = ctx->sticky; }
+        }
+        db->seq4_pending = !rc;
+        /* an asynchronous upload leaves the expansion to the first run (on the compute stream, after ev_seq): the copy stream only copies */
+        if (!rc && !async) rc = lcr_unpack_seq4(ctx, db, ctx->stream);
+    }
+    db->qual_on_host = false;
+    if (!rc && n_bases && (ctx->P.flags & LCR_FLAG_QUAL_ON_DEMAND)) {
+        /* qualities are read at candidate sites only: leave a page-locked array where it is and let the kernels fetch those bytes */
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, b->qual) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            db->qual = static_cast<uint8_t *>(at.devicePointer);
+            db->qual_on_host = true;
+        } else cudaGetLastError();
+    }
+    if (!rc && !db->qual_on_host) rc = h2d_padded(ctx, &db->qual, b->qual, (size_t)n_bases, 64, &bytes);
 #undef UP
+#undef UPS
     if (!rc) {
         cudaError_t e = cudaSuccess;
         if (async) {
@@ -644,10 +776,14 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     /* one sweep iteration (sigma pass + delta / eta pass) touches every phase-site cell twice (1 B cell + 4 B index), every fragment's row
        pointer and haplotag, every site's column pointer and state: B_sweep of SURVEY 8(d), times the iterations executed */
     db->timing.phase_alg_bytes = (10ull * ctx->h_stats->nnz_phase + 6ull * db->n_frag + 8ull * K.n_cand) * (ctx->h_stats->n_cross_optimize ? ctx->h_stats->n_sweep_iters / std::max<uint64_t>(1, ctx->h_stats->n_cross_optimize) : 0) ;
-    /* algorithmic bytes of the tile kernel: base + qual of every aligned base, the segment and item descriptors it stages, one tile
-       descriptor and the reference bytes per processed tile, the surviving sites it writes */
-    db->timing.pileup_alg_bytes = 2ull * ctx->h_stats->n_aligned_bases + 16ull * K.n_segs_used + 16ull * K.n_items_used + 48ull * K.n_tiles_done + K.n_pos_done +
+    /* algorithmic bytes of the tile kernel = what it has to read and write: the base of every aligned base (it does not read qualities:
+       those are fetched by k_site_ll at the surviving sites only), the segment and item descriptors it stages, one tile descriptor and the
+       reference bytes per processed tile, the surviving sites it writes */
+    db->timing.pileup_alg_bytes = 1ull * ctx->h_stats->n_aligned_bases + 16ull * K.n_segs_used + 16ull * K.n_items_used + 48ull * K.n_tiles_done + K.n_pos_done +
                                   72ull * std::min<uint64_t>(K.n_pre, db->caps.pre);
+    /* LCR_FLAG_QUAL_ON_DEMAND: the qualities fetched from the caller's page-locked array cross the bus in 32-byte sectors: k_site_ll's
+       reads are counted on the device, the fragment build reads one per element in each of its two passes */
+    if (db->qual_on_host) db->timing.h2d_bytes += 32ull * (K.qual_reads + 2ull * K.n_elem);
     if ((ctx->P.flags & LCR_FLAG_EMIT_FRAGMENTS) && !(ctx->P.flags & LCR_FLAG_SKIP_PHASING)) {
         FragDebug &fd = db->extra.fragdbg;
         const uint32_t nf = db->n_frag;
@@ -781,10 +917,12 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     DFREE(db->pl_acgt); DFREE(db->pl_fwd); DFREE(db->pl_d); DFREE(db->pl_n); DFREE(db->pl_ts);
     DFREE(db->slot_flags); DFREE(db->status0); DFREE(db->big_list);
     DFREE(db->regions); DFREE(db->pos); DFREE(db->flag); DFREE(db->mapq); DFREE(db->ts); DFREE(db->de);
-    DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); DFREE(db->qual); DFREE(db->cigar);
+    DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); if (db->qual_on_host) db->qual = nullptr; DFREE(db->qual); DFREE(db->cigar);
     DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
+    DFREE(db->seq4); DFREE(db->seq4_off);
     cudaStreamSynchronize(ctx->stream);
     if (db->ev_seq) { cudaEventSynchronize(db->ev_seq); cudaEventDestroy(db->ev_seq); }
+    stage_give_back(ctx, db->extra); /* after the copies out of it have completed */
     if (db->ev_meta) cudaEventDestroy(db->ev_meta);
     delete db;
 }
@@ -896,6 +1034,7 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
         v.ts = batch->ts + ck.read_lo; v.de = batch->de + ck.read_lo;
         v.seq_off = ck.seq_off.data(); v.cig_off = ck.cig_off.data();
         v.seq = batch->seq ? batch->seq + sb : nullptr; v.qual = batch->qual ? batch->qual + sb : nullptr;
+        v.seq4 = batch->seq4; v.seq4_off = batch->seq4 && batch->seq4_off ? batch->seq4_off + ck.read_lo : nullptr; /* absolute offsets: upload_impl rebases */
         v.cigar = batch->cigar ? batch->cigar + cb : nullptr;
     }
 
@@ -908,13 +1047,33 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
     all->is_fragment.assign(batch->n_reads, 0);
     lcr_stats st{};
     int rc = 0;
-    lcr_device_batch *cur = nullptr, *nxt = nullptr;
-    rc = upload_impl(ctx, &chunks[0].view, &cur, true);
+    /* uploads run ahead of the runs on the copy stream (bounded by the bytes they pin on the device): the bus stays busy while a chunk computes */
+    std::vector<lcr_device_batch *> up(chunks.size(), nullptr);
+    std::vector<uint64_t> up_bytes(chunks.size(), 0);
+    for (size_t k = 0; k < chunks.size(); ++k) up_bytes[k] = 3 * (chunks[k].seq_off.empty() ? 0 : chunks[k].seq_off.back());
+    const uint64_t ahead_cap = 12ull << 30;
+    uint64_t ahead = 0;
+    size_t next_up = 0;
+    auto pump = [&](size_t k_cur) {
+        while (!rc && next_up < chunks.size() && (next_up <= k_cur + 1 || ahead + up_bytes[next_up] <= ahead_cap)) {
+            rc = upload_impl(ctx, &chunks[next_up].view, &up[next_up], true);
+            ahead += up_bytes[next_up];
+            ++next_up;
+        }
+    };
+    static const bool prof = getenv("LCR_SUBMIT_PROF") != nullptr; /* bring-up aid: host wall time per phase of the chunk loop */
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_up = 0, t_run = 0, t_fetch = 0, t_merge = 0, t0 = now();
     for (size_t k = 0; k < chunks.size() && !rc; ++k) {
-        if (k + 1 < chunks.size()) rc = upload_impl(ctx, &chunks[k + 1].view, &nxt, true); /* overlaps the run below */
+        t0 = now();
+        pump(k);
+        lcr_device_batch *cur = up[k];
+        t_up += now() - t0; t0 = now();
         lcr_result *part = nullptr;
         if (!rc) rc = lcr_run_device(ctx, cur);
+        t_run += now() - t0; t0 = now();
         if (!rc) rc = lcr_fetch(ctx, cur, &part);
+        t_fetch += now() - t0; t0 = now();
         if (!rc) {
             const SubmitChunk &ck = chunks[k];
             add_timing(ctx->last_submit, cur->timing);
@@ -942,11 +1101,12 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
             lcr_free_result(part);
         }
         if (cur) lcr_release(ctx, cur);
-        cur = nxt;
-        nxt = nullptr;
+        up[k] = nullptr;
+        ahead -= up_bytes[k];
+        t_merge += now() - t0;
     }
-    if (cur) lcr_release(ctx, cur);
-    if (nxt) lcr_release(ctx, nxt);
+    if (prof) fprintf(stderr, "lcr_submit: %zu chunks, host ms: upload %.2f run %.2f fetch %.2f merge+release %.2f\n", chunks.size(), t_up, t_run, t_fetch, t_merge);
+    for (lcr_device_batch *h : up) if (h) lcr_release(ctx, h);
     if (rc) { delete all; return rc; }
     lcr_result &res = all->res;
     res.n_regions = batch->n_regions; res.n_reads = batch->n_reads; res.n_cand = (uint32_t)all->cand.size();

@@ -86,6 +86,8 @@ struct lcr_ctx {
     int tile_variant;            /* LCR_TILE_VARIANT: launch shape of the tile pileup kernel (pileup.cu) */
     LcrCaps caps_hint;           /* largest capacities any batch of this context has needed: first guess for the next upload */
     int debug_sync;              /* LCR_DEBUG_SYNC: synchronise and check after every launch group (bring-up only) */
+    /* page-locked staging blocks for the small host-side tables of an upload (pageable sources would make every copy wait for the stream) */
+    std::vector<std::pair<char *, size_t>> stage_free;
 };
 
 struct lcr_device_batch {
@@ -100,6 +102,7 @@ struct lcr_device_batch {
     float *de;
     uint64_t *seq_off, *cig_off;
     uint8_t *seq, *qual;
+    bool qual_on_host;     /* LCR_FLAG_QUAL_ON_DEMAND: `qual` is the device alias of the caller's page-locked array, not a copy */
     uint32_t *cigar;
     /* derived on the host at upload: cheap prefix sums over region lengths / read ranges */
     uint32_t *slot_off;    /* [n_regions+1] */
@@ -140,6 +143,10 @@ struct lcr_device_batch {
     /* asynchronous upload (lcr_submit): the small tables are ready at ev_meta, seq / qual at ev_seq (null: synchronous upload) */
     cudaEvent_t ev_meta, ev_seq;
     bool seq_wait_pending; /* the run has not waited for ev_seq yet */
+    /* lcr_batch.seq4 of an asynchronous upload: the packed bases wait here until the first run expands them into `seq` (after ev_seq) */
+    uint8_t *seq4;
+    uint64_t *seq4_off;
+    bool seq4_pending;
 };
 
 /* rust-htslib CigarStringView::leading_softclips / trailing_softclips (util.rs:682-690, fragment.rs:59): the soft clip at that
@@ -166,6 +173,9 @@ __device__ __forceinline__ int64_t lcr_trailing_softclips(const uint32_t *cigar,
     return 0;
 }
 #endif
+
+/* expands db->seq4 into db->seq on `st` and releases the packed copy (api.cu); called where a run first needs the bases */
+int lcr_unpack_seq4(lcr_ctx *ctx, lcr_device_batch *db, cudaStream_t st);
 
 /* bring-up aid: with LCR_DEBUG_SYNC set, wait for the stream after a launch group and attribute a failure to it */
 #define LCR_DEBUG_CHECK(ctx, what)                                                      \

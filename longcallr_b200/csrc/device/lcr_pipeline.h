@@ -49,6 +49,7 @@ struct LcrCounters {
     uint32_t pad0;
     unsigned long long big_cfgs; /* configurations of the 5+ site enumeration regions (launch-shape choice) */
     unsigned long long n_pos_done; /* positions of the processed tiles */
+    unsigned long long qual_reads; /* base qualities k_site_ll fetched (accounting of LCR_FLAG_QUAL_ON_DEMAND) */
     uint32_t enum_cnt[LCR_ENUM_BINS], enum_off[LCR_ENUM_BINS], enum_ticket[LCR_ENUM_BINS];
     uint32_t n_big;          /* LD-path regions handed to the cooperative kernel */
     uint32_t pair_need;      /* LD pair table entries the batch asks for */

@@ -1360,6 +1360,7 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
         long long ll0 = 0, ll2 = 0;
         uint32_t q0flags = 0;
         uint32_t npass[4] = {0, 0, 0, 0}; /* bases of each letter with (capped) quality >= min_baseq (candidate.rs:177-194) */
+        uint32_t nq = 0;
         /* one lane per read of the tile: its segments are in column order and hold exactly the unmasked aligned bases */
         const uint32_t colr = pc.col;
         const LcrTileDesc *dp = a.desc + tile;
@@ -1375,10 +1376,11 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
                 if ((raw.z & 3u) == SEG_M) {
                     const uint64_t sp = (((uint64_t)raw.y << 32) | raw.x) + (colr - scol);
                     const uint8_t b = a.seq[sp];
-                    const uint32_t rq = a.qual[sp];
-                    const uint32_t q = rq < LCR_MAX_BASE_QUALITY ? rq : LCR_MAX_BASE_QUALITY;
                     const int bc = base_code_dev(b);
                     if (bc >= 0) {
+                        const uint32_t rq = a.qual[sp]; /* with LCR_FLAG_QUAL_ON_DEMAND this is a read of mapped host memory */
+                        const uint32_t q = rq < LCR_MAX_BASE_QUALITY ? rq : LCR_MAX_BASE_QUALITY;
+                        ++nq;
                         const bool is_ref = bc == refc;
                         const long long E = a.tables->gl_fx_err[q], K = a.tables->gl_fx_ok[q];
                         ll0 += is_ref ? E : K;
@@ -1397,10 +1399,12 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, o);
             ll2 += __shfl_xor_sync(0xffffffffu, ll2, o);
             q0flags |= __shfl_xor_sync(0xffffffffu, q0flags, o);
+            nq += __shfl_xor_sync(0xffffffffu, nq, o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) npass[i] += __shfl_xor_sync(0xffffffffu, npass[i], o);
         }
         if (lane != 0) continue;
+        if (nq) atomicAdd(&a.ctr->qual_reads, (unsigned long long)nq);
         SiteCounters sc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { sc.cnt[i] = pc.cnt[i]; sc.pass[i] = npass[i]; sc.fwd[i] = pc.fwd[i]; }
@@ -1559,9 +1563,16 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     pa.items = items; pa.segs = segs; pa.items_cap = C.items; pa.segs_cap = C.segs;
     const uint32_t pb = 128, pg = (n_slots + pb - 1) / pb;
     /* HiFi presets read the bases of the read ends in the span pass; ONT presets read no base before the tile kernel */
-    if (db->seq_wait_pending && ctx->P.platform != 1) {
-        TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
-        db->seq_wait_pending = false;
+    if (ctx->P.platform != 1) {
+        if (db->seq_wait_pending) {
+            TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
+            db->seq_wait_pending = false;
+        }
+        if (db->seq4_pending) { /* bases arrived in the BAM record's 4-bit form */
+            const int urc = lcr_unpack_seq4(ctx, db, st);
+            if (urc) return urc;
+            db->timing.kernel_launches += 1;
+        }
     }
     LCR_DEBUG_CHECK(ctx, "pileup stage memsets");
     if (pg) {
@@ -1607,6 +1618,11 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     if (db->seq_wait_pending) { /* asynchronous upload: seq / qual are first read here */
         TRY(cudaStreamWaitEvent(st, db->ev_seq, 0));
         db->seq_wait_pending = false;
+    }
+    if (db->seq4_pending) {
+        const int urc = lcr_unpack_seq4(ctx, db, st);
+        if (urc) return urc;
+        db->timing.kernel_launches += 1;
     }
     LCR_DEBUG_CHECK(ctx, "k_tile_desc");
     TRY(cudaEventRecord(ctx->ev_t[0], st));

@@ -297,6 +297,40 @@ static int write_phased_bam(const char *in_bam, const char *out_bam, const lcr_r
 
 extern "C" {
 
+int lcr_host_pack_seq4(const lcr_reads *R, uint64_t *seq4_off, uint8_t *seq4, int n_threads) {
+    if (!R || !seq4_off || (R->n_reads && !R->seq_off)) return LCR_ERR_INVALID_ARG;
+    seq4_off[0] = 0;
+    for (uint32_t i = 0; i < R->n_reads; ++i) seq4_off[i + 1] = seq4_off[i] + (R->seq_off[i + 1] - R->seq_off[i] + 1) / 2;
+    if (!seq4 || !R->n_reads) return 0;
+    if (!R->seq) return LCR_ERR_INVALID_ARG;
+    uint8_t code[256];
+    memset(code, 15, sizeof code);
+    const char *nib = "=ACMGRSVTWYHKDBN";
+    for (int k = 0; k < 16; ++k) code[(uint8_t)nib[k]] = (uint8_t)k;
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t i0 = next.fetch_add(1024);
+            if (i0 >= R->n_reads) break;
+            const uint32_t i1 = std::min<uint32_t>(R->n_reads, i0 + 1024);
+            for (uint32_t i = i0; i < i1; ++i) {
+                const uint8_t *s = R->seq + R->seq_off[i];
+                const uint64_t l = R->seq_off[i + 1] - R->seq_off[i];
+                uint8_t *o = seq4 + seq4_off[i];
+                for (uint64_t k = 0; k + 1 < l; k += 2) o[k >> 1] = (uint8_t)(code[s[k]] << 4 | code[s[k + 1]]);
+                if (l & 1) o[l >> 1] = (uint8_t)(code[s[l - 1]] << 4);
+            }
+        }
+    };
+    if (n_threads <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
+        for (auto &t : th) t.join();
+    }
+    return 0;
+}
+
 int lcr_host_write_bam(const char *path, const lcr_reads *reads, const char *header_text, int n_threads) {
     if (!path || !reads) return LCR_ERR_INVALID_ARG;
     return lcrhost::write_bam(path, *reads, header_text, n_threads);

@@ -78,6 +78,11 @@ int lcr_host_format_vcf_header(const char *const *contig_names, const uint64_t *
                                char **out, uint64_t *out_len);
 void lcr_host_free_text(char *t);
 
+/* Bases in the BAM record's own form (two per byte, high nibble first, every read starting on a byte): fills seq4_off[n_reads+1]
+   and, when seq4 is not NULL, the packed bytes (seq4_off[n_reads] of them; call once with NULL to size the buffer).
+   Letters outside "=ACMGRSVTWYHKDBN" pack as N (15), as htslib does. */
+int lcr_host_pack_seq4(const lcr_reads *reads, uint64_t *seq4_off, uint8_t *seq4, int n_threads);
+
 /* ---- BAM output ---- */
 
 /* A BAM file (BGZF, no index) holding `reads` as records: what tests and the bench use to put synthetic alignments

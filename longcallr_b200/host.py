@@ -293,19 +293,43 @@ def find_regions(reads, params, truncation=False, truncation_coverage=200000):
     return regions, maxcov
 
 
-class BatchView:
-    """An lcr_batch over numpy arrays (kept alive here)."""
+def pack_seq4(reads, alloc=None, threads=8):
+    """(seq4, seq4_off): the bases of a read set in the BAM record's 4-bit form (lcr_host_pack_seq4).  alloc(nbytes) -> writable
+    uint8 array lets the caller place the packed bytes in pinned memory."""
+    L = host_lib()
+    L.lcr_host_pack_seq4.argtypes = [C.POINTER(abi.Reads), C.c_void_p, C.c_void_p, C.c_int]
+    rs = reads_struct(reads)
+    off = np.zeros(reads.n_reads + 1, dtype="<u8")
+    rc = L.lcr_host_pack_seq4(rs, off.ctypes.data, None, threads)
+    if rc:
+        raise LcrError(rc, "lcr_host_pack_seq4")
+    n = int(off[-1])
+    buf = (alloc(max(n, 1)) if alloc else np.empty(max(n, 1), dtype="u1"))[:n]
+    rc = L.lcr_host_pack_seq4(rs, off.ctypes.data, buf.ctypes.data, threads)
+    if rc:
+        raise LcrError(rc, "lcr_host_pack_seq4")
+    return buf, off
 
-    def __init__(self, reads, regions):
+
+class BatchView:
+    """An lcr_batch over numpy arrays (kept alive here).  seq4 = (packed bytes, offsets) from pack_seq4 hands the bases over in the
+    BAM record's 4-bit form instead of ASCII (the `seq` pointer is then NULL)."""
+
+    def __init__(self, reads, regions, seq4=None):
         self.reads = reads
         self.regions = np.ascontiguousarray(regions, dtype=abi.REGION_DTYPE)
-        self._keep = [np.ascontiguousarray(a) for a in (reads.pos, reads.flag, reads.mapq, reads.ts, reads.de, reads.seq_off, reads.cig_off, reads.seq, reads.qual, reads.cigar)]
+        names = ["pos", "flag", "mapq", "ts", "de", "seq_off", "cig_off", "qual", "cigar"] + ([] if seq4 is not None else ["seq"])
+        self._keep = [np.ascontiguousarray(getattr(reads, n)) for n in names]
         b = abi.Batch()
         b.n_regions = len(self.regions)
         b.n_reads = reads.n_reads
         b.regions = self.regions.ctypes.data
-        for name, a in zip(("pos", "flag", "mapq", "ts", "de", "seq_off", "cig_off", "seq", "qual", "cigar"), self._keep):
+        for name, a in zip(names, self._keep):
             setattr(b, name, a.ctypes.data)
+        if seq4 is not None:
+            s4, o4 = np.ascontiguousarray(seq4[0], dtype="u1"), np.ascontiguousarray(seq4[1], dtype="<u8")
+            self._keep += [s4, o4]
+            b.seq4, b.seq4_off = s4.ctypes.data, o4.ctypes.data
         self.c = b
 
     @property

@@ -321,3 +321,74 @@ def test_full_size_cfg5_against_golden():
         agree += max(a, m.sum() - a)
         total += m.sum()
     assert total > 50000 and agree / total > 0.9  # a sanity bound on the algorithm itself (0.926 here), not a parity claim
+
+
+def _pinned(nbytes):
+    import torch
+
+    t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+    _pinned.keep.append(t)
+    return t.numpy()
+
+
+_pinned.keep = []
+
+
+@pytest.mark.parametrize("preset,platform,chunk_mb", [("hifi-masseq", 0, "100000"), ("ont-cdna", 1, "100000"), ("hifi-masseq", 0, "1")])
+def test_bam_form_inputs_match_decoded_inputs(monkeypatch, preset, platform, chunk_mb):
+    """ABI 3: bases handed over in the BAM record's 4-bit form (expanded on the device) and, with LCR_FLAG_QUAL_ON_DEMAND, qualities
+    left in page-locked host memory and fetched at candidate sites only: the result is that of decoded ASCII inputs, whole and chunked."""
+    syn = host.Synthetic(seed=41 + platform, contig_len=200_000, n_contigs=2, platform=platform, depth=30.0, n_het=160, n_edit=30, both_strands=platform, n_threads=4)
+    refs = syn.reference.for_reads(syn.reads)
+    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", chunk_mb)
+    p = host.params_preset(preset, seed=6)
+    regions, _ = host.find_regions(syn.reads, p)
+    want = ob.run(p, host.BatchView(syn.reads, regions), refs, mode=0)
+    # (a) packed bases, pageable qualities (copied)
+    seq4 = host.pack_seq4(syn.reads)
+    assert len(seq4[0]) == int(((np.diff(syn.reads.seq_off.astype(np.int64)) + 1) // 2).sum())
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
+    got = eng.submit(host.BatchView(syn.reads, regions, seq4=seq4))
+    t_copy = eng.last_submit_timing()
+    eng.close()
+    helpers.compare_results(got, want, preset + "/seq4")
+    # (b) packed bases and on-demand qualities from pinned memory
+    pinned = host.ArrayReadSet.like(syn.reads, _pinned)
+    p2 = host.params_preset(preset, seed=6, flags=abi.LCR_FLAG_QUAL_ON_DEMAND)
+    eng = host.Engine(p2, device=0)
+    eng.set_references(refs)
+    got2 = eng.submit(host.BatchView(pinned, regions, seq4=host.pack_seq4(pinned, _pinned)))
+    t_dem = eng.last_submit_timing()
+    # (c) the flag with a pageable array falls back to the copy
+    got3 = eng.submit(host.BatchView(syn.reads, regions, seq4=seq4))
+    eng.close()
+    helpers.compare_results(got2, want, preset + "/seq4+on-demand")
+    helpers.compare_results(got3, want, preset + "/seq4+on-demand(pageable)")
+    n_bases = int(syn.reads.seq_off[-1])
+    # copied: half a byte per base + a byte per quality (+ tables); on demand: no bulk quality copy, but 32 bytes per fetched quality
+    assert n_bases * 1.5 < t_copy["h2d_bytes"] < n_bases * 1.8, (t_copy["h2d_bytes"], n_bases)
+    assert t_dem["h2d_bytes"] != t_copy["h2d_bytes"] and (t_dem["h2d_bytes"] - (t_copy["h2d_bytes"] - n_bases)) % 32 == 0
+    _pinned.keep.clear()
+
+
+def test_packed_bases_validation():
+    """seq4 without offsets, or with a span shorter than the read needs, is refused before anything is copied."""
+    import ctypes as C
+
+    syn = host.Synthetic(seed=3, contig_len=30_000, n_contigs=1, platform=0, depth=10.0, n_het=10, n_edit=2, both_strands=0, n_threads=2)
+    p = host.params_preset("hifi-masseq")
+    regions, _ = host.find_regions(syn.reads, p)
+    eng = host.Engine(p, device=0)
+    eng.set_references(syn.reference.for_reads(syn.reads))
+    s4, o4 = host.pack_seq4(syn.reads)
+    bad = host.BatchView(syn.reads, regions, seq4=(s4, o4))
+    bad.c.seq4_off = None
+    with pytest.raises(host.LcrError):
+        eng.submit(bad)
+    o_short = o4.copy()
+    o_short[1:] -= 1
+    with pytest.raises(host.LcrError):
+        eng.submit(host.BatchView(syn.reads, regions, seq4=(s4, o_short)))
+    eng.close()
+    assert C.sizeof(abi.Batch) == 8 + 13 * 8
