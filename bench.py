@@ -78,7 +78,7 @@ class ClockSampler:
                     self.samples.append((sm, mx, int(rs)))
                 except Exception:
                     pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.01)
 
     def start(self):
         if self.handles:
@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs (ncu launch lists): skip the end-to-end loop; the e2e keys are then null")
     ap.add_argument("--e2e-input", default="bam4", choices=["bam4", "bam4-ondemand", "ascii"],
                     help="host buffers of the end-to-end path: bam4 = 4-bit bases as the BAM record stores them + byte qualities, bam4-ondemand = qualities fetched from pinned memory by the kernels, ascii = decoded bases")
     args = ap.parse_args()
@@ -296,36 +297,50 @@ def main():
 
     gbuf = {}
 
-    def gather_results(cand_u8, hp_u8, ps_u8):
-        """The per-rank VCF records and (read, HP, PS) arrays go to rank 0 (device tensors in, padded to the largest rank):
-        one all_gather of the three sizes, one gather of the packed payload.  Buffers are reused across steps."""
-        n = torch.tensor([cand_u8.numel(), hp_u8.numel(), ps_u8.numel()], device=dev, dtype=torch.int64)
-        sizes = gbuf.setdefault("sizes", [torch.zeros_like(n) for _ in range(world)])
-        dist.all_gather(sizes, n)
-        tot = torch.stack(sizes).sum(dim=1).tolist()
-        mx = (int(max(tot)) + 255) // 256 * 256
-        if gbuf.get("cap", 0) < mx:
-            gbuf["cap"] = mx + mx // 8
-            gbuf["send"] = torch.empty(gbuf["cap"], dtype=torch.uint8, device=dev)
-            gbuf["recv"] = [torch.empty(gbuf["cap"], dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-        send = gbuf["send"][:mx]
-        a, b = cand_u8.numel(), cand_u8.numel() + hp_u8.numel()
-        send[:a].copy_(cand_u8)
+    def gather_results(cand_u8, hp_u8, ps_u8, setup=False):
+        """The per-rank VCF records and (read, HP, PS) arrays go to rank 0 (device tensors in): ONE gather of a fixed-capacity
+        payload whose first 24 bytes carry the three sizes.  The capacity (1.25 x the largest rank) comes from one exchange of
+        sizes before the timed region (`setup=True`); a step whose payload outgrew it is an error, never a silent truncation."""
+        sz = [cand_u8.numel(), hp_u8.numel(), ps_u8.numel()]
+        need = 24 + sum(sz)
+        if setup:
+            n = torch.tensor([need], device=dev, dtype=torch.int64)
+            allv = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(allv, n)
+            mx = max(int(v.item()) for v in allv)
+            cap = (mx + mx // 4 + 4095) // 4096 * 4096
+            if gbuf.get("cap", 0) < cap:
+                gbuf["cap"] = cap
+                gbuf["send"] = torch.zeros(cap, dtype=torch.uint8, device=dev)
+                gbuf["recv"] = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+                gbuf["hdr"] = torch.zeros(3, dtype=torch.int64).pin_memory()
+        if need > gbuf["cap"]:
+            raise RuntimeError(f"rank {rank}: gather payload {need} B exceeds the capacity {gbuf['cap']} B agreed before the timed region")
+        send = gbuf["send"]
+        gbuf["hdr"][:] = torch.tensor(sz, dtype=torch.int64)
+        send[:24].view(torch.int64).copy_(gbuf["hdr"], non_blocking=True)
+        a, b = 24 + sz[0], 24 + sz[0] + sz[1]
+        send[24:a].copy_(cand_u8)
         send[a:b].copy_(hp_u8)
-        send[b:b + ps_u8.numel()].copy_(ps_u8)
-        outl = [r[:mx] for r in gbuf["recv"]] if rank == 0 else None
-        dist.gather(send, outl, dst=0)
-        return sizes, outl
+        send[b:b + sz[2]].copy_(ps_u8)
+        dist.gather(send, gbuf["recv"], dst=0)
+        return gbuf["recv"]
+
+    def device_results(handle):
+        v = eng.device_view(handle)
+        cand_u8 = torch.as_tensor(_DevBuf(v.cand, v.n_cand * abi.CANDIDATE_DTYPE.itemsize), device=dev) if v.n_cand else torch.zeros(0, dtype=torch.uint8, device=dev)
+        hp_u8 = torch.as_tensor(_DevBuf(v.hp, v.n_reads), device=dev) if v.n_reads else torch.zeros(0, dtype=torch.uint8, device=dev)
+        ps_u8 = torch.as_tensor(_DevBuf(v.ps, 4 * v.n_reads), device=dev) if v.n_reads else torch.zeros(0, dtype=torch.uint8, device=dev)
+        return cand_u8, hp_u8, ps_u8
 
     # ---- device-resident timing ----
     handle = eng.upload(batch)
     for _ in range(args.warmup):
         eng.run_device(handle)
-    if world > 1:  # the first collective of each kind sets up its peer connections: not part of a step
+    if world > 1:  # before the timed region: peer connections of both collectives, and the payload capacity from the real sizes
         for _ in range(2):
-            z = torch.zeros(1024, dtype=torch.uint8, device=dev)
-            gather_results(z, z[:100], z[:400])
-        gbuf.clear()
+            gather_results(*device_results(handle), setup=True)
+        torch.cuda.synchronize()
     sampler = ClockSampler(list(range(world)) if rank == 0 else [])
     barrier()
     sampler.start()
@@ -345,17 +360,13 @@ def main():
         launches += t["kernel_launches"]
         attempts += t["run_attempts"]
         if world > 1:
-            v = eng.device_view(handle)
             g0.record()
-            cand_u8 = torch.as_tensor(_DevBuf(v.cand, v.n_cand * abi.CANDIDATE_DTYPE.itemsize), device=dev) if v.n_cand else torch.zeros(0, dtype=torch.uint8, device=dev)
-            hp_u8 = torch.as_tensor(_DevBuf(v.hp, v.n_reads), device=dev) if v.n_reads else torch.zeros(0, dtype=torch.uint8, device=dev)
-            ps_u8 = torch.as_tensor(_DevBuf(v.ps, 4 * v.n_reads), device=dev) if v.n_reads else torch.zeros(0, dtype=torch.uint8, device=dev)
-            sizes, outl = gather_results(cand_u8, hp_u8, ps_u8)
+            outl = gather_results(*device_results(handle))
             g1.record()
             torch.cuda.synchronize()
             gather_ms += g0.elapsed_time(g1)
             if rank == 0:
-                gathered_cands = sum(int(s[0].item()) for s in sizes) // abi.CANDIDATE_DTYPE.itemsize
+                gathered_cands = sum(int(o[:24].view(torch.int64)[0].item()) for o in outl) // abi.CANDIDATE_DTYPE.itemsize
     barrier()
     clocks = sampler.finish()
     dev_ms = acc["ms_total"] + gather_ms
@@ -364,24 +375,31 @@ def main():
     units = res.stats["n_aligned_bases"] + res.stats["nnz_phase"]
 
     # ---- end to end through lcr_submit with host buffers ----
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         r = eng_e2e.submit_raw(batch_e2e)
         eng_e2e.free_result(r)
     barrier()
     e2e_t0 = time.perf_counter()
     h2d = d2h = 0
-    for _ in range(args.steps):
+    for _ in range(0 if args.no_e2e else args.steps):
         flush_l2()
         raw = eng_e2e.submit_raw(batch_e2e)  # the reference-facing call: host buffers in, host results (lcr_result) out
         n_cand_last = raw.contents.n_cand  # the result is in host memory: a caller reads it in place
         if world > 1:
-            rr = host.ResultView(raw)
-            cand_u8 = torch.from_numpy(np.frombuffer(rr.cand.tobytes(), dtype=np.uint8).copy()).to(dev)
-            hp_u8 = torch.from_numpy(rr.hp.view(np.uint8).copy()).to(dev)
-            ps_u8 = torch.from_numpy(rr.ps.view(np.uint8).copy()).to(dev)
-            sizes, outl = gather_results(cand_u8, hp_u8, ps_u8)
+            # the call left its results in host memory; they travel to rank 0 over NCCL (staged through the device), and rank 0
+            # brings the valid part of every rank's payload back to pinned host memory, where it would write the VCF / tag the BAM
+            r0 = raw.contents
+            cand_u8 = torch.from_numpy(abi.as_array(r0.cand, "u1", r0.n_cand * abi.CANDIDATE_DTYPE.itemsize)).to(dev, non_blocking=True)
+            hp_u8 = torch.from_numpy(abi.as_array(r0.hp, "u1", r0.n_reads)).to(dev, non_blocking=True)
+            ps_u8 = torch.from_numpy(abi.as_array(r0.ps, "u1", 4 * r0.n_reads)).to(dev, non_blocking=True)
+            outl = gather_results(cand_u8, hp_u8, ps_u8)
             if rank == 0:
-                _ = [o.cpu() for o in outl]  # rank 0 writes the VCF / tags the BAM from host memory
+                torch.cuda.synchronize()
+                if "host" not in gbuf:
+                    gbuf["host"] = [torch.empty(gbuf["cap"], dtype=torch.uint8).pin_memory() for _ in range(world)]
+                for o, hbuf in zip(outl, gbuf["host"]):
+                    nb = 24 + int(o[:24].view(torch.int64).sum().item())
+                    hbuf[:nb].copy_(o[:nb], non_blocking=True)
             torch.cuda.synchronize()
         eng_e2e.free_result(raw)
         tt = eng_e2e.last_submit_timing()
@@ -443,7 +461,7 @@ def main():
                        "l2": "flushed between steps (512 MiB write)",
                        "sharding": "contigs dealt by LPT (shard.plan_shards); per step one NCCL gather of candidate records + per-read HP/PS to rank 0 inside the timed region" if world > 1 else "single GPU",
                        "reference_broadcast_ms": bcast_ms, "gather_ms_per_step": gather_ms_max / args.steps, "run_attempts_per_step": attempts / steps},
-            "e2e": {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps,
+            "e2e": {"value": None, "unit": UNIT, "skipped": "--no-e2e"} if args.no_e2e else {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps,
                     "input": {"bam4": "4-bit bases as the BAM record stores them, byte qualities, per-read tables: all copied from pinned memory",
                               "bam4-ondemand": "4-bit bases + per-read tables copied; qualities stay in pinned host memory and the kernels fetch the 32-byte sectors they need (counted in h2d_bytes_per_step)",
                               "ascii": "decoded ASCII bases + qualities copied"}[args.e2e_input]},

@@ -292,8 +292,9 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     LCR_DEBUG_CHECK(ctx, "enum_plan");
     TRY(cudaEventRecord(ctx->ev_fork, st));
     for (int i = 0; i < 4; ++i) TRY(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
-    for (int b = 0; b < LCR_ENUM_BINS; ++b) {
-        int e = lcr_launch_enum_search(b, pa, ctx->sm_count, ctx->side[b % 4]);
+    for (int b = 0, nl = 0; b < LCR_ENUM_BINS; ++b) {
+        if (!lcr_enum_bin_possible(b, db->max_region_slots)) continue;
+        int e = lcr_launch_enum_search(b, pa, ctx->sm_count, ctx->side[nl++ % 4]);
         if (e) { ctx->last_error = std::string("k_enum_search: ") + cudaGetErrorString((cudaError_t)e); ctx->sticky = LCR_ERR_CUDA; return ctx->sticky; }
         db->timing.kernel_launches += 1;
     }

@@ -97,5 +97,7 @@ int lcr_launch_phase_grid(const PhaseArgs &a, const uint32_t *big_list, uint32_t
 size_t lcr_phase_bcast_bytes();
 void lcr_launch_enum_plan(const PhaseArgs &a, uint32_t work_cap, int sm_count, cudaStream_t st);
 int lcr_launch_enum_search(int bin, const PhaseArgs &a, int sm_count, cudaStream_t st);
+/* false when no region of the batch can fall into the bin (its fragment class needs more reads than any region has) */
+bool lcr_enum_bin_possible(int bin, uint32_t max_region_reads);
 
 #endif

@@ -467,8 +467,14 @@ static size_t smem_bytes(uint32_t nf_cap, int ew, bool pre) { return (size_t)nf_
 template <int EW, int CPW, bool PRE>
 static int launch_shape(const PhaseArgs &a, int bin, uint32_t nf_cap, int grid, cudaStream_t st) {
     const size_t smem = smem_bytes(nf_cap, EW, PRE);
-    cudaError_t e = cudaFuncSetAttribute(k_enum_search<EW, CPW, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* per device: the attribute is set once per instantiation and size, not per launch */
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 8 || smem_set[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_enum_search<EW, CPW, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 8) smem_set[dev] = smem;
+    }
     k_enum_search<EW, CPW, PRE><<<grid, EW * 32, smem, st>>>(a, bin, nf_cap);
     return (int)cudaGetLastError();
 }
@@ -479,6 +485,11 @@ void lcr_launch_enum_plan(const PhaseArgs &a, uint32_t work_cap, int sm_count, c
 
 /* one persistent launch per (shape, class) bin; bins without work cost one ticket per CTA.  pre: regions with few fragments
    (class 0) of the 5+ site shapes keep the signed-term table in shared memory */
+bool lcr_enum_bin_possible(int bin, uint32_t max_region_reads) {
+    const int cls = bin % LCR_ENUM_CLASSES;
+    return cls == 0 || max_region_reads > CLASS_ROWS[cls - 1]; /* a region has at most as many fragments as reads */
+}
+
 int lcr_launch_enum_search(int bin, const PhaseArgs &a, int sm_count, cudaStream_t st) {
     const int shape = bin / LCR_ENUM_CLASSES, cls = bin % LCR_ENUM_CLASSES;
     const uint32_t nf_cap = CLASS_ROWS[cls];

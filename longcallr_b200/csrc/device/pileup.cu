@@ -2,17 +2,20 @@
  * pileup.cu — read filter, tile work items, fused pileup + site genotyping, candidate lists.
  *
  * Replaces, on the device:
- *   src/util.rs:636-668      read filter and fetch window             (k_slot_prep / k_slot_prep_w)
- *   src/util.rs:650-948      Profile::fill_data_into_freq_vec         (k_slot_prep: CIGAR walk + masks; k_pileup_tile: counts)
+ *   src/util.rs:636-668      read filter and fetch window             (k_read_span)
+ *   src/util.rs:650-948      Profile::fill_data_into_freq_vec         (k_read_walk: CIGAR walk + masks -> segments; k_pileup_tile: counts)
  *   src/util.rs:162-176      BaseFreq::get_two_major_alleles          (site_call)
- *   src/candidate.rs:75-463  filter cascade, genotype likelihood      (site_call, k_site_ll)
+ *   src/candidate.rs:75-463  filter cascade, genotype likelihood      (site_call<true> in k_pileup_tile, k_site_ll + site_call<false>)
  *   src/candidate.rs:465-526 dense-cluster filters                    (k_cand_ranges, k_cand_dense)
  *
- * Layout: reads are decomposed on the device into (read, tile) items and, per item, segments (runs of unmasked aligned
- * bases / deleted / intron positions on consecutive columns); one CTA owns one tile of LCR_TILE reference positions,
- * stages the reads of the tile as one-hot byte planes in shared memory and sums the columns with carry-save adders:
- * no atomics on the counters, no per-position record in HBM.  Only candidate sites (and, on request, the debug planes)
- * are written out.
+ * Layout: the reads of a batch are decomposed on the device into (read, tile) items and, per item, segments (runs of unmasked
+ * aligned bases / deleted / intron positions on consecutive columns of one tile of LCR_TILE reference positions).  The tile
+ * kernel is persistent and warp-specialised: producer warps stream the rows of a tile into shared memory with asynchronous
+ * copies (cp.async completing on mbarriers, a bulk copy for the tile's reference bytes), consumer warps count by difference
+ * from the reference (range updates for coverage, a byte-wise XOR against the reference for the bases, shared-memory atomics
+ * only for the ~1 % of bytes that differ).  No per-position record goes to HBM: only the sites that pass the count-based
+ * filters (and, on request, the debug planes) are written.  The whole stage is enqueued without a host round trip: sizes
+ * live in the device counter block (lcr_pipeline.h) and capacities are checked there.
  */
 #include <cub/cub.cuh>
 
@@ -571,29 +574,33 @@ __global__ void __launch_bounds__(128, 6) k_read_walk(PrepArgs a) {
 }
 
 /* ------------------------------------------------------------------------- *
- * Tile pileup, version 6: persistent, warp-specialised, bulk-async, reference-differential.
+ * Tile pileup: persistent, warp-specialised, asynchronous copies, reference-differential.
  *
- * k_pileup_tile runs CTAs of 8 consumer warps + 3 producer warps (2 CTAs per SM) over a dynamic list of tiles.
+ * k_pileup_tile runs CTAs of PT_CONS consumer threads + PT_PROD_WARPS producer warps (4 CTAs per SM by default) over a
+ * device-built list of tiles (dynamic tickets).
  *
- * Producers turn the items of a tile into batches of rows: for every item they issue 1-D bulk copies
- * (cp.async.bulk.shared::cluster.global, completion counted in bytes on an mbarrier) of the item's contiguous seq and
- * qual bytes and of its segment descriptors into a shared-memory stage, plus the tile's reference bytes with the first
- * batch, so no consumer ever waits on a global load.
+ * Producers turn the items (rows) of a tile into batches of up to 32 rows: producer warp 0 copies the contiguous seq bytes
+ * every row covers, 16 bytes per lane with cp.async.ca.shared.global, producer warp 1 the rows' segment descriptors, and both
+ * tie their copies to the stage's "full" mbarrier with cp.async.mbarrier.arrive.noinc; the tile's reference bytes come with
+ * the first batch as one 1-D bulk copy (cp.async.bulk.shared::cluster.global, byte count expected on the same mbarrier).
+ * Consumers release a stage through its "empty" mbarrier; no consumer ever waits on a global load of its own.
  *
  * Consumers count by difference from the reference.  Almost every aligned base equals the reference base, so a base
  * is not expanded into counters at all:
  *   - coverage of every (strand, transcript-strand) class, deletions and introns are range updates: +1 / -1 on a
  *     per-class difference array at the ends of each segment, prefix-summed once per tile;
- *   - one lane takes a 16-column block of an aligned segment and XORs the 16 read bytes with the 16 reference bytes
- *     of its columns with word-wide logic; blocks holding a byte that differs are appended (with a 16-bit mask of
- *     those bytes) to a short list;
+ *   - one lane takes a 16-column block of an aligned segment and XORs the 16 read bytes with the 16 compare bytes of its
+ *     columns (the reference byte, or 0x80 where the reference is no A/C/G/T) with word-wide logic; blocks holding a byte
+ *     that differs are appended (with a 16-bit mask of those bytes) to a short list;
  *   - a second pass takes the listed bytes (mismatches, lower-case and non-ACGT bytes: ~1 % of the bases) to
- *     per-column event counters with shared-memory atomics.
+ *     per-column event counters with shared-memory atomics (two 16-bit counters per word; tiles of more than 65535 rows
+ *     take the BIG instantiation with 32-bit counters).
  * Base qualities are not read here: the only count filter that needs them (candidate.rs:177-194) is evaluated by
  * k_site_ll, which reads the qualities of the surviving sites anyway.
  * At the end of the tile the per-column counters of util.rs:100-127 follow exactly from coverage minus events
- * (all integers), the count-based site filters run on the columns with a mismatch, and the surviving sites are
- * appended in column order to the tile's range of the pre-candidate list.  32-bit counters: any depth.
+ * (all integers); columns with any mismatch that pass a cheap depth / fraction prefilter are compacted, the count-based
+ * site filters (site_call<true>) run on those, and the surviving sites are appended in column order to the tile's range
+ * of the pre-candidate list (slots reserved PT_PRE_CHUNK at a time; unused slots are marked and skipped downstream).
  * ------------------------------------------------------------------------- */
 #ifdef LCR_TILE_PROF
 #define PROF_T(var) const long long var = clock64()
@@ -607,7 +614,6 @@ __global__ void __launch_bounds__(128, 6) k_read_walk(PrepArgs a) {
 #endif
 #define PT_PROD_WARPS 2                   /* producer warps: one per copied stream (seq bytes; segment descriptors + reference + row tables) */
 #define PT_THREADS (PT_CONS + 32 * PT_PROD_WARPS)
-#define PT_WORDS (LCR_TILE / 4)
 #define PT_ROW_BYTES_MAX 2048u            /* largest item span staged as one row (larger ones are cut into pieces by the producer) */
 #define PT_FLAG_FIRST 1u
 #define PT_FLAG_LAST 2u
@@ -680,48 +686,6 @@ __global__ void k_tile_desc(DescArgs a) {
     }
 }
 
-__device__ __forceinline__ uint32_t lop3_xor3(uint32_t x, uint32_t y, uint32_t z) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
-    return r;
-}
-__device__ __forceinline__ uint32_t lop3_maj(uint32_t x, uint32_t y, uint32_t z) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
-    return r;
-}
-/* carry-save adder: (hi, lo) = x + y + z per bit */
-#define CSA(hi, lo, x, y, z) do { const uint32_t x__ = (x), y__ = (y), z__ = (z); hi = lop3_maj(x__, y__, z__); lo = lop3_xor3(x__, y__, z__); } while (0)
-
-/* PTX prmt in its generic form: bit 3 of a selector nibble replicates the sign bit of the selected byte
-   (__byte_perm is specified to ignore that bit) */
-__device__ __forceinline__ uint32_t prmt_sign(uint32_t x) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
-    return r;
-}
-
-/* 4 read bases + 4 qualities (column order) -> plane bytes; ALLPASS: the caller has checked that every quality of the block is >= min_baseq */
-template <bool ALLPASS>
-__device__ __forceinline__ void onehot4(uint32_t s, uint32_t q, uint32_t minq4, uint32_t pass_allow, uint32_t fmask, uint32_t tsb, uint32_t &x, uint32_t &y) {
-    /* PRMT as an 8-entry table on the low three bits of each letter: A=..001 C=..011 T=..100 G=..111 */
-    const uint32_t t = s & 0x07070707u;
-    const uint32_t u = t | (t >> 4);
-    const uint32_t sel = __byte_perm(u, 0, 0x4420);
-    uint32_t oh = __byte_perm(0x02000100u, 0x04000008u, sel);
-    const uint32_t canon = __byte_perm(0x43004100u, 0x47000054u, sel);
-    const uint32_t d = (s & 0xdfdfdfdfu) ^ canon;                       /* non-zero byte: not exactly that letter (either case) */
-    const uint32_t nz = ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d;
-    oh &= ~prmt_sign(nz);
-    if (ALLPASS) x = oh * 17u; /* oh | oh << 4 */
-    else {
-        const uint32_t ge = ((((q & 0x7f7f7f7fu) | 0x80808080u) - minq4) | q);
-        const uint32_t pm = prmt_sign(ge) & pass_allow;
-        x = oh | ((oh << 4) & pm);
-    }
-    y = (oh & fmask) | tsb;
-}
-
 struct PileArgs {
     lcr_params P;
     const lcr_region *regions;
@@ -748,7 +712,6 @@ struct PileArgs {
 
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PT_CONS) : "memory"); }
 __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, %0;" ::"n"(32 * PT_PROD_WARPS) : "memory"); }
-__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -1505,8 +1468,14 @@ __global__ void k_cand_dense(lcr_params P, const LcrCounters *ctr, lcr_candidate
 template <bool BIG, int STAGES, int MINB>
 static cudaError_t launch_tile(const PileArgs &ka, int sms, uint32_t n_tiles, cudaStream_t st) {
     const size_t smem = PtLayout<BIG, STAGES>::bytes();
-    cudaError_t e = cudaFuncSetAttribute(k_pileup_tile<BIG, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static bool smem_set[8] = {false, false, false, false, false, false, false, false}; /* per device, once per instantiation */
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 8 || !smem_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_pileup_tile<BIG, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 8) smem_set[dev] = true;
+    }
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)(MINB * sms));
     k_pileup_tile<BIG, STAGES, MINB><<<grid, PT_THREADS, smem, st>>>(ka);
     return cudaGetLastError();
