@@ -433,7 +433,7 @@ def main():
 
         # the kernels / kernel groups of one step with their measured time (CUDA events on the library stream) and algorithmic bytes
         kernels = {
-            "k_pileup_tile": dict(ms=acc["ms_pileup_kernel"] / steps, bytes=pile_bytes / steps, what="tile pileup + count filters: 2 B per aligned base + 16 B per segment and item + 48 B and the reference bytes per tile"),
+            "k_pileup_tile": dict(ms=acc["ms_pileup_kernel"] / steps, bytes=pile_bytes / steps, what="tile pileup + count filters: 1 B per aligned base (the kernel reads no qualities) + 16 B per segment and item + 48 B and the reference bytes per tile + 72 B per surviving site"),
             "k_read_span+k_read_walk": dict(ms=acc["ms_prep"] / steps, bytes=None, what="read filter, reference spans, CIGAR walk into items / segments (latency-bound walks)"),
             "k_enum_search": dict(ms=acc["ms_enum"] / steps, bytes=None, what="2^n enumeration of regions with <= 10 sites (shared-memory resident)"),
             "k_phase": dict(ms=acc["ms_phase_kernel"] / steps, bytes=phase_bytes / steps, what="LD path, read / SNP assignment, rescue, phase sets (L2 resident): B_sweep x iterations"),

@@ -208,6 +208,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     pa.label = A.take<uint32_t>(cn); pa.rank = A.take<uint32_t>(cn);
     pa.work = A.take<uint32_t>(C.adj + cn + 1);
     pa.blk_q = A.take<long long>(cn); pa.blk_qflip = A.take<long long>(cn);
+    pa.piece_off = A.take<uint32_t>(cn + 1); pa.piece_col = A.take<uint32_t>(C.elems / LCR_COL_PIECE + cn + 1); pa.col_acc = A.take<long long>(5 * cn);
     pa.tag = A.take<int8_t>(sn); pa.best_tag = A.take<int8_t>(sn); pa.fp = A.take<uint8_t>(sn); pa.assign = A.take<uint8_t>(sn);
     pa.hp_key = A.take<uint32_t>(n_reads); pa.ps_key = A.take<unsigned long long>(n_reads);
     pa.es_base = A.take<uint32_t>(rn); pa.es_cfg = A.take<uint32_t>(C.enum_work); pa.es_prob = A.take<long long>(C.enum_work);
@@ -757,7 +758,7 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
     const LcrCounters &K = db->counters;
     if (getenv("LCR_TILE_PROF")) {
         fprintf(stderr, "tile prof (cycles, consumer warp 0 / producer warp 0, summed over CTAs):");
-        for (int i = 0; i < 10; ++i) fprintf(stderr, " [%d]=%llu", i, K.prof[i]);
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " [%d]=%llu", i, K.prof[i]);
         fprintf(stderr, " tiles=%u\n", K.n_tiles_done);
     }
     db->n_cand = K.n_cand;

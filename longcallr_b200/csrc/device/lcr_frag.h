@@ -45,6 +45,8 @@ struct FragArgs {
 };
 
 /* everything the phasing kernel reads and writes */
+#define LCR_COL_PIECE 128u
+
 struct PhaseArgs {
     lcr_params P;
     uint32_t n_regions;
@@ -67,6 +69,10 @@ struct PhaseArgs {
     int8_t *best_hap, *best_gen;
     uint32_t *label, *rank, *work; /* work: adj_total + n_cand entries per region segment */
     long long *blk_q, *blk_qflip;
+    /* cooperative kernel: the delta / eta sweep cuts every column into pieces of LCR_COL_PIECE covering reads so that a deep site does
+       not hold the whole grid at the barrier; piece_col[p] = site of piece p, piece_off[i] = first piece of site i, col_acc = 5 sums per site */
+    uint32_t *piece_off, *piece_col;
+    long long *col_acc;
     /* state, per fragment (global index) */
     int8_t *tag, *best_tag;
     uint8_t *fp, *assign;

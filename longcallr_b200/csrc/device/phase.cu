@@ -58,6 +58,9 @@ struct Ctx {
     long long *blk_q, *blk_qflip;
     const uint32_t *frag_slot, *frag_elem_off, *frag_links, *cover_off, *adj_off;
     long long *sh; /* shared scratch, PB/32 * 8 entries */
+    uint32_t *piece_off, *piece_col; /* grid teams: column pieces of the delta / eta sweep */
+    long long *col_acc;
+    uint32_t n_pieces;
     unsigned long long n_iters;
 };
 
@@ -140,14 +143,23 @@ __device__ __forceinline__ void col_L(const LcrDeviceTables &T, const ColFx &c, 
     D = L[3] + L[0] + L[2] + L[1];
 }
 
+#ifdef LCR_PHASE_PROF /* cycles of one thread of the cooperative grid per part of cross_optimize (prof[10..15] of the counter block) */
+#define GP_T(var) const long long var = clock64()
+#define GP_ADD(slot, t0, t1) do { if (x.grid && x.tid == 0) x.a.ctr->prof[slot] += (unsigned long long)((t1) - (t0)); } while (0)
+#else
+#define GP_T(var)
+#define GP_ADD(slot, t0, t1)
+#endif
+
 /* cal_overall_probability (phase.rs:257-276) */
 __device__ long long objective(Ctx &x) {
     long long s = 0;
-    /* eight lanes per fragment row */
-    for (uint32_t k = x.tid >> 3; k < x.nf; k += x.nthreads >> 3) {
+    /* eight lanes per fragment row (four on the cooperative grid: more rows in flight per pass) */
+    const uint32_t lsh = x.grid ? 2u : 3u, lpr = 1u << lsh;
+    for (uint32_t k = x.tid >> lsh; k < x.nf; k += x.nthreads >> lsh) {
         if (!x.fp[k] || x.tag[k] == 0) continue;
         const int sg = x.tag[k];
-        for (uint32_t e = x.frag_elem_off[k] + (x.tid & 7); e < x.frag_elem_off[k + 1]; e += 8) {
+        for (uint32_t e = x.frag_elem_off[k] + (x.tid & (lpr - 1)); e < x.frag_elem_off[k + 1]; e += lpr) {
             const char4 st = x.st[x.a.elem_snp[e]];
             if (!st.z) continue;
             const int8_t cell = x.a.elem_cell[e];
@@ -164,15 +176,17 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
     while (hg_increase | ht_increase) {
         x.n_iters++;
         int better = 0;
+        GP_T(g0);
         /* sigma sweep (phase.rs:823-868) */
-        /* eight lanes per fragment row; the row sum is shuffled together inside the group */
-        for (uint32_t k0 = 0; k0 < x.nf; k0 += x.nthreads >> 3) {
-            const uint32_t k = k0 + (x.tid >> 3);
+        /* eight lanes per fragment row (four on the cooperative grid); the row sum is shuffled together inside the group */
+        const uint32_t lsh = x.grid ? 2u : 3u, lpr = 1u << lsh;
+        for (uint32_t k0 = 0; k0 < x.nf; k0 += x.nthreads >> lsh) {
+            const uint32_t k = k0 + (x.tid >> lsh);
             long long diff = 0;
             int sg = 0;
             if (k < x.nf && x.fp[k]) sg = x.tag[k];
             if (sg != 0) {
-                for (uint32_t e = x.frag_elem_off[k] + (x.tid & 7); e < x.frag_elem_off[k + 1]; e += 8) {
+                for (uint32_t e = x.frag_elem_off[k] + (x.tid & (lpr - 1)); e < x.frag_elem_off[k + 1]; e += lpr) {
                     const char4 st = x.st[x.a.elem_snp[e]];
                     if (!st.z || st.y != 0) continue;
                     const int8_t cell = x.a.elem_cell[e];
@@ -182,32 +196,21 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             }
             diff += __shfl_xor_sync(0xffffffffu, diff, 1);
             diff += __shfl_xor_sync(0xffffffffu, diff, 2);
-            diff += __shfl_xor_sync(0xffffffffu, diff, 4);
+            if (lpr == 8) diff += __shfl_xor_sync(0xffffffffu, diff, 4);
             if (sg != 0 && diff < 0) {
-                if ((x.tid & 7) == 0) x.tag[k] = (int8_t)(-sg);
+                if ((x.tid & (lpr - 1)) == 0) x.tag[k] = (int8_t)(-sg);
                 better = 1;
             }
         }
+        GP_T(g1);
         better = tany(x, better);
+        GP_T(g2);
+        GP_ADD(10, g0, g1); GP_ADD(11, g1, g2);
         if (!better) ht_increase = false;
         else { ht_increase = true; hg_increase = true; }
         /* delta / eta sweep (phase.rs:872-958) */
         better = 0;
-        /* one warp per SNP: lanes stride the column, five shuffled sums */
-        for (uint32_t i = x.tid >> 5; i < x.n; i += x.nthreads >> 5) {
-            if (!x.st[i].z) continue;
-            if (keep_conserved && x.st[i].w) continue;
-            const int d = x.st[i].x, eta = x.st[i].y;
-            ColFx col(x);
-            for (uint32_t w = x.cover_off[i] + (x.tid & 31); w < x.cover_off[i + 1]; w += 32) {
-                const uint32_t k = x.a.cover_frag[w];
-                if (!x.fp[k] || x.tag[k] == 0) continue;
-                const int8_t cell = x.a.cover_cell[w];
-                col_add(x.T, col, x.tag[k], d, cell_p(cell), cell_q(cell));
-            }
-            col_reduce(col);
-            if ((x.tid & 31) != 0) continue;
-            if (!col.cov) continue;
+        auto decide = [&](uint32_t i, const ColFx &col, int d, int eta) {
             long long L[4], D;
             col_L(x.T, col, L, D);
             const long long L_old = eta == 0 ? L[0] : (eta == 1 ? L[2] : L[3]);
@@ -229,13 +232,89 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             x.st[i].x = (int8_t)nd;
             x.st[i].y = (int8_t)ne;
             if (L_new > L_old) better = 1;
+        };
+        if (x.grid) {
+            /* the whole GPU on one region: one warp per PIECE of a column (a deep site would otherwise hold every CTA at the barrier),
+               partial sums by 64-bit atomics (exact integers: any order), then one thread per site decides */
+            for (uint32_t p = x.tid >> 5; p < x.n_pieces; p += x.nthreads >> 5) {
+                const uint32_t i = x.piece_col[p];
+                const char4 sti = x.st[i];
+                if (!sti.z) continue;
+                if (keep_conserved && sti.w) continue;
+                const uint32_t w0 = x.cover_off[i] + (p - x.piece_off[i]) * LCR_COL_PIECE;
+                const uint32_t w1 = min(w0 + LCR_COL_PIECE, x.cover_off[i + 1]);
+                ColFx col(x);
+                /* the piece's four 32-element trips with their loads issued together (each is an L2 round trip);
+                   during phase() a haplotag is non-zero only on a fragment used for phasing (init_assignment, sign flips) */
+                uint32_t kk[LCR_COL_PIECE / 32];
+                int tg[LCR_COL_PIECE / 32];
+                int8_t cl[LCR_COL_PIECE / 32];
+#pragma unroll
+                for (uint32_t j = 0; j < LCR_COL_PIECE / 32; ++j) {
+                    const uint32_t w = w0 + (x.tid & 31) + 32 * j;
+                    kk[j] = w < w1 ? x.a.cover_frag[w] : NONE32;
+                    cl[j] = w < w1 ? x.a.cover_cell[w] : (int8_t)1;
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < LCR_COL_PIECE / 32; ++j) tg[j] = kk[j] != NONE32 ? (int)x.tag[kk[j]] : 0;
+#pragma unroll
+                for (uint32_t j = 0; j < LCR_COL_PIECE / 32; ++j)
+                    if (tg[j] != 0) col_add(x.T, col, tg[j], sti.x, cell_p(cl[j]), cell_q(cl[j]));
+                col_reduce(col);
+                if ((x.tid & 31) == 0 && col.cov) {
+                    unsigned long long *acc = reinterpret_cast<unsigned long long *>(x.col_acc + 5 * (size_t)i);
+                    atomicAdd(acc + 0, (unsigned long long)col.het_d);
+                    atomicAdd(acc + 1, (unsigned long long)col.het_nd);
+                    atomicAdd(acc + 2, (unsigned long long)col.homref);
+                    atomicAdd(acc + 3, (unsigned long long)col.homvar);
+                    atomicAdd(acc + 4, (unsigned long long)col.cov);
+                }
+            }
+            tsync(x);
+            for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
+                const char4 sti = x.st[i];
+                if (!sti.z) continue;
+                if (keep_conserved && sti.w) continue;
+                long long *acc = x.col_acc + 5 * (size_t)i;
+                ColFx col(x);
+                col.het_d = __ldcg(acc + 0); col.het_nd = __ldcg(acc + 1); col.homref = __ldcg(acc + 2); col.homvar = __ldcg(acc + 3);
+                col.cov = (uint32_t)__ldcg(acc + 4);
+                if (!col.cov) continue;
+                acc[0] = 0; acc[1] = 0; acc[2] = 0; acc[3] = 0; acc[4] = 0;
+                decide(i, col, sti.x, sti.y);
+            }
+        } else {
+            /* one warp per SNP: lanes stride the column, five shuffled sums */
+            for (uint32_t i = x.tid >> 5; i < x.n; i += x.nthreads >> 5) {
+                if (!x.st[i].z) continue;
+                if (keep_conserved && x.st[i].w) continue;
+                const int d = x.st[i].x, eta = x.st[i].y;
+                ColFx col(x);
+                for (uint32_t w = x.cover_off[i] + (x.tid & 31); w < x.cover_off[i + 1]; w += 32) {
+                    const uint32_t k = x.a.cover_frag[w];
+                    if (!x.fp[k] || x.tag[k] == 0) continue;
+                    const int8_t cell = x.a.cover_cell[w];
+                    col_add(x.T, col, x.tag[k], d, cell_p(cell), cell_q(cell));
+                }
+                col_reduce(col);
+                if ((x.tid & 31) != 0) continue;
+                if (!col.cov) continue;
+                decide(i, col, d, eta);
+            }
         }
+        GP_T(g3);
         better = tany(x, better);
+        GP_T(g4);
+        GP_ADD(12, g2, g3); GP_ADD(13, g3, g4);
         if (!better) hg_increase = false;
         else { hg_increase = true; ht_increase = true; }
         if (++num_iters > 20) break;
     }
-    return objective(x);
+    GP_T(g5);
+    const long long obj = objective(x);
+    GP_T(g6);
+    GP_ADD(14, g5, g6);
+    return obj;
 }
 
 __device__ void save_best(Ctx &x) {
@@ -346,6 +425,7 @@ __device__ void phase_ld(Ctx &x) {
     const uint32_t *adj_off = x.adj_off;
     const uint32_t adj_base = adj_off[0];
     const uint32_t *adj = x.a.adj;
+    GP_T(gb0);
     /* init_haplotypes_LD2 (phase.rs:600-652) */
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         x.st[i].x = uniform(x, LCR_RNG_INIT_DELTA, 0, i) < 0.5 ? 1 : -1;
@@ -354,48 +434,70 @@ __device__ void phase_ld(Ctx &x) {
         x.st[i].w = adj_off[i + 1] > adj_off[i] ? 1 : 0;
     }
     tsync(x);
-    if (x.tid == 0) {
-        /* Bfs from the first node of every block: a node takes its sign from the neighbour that was
-           dequeued first, which is the node that discovered it */
+    if (x.tid < 32) {
+        /* Bfs from the first node of every block: a node takes its sign from the neighbour that was dequeued first, which is
+           the node that discovered it.  One warp walks the queue in the serial order; the lanes look at 32 neighbours of the
+           dequeued node at a time and append the undiscovered ones in adjacency order (prefix counts of the ballot), which is
+           exactly what the one-by-one loop does because a node's adjacency list holds no duplicates. */
+        const uint32_t lane = x.tid, lt = (1u << lane) - 1u;
         uint32_t root0 = NONE32;
         uint32_t *queue = x.work;
         for (uint32_t r = 0; r < x.n; ++r) {
-            if (adj_off[r + 1] == adj_off[r] || x.label[r] != NONE32) continue;
+            if (adj_off[r + 1] == adj_off[r] || *(volatile uint32_t *)&x.label[r] != NONE32) continue;
             if (root0 == NONE32) root0 = r;
-            uint32_t qh = 0, qt = 0;
-            x.label[r] = r;
-            x.st[r].x = 1;
-            queue[qt++] = r;
+            uint32_t qh = 0, qt = 1;
+            if (lane == 0) { x.label[r] = r; x.st[r].x = 1; queue[0] = r; }
+            __syncwarp();
             while (qh < qt) {
-                const uint32_t nx = queue[qh++];
-                for (uint32_t w = adj_off[nx]; w < adj_off[nx + 1]; ++w) {
-                    const uint32_t v = adj[w] & 0x7fffffffu;
-                    if (x.label[v] != NONE32) continue;
-                    x.label[v] = r;
-                    x.st[v].x = (adj[w] & 0x80000000u) ? (int8_t)(-x.st[nx].x) : x.st[nx].x;
-                    queue[qt++] = v;
+                const uint32_t nx = *(volatile uint32_t *)&queue[qh++];
+                const int8_t sx = *(volatile int8_t *)&x.st[nx].x;
+                for (uint32_t w0 = adj_off[nx]; w0 < adj_off[nx + 1]; w0 += 32) {
+                    const uint32_t w = w0 + lane;
+                    const bool valid = w < adj_off[nx + 1];
+                    const uint32_t av = valid ? adj[w] : 0u, v = av & 0x7fffffffu;
+                    const bool fresh = valid && *(volatile uint32_t *)&x.label[v] == NONE32;
+                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                    if (fresh) {
+                        x.label[v] = r;
+                        x.st[v].x = (av & 0x80000000u) ? (int8_t)(-sx) : sx;
+                        queue[qt + __popc(m & lt)] = v;
+                    }
+                    qt += __popc(m);
+                    __syncwarp();
                 }
             }
         }
-        /* order of block[0..] for the last block: petgraph Dfs from its first node */
+        /* order of block[0..] for the last block: petgraph Dfs from its first node (pop; skip if seen; number it; push its unseen
+           neighbours in adjacency order) with the same 32-wide pushes */
         if (root0 != NONE32) {
             uint32_t *stack = x.work;
-            uint32_t sp = 0, order = 0;
-            stack[sp++] = root0;
+            uint32_t sp = 1, order = 0;
+            if (lane == 0) stack[0] = root0;
+            __syncwarp();
             while (sp) {
-                const uint32_t node = stack[--sp];
-                if (x.rank[node]) continue;
-                x.rank[node] = ++order;
-                for (uint32_t w = adj_off[node]; w < adj_off[node + 1]; ++w) {
-                    const uint32_t v = adj[w] & 0x7fffffffu;
-                    if (!x.rank[v]) stack[sp++] = v;
+                const uint32_t node = *(volatile uint32_t *)&stack[--sp];
+                if (*(volatile uint32_t *)&x.rank[node]) continue;
+                ++order;
+                if (lane == 0) x.rank[node] = order;
+                __syncwarp();
+                for (uint32_t w0 = adj_off[node]; w0 < adj_off[node + 1]; w0 += 32) {
+                    const uint32_t w = w0 + lane;
+                    const bool valid = w < adj_off[node + 1];
+                    const uint32_t v = valid ? (adj[w] & 0x7fffffffu) : 0u;
+                    const bool push = valid && !*(volatile uint32_t *)&x.rank[v];
+                    const uint32_t m = __ballot_sync(0xffffffffu, push);
+                    if (push) stack[sp + __popc(m & lt)] = v;
+                    sp += __popc(m);
+                    __syncwarp();
                 }
             }
         }
-        x.bc->root0 = root0;
+        if (lane == 0) x.bc->root0 = root0;
         (void)adj_base;
     }
     tsync(x);
+    GP_T(gb1);
+    GP_ADD(9, gb0, gb1);
     const uint32_t root0 = *(volatile uint32_t *)&x.bc->root0;
     init_genotype(x);
     init_assignment(x, 0);
@@ -403,7 +505,10 @@ __device__ void phase_ld(Ctx &x) {
     long long best = cross_optimize(x, true, false);
     save_best(x);
     load_best(x);
+    GP_T(gb2);
     long long prob = cross_optimize_by_block(x, root0);
+    GP_T(gb3);
+    GP_ADD(8, gb2, gb3);
     if (prob > best) { best = prob; save_best(x); }
     load_best(x);
     for (uint32_t t = 0; t <= x.n / 4; ++t) {
@@ -684,6 +789,30 @@ __device__ void run_region(Ctx &x) {
     x.n_iters = 0;
     x.epoch_any = 0;
     x.epoch_sum = 0;
+    x.n_pieces = 0;
+    if (x.grid) { /* column pieces of the delta / eta sweep: offsets by one warp (a few thousand sites), the list by everybody */
+        x.piece_off = a.piece_off + x.cb; x.piece_col = a.piece_col; x.col_acc = a.col_acc + 5 * (size_t)x.cb;
+        if (x.tid < 32) {
+            uint32_t run = 0;
+            for (uint32_t i0 = 0; i0 < x.n; i0 += 32) {
+                const uint32_t i = i0 + x.tid;
+                const uint32_t np = i < x.n ? (x.cover_off[i + 1] - x.cover_off[i] + LCR_COL_PIECE - 1) / LCR_COL_PIECE : 0u;
+                uint32_t incl = np;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)x.tid >= o) incl += v;
+                }
+                if (i < x.n) x.piece_off[i] = run + incl - np;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (x.tid == 0) x.piece_off[x.n] = run;
+        }
+        for (uint32_t i = x.tid; i < 5 * x.n; i += x.nthreads) x.col_acc[i] = 0;
+        tsync(x);
+        x.n_pieces = __ldcg(&x.piece_off[x.n]);
+        for (uint32_t i = x.tid; i < x.n; i += x.nthreads)
+            for (uint32_t p = __ldcg(&x.piece_off[i]); p < __ldcg(&x.piece_off[i + 1]); ++p) x.piece_col[p] = i;
+    }
 
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
         x.st[i].x = 0;
@@ -699,8 +828,11 @@ __device__ void run_region(Ctx &x) {
     tsync(x);
     uint64_t n_calls;
     bool counted_elsewhere = false;
+    GP_T(gr0);
     if (x.n <= a.P.max_enum_snps) { counted_elsewhere = phase_enum(x); n_calls = 1ull << x.n; }
     else { phase_ld(x); n_calls = 1ull + 2ull * (x.n / 4 + 1); }
+    GP_T(gr1);
+    GP_ADD(7, gr0, gr1);
     for (uint32_t i = x.tid; i < x.n; i += x.nthreads) { x.c[i].haplotype = x.st[i].x; x.c[i].genotype = x.st[i].y; }
     tsync(x);
     /* thread.rs:168-201 */
@@ -762,7 +894,10 @@ __global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, const uint32_t 
         if (x.tid == 0) { TeamBcast z{}; *gbc = z; }
         cg::this_grid().sync();
         x.reg = reg;
+        GP_T(gq0);
         run_region(x);
+        GP_T(gq1);
+        GP_ADD(6, gq0, gq1);
         cg::this_grid().sync();
     }
 }
