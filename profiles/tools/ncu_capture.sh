@@ -3,7 +3,7 @@
 #   profiles/tools/ncu_capture.sh <tag> <workload> <kernel regex> [skip]
 # writes gpurun_out/<tag>.ncu-rep (kept small: one launch), <tag>_details.txt (section pages) and <tag>_raw.csv (all metrics)
 tag=$1; wl=$2; rx=$3; skip=${4:-1}
-ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o gpurun_out/$tag \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:$rx -s $skip -c 1 -f -o gpurun_out/$tag \
     python bench.py --workload $wl --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${tag}.log 2>&1
 ncu -i gpurun_out/$tag.ncu-rep --page details > gpurun_out/${tag}_details.txt 2>/dev/null
 ncu -i gpurun_out/$tag.ncu-rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
