@@ -1331,11 +1331,18 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
         for (uint32_t idx = lane; idx < n_items; idx += 32) {
             const uint4 it = __ldg(reinterpret_cast<const uint4 *>(a.items + it0 + idx));
             const uint32_t ns = it.y >> 16, seg0 = it.z;
-            for (uint32_t k = 0; k < ns; ++k) {
+            /* the row's segments are in column order and no two cover the same column: the one that can hold the site's column is
+               the last that starts at or before it (binary search: ONT rows carry tens of segments) */
+            uint32_t lo = 0, hi = ns;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t scol_mid = __ldg(reinterpret_cast<const uint32_t *>(a.segs + seg0 + mid) + 3) & 0xffffu;
+                if (scol_mid <= colr) lo = mid + 1; else hi = mid;
+            }
+            for (uint32_t k = lo - 1; lo != 0;) {
                 const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.segs + seg0 + k));
                 const uint32_t scol = raw.w & 0xffffu, slen = raw.w >> 16;
-                if (scol > colr) break;
-                if (colr >= scol + slen) continue;
+                if (colr >= scol + slen) break;
                 if ((raw.z & 3u) == SEG_M) {
                     const uint64_t sp = (((uint64_t)raw.y << 32) | raw.x) + (colr - scol);
                     const uint8_t b = a.seq[sp];
