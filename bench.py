@@ -223,6 +223,18 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one rank per GPU: run (and first-touch the pinned staging buffers) on the CPUs next to that GPU, as `numactl` per rank would
+    numa = "unbound"
+    all_cpus = os.sched_getaffinity(0)
+    if not os.environ.get("LCR_NO_CPU_AFFINITY"):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = f"{len(os.sched_getaffinity(0))} CPUs next to GPU {local_rank} (nvmlDeviceSetCpuAffinity)"
+        except Exception as e:  # not fatal: the run is only slower
+            numa = f"unbound ({type(e).__name__})"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -461,7 +473,7 @@ def main():
                        "l2": "flushed between steps (512 MiB write)",
                        "sharding": "contigs dealt by LPT (shard.plan_shards); per step one NCCL gather of candidate records + per-read HP/PS to rank 0 inside the timed region" if world > 1 else "single GPU",
                        "reference_broadcast_ms": bcast_ms, "gather_ms_per_step": gather_ms_max / args.steps, "run_attempts_per_step": attempts / steps},
-            "e2e": {"value": None, "unit": UNIT, "skipped": "--no-e2e"} if args.no_e2e else {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps,
+            "e2e": {"value": None, "unit": UNIT, "skipped": "--no-e2e"} if args.no_e2e else {"value": total_units * args.steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps, "cpu_affinity": numa,
                     "input": {"bam4": "4-bit bases as the BAM record stores them, byte qualities, per-read tables: all copied from pinned memory",
                               "bam4-ondemand": "4-bit bases + per-read tables copied; qualities stay in pinned host memory and the kernels fetch the 32-byte sectors they need (counted in h2d_bytes_per_step)",
                               "ascii": "decoded ASCII bases + qualities copied"}[args.e2e_input]},
@@ -484,6 +496,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_binding as ob
 
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core back
             cores = os.cpu_count() or 1
             n_sample = bounded_sample(ob, host, p, syn, regions, refs, cores, budget_s=15.0)
             cb = host.BatchView(syn.reads, regions[:n_sample])

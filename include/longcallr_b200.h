@@ -36,7 +36,8 @@ typedef enum lcr_status {
     LCR_ERR_BAD_CIGAR = -5,     /* reference: panic "unknown cigar operation" util.rs:944, fragment.rs:191 */
     LCR_ERR_NO_REFERENCE = -6,  /* region on a contig never given to lcr_set_reference (thread.rs:79 unwrap) */
     LCR_ERR_BASEQ_ZERO = -7,    /* base quality 0 at a phase site: reference panics on NaN, phase.rs:307 */
-    LCR_ERR_INTERNAL = -8       /* a device-side invariant did not hold (a bug here, not in the input) */
+    LCR_ERR_INTERNAL = -8,      /* a device-side invariant did not hold (a bug here, not in the input) */
+    LCR_REGION_NO_EXON = 1      /* region_status only, not an error: --exon-only and no exon of the region's genes (thread.rs:88-91 returns early) */
 } lcr_status;
 
 /* Scalar parameters of the worker, src/thread.rs:17-51; defaults per preset in
@@ -111,6 +112,11 @@ typedef struct lcr_batch {
        used instead of seq (which may then be NULL) and expanded to the same ASCII letters on the device: half the bytes over the bus. */
     const uint8_t *seq4;
     const uint64_t *seq4_off; /* [n_reads+1] */
+    /* --exon-only (candidate.rs:80-89, thread.rs:80-91): the exon (CDS) intervals of the genes of every region, as parse_annotation
+       keeps them (util.rs:435-439): start 1-based inclusive, stop = end + 1, any order, overlaps allowed.  A position is a candidate only
+       if some interval holds it; a region without intervals is skipped (region_status LCR_REGION_NO_EXON).  NULL exon_off: no mask. */
+    const uint32_t *exon_off; /* [n_regions+1] offsets into exon_iv, in intervals */
+    const uint32_t *exon_iv;  /* [2 * exon_off[n_regions]] start, stop pairs */
 } lcr_batch;
 
 /* candidate flags (snp.rs:66-84) */

@@ -18,6 +18,7 @@ LCR_ERR_BAD_CIGAR = -5
 LCR_ERR_NO_REFERENCE = -6
 LCR_ERR_BASEQ_ZERO = -7
 LCR_ERR_INTERNAL = -8
+LCR_REGION_NO_EXON = 1
 
 LCR_FLAG_EMIT_PLANES = 1
 LCR_FLAG_SKIP_PHASING = 2
@@ -99,6 +100,8 @@ class Batch(C.Structure):
         ("cigar", C.c_void_p),
         ("seq4", C.c_void_p),
         ("seq4_off", C.c_void_p),
+        ("exon_off", C.c_void_p),
+        ("exon_iv", C.c_void_p),
     ]
 
 

@@ -498,6 +498,7 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     } swap_guard(ctx, async);
     if (ctx->sticky) return ctx->sticky;
     if (b->n_regions && !b->regions) return LCR_ERR_INVALID_ARG;
+    if (b->exon_off && b->n_regions && b->exon_off[b->n_regions] > b->exon_off[0] && !b->exon_iv) return LCR_ERR_INVALID_ARG;
     if (b->n_reads && (!b->pos || !b->flag || !b->mapq || !b->ts || !b->de || !b->seq_off || !b->cig_off)) return LCR_ERR_INVALID_ARG;
     /* the kernels index the pools with these offsets: they must be non-decreasing and the pools present */
     const uint64_t n_bases = b->n_reads ? b->seq_off[b->n_reads] : 0, n_cig = b->n_reads ? b->cig_off[b->n_reads] : 0;
@@ -516,6 +517,7 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     if (!db) return LCR_ERR_OOM;
     db->ev_meta = nullptr; db->ev_seq = nullptr; db->seq_wait_pending = false;
     db->seq4 = nullptr; db->seq4_off = nullptr; db->seq4_pending = false;
+    db->exon_off = nullptr; db->exon_iv = nullptr;
     db->n_regions = b->n_regions;
     db->n_reads = b->n_reads;
     db->ran = false;
@@ -533,6 +535,8 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         if (g.end < g.start || g.start < 1 || g.read_end < g.read_begin || g.read_end > b->n_reads) stt = LCR_ERR_INVALID_ARG;
         else if (g.tid < 0 || (size_t)g.tid >= ctx->d_ref.size() || !ctx->d_ref[g.tid]) stt = LCR_ERR_NO_REFERENCE;
         else if ((uint64_t)g.end - 1 > ctx->ref_len[g.tid]) stt = LCR_ERR_INVALID_ARG;
+        else if (b->exon_off && b->exon_off[r + 1] < b->exon_off[r]) stt = LCR_ERR_INVALID_ARG;
+        else if (b->exon_off && b->exon_off[r + 1] == b->exon_off[r]) stt = LCR_REGION_NO_EXON; /* thread.rs:88-91: the region is skipped */
         db->extra.h_status0[r] = stt;
         const uint64_t len = stt ? 0 : (uint64_t)(g.end - g.start);
         const uint32_t nreads = stt ? 0 : g.read_end - g.read_begin;
@@ -585,7 +589,8 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
                pin_de = !b->n_reads || host_is_pinned(b->de), pin_cig = !n_cig || host_is_pinned(b->cigar), pin_s4off = !packed || (host_is_pinned(b->seq4_off) && b->seq4_off[0] == 0);
     {
         size_t need = 4 * (slot_off.size() + slot_region.size() + tile_base.size() + tile_region.size() + big_list.size() + db->extra.h_status0.size()) + 8 * pos_off.size() +
-                      sizeof(lcr_region) * (size_t)b->n_regions + 64 * 16;
+                      sizeof(lcr_region) * (size_t)b->n_regions + 64 * 16 +
+                      (b->exon_off ? 4 * ((size_t)b->n_regions + 1) + 8 * (size_t)(b->exon_off[b->n_regions] - b->exon_off[0]) + 128 : 0);
         const size_t nr = b->n_reads;
         need += (pin_soff ? 0 : 8 * (nr + 1)) + (pin_coff ? 0 : 8 * (nr + 1)) + (pin_pos ? 0 : 4 * nr) + (pin_flag ? 0 : 2 * nr) + (pin_mapq ? 0 : nr) + (pin_ts ? 0 : nr) + (pin_de ? 0 : 4 * nr) +
                 (pin_s4off ? 0 : 8 * (nr + 1)) + ((pin_cig || n_cig * 4 > (64ull << 20)) ? 0 : 4 * (size_t)n_cig);
@@ -604,6 +609,27 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     UPS(status0, (const int32_t *)db->extra.h_status0.data(), db->extra.h_status0.size());
     UPS(big_list, (const uint32_t *)big_list.data(), big_list.size());
     UPS(regions, b->regions, b->n_regions);
+    if (b->exon_off && !rc) {
+        /* --exon-only: per region the union of its intervals, sorted by start: membership of a position is one binary search on the device
+           (the reference asks an interval tree whether anything overlaps [pos + 1, pos + 2): the same set of positions) */
+        std::vector<uint32_t> eoff((size_t)b->n_regions + 1, 0);
+        std::vector<uint2> eiv;
+        std::vector<std::pair<uint32_t, uint32_t>> tmp;
+        for (uint32_t r = 0; r < b->n_regions; ++r) {
+            tmp.clear();
+            if (db->extra.h_status0[r] == 0)
+                for (uint32_t e = b->exon_off[r]; e < b->exon_off[r + 1]; ++e)
+                    if (b->exon_iv[2 * e + 1] > b->exon_iv[2 * e]) tmp.emplace_back(b->exon_iv[2 * e], b->exon_iv[2 * e + 1]);
+            std::sort(tmp.begin(), tmp.end());
+            for (const auto &iv : tmp) {
+                if (eiv.size() > eoff[r] && iv.first <= eiv.back().y) eiv.back().y = std::max(eiv.back().y, iv.second);
+                else eiv.push_back(make_uint2(iv.first, iv.second));
+            }
+            eoff[r + 1] = (uint32_t)eiv.size();
+        }
+        rc = h2d(ctx, &db->exon_off, static_cast<const uint32_t *>(stage_copy(X, eoff.data(), 4 * eoff.size())), eoff.size(), &bytes);
+        if (!rc) rc = h2d(ctx, &db->exon_iv, static_cast<const uint2 *>(stage_copy(X, eiv.data(), 8 * eiv.size())), eiv.size(), &bytes);
+    }
     if (b->n_reads) {
         if (pin_soff) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); } else { UPS(seq_off, b->seq_off, (size_t)b->n_reads + 1); }
         if (pin_coff) { UP(cig_off, b->cig_off, (size_t)b->n_reads + 1); } else { UPS(cig_off, b->cig_off, (size_t)b->n_reads + 1); }
@@ -921,7 +947,7 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     DFREE(db->regions); DFREE(db->pos); DFREE(db->flag); DFREE(db->mapq); DFREE(db->ts); DFREE(db->de);
     DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); if (db->qual_on_host) db->qual = nullptr; DFREE(db->qual); DFREE(db->cigar);
     DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
-    DFREE(db->seq4); DFREE(db->seq4_off);
+    DFREE(db->seq4); DFREE(db->seq4_off); DFREE(db->exon_off); DFREE(db->exon_iv);
     cudaStreamSynchronize(ctx->stream);
     if (db->ev_seq) { cudaEventSynchronize(db->ev_seq); cudaEventDestroy(db->ev_seq); }
     stage_give_back(ctx, db->extra); /* after the copies out of it have completed */
@@ -1037,6 +1063,7 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
         v.seq_off = ck.seq_off.data(); v.cig_off = ck.cig_off.data();
         v.seq = batch->seq ? batch->seq + sb : nullptr; v.qual = batch->qual ? batch->qual + sb : nullptr;
         v.seq4 = batch->seq4; v.seq4_off = batch->seq4 && batch->seq4_off ? batch->seq4_off + ck.read_lo : nullptr; /* absolute offsets: upload_impl rebases */
+        v.exon_off = batch->exon_off ? batch->exon_off + ck.r0 : nullptr; v.exon_iv = batch->exon_iv; /* absolute interval offsets */
         v.cigar = batch->cigar ? batch->cigar + cb : nullptr;
     }
 

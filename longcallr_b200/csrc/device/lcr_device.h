@@ -103,6 +103,9 @@ struct lcr_device_batch {
     uint64_t *seq_off, *cig_off;
     uint8_t *seq, *qual;
     bool qual_on_host;     /* LCR_FLAG_QUAL_ON_DEMAND: `qual` is the device alias of the caller's page-locked array, not a copy */
+    /* --exon-only mask (lcr_batch.exon_off / exon_iv): per region the union of its intervals, sorted, as (start, stop) pairs; null = no mask */
+    uint32_t *exon_off;
+    uint2 *exon_iv;
     uint32_t *cigar;
     /* derived on the host at upload: cheap prefix sums over region lengths / read ranges */
     uint32_t *slot_off;    /* [n_regions+1] */

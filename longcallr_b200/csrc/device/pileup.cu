@@ -629,7 +629,8 @@ struct __align__(16) LcrTileDesc { /* 48 B, one per tile (k_tile_desc) */
     const uint8_t *ref;     /* reference base of column 0 */
     uint64_t pos_g;         /* index of column 0 in the debug planes */
     uint32_t it0, n_items;  /* items of the tile */
-    uint32_t reserved[2];
+    uint32_t pos1;          /* 1-based reference position of column 0 */
+    uint32_t reserved;
     uint32_t reg, npos;
     uint32_t full_n;        /* introns covering the whole tile */
     int32_t status;         /* of the region */
@@ -662,7 +663,7 @@ __global__ void k_tile_desc(DescArgs a) {
     d.ref = d.status == 0 ? a.ref_table[R.tid] + ((int64_t)R.start - 1) + tile_start : nullptr;
     d.pos_g = a.pos_off[reg] + (uint64_t)tile_start;
     d.it0 = a.tile_off[tile]; d.n_items = a.tile_cursor[tile];
-    d.reserved[0] = 0; d.reserved[1] = 0;
+    d.pos1 = (uint32_t)((int64_t)R.start + tile_start); d.reserved = 0;
     d.reg = reg; d.npos = (uint32_t)(tile_end - tile_start);
     d.full_n = a.tile_full_n[tile];
     a.desc[tile] = d;
@@ -702,6 +703,8 @@ struct PileArgs {
     LcrCounters *ctr;
     lcr_stats *stats;
     uint32_t *pl_acgt, *pl_fwd, *pl_d, *pl_n, *pl_ts; /* debug planes or null */
+    const uint32_t *exon_off;    /* --exon-only: per region the sorted union of its exon intervals, or null */
+    const uint2 *exon_iv;
     PreCand *pre;
     uint32_t pre_cap;
     uint2 *tile_pre;             /* per tile: first pre-candidate and count */
@@ -1242,7 +1245,15 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
             uint8_t rb;
             load_site(colr, sc, rb);
             lcr_candidate dummy;
-            if (site_call<true>(a.P, *a.tables, sc, rb, dummy)) atomicOr(&s_bitmap[colr >> 5], 1u << (colr & 31u));
+            bool ok = true;
+            if (a.exon_off) { /* candidate.rs:80-89: only positions inside an exon of the region's genes are looked at */
+                const uint32_t pos1 = D.pos1 + colr;
+                uint32_t lo = a.exon_off[D.reg], hi = a.exon_off[D.reg + 1];
+                const uint32_t first = lo;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.exon_iv[mid].x <= pos1) lo = mid + 1; else hi = mid; }
+                ok = lo > first && pos1 < a.exon_iv[lo - 1].y;
+            }
+            if (ok && site_call<true>(a.P, *a.tables, sc, rb, dummy)) atomicOr(&s_bitmap[colr >> 5], 1u << (colr & 31u));
         }
         cons_bar();
         /* (c) a contiguous range of the pre-candidate list for the tile, sub-allocated from a chunk the CTA reserves with one global atomic */
@@ -1584,6 +1595,7 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     ka.regions = db->regions;
     ka.tile_base = db->tile_base; ka.tile_region = db->tile_region;
     ka.seq = db->seq; ka.qual = db->qual;
+    ka.exon_off = db->exon_off; ka.exon_iv = db->exon_iv;
     ka.ref_table = ctx->d_ref_table;
     ka.desc = desc; ka.items = items; ka.segs = segs;
     ka.tables = ctx->d_tables;

@@ -313,9 +313,10 @@ def pack_seq4(reads, alloc=None, threads=8):
 
 class BatchView:
     """An lcr_batch over numpy arrays (kept alive here).  seq4 = (packed bytes, offsets) from pack_seq4 hands the bases over in the
-    BAM record's 4-bit form instead of ASCII (the `seq` pointer is then NULL)."""
+    BAM record's 4-bit form instead of ASCII (the `seq` pointer is then NULL); exons = per-region lists of (start, stop) turns on the
+    --exon-only mask."""
 
-    def __init__(self, reads, regions, seq4=None):
+    def __init__(self, reads, regions, seq4=None, exons=None):
         self.reads = reads
         self.regions = np.ascontiguousarray(regions, dtype=abi.REGION_DTYPE)
         names = ["pos", "flag", "mapq", "ts", "de", "seq_off", "cig_off", "qual", "cigar"] + ([] if seq4 is not None else ["seq"])
@@ -330,6 +331,12 @@ class BatchView:
             s4, o4 = np.ascontiguousarray(seq4[0], dtype="u1"), np.ascontiguousarray(seq4[1], dtype="<u8")
             self._keep += [s4, o4]
             b.seq4, b.seq4_off = s4.ctypes.data, o4.ctypes.data
+        if exons is not None:  # --exon-only: one list of (start, stop) per region, 1-based, stop exclusive (util.rs:435-439)
+            off = np.zeros(len(self.regions) + 1, dtype="<u4")
+            off[1:] = np.cumsum([len(e) for e in exons])
+            iv = np.array([x for e in exons for pair in e for x in pair], dtype="<u4").reshape(-1)
+            self._keep += [off, iv]
+            b.exon_off, b.exon_iv = off.ctypes.data, (iv.ctypes.data if len(iv) else None)
         self.c = b
 
     @property

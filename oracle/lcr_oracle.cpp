@@ -239,6 +239,7 @@ struct Worker {
     const uint8_t *ref_seq;
     uint64_t ref_len;
     uint64_t region_key;
+    uint32_t region_index; /* of reg in the batch (exon intervals are per region) */
     RegionOut &out;
 
     std::vector<Cand> &cands;
@@ -249,8 +250,8 @@ struct Worker {
 
     Worker(const lcr_params &p, const lcr_batch &b, const lcr_luts &t, const lcr_region &r, const uint8_t *rs,
            uint64_t rl, RegionOut &o)
-        : P(p), B(b), T(t), reg(r), ref_seq(rs), ref_len(rl), region_key(lcr_region_key(r.tid, r.start)), out(o),
-          cands(o.cands), frags(o.frags) {}
+        : P(p), B(b), T(t), reg(r), ref_seq(rs), ref_len(rl), region_key(lcr_region_key(r.tid, r.start)),
+          region_index((uint32_t)(&r - b.regions)), out(o), cands(o.cands), frags(o.frags) {}
 
     /* ---- P0: read filter (util.rs:652-668) and htslib fetch window (util.rs:636-638) */
     bool read_pass(uint32_t i) const {
@@ -440,6 +441,12 @@ struct Worker {
         int64_t position = (int64_t)reg.start - 1;
         for (size_t bfidx = 0; bfidx < pileup.size(); ++bfidx, ++position) {
             const BaseFreq &bf = pileup[bfidx];
+            if (B.exon_off) { /* --exon-only (candidate.rs:80-89): Lapper::find(position + 1, position + 2) over the region's exon intervals */
+                bool hit = false;
+                for (uint32_t e = B.exon_off[region_index]; e < B.exon_off[region_index + 1] && !hit; ++e)
+                    hit = (int64_t)B.exon_iv[2 * e] < position + 2 && (int64_t)B.exon_iv[2 * e + 1] > position + 1;
+                if (!hit) continue;
+            }
             const uint32_t total = bf.a + bf.c + bf.g + bf.t;
             if (total < P.min_depth || total > P.max_depth) continue;
             uint8_t allele1, allele2;
@@ -1552,6 +1559,7 @@ int lcr_oracle_run(const lcr_params *params, const lcr_batch *batch, const uint8
             RegionOut &ro = routs[r];
             if (reg.tid < 0 || reg.tid >= n_tids || !ref_seqs[reg.tid]) { ro.status = LCR_ERR_NO_REFERENCE; continue; }
             if (reg.end < reg.start || reg.start < 1 || reg.read_end < reg.read_begin || reg.read_end > batch->n_reads) { ro.status = LCR_ERR_INVALID_ARG; continue; }
+            if (batch->exon_off && batch->exon_off[r + 1] == batch->exon_off[r]) { ro.status = LCR_REGION_NO_EXON; continue; } /* thread.rs:88-91: nothing is done for the region */
             if (mode == 0) { Worker<true> w(*params, *batch, T, reg, ref_seqs[reg.tid], ref_lens[reg.tid], ro); w.run(); }
             else { Worker<false> w(*params, *batch, T, reg, ref_seqs[reg.tid], ref_lens[reg.tid], ro); w.run(); }
         }

@@ -252,12 +252,15 @@ def binomial_two_tailed(k, n):
 SOR_THRESHOLD = strand_odds_ratio(5, 5, 9, 1)
 
 
-def candidates(P, region, fv):
+def candidates(P, region, fv, exons=None):
+    """exons: None, or the (start, stop) intervals of parse_annotation (util.rs:435-439) for --exon-only (candidate.rs:80-89)."""
     cands, homo, het, edit, somatic = [], [], [], [], []
     position = region["start"] - 1
     for bf in fv:
         pos = position
         position += 1
+        if exons is not None and not any(s < pos + 2 and e > pos + 1 for s, e in exons):  # Lapper::find(position + 1, position + 2)
+            continue
         total = bf["a"] + bf["c"] + bf["g"] + bf["t"]
         if total < P["min_depth"] or total > P["max_depth"]:
             continue

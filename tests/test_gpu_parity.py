@@ -269,6 +269,22 @@ def test_full_size_cfg3_against_oracle():
     assert rescued.sum() > 100, "the rescue pass (snpfrags.rs:191-281) promoted no editing site"
 
 
+def test_full_size_cfg4_rank_against_oracle():
+    """BASELINE config 4 as one rank sees it (three 10 Mb ONT-dRNA contigs dealt by shard.plan_shards out of the 8-rank job, 20x,
+    390 k reads, 7.7 k regions, 2.4 M pre-candidates): the CUDA path against the oracle on every output, through the 4-bit input form."""
+    import bench
+
+    w, syn, p, regions = bench.make_workload("cfg4", 3, 8)
+    refs = syn.reference.for_reads(syn.reads)
+    eng = host.Engine(p)
+    eng.set_references(refs)
+    got = eng.submit(host.BatchView(syn.reads, regions, seq4=host.pack_seq4(syn.reads)))
+    eng.close()
+    assert got.stats["n_aligned_bases"] > 3e8 and got.n_cand > 10000 and (got.region_status == 0).all()
+    want = ob.run(p, host.BatchView(syn.reads, regions), refs, mode=0, threads=os.cpu_count() or 1)
+    helpers.compare_results(got, want, "cfg4 rank 3 of 8")
+
+
 @pytest.mark.parametrize("name", ["shared_reads_two_regions"])
 def test_shared_reads_are_deterministic(name):
     """A read that lies in two regions keeps the HP / PS entry of the lower region on every run (no cross-CTA write race)."""
@@ -391,4 +407,46 @@ def test_packed_bases_validation():
     with pytest.raises(host.LcrError):
         eng.submit(host.BatchView(syn.reads, regions, seq4=(s4, o_short)))
     eng.close()
-    assert C.sizeof(abi.Batch) == 8 + 13 * 8
+    assert C.sizeof(abi.Batch) == 8 + 15 * 8
+
+
+@pytest.mark.parametrize("chunk_mb", ["100000", "1"])
+def test_exon_only_mask(monkeypatch, chunk_mb):
+    """--exon-only (candidate.rs:80-89, thread.rs:80-91): per-region exon intervals (unsorted, overlapping, some ending exactly on a
+    candidate) restrict the candidate positions; a region without intervals is skipped with LCR_REGION_NO_EXON.  Whole and chunked."""
+    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", chunk_mb)
+    syn = host.Synthetic(seed=51, contig_len=200_000, n_contigs=2, platform=0, depth=30.0, n_het=200, n_edit=30, both_strands=0, n_threads=4)
+    refs = syn.reference.for_reads(syn.reads)
+    p = host.params_preset("hifi-masseq", seed=6)
+    regions, _ = host.find_regions(syn.reads, p)
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
+    plain = eng.submit(host.BatchView(syn.reads, regions))
+    rng = np.random.default_rng(3)
+    exons = []
+    for r, g in enumerate(regions):
+        if r % 7 == 3:
+            exons.append([])  # a gene region without CDS records
+            continue
+        pos = plain.cand["pos"][plain.cand_off[r]:plain.cand_off[r + 1]].astype(np.int64) + 1  # 1-based candidate positions of the region
+        iv = []
+        for q in pos[::2]:  # every other candidate sits on an interval edge: first base, last base, or one past the end
+            k = int(rng.integers(0, 3))
+            iv.append((int(q), int(q) + 40) if k == 0 else (int(q) - 40, int(q) + 1) if k == 1 else (int(q) - 40, int(q)))
+        span = int(g["end"]) - int(g["start"])
+        for _ in range(3):
+            a = int(g["start"]) + int(rng.integers(0, max(span, 1)))
+            iv.append((a, a + int(rng.integers(1, 400))))
+        rng.shuffle(iv)
+        exons.append([(max(int(s), 1), int(e)) for s, e in iv])
+    batch = host.BatchView(syn.reads, regions, exons=exons)
+    got = eng.submit(batch)
+    eng.close()
+    want = ob.run(p, batch, refs, mode=0)
+    helpers.compare_results(got, want, "exon-only")
+    st = np.array([abi.LCR_REGION_NO_EXON if r % 7 == 3 else 0 for r in range(len(regions))])
+    np.testing.assert_array_equal(got.region_status, st)
+    assert 0 < got.n_cand < plain.n_cand
+    for r in range(len(regions)):
+        for q in got.cand["pos"][got.cand_off[r]:got.cand_off[r + 1]]:
+            assert any(s <= int(q) + 1 < e for s, e in exons[r])

@@ -192,6 +192,33 @@ def test_pileup_candidates_fragments_agree(case):
             assert same or mirrored, (m, list(g.cand["haplotype"]), list(hap), list(g.hp), list(want_hp))
 
 
+@settings(max_examples=int(os.environ.get("LCR_FUZZ_EXAMPLES", "300")) // 3, deadline=None, suppress_health_check=list(HealthCheck), derandomize=not os.environ.get("LCR_FUZZ_RANDOM"), database=None)
+@given(regions(), st.lists(st.tuples(st.integers(0, 400), st.integers(1, 60)), min_size=1, max_size=5))
+def test_exon_only_mask_agrees(case, raw_exons):
+    """--exon-only (candidate.rs:80-89): candidates only at positions some exon interval of the region holds; both restatements."""
+    preset, ref, recs, start, end = case
+    reads = helpers.make_reads(len(ref), recs)
+    region = helpers.one_region(start, end, len(recs))
+    exons = [(start + a, start + a + ln) for a, ln in raw_exons]  # 1-based start, stop exclusive, unsorted, overlapping
+    p = host.params_preset(preset, seed=5, min_read_length=30, min_depth=4, flags=abi.LCR_FLAG_EMIT_PLANES | abi.LCR_FLAG_SKIP_PHASING)
+    P = params_dict(p)
+    reg = dict(tid=0, start=start, end=end)
+    fv, _, _ = py.pileup(P, reg, to_py_reads(recs), ref)
+    cands, _, _ = py.candidates(P, reg, fv, exons)
+    every, _, _ = py.candidates(P, reg, fv)
+    inside = lambda pos: any(s <= pos + 1 < e for s, e in exons)  # noqa: E731
+    assert [c["pos"] for c in cands] == [c["pos"] for c in every if inside(c["pos"])]
+    for m in (0, 1):
+        g = ob.run(p, host.BatchView(reads, region, exons=[exons]), [ref], mode=m)
+        assert list(g.region_status) == [0] and [int(x) for x in g.cand["pos"]] == [c["pos"] for c in cands]
+        for i, c in enumerate(cands):
+            for name, bit in FLAG_OF.items():
+                assert bool(g.cand[i]["flags"] & bit) == c[name], (m, i, name)
+    # a region whose genes have no exon is skipped altogether (thread.rs:88-91)
+    g = ob.run(p, host.BatchView(reads, region, exons=[[]]), [ref], mode=0)
+    assert list(g.region_status) == [abi.LCR_REGION_NO_EXON] and g.n_cand == 0 and g.stats["n_reads_pass"] == 0
+
+
 def test_contract_math_against_libm():
     """lcr_log10 / lcr_exp10 / lcr_log (the deterministic math both the oracle's contract mode and the CUDA path use) against libm
     on the values the path feeds them: the q = 0..30 tables, likelihood sums, posteriors."""
