@@ -117,6 +117,15 @@ typedef struct lcr_batch {
        if some interval holds it; a region without intervals is skipped (region_status LCR_REGION_NO_EXON).  NULL exon_off: no mask. */
     const uint32_t *exon_off; /* [n_regions+1] offsets into exon_iv, in intervals */
     const uint32_t *exon_iv;  /* [2 * exon_off[n_regions]] start, stop pairs */
+    /* -v / --input-vcf (thread.rs:107-116, candidate.rs:530-613): candidates are imported instead of called.  Per region the VCF
+       records that fall inside it: position (0-based, ascending, one record per position: the reference keeps them in a map),
+       genotype class (vcf.rs:443-449: 0 = 0/0, 1 = 0/1, 2 = 1/1, 3 = 1/2, 4 = anything else) and QUAL (NaN when missing).
+       Alleles, frequencies and depth still come from the pileup; no count filter, likelihood, dense filter or exon mask applies.
+       NULL ext_off: candidates are called from the pileup. */
+    const uint32_t *ext_off;  /* [n_regions+1] offsets into the three arrays below */
+    const uint32_t *ext_pos;
+    const uint8_t *ext_gt;
+    const float *ext_qual;
 } lcr_batch;
 
 /* candidate flags (snp.rs:66-84) */

@@ -102,6 +102,10 @@ class Batch(C.Structure):
         ("seq4_off", C.c_void_p),
         ("exon_off", C.c_void_p),
         ("exon_iv", C.c_void_p),
+        ("ext_off", C.c_void_p),
+        ("ext_pos", C.c_void_p),
+        ("ext_gt", C.c_void_p),
+        ("ext_qual", C.c_void_p),
     ]
 
 

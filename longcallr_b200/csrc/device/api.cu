@@ -499,6 +499,14 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     if (ctx->sticky) return ctx->sticky;
     if (b->n_regions && !b->regions) return LCR_ERR_INVALID_ARG;
     if (b->exon_off && b->n_regions && b->exon_off[b->n_regions] > b->exon_off[0] && !b->exon_iv) return LCR_ERR_INVALID_ARG;
+    if (b->ext_off) { /* imported candidates: offsets non-decreasing, positions ascending inside a region (the reference keeps one record per position) */
+        for (uint32_t r = 0; r < b->n_regions; ++r) {
+            if (b->ext_off[r + 1] < b->ext_off[r]) return LCR_ERR_INVALID_ARG;
+            if (b->ext_off[r + 1] > b->ext_off[r] && (!b->ext_pos || !b->ext_gt || !b->ext_qual)) return LCR_ERR_INVALID_ARG;
+            for (uint32_t e = b->ext_off[r] + 1; e < b->ext_off[r + 1]; ++e)
+                if (b->ext_pos[e] <= b->ext_pos[e - 1]) return LCR_ERR_INVALID_ARG;
+        }
+    }
     if (b->n_reads && (!b->pos || !b->flag || !b->mapq || !b->ts || !b->de || !b->seq_off || !b->cig_off)) return LCR_ERR_INVALID_ARG;
     /* the kernels index the pools with these offsets: they must be non-decreasing and the pools present */
     const uint64_t n_bases = b->n_reads ? b->seq_off[b->n_reads] : 0, n_cig = b->n_reads ? b->cig_off[b->n_reads] : 0;
@@ -518,6 +526,7 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     db->ev_meta = nullptr; db->ev_seq = nullptr; db->seq_wait_pending = false;
     db->seq4 = nullptr; db->seq4_off = nullptr; db->seq4_pending = false;
     db->exon_off = nullptr; db->exon_iv = nullptr;
+    db->ext_off = nullptr; db->ext_pos = nullptr; db->ext_gt = nullptr; db->ext_qual = nullptr;
     db->n_regions = b->n_regions;
     db->n_reads = b->n_reads;
     db->ran = false;
@@ -571,6 +580,7 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         C.items = 3ull * db->n_slots + 4ull * db->n_tiles + 1024;
         C.segs = n_cig * factor + 32ull * db->n_slots + 1024;
         C.pre = db->n_pos / 64 + 65536;
+        if (b->ext_off && b->n_regions) C.pre = std::max<uint64_t>(C.pre, 2ull * (b->ext_off[b->n_regions] - b->ext_off[0]) + 65536); /* -v: one pre-candidate per imported record */
         C.elems = 16ull * db->n_slots + (1ull << 20);
         C.pairs = 1ull << 20;
         C.adj = 1ull << 20;
@@ -590,7 +600,8 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
     {
         size_t need = 4 * (slot_off.size() + slot_region.size() + tile_base.size() + tile_region.size() + big_list.size() + db->extra.h_status0.size()) + 8 * pos_off.size() +
                       sizeof(lcr_region) * (size_t)b->n_regions + 64 * 16 +
-                      (b->exon_off ? 4 * ((size_t)b->n_regions + 1) + 8 * (size_t)(b->exon_off[b->n_regions] - b->exon_off[0]) + 128 : 0);
+                      (b->exon_off ? 4 * ((size_t)b->n_regions + 1) + 8 * (size_t)(b->exon_off[b->n_regions] - b->exon_off[0]) + 128 : 0) +
+                      (b->ext_off ? 4 * ((size_t)b->n_regions + 1) + 9 * (size_t)(b->ext_off[b->n_regions] - b->ext_off[0]) + 512 : 0);
         const size_t nr = b->n_reads;
         need += (pin_soff ? 0 : 8 * (nr + 1)) + (pin_coff ? 0 : 8 * (nr + 1)) + (pin_pos ? 0 : 4 * nr) + (pin_flag ? 0 : 2 * nr) + (pin_mapq ? 0 : nr) + (pin_ts ? 0 : nr) + (pin_de ? 0 : 4 * nr) +
                 (pin_s4off ? 0 : 8 * (nr + 1)) + ((pin_cig || n_cig * 4 > (64ull << 20)) ? 0 : 4 * (size_t)n_cig);
@@ -629,6 +640,15 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         }
         rc = h2d(ctx, &db->exon_off, static_cast<const uint32_t *>(stage_copy(X, eoff.data(), 4 * eoff.size())), eoff.size(), &bytes);
         if (!rc) rc = h2d(ctx, &db->exon_iv, static_cast<const uint2 *>(stage_copy(X, eiv.data(), 8 * eiv.size())), eiv.size(), &bytes);
+    }
+    if (b->ext_off && !rc) { /* -v: the regions' slices of the imported records, offsets rebased to the first one */
+        const uint32_t e0 = b->n_regions ? b->ext_off[0] : 0, ne = b->n_regions ? b->ext_off[b->n_regions] - e0 : 0;
+        std::vector<uint32_t> xoff((size_t)b->n_regions + 1, 0);
+        for (uint32_t r = 0; r <= b->n_regions && b->n_regions; ++r) xoff[r] = b->ext_off[r] - e0;
+        rc = h2d(ctx, &db->ext_off, static_cast<const uint32_t *>(stage_copy(X, xoff.data(), 4 * xoff.size())), xoff.size(), &bytes);
+        if (!rc) rc = h2d(ctx, &db->ext_pos, static_cast<const uint32_t *>(stage_copy(X, ne ? b->ext_pos + e0 : nullptr, 4 * (size_t)ne)), (size_t)ne, &bytes);
+        if (!rc) rc = h2d(ctx, &db->ext_gt, static_cast<const uint8_t *>(stage_copy(X, ne ? b->ext_gt + e0 : nullptr, (size_t)ne)), (size_t)ne, &bytes);
+        if (!rc) rc = h2d(ctx, &db->ext_qual, static_cast<const float *>(stage_copy(X, ne ? b->ext_qual + e0 : nullptr, 4 * (size_t)ne)), (size_t)ne, &bytes);
     }
     if (b->n_reads) {
         if (pin_soff) { UP(seq_off, b->seq_off, (size_t)b->n_reads + 1); } else { UPS(seq_off, b->seq_off, (size_t)b->n_reads + 1); }
@@ -947,7 +967,7 @@ void lcr_release(lcr_ctx *ctx, lcr_device_batch *dbb) {
     DFREE(db->regions); DFREE(db->pos); DFREE(db->flag); DFREE(db->mapq); DFREE(db->ts); DFREE(db->de);
     DFREE(db->seq_off); DFREE(db->cig_off); DFREE(db->seq); if (db->qual_on_host) db->qual = nullptr; DFREE(db->qual); DFREE(db->cigar);
     DFREE(db->slot_off); DFREE(db->slot_region); DFREE(db->tile_base); DFREE(db->tile_region); DFREE(db->pos_off);
-    DFREE(db->seq4); DFREE(db->seq4_off); DFREE(db->exon_off); DFREE(db->exon_iv);
+    DFREE(db->seq4); DFREE(db->seq4_off); DFREE(db->exon_off); DFREE(db->exon_iv); DFREE(db->ext_off); DFREE(db->ext_pos); DFREE(db->ext_gt); DFREE(db->ext_qual);
     cudaStreamSynchronize(ctx->stream);
     if (db->ev_seq) { cudaEventSynchronize(db->ev_seq); cudaEventDestroy(db->ev_seq); }
     stage_give_back(ctx, db->extra); /* after the copies out of it have completed */
@@ -1064,6 +1084,7 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
         v.seq = batch->seq ? batch->seq + sb : nullptr; v.qual = batch->qual ? batch->qual + sb : nullptr;
         v.seq4 = batch->seq4; v.seq4_off = batch->seq4 && batch->seq4_off ? batch->seq4_off + ck.read_lo : nullptr; /* absolute offsets: upload_impl rebases */
         v.exon_off = batch->exon_off ? batch->exon_off + ck.r0 : nullptr; v.exon_iv = batch->exon_iv; /* absolute interval offsets */
+        v.ext_off = batch->ext_off ? batch->ext_off + ck.r0 : nullptr; v.ext_pos = batch->ext_pos; v.ext_gt = batch->ext_gt; v.ext_qual = batch->ext_qual;
         v.cigar = batch->cigar ? batch->cigar + cb : nullptr;
     }
 

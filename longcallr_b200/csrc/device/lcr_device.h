@@ -106,6 +106,10 @@ struct lcr_device_batch {
     /* --exon-only mask (lcr_batch.exon_off / exon_iv): per region the union of its intervals, sorted, as (start, stop) pairs; null = no mask */
     uint32_t *exon_off;
     uint2 *exon_iv;
+    /* -v (lcr_batch.ext_*): imported candidate positions per region; null = candidates are called from the pileup */
+    uint32_t *ext_off, *ext_pos;
+    uint8_t *ext_gt;
+    float *ext_qual;
     uint32_t *cigar;
     /* derived on the host at upload: cheap prefix sums over region lengths / read ranges */
     uint32_t *slot_off;    /* [n_regions+1] */

@@ -218,6 +218,43 @@ __device__ bool site_call(const lcr_params &P, const LcrDeviceTables &T, const S
     return true;
 }
 
+/* import_external_candidates (candidate.rs:530-613) for one listed position: alleles, frequencies and depth from the pileup counters,
+   QUAL and genotype class from the record; 0/0 and unknown classes produce no candidate, a negative QUAL is dropped (min_variant_qual = 0.0) */
+__device__ bool site_import(const uint32_t (&cnt)[4], uint8_t ref_base, uint32_t gt, float quality, lcr_candidate &o) {
+    if (quality < 0.0f) return false;
+    if (gt < 1u || gt > 3u) return false;
+    const uint32_t total = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    /* get_two_major_alleles (util.rs:162-176), as in site_call */
+    uint32_t k0 = (cnt[0] << 2) | 3u, k1 = (cnt[1] << 2) | 2u, k2 = (cnt[2] << 2) | 1u, k3 = cnt[3] << 2;
+#define LCR_CX(x, y) do { const uint32_t hi__ = max(x, y), lo__ = min(x, y); x = hi__; y = lo__; } while (0)
+    LCR_CX(k0, k1); LCR_CX(k2, k3); LCR_CX(k0, k2); LCR_CX(k1, k3); LCR_CX(k1, k2);
+#undef LCR_CX
+    const int ord[4] = {3 - (int)(k0 & 3u), 3 - (int)(k1 & 3u), 3 - (int)(k2 & 3u), 3 - (int)(k3 & 3u)};
+    const uint32_t oc[4] = {k0 >> 2, k1 >> 2, k2 >> 2, k3 >> 2};
+    auto letter = [](int c) -> uint8_t { return (uint8_t)(0x54474341u >> (8 * c)); };
+    int i2 = ord[1];
+    uint32_t c2 = oc[1];
+    if (letter(ord[0]) != ref_base && letter(ord[1]) != ref_base) {
+        if (oc[2] == oc[1] && letter(ord[2]) == ref_base) { i2 = ord[2]; c2 = oc[2]; }
+        else if (oc[3] == oc[1] && letter(ord[3]) == ref_base) { i2 = ord[3]; c2 = oc[3]; }
+    }
+    o.variant_quality = (double)quality;
+    o.genotype_quality = (double)quality;
+    o.phase_score = 0.0;
+    o.genotype_probability[0] = 0.0; o.genotype_probability[1] = 0.0; o.genotype_probability[2] = 0.0;
+    o.allele_freqs[0] = (float)oc[0] / (float)total; o.allele_freqs[1] = (float)c2 / (float)total; /* 0 / 0 = NaN on an uncovered position, as in the reference */
+    o.depth = total;
+    o.phase_set = 0;
+    o.reference = ref_base;
+    o.alleles[0] = letter(ord[0]); o.alleles[1] = letter(i2);
+    o.haplotype = 0;
+    o.reserved = 0;
+    if (gt == 1u) { o.variant_type = 1; o.genotype = 0; o.flags = LCR_CF_HET_VAR | LCR_CF_FOR_PHASING; }
+    else if (gt == 2u) { o.variant_type = 2; o.genotype = -1; o.flags = LCR_CF_HOM_VAR | LCR_CF_FOR_PHASING; }
+    else { o.variant_type = 3; o.genotype = -1; o.flags = LCR_CF_HOM_VAR; }
+    return true;
+}
+
 struct LcrSeg {             /* 16 B: a run of unmasked aligned bases, deleted or intron positions of one read inside one tile */
     uint64_t spos;          /* M: offset of the first base in the seq / qual pools */
     uint32_t typ;           /* bits 0-1 type, bit 2 forward strand, bits 3-4 transcript strand code */
@@ -646,7 +683,7 @@ struct DescArgs {
     LcrTileDesc *desc;
     uint32_t *list[2];      /* work lists: tiles of at most / more than 255 items */
     LcrCounters *ctr;
-    int all_tiles;          /* debug planes requested: empty tiles are processed too */
+    int all_tiles;          /* debug planes requested or candidates imported: empty tiles are processed too */
     uint32_t big_rows;      /* tiles with more rows than this take the 32-bit event counters */
 };
 
@@ -705,6 +742,9 @@ struct PileArgs {
     uint32_t *pl_acgt, *pl_fwd, *pl_d, *pl_n, *pl_ts; /* debug planes or null */
     const uint32_t *exon_off;    /* --exon-only: per region the sorted union of its exon intervals, or null */
     const uint2 *exon_iv;
+    const uint32_t *ext_off, *ext_pos; /* -v: imported candidate positions per region (ascending), or null */
+    const uint8_t *ext_gt;
+    const float *ext_qual;
     PreCand *pre;
     uint32_t pre_cap;
     uint2 *tile_pre;             /* per tile: first pre-candidate and count */
@@ -1210,7 +1250,13 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 for (int i = 0; i < 4; ++i) { a.pl_acgt[g * 4 + i] = sc.cnt[i]; a.pl_fwd[g * 4 + i] = sc.fwd[i]; }
                 a.pl_d[g] = sc.d; a.pl_n[g] = sc.n; a.pl_ts[g * 2] = sc.ts[0]; a.pl_ts[g * 2 + 1] = sc.ts[1];
             }
-            if (maybe) {
+            if (maybe && a.ext_off) { /* -v (candidate.rs:544): the columns the imported records name, whatever was piled on them */
+                const uint32_t pos0 = D.pos1 - 1u + colr;
+                uint32_t lo = a.ext_off[D.reg], hi = a.ext_off[D.reg + 1];
+                const uint32_t end = hi;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.ext_pos[mid] < pos0) lo = mid + 1; else hi = mid; }
+                maybe = lo < end && a.ext_pos[lo] == pos0;
+            } else if (maybe) {
                 const uint32_t m0 = ev_get(EV_MIS, colr), m1 = ev_get(EV_MIS + 1, colr), m2 = ev_get(EV_MIS + 2, colr), m3 = ev_get(EV_MIS + 3, colr);
                 maybe = (m0 | m1 | m2 | m3) != 0u && s_ref[colr] != 0x80;
                 if (maybe) {
@@ -1246,6 +1292,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
             load_site(colr, sc, rb);
             lcr_candidate dummy;
             bool ok = true;
+            if (a.ext_off) { atomicOr(&s_bitmap[colr >> 5], 1u << (colr & 31u)); continue; } /* imported: no filter of the cascade applies */
             if (a.exon_off) { /* candidate.rs:80-89: only positions inside an exon of the region's genes are looked at */
                 const uint32_t pos1 = D.pos1 + colr;
                 uint32_t lo = a.exon_off[D.reg], hi = a.exon_off[D.reg + 1];
@@ -1330,6 +1377,22 @@ __global__ void __launch_bounds__(256) k_site_ll(PileArgs a) {
         const int32_t tile_start = (int32_t)((tile - a.tile_base[reg]) * LCR_TILE);
         const int32_t col = tile_start + (int32_t)pc.col;
         const uint8_t ref_base = a.ref_table[R.tid][((int64_t)R.start - 1) + col];
+        if (a.ext_off) { /* -v: the record of this position decides; no base or quality is read */
+            if (lane == 0) {
+                const uint32_t pos0 = (uint32_t)((int64_t)R.start - 1 + col);
+                uint32_t lo = a.ext_off[reg], hi = a.ext_off[reg + 1];
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.ext_pos[mid] < pos0) lo = mid + 1; else hi = mid; }
+                lcr_candidate o;
+                const bool keep = lo < a.ext_off[reg + 1] && a.ext_pos[lo] == pos0 && site_import(pc.cnt, ref_base, a.ext_gt[lo], a.ext_qual[lo], o);
+                if (keep) {
+                    o.pos = (int64_t)pos0;
+                    o.region = reg;
+                    a.cand_raw[w] = o;
+                }
+                a.cand_keep[w] = keep ? 1 : 0;
+            }
+            continue;
+        }
         const int refc = (ref_base == 'A') ? 0 : (ref_base == 'C') ? 1 : (ref_base == 'G') ? 2 : (ref_base == 'T') ? 3 : 8;
         long long ll0 = 0, ll2 = 0;
         uint32_t q0flags = 0;
@@ -1582,7 +1645,7 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     da.tile_base = db->tile_base; da.tile_region = db->tile_region; da.tile_off = tile_off; da.tile_cursor = tile_cursor; da.tile_full_n = tile_full_n;
     da.pos_off = db->pos_off; da.ref_table = ctx->d_ref_table; da.rstate = db->rstate; da.desc = desc;
     da.list[0] = list0; da.list[1] = list1; da.ctr = ctr;
-    da.all_tiles = db->pl_acgt != nullptr;
+    da.all_tiles = db->pl_acgt != nullptr || db->ext_off != nullptr; /* imported candidates may sit on tiles no read row touches (whole-tile introns) */
     const bool force_big = ctx->tile_variant == 3; /* tests: every non-empty tile through the 32-bit flavour */
     da.big_rows = force_big ? 0u : 65535u;
     if (n_tiles) {
@@ -1596,6 +1659,7 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
     ka.tile_base = db->tile_base; ka.tile_region = db->tile_region;
     ka.seq = db->seq; ka.qual = db->qual;
     ka.exon_off = db->exon_off; ka.exon_iv = db->exon_iv;
+    ka.ext_off = db->ext_off; ka.ext_pos = db->ext_pos; ka.ext_gt = db->ext_gt; ka.ext_qual = db->ext_qual;
     ka.ref_table = ctx->d_ref_table;
     ka.desc = desc; ka.items = items; ka.segs = segs;
     ka.tables = ctx->d_tables;
@@ -1640,8 +1704,8 @@ int lcr_stage_pileup(lcr_ctx *ctx, lcr_device_batch *db, LcrArena &A, LcrCounter
         db->timing.kernel_launches += 3;
         if (n_regions) {
             k_cand_ranges<<<(n_regions + 63) / 64, 64, 0, st>>>(n_regions, db->tile_base, tile_cand_off, db->rstate);
-            k_cand_dense<<<sms * 4, 64, 0, st>>>(ctx->P, ctr, db->cand, db->rstate);
-            db->timing.kernel_launches += 2;
+            if (!db->ext_off) k_cand_dense<<<sms * 4, 64, 0, st>>>(ctx->P, ctr, db->cand, db->rstate); /* imported candidates skip the dense filters (candidate.rs:530-613 has none) */
+            db->timing.kernel_launches += db->ext_off ? 1 : 2;
         }
     }
     LCR_DEBUG_CHECK(ctx, "candidate compaction");

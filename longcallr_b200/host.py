@@ -314,9 +314,9 @@ def pack_seq4(reads, alloc=None, threads=8):
 class BatchView:
     """An lcr_batch over numpy arrays (kept alive here).  seq4 = (packed bytes, offsets) from pack_seq4 hands the bases over in the
     BAM record's 4-bit form instead of ASCII (the `seq` pointer is then NULL); exons = per-region lists of (start, stop) turns on the
-    --exon-only mask."""
+    --exon-only mask; external = per-region lists of (pos0, genotype class, qual) imports the candidates (-v) instead of calling them."""
 
-    def __init__(self, reads, regions, seq4=None, exons=None):
+    def __init__(self, reads, regions, seq4=None, exons=None, external=None):
         self.reads = reads
         self.regions = np.ascontiguousarray(regions, dtype=abi.REGION_DTYPE)
         names = ["pos", "flag", "mapq", "ts", "de", "seq_off", "cig_off", "qual", "cigar"] + ([] if seq4 is not None else ["seq"])
@@ -337,6 +337,17 @@ class BatchView:
             iv = np.array([x for e in exons for pair in e for x in pair], dtype="<u4").reshape(-1)
             self._keep += [off, iv]
             b.exon_off, b.exon_iv = off.ctypes.data, (iv.ctypes.data if len(iv) else None)
+        if external is not None:  # -v: one list of (pos0, genotype class, qual) per region, ascending positions
+            off = np.zeros(len(self.regions) + 1, dtype="<u4")
+            off[1:] = np.cumsum([len(e) for e in external])
+            flat = [x for e in external for x in e]
+            pos = np.array([x[0] for x in flat], dtype="<u4")
+            gt = np.array([x[1] for x in flat], dtype="u1")
+            ql = np.array([x[2] for x in flat], dtype="<f4")
+            self._keep += [off, pos, gt, ql]
+            b.ext_off = off.ctypes.data
+            if len(flat):
+                b.ext_pos, b.ext_gt, b.ext_qual = pos.ctypes.data, gt.ctypes.data, ql.ctypes.data
         self.c = b
 
     @property

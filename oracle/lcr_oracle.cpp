@@ -436,6 +436,38 @@ struct Worker {
     static double xlog10(double v) { return FX ? lcr_log10(v) : std::log10(v); }
     static double xexp10(double v) { return FX ? lcr_exp10(v) : std::pow(10.0, v); }
 
+    /* ---- SNPFrag::import_external_candidates (candidate.rs:530-613), called with min_variant_qual = 0.0 (thread.rs:110-115) */
+    void import_external_candidates(const std::vector<BaseFreq> &pileup) {
+        int64_t position = (int64_t)reg.start - 1;
+        uint32_t e = B.ext_off[region_index];
+        const uint32_t e1 = B.ext_off[region_index + 1];
+        for (size_t bfidx = 0; bfidx < pileup.size(); ++bfidx, ++position) {
+            while (e < e1 && (int64_t)B.ext_pos[e] < position) ++e;
+            if (e >= e1 || (int64_t)B.ext_pos[e] != position) continue; /* contains_key(position) */
+            const BaseFreq &bf = pileup[bfidx];
+            uint8_t allele1, allele2;
+            uint32_t allele1_cnt, allele2_cnt;
+            two_major(bf, bf.ref_base, allele1, allele1_cnt, allele2, allele2_cnt);
+            const float quality = B.ext_qual[e];
+            if (quality < 0.0f) continue;
+            const uint32_t total = bf.a + bf.c + bf.g + bf.t;
+            Cand cs;
+            cs.pos = position;
+            cs.reference = bf.ref_base; /* ref_seq[ref_pos]: the same byte the pileup recorded */
+            cs.alleles[0] = allele1; cs.alleles[1] = allele2;
+            cs.allele_freqs[0] = (float)allele1_cnt / (float)total; cs.allele_freqs[1] = (float)allele2_cnt / (float)total;
+            cs.depth = total;
+            cs.variant_quality = (double)quality;
+            cs.genotype_quality = (double)quality;
+            switch (B.ext_gt[e]) {
+                case 1: cs.variant_type = 1; cs.genotype = 0; cs.for_phasing = true; cs.het_var = true; cands.push_back(cs); break;
+                case 2: cs.variant_type = 2; cs.genotype = -1; cs.for_phasing = true; cs.hom_var = true; cands.push_back(cs); break;
+                case 3: cs.variant_type = 3; cs.genotype = -1; cs.hom_var = true; cands.push_back(cs); break;
+                default: break; /* 0/0 builds a record that is never pushed; other genotypes are reported and skipped */
+            }
+        }
+    }
+
     /* ---- P3-P7: SNPFrag::get_candidate_snps (candidate.rs:54-528) */
     void get_candidate_snps(const std::vector<BaseFreq> &pileup) {
         int64_t position = (int64_t)reg.start - 1;
@@ -1496,7 +1528,8 @@ struct Worker {
             if (P.flags & LCR_FLAG_EMIT_PLANES) out.pileup.assign((size_t)(reg.end - reg.start), BaseFreq());
             return;
         }
-        get_candidate_snps(pile);
+        if (B.ext_off) import_external_candidates(pile);
+        else get_candidate_snps(pile);
         if (P.flags & LCR_FLAG_EMIT_PLANES) out.pileup = std::move(pile);
         else std::vector<BaseFreq>().swap(pile);
         out.st.n_candidates = cands.size();

@@ -616,6 +616,39 @@ def phase_enum(P, region, cands, frags, reads_in_region_index):
     return counters
 
 
+# ---------------------------------------------------------------- X2 imported candidates   candidate.rs:530-613
+def import_external_candidates(region, fv, records, min_variant_qual=0.0):
+    """records: {0-based position: (genotype class, quality)} of the region's contig (vcf.rs:400-462).  Returns the candidate list in
+    the form candidates() returns it (the flags import never sets are False)."""
+    cands = []
+    position = region["start"] - 1
+    for bf in fv:
+        pos = position
+        position += 1
+        if pos not in records:
+            continue
+        gt, quality = records[pos]
+        a1, c1, a2, c2 = two_major(bf)
+        if f32(quality) < f32(min_variant_qual):
+            continue
+        total = bf["a"] + bf["c"] + bf["g"] + bf["t"]
+        with_nan = lambda c: f32(f32(c) / f32(total)) if total else float("nan")  # noqa: E731  (0 / 0 in f32)
+        c = dict(pos=pos, reference=bf["ref_base"], alleles=(a1, a2), freqs=(with_nan(c1), with_nan(c2)), depth=total,
+                 variant_quality=float(f32(quality)), genotype_quality=float(f32(quality)), gp=[0.0, 0.0, 0.0], haplotype=0, phase_score=0.0,
+                 rna_editing=False, dense=False, het_var=False, for_phasing=False, hom_var=False, cand_somatic=False, single=False, non_selected=False,
+                 cover=[])
+        if gt == 1:
+            c.update(variant_type=1, genotype=0, for_phasing=True, het_var=True)
+        elif gt == 2:
+            c.update(variant_type=2, genotype=-1, for_phasing=True, hom_var=True)
+        elif gt == 3:
+            c.update(variant_type=3, genotype=-1, hom_var=True)
+        else:  # 0/0 is built but never pushed; anything else is reported and skipped
+            continue
+        cands.append(c)
+    return cands
+
+
 # ---------------------------------------------------------------- R0 isolated regions   util.rs:236-332
 def find_isolated_regions(ref_len, reads, min_mapq, min_read_length, divergence, truncation=False, truncation_coverage=200000):
     """One contig.  reads: iterable of dicts {mapq, l_seq, flag, de (float or None), pos, end} with [pos, end) the

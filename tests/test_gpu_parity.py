@@ -407,7 +407,7 @@ def test_packed_bases_validation():
     with pytest.raises(host.LcrError):
         eng.submit(host.BatchView(syn.reads, regions, seq4=(s4, o_short)))
     eng.close()
-    assert C.sizeof(abi.Batch) == 8 + 15 * 8
+    assert C.sizeof(abi.Batch) == 8 + 19 * 8
 
 
 @pytest.mark.parametrize("chunk_mb", ["100000", "1"])
@@ -450,3 +450,40 @@ def test_exon_only_mask(monkeypatch, chunk_mb):
     for r in range(len(regions)):
         for q in got.cand["pos"][got.cand_off[r]:got.cand_off[r + 1]]:
             assert any(s <= int(q) + 1 < e for s, e in exons[r])
+
+
+@pytest.mark.parametrize("preset,platform,chunk_mb", [("hifi-masseq", 0, "100000"), ("ont-cdna", 1, "100000"), ("hifi-masseq", 0, "1")])
+def test_imported_candidates(monkeypatch, preset, platform, chunk_mb):
+    """-v (thread.rs:107-116, candidate.rs:530-613): candidates imported from listed positions - the sites a normal run calls, planted het
+    sites, random positions (some uncovered: NaN frequencies), every genotype class, negative and missing QUAL - then fragments, phasing,
+    HP / PS as usual.  Whole and chunked, against the oracle."""
+    monkeypatch.setenv("LCR_SUBMIT_CHUNK_MB", chunk_mb)
+    syn = host.Synthetic(seed=61 + platform, contig_len=200_000, n_contigs=2, platform=platform, depth=30.0, n_het=200, n_edit=30, both_strands=platform, n_threads=4)
+    refs = syn.reference.for_reads(syn.reads)
+    p = host.params_preset(preset, seed=8)
+    regions, _ = host.find_regions(syn.reads, p)
+    eng = host.Engine(p, device=0)
+    eng.set_references(refs)
+    plain = eng.submit(host.BatchView(syn.reads, regions))
+    rng = np.random.default_rng(4)
+    external = []
+    for r, g in enumerate(regions):
+        pos = set(int(x) for x in plain.cand["pos"][plain.cand_off[r]:plain.cand_off[r + 1]])
+        lo, hi = int(g["start"]) - 1, int(g["end"]) - 1
+        pos |= set(int(x) for x in rng.integers(lo, max(hi, lo + 1), size=6))
+        if r % 5 == 0:
+            pos = set()  # a region the VCF has nothing for
+        recs = []
+        for q in sorted(x for x in pos if lo <= x < hi):
+            gt = int(rng.choice([1, 1, 1, 2, 3, 0, 4]))
+            ql = float(rng.choice([30.0, 12.5, 3000.0, -1.0, np.nan], p=[0.5, 0.2, 0.1, 0.1, 0.1]))
+            recs.append((q, gt, ql))
+        external.append(recs)
+    batch = host.BatchView(syn.reads, regions, external=external)
+    got = eng.submit(batch)
+    eng.close()
+    want = ob.run(p, batch, refs, mode=0)
+    helpers.compare_results(got, want, preset + "/imported")
+    n_expected = sum(1 for recs in external for q, gt, ql in recs if gt in (1, 2, 3) and not ql < 0)
+    assert got.n_cand == n_expected > 100 and int((got.hp > 0).sum()) > 100
+    assert np.isnan(got.cand["variant_quality"]).any() and np.isnan(got.cand["allele_freqs"]).any() or platform == 1

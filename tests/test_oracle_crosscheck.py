@@ -219,6 +219,40 @@ def test_exon_only_mask_agrees(case, raw_exons):
     assert list(g.region_status) == [abi.LCR_REGION_NO_EXON] and g.n_cand == 0 and g.stats["n_reads_pass"] == 0
 
 
+@settings(max_examples=int(os.environ.get("LCR_FUZZ_EXAMPLES", "300")) // 3, deadline=None, suppress_health_check=list(HealthCheck), derandomize=not os.environ.get("LCR_FUZZ_RANDOM"), database=None)
+@given(regions(), st.lists(st.tuples(st.integers(0, 300), st.integers(0, 4), st.one_of(st.floats(-5, 60, width=32), st.just(float("nan")))), min_size=1, max_size=12, unique_by=lambda t: t[0]))
+def test_imported_candidates_agree(case, raw):
+    """-v (candidate.rs:530-613): candidates at the listed positions with the record's genotype class and QUAL, alleles / frequencies /
+    depth from the pileup (also on uncovered positions), no filter, no dense pass; fragments are then built on those candidates."""
+    preset, ref, recs, start, end = case
+    reads = helpers.make_reads(len(ref), recs)
+    region = helpers.one_region(start, end, len(recs))
+    ext = sorted((start - 1 + a, gt, q) for a, gt, q in raw if start - 1 + a < end - 1)
+    p = host.params_preset(preset, seed=5, min_read_length=30, min_depth=4, flags=abi.LCR_FLAG_EMIT_PLANES | abi.LCR_FLAG_EMIT_FRAGMENTS | STOP_AFTER_PHASE)
+    P = params_dict(p)
+    reg = dict(tid=0, start=start, end=end)
+    prr = to_py_reads(recs)
+    fv, _, _ = py.pileup(P, reg, prr, ref)
+    cands = py.import_external_candidates(reg, fv, {pos: (gt, q) for pos, gt, q in ext})
+    frags = py.fragments(P, reg, prr, cands) if cands else []
+    for m in (0, 1):
+        g = ob.run(p, host.BatchView(reads, region, external=[ext]), [ref], mode=m)
+        assert list(g.region_status) == [0] and [int(x) for x in g.cand["pos"]] == [c["pos"] for c in cands], (m, ext)
+        for i, c in enumerate(cands):
+            r = g.cand[i]
+            assert chr(r["reference"]) == c["reference"] and (chr(r["alleles"][0]), chr(r["alleles"][1])) == c["alleles"] and int(r["depth"]) == c["depth"]
+            assert int(r["variant_type"]) == c["variant_type"]
+            for a, b in zip([float(x) for x in r["allele_freqs"]] + [float(r["variant_quality"]), float(r["genotype_quality"])], list(c["freqs"]) + [c["variant_quality"], c["genotype_quality"]]):
+                assert (math.isnan(a) and math.isnan(b)) or a == b, (m, i, a, b)
+            for name, bit in FLAG_OF.items():
+                assert bool(r["flags"] & bit) == c[name], (m, i, name)
+            assert bool(r["flags"] & abi.CF_FOR_PHASING) == c["for_phasing"]
+        fr = g.fragments
+        assert int(fr["frag_off"][-1]) == len(frags)
+        np.testing.assert_array_equal(fr["elem_snp"], [fe["snp"] for f in frags for fe in f["list"]])
+        np.testing.assert_array_equal(fr["elem_cell"], [fe["p"] * (fe["baseq"] + 1) for f in frags for fe in f["list"]])
+
+
 def test_contract_math_against_libm():
     """lcr_log10 / lcr_exp10 / lcr_log (the deterministic math both the oracle's contract mode and the CUDA path use) against libm
     on the values the path feeds them: the q = 0..30 tables, likelihood sums, posteriors."""
