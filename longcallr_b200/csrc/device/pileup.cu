@@ -1267,7 +1267,8 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                     const uint32_t rc = total - (m0 + m1 + m2 + m3), alt = max(max(m0, m1), max(m2, m3));
                     if (total < a.P.min_depth || total > a.P.max_depth) maybe = false;
                     else if (rc > alt) { /* the reference base strictly ahead: it is allele 1 and the largest other count the only alternative allele */
-                        if (total < 200u) { if ((float)alt / (float)total < a.P.low_allele_frac_cutoff) maybe = false; }
+                        if (alt == 1u) maybe = false; /* one base cannot hold the two passing ones candidate.rs:177-194 asks for (site_call<PRE>) */
+                        else if (total < 200u) { if ((float)alt / (float)total < a.P.low_allele_frac_cutoff) maybe = false; }
                         else if (alt < a.P.low_allele_cnt_cutoff) maybe = false;
                     }
                 }
