@@ -388,6 +388,7 @@ int lcr_create(const lcr_params *p, int device, lcr_ctx **out) {
     ctx->ref_dirty = true;
     ctx->d_ctr = nullptr; ctx->h_ctr = nullptr; ctx->h_stats = nullptr;
     memset(&ctx->caps_hint, 0, sizeof ctx->caps_hint);
+    ctx->hint_pre_q10 = ctx->hint_elems_q10 = ctx->hint_items_q10 = ctx->hint_segs_q10 = 0;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
@@ -589,6 +590,12 @@ static int upload_impl(lcr_ctx *ctx, const lcr_batch *b, lcr_device_batch **out,
         const LcrCaps &Hc = ctx->caps_hint;
         C.items = std::max(C.items, Hc.items); C.segs = std::max(C.segs, Hc.segs); C.pre = std::max(C.pre, Hc.pre); C.elems = std::max(C.elems, Hc.elems);
         C.pairs = std::max(C.pairs, Hc.pairs); C.adj = std::max(C.adj, Hc.adj);
+        /* densities seen so far on this context (+ 25 %) */
+        auto scaled = [](uint64_t units, uint64_t q10) { return (units * q10 >> 10) + (units * q10 >> 12) + 4096; };
+        if (ctx->hint_pre_q10) C.pre = std::max(C.pre, scaled(db->n_pos, ctx->hint_pre_q10));
+        if (ctx->hint_elems_q10) C.elems = std::max(C.elems, scaled(db->n_slots, ctx->hint_elems_q10));
+        if (ctx->hint_items_q10) C.items = std::max(C.items, scaled(db->n_slots, ctx->hint_items_q10));
+        if (ctx->hint_segs_q10) C.segs = std::max(C.segs, scaled(n_cig * factor, ctx->hint_segs_q10));
     }
     uint64_t bytes = 0;
     int rc = 0;
@@ -802,6 +809,14 @@ int lcr_run_device(lcr_ctx *ctx, lcr_device_batch *dbb) {
         ctx->caps_hint.adj = std::max(ctx->caps_hint.adj, C.adj);
     }
     const LcrCounters &K = db->counters;
+    { /* remember the densities of this batch for the first attempt of the next upload */
+        auto ratio = [](uint64_t need, uint64_t units) { return units ? (need * 1024 + units - 1) / units : 0; };
+        const uint64_t cig_units = db->n_cigar * std::max<uint64_t>(1, (db->n_slots + (uint64_t)std::max<uint32_t>(db->n_reads, 1) - 1) / std::max<uint32_t>(db->n_reads, 1));
+        ctx->hint_pre_q10 = std::max(ctx->hint_pre_q10, ratio(K.n_pre, db->n_pos));
+        ctx->hint_elems_q10 = std::max(ctx->hint_elems_q10, ratio(K.n_elem, db->n_slots));
+        ctx->hint_items_q10 = std::max(ctx->hint_items_q10, ratio(K.n_items, db->n_slots));
+        ctx->hint_segs_q10 = std::max(ctx->hint_segs_q10, ratio(K.n_segs, cig_units));
+    }
     if (getenv("LCR_TILE_PROF")) {
         fprintf(stderr, "tile prof (cycles, consumer warp 0 / producer warp 0, summed over CTAs):");
         for (int i = 0; i < 16; ++i) fprintf(stderr, " [%d]=%llu", i, K.prof[i]);

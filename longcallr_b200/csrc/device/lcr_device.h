@@ -85,6 +85,9 @@ struct lcr_ctx {
     size_t submit_chunk_bytes;   /* LCR_SUBMIT_CHUNK_MB: seq + qual bytes per chunk of lcr_submit */
     int tile_variant;            /* LCR_TILE_VARIANT: launch shape of the tile pileup kernel (pileup.cu) */
     LcrCaps caps_hint;           /* largest capacities any batch of this context has needed: first guess for the next upload */
+    /* what the batches of this context needed per unit of input (x 1024): pre-candidates per position, elements and items per slot,
+       segments per CIGAR op; a new upload (every chunk of lcr_submit is one) sizes its first attempt with them instead of overflowing again */
+    uint64_t hint_pre_q10, hint_elems_q10, hint_items_q10, hint_segs_q10;
     int debug_sync;              /* LCR_DEBUG_SYNC: synchronise and check after every launch group (bring-up only) */
     /* page-locked staging blocks for the small host-side tables of an upload (pageable sources would make every copy wait for the stream) */
     std::vector<std::pair<char *, size_t>> stage_free;
