@@ -1058,13 +1058,21 @@ int lcr_submit(lcr_ctx *ctx, const lcr_batch *batch, lcr_result **out) {
             ck.r0 = r;
             ck.read_lo = 0xffffffffu; ck.read_hi = 0;
             uint64_t bases = 0;
+            /* the last chunk's run is the only one no copy hides: when what is left fits 1.25 chunks, cut it so that a quarter chunk comes last */
+            uint64_t limit = chunk_bytes;
+            {
+                const lcr_region &g0 = batch->regions[r];
+                const bool ok0 = g0.read_end >= g0.read_begin && g0.read_end <= batch->n_reads;
+                const uint64_t left = ok0 ? 2 * (total_bases - batch->seq_off[g0.read_begin]) : 0;
+                if (ok0 && left > chunk_bytes / 2 && left <= chunk_bytes + chunk_bytes / 4) limit = left - chunk_bytes / 4;
+            }
             while (r < batch->n_regions) {
                 const lcr_region &g = batch->regions[r];
                 const bool ok = g.read_end >= g.read_begin && g.read_end <= batch->n_reads;
                 if (ok && g.read_end > g.read_begin) {
                     const uint32_t lo = std::min(ck.read_lo, g.read_begin), hi = std::max(ck.read_hi, g.read_end);
                     const uint64_t nb = batch->seq_off[hi] - batch->seq_off[lo];
-                    if (r > ck.r0 && 2 * nb > chunk_bytes) break;
+                    if (r > ck.r0 && 2 * nb > limit) break;
                     ck.read_lo = lo; ck.read_hi = hi; bases = nb;
                 }
                 ++r;
