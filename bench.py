@@ -307,36 +307,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from longcallr_b200 import shard
+
     gbuf = {}
+    pg = shard.PackedGather(dist, rank, world, dev) if world > 1 else None
 
     def gather_results(cand_u8, hp_u8, ps_u8, setup=False):
-        """The per-rank VCF records and (read, HP, PS) arrays go to rank 0 (device tensors in): ONE gather of a fixed-capacity
-        payload whose first 24 bytes carry the three sizes.  The capacity (1.25 x the largest rank) comes from one exchange of
-        sizes before the timed region (`setup=True`); a step whose payload outgrew it is an error, never a silent truncation."""
-        sz = [cand_u8.numel(), hp_u8.numel(), ps_u8.numel()]
-        need = 24 + sum(sz)
-        if setup:
-            n = torch.tensor([need], device=dev, dtype=torch.int64)
-            allv = [torch.zeros_like(n) for _ in range(world)]
-            dist.all_gather(allv, n)
-            mx = max(int(v.item()) for v in allv)
-            cap = (mx + mx // 4 + 4095) // 4096 * 4096
-            if gbuf.get("cap", 0) < cap:
-                gbuf["cap"] = cap
-                gbuf["send"] = torch.zeros(cap, dtype=torch.uint8, device=dev)
-                gbuf["recv"] = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-                gbuf["hdr"] = torch.zeros(3, dtype=torch.int64).pin_memory()
-        if need > gbuf["cap"]:
-            raise RuntimeError(f"rank {rank}: gather payload {need} B exceeds the capacity {gbuf['cap']} B agreed before the timed region")
-        send = gbuf["send"]
-        gbuf["hdr"][:] = torch.tensor(sz, dtype=torch.int64)
-        send[:24].view(torch.int64).copy_(gbuf["hdr"], non_blocking=True)
-        a, b = 24 + sz[0], 24 + sz[0] + sz[1]
-        send[24:a].copy_(cand_u8)
-        send[a:b].copy_(hp_u8)
-        send[b:b + sz[2]].copy_(ps_u8)
-        dist.gather(send, gbuf["recv"], dst=0)
-        return gbuf["recv"]
+        """The per-rank VCF records and (read, HP, PS) arrays go to rank 0 (device tensors in): one NCCL gather (shard.PackedGather)."""
+        out = pg.gather(cand_u8, hp_u8, ps_u8, setup=setup)
+        gbuf["cap"] = pg.cap
+        return out
 
     def device_results(handle):
         v = eng.device_view(handle)

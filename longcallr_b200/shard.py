@@ -112,3 +112,56 @@ def gather_candidates(dist, cand, region_ids, rank, world_size, device=None):
         parts.append(c)
     allc = np.concatenate(parts) if parts else np.zeros(0, abi.CANDIDATE_DTYPE)
     return allc[np.lexsort((allc["pos"], allc["region"]))]
+
+
+class PackedGather:
+    """One collective per step for the per-rank results: the candidate records and the per-read (HP, PS) arrays of every rank go to
+    rank 0 as ONE gather of a fixed-capacity byte payload whose first 24 bytes carry the three sizes ("gather of per-region
+    VCF records" and of the (read, HP, PS) tuples the phased BAM needs).  The capacity (1.25 x the largest rank) is agreed by one
+    exchange of sizes (`setup=True`, outside a timed region); a later payload that outgrew it is an error, never a silent truncation.
+    Works on device tensors over NCCL (bench.py) and on CPU tensors over gloo (tests)."""
+
+    HEADER = 24
+
+    def __init__(self, dist, rank, world, device=None):
+        self.dist, self.rank, self.world, self.device = dist, rank, world, device
+        self.cap = 0
+        self.send = self.recv = self.hdr = None
+
+    def gather(self, cand_u8, hp_u8, ps_u8, setup=False):
+        import torch
+
+        sz = [int(cand_u8.numel()), int(hp_u8.numel()), int(ps_u8.numel())]
+        need = self.HEADER + sum(sz)
+        if setup:
+            n = torch.tensor([need], device=self.device, dtype=torch.int64)
+            allv = [torch.zeros_like(n) for _ in range(self.world)]
+            self.dist.all_gather(allv, n)
+            mx = max(int(v.item()) for v in allv)
+            cap = (mx + mx // 4 + 4095) // 4096 * 4096
+            if self.cap < cap:
+                self.cap = cap
+                self.send = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+                self.recv = [torch.empty(cap, dtype=torch.uint8, device=self.device) for _ in range(self.world)] if self.rank == 0 else None
+                self.hdr = torch.zeros(3, dtype=torch.int64)
+                if self.device is not None and torch.device(self.device).type == "cuda":
+                    self.hdr = self.hdr.pin_memory()
+        if need > self.cap:
+            raise RuntimeError(f"rank {self.rank}: gather payload {need} B exceeds the capacity {self.cap} B agreed at setup")
+        self.hdr[:] = torch.tensor(sz, dtype=torch.int64)
+        self.send[: self.HEADER].view(torch.int64).copy_(self.hdr, non_blocking=True)
+        a, b = self.HEADER + sz[0], self.HEADER + sz[0] + sz[1]
+        self.send[self.HEADER:a].copy_(cand_u8)
+        self.send[a:b].copy_(hp_u8)
+        self.send[b:b + sz[2]].copy_(ps_u8)
+        self.dist.gather(self.send, self.recv, dst=0)
+        return self.recv
+
+    @classmethod
+    def unpack(cls, payload):
+        """(candidate bytes, hp bytes, ps bytes) views of one rank's payload on rank 0."""
+        import torch
+
+        sz = [int(x) for x in payload[: cls.HEADER].view(torch.int64).tolist()]
+        a, b = cls.HEADER + sz[0], cls.HEADER + sz[0] + sz[1]
+        return payload[cls.HEADER:a], payload[a:b], payload[b:b + sz[2]]
