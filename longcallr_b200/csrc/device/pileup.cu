@@ -774,11 +774,13 @@ __device__ __forceinline__ void sts8a(uint32_t addr, uint32_t v) { asm volatile(
 #define EV_NONACGT 8                      /* aligned bytes that are no A/C/G/T letter */
 #define EV_NONACGT_FWD 9                  /* ... on forward reads */
 
-template <bool BIG, int STAGES>
+template <bool BIG, int STAGES, int MINB = 4>
 struct PtLayout { /* dynamic shared memory of k_pileup_tile, byte offsets */
-    static constexpr uint32_t ROWS = 32u;                                    /* rows per batch */
-    static constexpr uint32_t STAGE_BYTES = STAGES == 1 ? 12288u : 8192u;    /* seq bytes per stage */
-    static constexpr uint32_t SEG_CAP = 256u;                                /* segments per batch */
+    /* three CTAs per SM leave room for batches that hold a whole 30x tile (48 rows, 16 KB of bases); four CTAs per SM take 32 rows / 12 KB */
+    static constexpr bool WIDE = STAGES == 1 && MINB <= 3;
+    static constexpr uint32_t ROWS = WIDE ? 48u : 32u;                       /* rows per batch */
+    static constexpr uint32_t STAGE_BYTES = WIDE ? 16000u : (STAGES == 1 ? 12288u : 8192u); /* seq bytes per stage */
+    static constexpr uint32_t SEG_CAP = WIDE ? 320u : 256u;                  /* segments per batch */
     static constexpr uint32_t ROW_SEG_MAX = 128u;                            /* segments of one row */
     static constexpr uint32_t BLK_CAP = ROWS * (LCR_TILE / 16) + SEG_CAP;    /* 16-column blocks per batch */
     static constexpr uint32_t PAD = 32u;                                     /* slack before / after the staged bytes (block loads start up to 15 B early, read 20 B) */
@@ -796,7 +798,7 @@ struct PtLayout { /* dynamic shared memory of k_pileup_tile, byte offsets */
     static constexpr uint32_t st_rowdelta = st_rowseg + (ROWS + 1u) * 4u;    /* [ROWS] staged byte offset minus pool offset (mod 2^32) */
     static constexpr uint32_t st_hdr = (st_rowdelta + ROWS * 4u + 15u) & ~15u; /* tile, rows, segments, flags */
     static constexpr uint32_t stage_size = (st_hdr + 16u + 127u) & ~127u;
-    static constexpr uint32_t blk = stage0 + STAGES * stage_size;            /* [BLK_CAP] u32 per 16-column block: staged byte of its first column | block << 14 | first byte << 19 | last byte << 23 | forward << 27 */
+    static constexpr uint32_t blk = stage0 + STAGES * stage_size;            /* [BLK_CAP] u32 per 16-column block: staged byte of its first column | block << 15 | first byte << 20 | last byte << 24 | forward << 28 */
     static constexpr uint32_t evl = blk + BLK_CAP * 4u;                      /* [BLK_CAP] u32: blocks with exceptional bytes: block list index | byte mask << 16 */
     static constexpr uint32_t bytes() { return evl + BLK_CAP * 4u; }
 };
@@ -804,11 +806,11 @@ struct PtLayout { /* dynamic shared memory of k_pileup_tile, byte offsets */
 /* BIG: tiles of more than 65535 rows (32-bit event counters); the others pack two 16-bit event counters per word */
 template <bool BIG, int PT_STAGES, int MINB>
 __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
-    using L = PtLayout<BIG, PT_STAGES>;
+    using L = PtLayout<BIG, PT_STAGES, MINB>;
     constexpr uint32_t ROWS = L::ROWS;
     static_assert(ROWS <= 64 && L::SEG_CAP <= 1024, "row ids take 6 bits, segment ids 10");
     static_assert(LCR_TILE % PT_CONS == 0, "whole columns per consumer thread");
-    static_assert(L::PAD + L::STAGE_BYTES + 16 <= (1u << 14) && LCR_TILE / 16 <= 32, "block entries: 14 bits of staged offset, 5 bits of block index");
+    static_assert(L::PAD + L::STAGE_BYTES + 16 <= (1u << 15) && LCR_TILE / 16 <= 32, "block entries: 15 bits of staged offset, 5 bits of block index");
     static_assert(L::BLK_CAP <= 65536, "block list indices take 16 bits");
     static_assert(PT_ROW_BYTES_MAX + 32 <= L::STAGE_BYTES && L::ROW_SEG_MAX <= L::SEG_CAP, "one row always fits an empty batch");
     extern __shared__ __align__(128) unsigned char pt_smem[];
@@ -1088,7 +1090,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                         arr = ((sg.z & 4u) ? 3u : 0u) + ((sg.z >> 3) & 3u); /* class: forward strand x transcript-strand code */
                         /* staged byte of the first column of the segment's first block (mod 2^32 arithmetic on the pool offset) */
                         const uint32_t src0 = s_rowdelta[s_segrow[i]] + sg.x - (col & 15u);
-                        ent0 = src0 | ((col >> 4) << 14) | ((sg.z & 4u) << 25);
+                        ent0 = src0 | ((col >> 4) << 15) | ((sg.z & 4u) << 26);
                         lo0 = col & 15u; hi1 = (col + len - 1u) & 15u;
                     } else arr = typ == SEG_D ? 6u : 7u;
                     atomicAdd(&s_diff[arr * PT_DIFF_LEN + col], 1);
@@ -1108,7 +1110,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 base = __shfl_sync(0xffffffffu, base, 31);
                 const uint32_t run = base + incl - n;
                 for (uint32_t k = 0; k < n; ++k) /* next block: 16 staged bytes and one block further; only the first / last block are partial */
-                    s_blk[run + k] = (ent0 + k * (16u + (1u << 14))) | ((k == 0 ? lo0 : 0u) << 19) | ((k + 1 == n ? hi1 : 15u) << 23);
+                    s_blk[run + k] = (ent0 + k * (16u + (1u << 15))) | ((k == 0 ? lo0 : 0u) << 20) | ((k + 1 == n ? hi1 : 15u) << 24);
             }
         }
         cons_bar(); /* also: the compare bytes are in place */
@@ -1120,7 +1122,7 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
         const uint32_t seq_s = stg_s + L::st_seq;
         auto detect = [&](uint32_t g) -> uint32_t { /* bit i of the result: byte i of block g differs from its compare byte */
             const uint32_t e = s_blk[g];
-            const uint32_t src = e & 0x3fffu, c0 = ((e >> 14) & 31u) << 4, lo = (e >> 19) & 15u, hi = ((e >> 23) & 15u) + 1u;
+            const uint32_t src = e & 0x7fffu, c0 = ((e >> 15) & 31u) << 4, lo = (e >> 20) & 15u, hi = ((e >> 24) & 15u) + 1u;
             const uint32_t al = src & ~3u, rot = 0x3210u + 0x1111u * (src & 3u);
             const uint32_t sa = seq_s + al;
             const uint32_t s0 = lds32(sa), s1 = lds32(sa + 4), s2 = lds32(sa + 8), s3 = lds32(sa + 12), s4w = lds32(sa + 16);
@@ -1162,8 +1164,8 @@ __global__ void __launch_bounds__(PT_THREADS, MINB) k_pileup_tile(PileArgs a) {
                 const uint32_t ent = s_evl[x];
                 const uint32_t e = s_blk[ent & 0xffffu];
                 uint32_t m16 = ent >> 16;
-                const uint32_t src = e & 0x3fffu, c0 = ((e >> 14) & 31u) << 4;
-                const bool fwd = (e >> 27) & 1u;
+                const uint32_t src = e & 0x7fffu, c0 = ((e >> 15) & 31u) << 4;
+                const bool fwd = (e >> 28) & 1u;
                 while (m16) {
                     const uint32_t t = (uint32_t)__ffs((int)m16) - 1u;
                     m16 &= m16 - 1u;
@@ -1549,7 +1551,7 @@ __global__ void k_cand_dense(lcr_params P, const LcrCounters *ctr, lcr_candidate
 
 template <bool BIG, int STAGES, int MINB>
 static cudaError_t launch_tile(const PileArgs &ka, int sms, uint32_t n_tiles, cudaStream_t st) {
-    const size_t smem = PtLayout<BIG, STAGES>::bytes();
+    const size_t smem = PtLayout<BIG, STAGES, MINB>::bytes();
     static bool smem_set[8] = {false, false, false, false, false, false, false, false}; /* per device, once per instantiation */
     int dev = 0;
     cudaGetDevice(&dev);
