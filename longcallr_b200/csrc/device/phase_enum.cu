@@ -3,9 +3,11 @@
  * one warp per configuration.
  *
  * Every configuration is an independent cross_optimize run (src/phase.rs:810-976) from its own
- * random haplotags, so the 2^n runs of a region spread over warps and CTAs; only the winning
- * configuration index comes back (strict `>` in enumeration order == highest objective, lowest
- * index on ties) and k_phase replays that single configuration to materialise the state.
+ * random haplotags, so the 2^n runs of a region spread over warps and CTAs (persistent kernels that
+ * draw (region, chunk) work items from device-built lists, k_enum_plan).  The winner is the highest
+ * objective, lowest index on ties (strict `>` in enumeration order); the CTA that finishes a region's
+ * last chunk runs the winning configuration once more and leaves its final state (haplotypes,
+ * genotypes, haplotags) for k_phase, which continues from there.
  *
  * The region's fragment matrix is staged once per CTA in shared memory as one 64-bit word per
  * read (n <= 10 sites x 6 bits: sign and capped quality + 1), haplotags are one bit per read per

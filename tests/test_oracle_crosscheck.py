@@ -173,8 +173,16 @@ def test_pileup_candidates_fragments_agree(case):
         gen = np.array([c["genotype"] for c in cands], dtype=np.int8)
         # reads whose phase sites are all homozygous in the final state keep the random haplotag of the winning start: arbitrary
         informative = np.zeros(len(pr), dtype=bool)
+        tied = np.zeros(len(pr), dtype=bool)
         for f in frags:
             informative[f["read"]] = f["for_phasing"] and any(fe["phase_site"] and cands[fe["snp"]]["genotype"] == 0 for fe in f["list"])
+            # a read whose heterozygous phase sites split into two sides of identical (capped) qualities: the two sums are the same terms
+            # in a different order - an exact tie for the contract's integers, rounding noise for f64 - and the read keeps whatever it had
+            side = {1: [], -1: []}
+            for fe in f["list"]:
+                if fe["phase_site"] and cands[fe["snp"]]["genotype"] == 0:
+                    side[fe["p"] * cands[fe["snp"]]["haplotype"]].append(min(fe["baseq"], 30))
+            tied[f["read"]] = bool(side[1]) and sorted(side[1]) == sorted(side[-1])
         for m in (0, 1):
             g = got[m]
             assert g.stats["n_cross_optimize"] == counters["calls"], (m, g.stats, counters)
@@ -187,8 +195,10 @@ def test_pileup_candidates_fragments_agree(case):
             # the fixed-point contract breaks exact ties between starts by index where f64 breaks them by rounding noise: a start and its
             # complement reach mirror-image optima of equal objective, so the contract's answer may be the mirror image
             het = gen == 0
+            decided = informative & ~tied
+            same = np.array_equal(g.cand["haplotype"], hap) and np.array_equal(g.hp[decided], want_hp[decided])
             mirror_hp = np.where(want_hp == 1, 2, np.where(want_hp == 2, 1, want_hp))
-            mirrored = np.array_equal(g.cand["haplotype"][het], -hap[het]) and np.array_equal(g.hp[informative], mirror_hp[informative])
+            mirrored = np.array_equal(g.cand["haplotype"][het], -hap[het]) and np.array_equal(g.hp[decided], mirror_hp[decided])
             assert same or mirrored, (m, list(g.cand["haplotype"]), list(hap), list(g.hp), list(want_hp))
 
 
