@@ -293,6 +293,9 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     LCR_DEBUG_CHECK(ctx, "enum_plan");
     TRY(cudaEventRecord(ctx->ev_fork, st));
     for (int i = 0; i < 4; ++i) TRY(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+    /* the LD-path regions do not wait for the search: their CTAs (long, latency-bound chains of sweeps) run on the main stream beside it */
+    lcr_launch_phase(pa, 1, st);
+    db->timing.kernel_launches += 1;
     for (int b = 0, nl = 0; b < LCR_ENUM_BINS; ++b) {
         if (!lcr_enum_bin_possible(b, db->max_region_slots)) continue;
         int e = lcr_launch_enum_search(b, pa, ctx->sm_count, ctx->side[nl++ % 4]);
@@ -305,7 +308,7 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     }
     LCR_DEBUG_CHECK(ctx, "enum_search");
     TRY(cudaEventRecord(ctx->ev_t[6], st));
-    lcr_launch_phase(pa, st);
+    lcr_launch_phase(pa, 2, st);
     db->timing.kernel_launches += 1;
     LCR_DEBUG_CHECK(ctx, "k_phase");
     /* regions too large for one CTA take the whole GPU, one after the other */

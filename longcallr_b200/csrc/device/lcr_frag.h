@@ -98,7 +98,8 @@ void lcr_launch_pair_build(const FragArgs &a, uint32_t n_regions, LcrPairEntry *
 void lcr_launch_ld_edges(bool fill, const FragArgs &a, const LcrPairEntry *table, const uint32_t *entry_region, uint32_t *deg, const uint32_t *adj_off, uint32_t *adj_cursor,
                          uint32_t *adj, int sm_count, cudaStream_t st);
 void lcr_launch_adj_finish(const FragArgs &a, const uint32_t *adj_off, uint32_t *adj, bool sort, int sm_count, cudaStream_t st);
-void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st);
+/* which: 0 every region, 1 the regions outside the enumeration search's plan (es_base), 2 the regions inside it */
+void lcr_launch_phase(const PhaseArgs &a, int which, cudaStream_t st);
 int lcr_launch_phase_grid(const PhaseArgs &a, const uint32_t *big_list, uint32_t n_big_list, void *bcast_scratch, int sm_count, cudaStream_t st);
 size_t lcr_phase_bcast_bytes();
 void lcr_launch_enum_plan(const PhaseArgs &a, uint32_t work_cap, int sm_count, cudaStream_t st);

@@ -23,7 +23,7 @@
 
 namespace cg = cooperative_groups;
 
-#define PB 256          /* threads per CTA of the per-region kernel */
+#define PB 128          /* threads per CTA of the per-region kernel (small regions dominate: more of them in flight per SM) */
 #define PBG 512         /* threads per CTA of the cooperative (whole-GPU) kernel */
 #define NONE32 0xffffffffu
 
@@ -852,7 +852,7 @@ __device__ void run_region(Ctx &x) {
 }
 
 /* one CTA per region (everything except the few regions handed to the cooperative kernel) */
-__global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
+__global__ void __launch_bounds__(PB) k_phase(PhaseArgs a, int which) {
     __shared__ long long sh[32];
     __shared__ long long tabs[3][32];
     __shared__ TeamBcast bc;
@@ -860,6 +860,8 @@ __global__ void __launch_bounds__(PB) k_phase(PhaseArgs a) {
     if (a.ctr->overflow) return; /* a capacity was exceeded: the run is repeated with larger buffers */
     const LcrRegionState rs = a.rstate[reg];
     if (rs.status != 0) return;
+    /* which: 0 every region; 1 the regions the enumeration search does not cover (they can run beside it); 2 the ones it covers */
+    if (which && a.es_base && ((a.es_base[reg + 1] > a.es_base[reg]) != (which == 2))) return;
     if (rs.n_cand == 0) { /* phase() still runs its single (empty) configuration: one cross_optimize call of one iteration (phase.rs:1097-1122) */
         if (threadIdx.x == 0) {
             atomicAdd((unsigned long long *)&a.stats->n_cross_optimize, 1ull);
@@ -904,8 +906,8 @@ __global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, const uint32_t 
 
 } // namespace
 
-void lcr_launch_phase(const PhaseArgs &a, cudaStream_t st) {
-    if (a.n_regions) k_phase<<<a.n_regions, PB, 0, st>>>(a);
+void lcr_launch_phase(const PhaseArgs &a, int which, cudaStream_t st) {
+    if (a.n_regions) k_phase<<<a.n_regions, PB, 0, st>>>(a, which);
 }
 
 int lcr_launch_phase_grid(const PhaseArgs &a, const uint32_t *big_list, uint32_t n_big_list, void *bcast_scratch, int sm_count, cudaStream_t st) {
