@@ -67,6 +67,8 @@ typedef struct lcr_params {
     uint32_t ld_weight_threshold;         /* hard-coded 1 at thread.rs:166                         */
     uint32_t flags;                       /* LCR_FLAG_*                                            */
     uint64_t seed;                        /* seeds lcr_uniform(); replaces thread_rng              */
+    uint32_t downsample_depth;            /* thread.rs:38, default 10000; used with LCR_FLAG_DOWNSAMPLE */
+    uint32_t reserved0;
 } lcr_params;
 
 #define LCR_FLAG_EMIT_PLANES 1u  /* also return the per-position pileup counters (debug / parity) */
@@ -76,6 +78,10 @@ typedef struct lcr_params {
    lies in page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister, lcr_pin_host) is not copied; the kernels
    fetch the bytes they need over the bus.  A pageable `qual` is copied as usual.  Results are identical either way. */
 #define LCR_FLAG_QUAL_ON_DEMAND 8u
+/* --downsample (thread.rs:144-151, phase.rs:693-701): in a region with at least downsample_depth fragments only downsample_depth of
+   them, chosen by the reference's seeded shuffle (StdRng::seed_from_u64(2025) = ChaCha12, SliceRandom::shuffle of rand 0.8.5, restated
+   in include/lcr_contract.h), take part in phasing, the first two assignment rounds and the rescue passes */
+#define LCR_FLAG_DOWNSAMPLE 16u
 
 enum { LCR_PRESET_ONT_CDNA = 0, LCR_PRESET_ONT_DRNA = 1, LCR_PRESET_HIFI_ISOSEQ = 2, LCR_PRESET_HIFI_MASSEQ = 3 };
 

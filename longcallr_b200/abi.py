@@ -24,6 +24,7 @@ LCR_FLAG_EMIT_PLANES = 1
 LCR_FLAG_SKIP_PHASING = 2
 LCR_FLAG_EMIT_FRAGMENTS = 4
 LCR_FLAG_QUAL_ON_DEMAND = 8
+LCR_FLAG_DOWNSAMPLE = 16
 
 PRESETS = {"ont-cdna": 0, "ont-drna": 1, "hifi-isoseq": 2, "hifi-masseq": 3}
 
@@ -65,6 +66,8 @@ class Params(C.Structure):
         ("ld_weight_threshold", C.c_uint32),
         ("flags", C.c_uint32),
         ("seed", C.c_uint64),
+        ("downsample_depth", C.c_uint32),
+        ("reserved0", C.c_uint32),
     ]
 
 

@@ -210,6 +210,9 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     pa.blk_q = A.take<long long>(cn); pa.blk_qflip = A.take<long long>(cn);
     pa.piece_off = A.take<uint32_t>(cn + 1); pa.piece_col = A.take<uint32_t>(C.elems / LCR_COL_PIECE + cn + 1); pa.col_acc = A.take<long long>(5 * cn);
     pa.tag = A.take<int8_t>(sn); pa.best_tag = A.take<int8_t>(sn); pa.fp = A.take<uint8_t>(sn); pa.assign = A.take<uint8_t>(sn);
+    const bool ds_on = (ctx->P.flags & LCR_FLAG_DOWNSAMPLE) && ctx->P.downsample_depth > 0;
+    pa.ds = ds_on ? A.take<uint8_t>(sn) : nullptr; /* --downsample: the sampled set, and the shuffle's index scratch for very large regions */
+    uint32_t *ds_scratch = ds_on ? A.take<uint32_t>(sn) : nullptr;
     pa.hp_key = A.take<uint32_t>(n_reads); pa.ps_key = A.take<unsigned long long>(n_reads);
     pa.es_base = A.take<uint32_t>(rn); pa.es_cfg = A.take<uint32_t>(C.enum_work); pa.es_prob = A.take<long long>(C.enum_work);
     pa.work_region = A.take<uint32_t>(C.enum_work); pa.work_chunk = A.take<uint32_t>(C.enum_work);
@@ -286,6 +289,12 @@ static int stage_fragments_phase(lcr_ctx *ctx, lcr_device_batch_full *db, LcrAre
     pa.adj_off = adj_off; pa.adj = adj;
     pa.ctr = ctr;
     pa.big_frag_threshold = ctx->big_frag_threshold;
+    if (ds_on) { /* thread.rs:144-151: mark the sampled fragments of the regions deep enough to downsample */
+        TRY(cudaMemsetAsync(pa.ds, 0, sn, st));
+        lcr_launch_downsample(pa, ds_scratch, st);
+        db->timing.kernel_launches += 1;
+        LCR_DEBUG_CHECK(ctx, "k_downsample");
+    }
     /* enumeration search (regions with at most min(max_enum_snps, 10) candidates): work lists on the device, one persistent launch
        per (shape, class) bin; the bins are independent: fork them onto side streams so that small and large shapes overlap */
     lcr_launch_enum_plan(pa, (uint32_t)std::min<uint64_t>(C.enum_work, 0xfffffff0u), ctx->sm_count, st);

@@ -76,6 +76,7 @@ struct PhaseArgs {
     /* state, per fragment (global index) */
     int8_t *tag, *best_tag;
     uint8_t *fp, *assign;
+    uint8_t *ds; /* --downsample: 1 = fragment inside the sampled set of its region (k_downsample); null when the flag is off */
     /* outputs per read: (region << 2 | HP) and (region << 32 | PS) under atomicMin, so that a read shared by several regions
        keeps the entry of the lowest region whatever the CTA order; unpacked by k_finalize_reads */
     uint32_t *hp_key;
@@ -100,6 +101,8 @@ void lcr_launch_ld_edges(bool fill, const FragArgs &a, const LcrPairEntry *table
 void lcr_launch_adj_finish(const FragArgs &a, const uint32_t *adj_off, uint32_t *adj, bool sort, int sm_count, cudaStream_t st);
 /* which: 0 every region, 1 the regions outside the enumeration search's plan (es_base), 2 the regions inside it */
 void lcr_launch_phase(const PhaseArgs &a, int which, cudaStream_t st);
+/* marks PhaseArgs.ds for the regions that downsample (scratch: one uint32 per fragment, for regions too large for shared memory) */
+void lcr_launch_downsample(const PhaseArgs &a, uint32_t *scratch, cudaStream_t st);
 int lcr_launch_phase_grid(const PhaseArgs &a, const uint32_t *big_list, uint32_t n_big_list, void *bcast_scratch, int sm_count, cudaStream_t st);
 size_t lcr_phase_bcast_bytes();
 void lcr_launch_enum_plan(const PhaseArgs &a, uint32_t work_cap, int sm_count, cudaStream_t st);

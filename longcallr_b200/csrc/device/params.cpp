@@ -31,5 +31,6 @@ extern "C" int lcr_params_preset(int preset, lcr_params *p) {
     p->ld_weight_threshold = 1;                      /* thread.rs:166 */
     p->flags = 0;
     p->seed = 0;
+    p->downsample_depth = 10000;                     /* main.rs:296,327,358,389 */
     return LCR_OK;
 }

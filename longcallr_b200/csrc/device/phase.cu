@@ -26,6 +26,7 @@ namespace cg = cooperative_groups;
 #define PB 128          /* threads per CTA of the per-region kernel (small regions dominate: more of them in flight per SM) */
 #define PBG 512         /* threads per CTA of the cooperative (whole-GPU) kernel */
 #define NONE32 0xffffffffu
+#define FA(x, k) (((x).fp[k] & (x).need) == (x).need) /* fragment k takes part in the current stage */
 
 namespace {
 
@@ -61,6 +62,11 @@ struct Ctx {
     uint32_t *piece_off, *piece_col; /* grid teams: column pieces of the delta / eta sweep */
     long long *col_acc;
     uint32_t n_pieces;
+    /* fp[k]: bit 0 = fragment used for phasing (num_hete_links >= min_linkers, or promoted by a rescue pass), bit 1 = inside the
+       --downsample set (always set when the region does not downsample).  need = 3 while the reference passes apply_downsampling,
+       1 for the last assignment round and the phase sets (thread.rs:166-182) */
+    uint8_t need;
+    bool apply_ds; /* the region downsamples */
     unsigned long long n_iters;
 };
 
@@ -157,7 +163,7 @@ __device__ long long objective(Ctx &x) {
     /* eight lanes per fragment row (four on the cooperative grid: more rows in flight per pass) */
     const uint32_t lsh = x.grid ? 2u : 3u, lpr = 1u << lsh;
     for (uint32_t k = x.tid >> lsh; k < x.nf; k += x.nthreads >> lsh) {
-        if (!x.fp[k] || x.tag[k] == 0) continue;
+        if (!FA(x, k) || x.tag[k] == 0) continue;
         const int sg = x.tag[k];
         for (uint32_t e = x.frag_elem_off[k] + (x.tid & (lpr - 1)); e < x.frag_elem_off[k + 1]; e += lpr) {
             const char4 st = x.st[x.a.elem_snp[e]];
@@ -184,7 +190,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             const uint32_t k = k0 + (x.tid >> lsh);
             long long diff = 0;
             int sg = 0;
-            if (k < x.nf && x.fp[k]) sg = x.tag[k];
+            if (k < x.nf && FA(x, k)) sg = x.tag[k];
             if (sg != 0) {
                 for (uint32_t e = x.frag_elem_off[k] + (x.tid & (lpr - 1)); e < x.frag_elem_off[k + 1]; e += lpr) {
                     const char4 st = x.st[x.a.elem_snp[e]];
@@ -244,8 +250,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
                 const uint32_t w0 = x.cover_off[i] + (p - x.piece_off[i]) * LCR_COL_PIECE;
                 const uint32_t w1 = min(w0 + LCR_COL_PIECE, x.cover_off[i + 1]);
                 ColFx col(x);
-                /* the piece's four 32-element trips with their loads issued together (each is an L2 round trip);
-                   during phase() a haplotag is non-zero only on a fragment used for phasing (init_assignment, sign flips) */
+                /* the piece's four 32-element trips with their loads issued together (each is an L2 round trip) */
                 uint32_t kk[LCR_COL_PIECE / 32];
                 int tg[LCR_COL_PIECE / 32];
                 int8_t cl[LCR_COL_PIECE / 32];
@@ -257,6 +262,11 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
                 }
 #pragma unroll
                 for (uint32_t j = 0; j < LCR_COL_PIECE / 32; ++j) tg[j] = kk[j] != NONE32 ? (int)x.tag[kk[j]] : 0;
+                if (x.apply_ds) { /* without downsampling a haplotag is non-zero only on a fragment that takes part (init_assignment, sign flips) */
+#pragma unroll
+                    for (uint32_t j = 0; j < LCR_COL_PIECE / 32; ++j)
+                        if (tg[j] != 0 && !FA(x, kk[j])) tg[j] = 0;
+                }
 #pragma unroll
                 for (uint32_t j = 0; j < LCR_COL_PIECE / 32; ++j)
                     if (tg[j] != 0) col_add(x.T, col, tg[j], sti.x, cell_p(cl[j]), cell_q(cl[j]));
@@ -292,7 +302,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
                 ColFx col(x);
                 for (uint32_t w = x.cover_off[i] + (x.tid & 31); w < x.cover_off[i + 1]; w += 32) {
                     const uint32_t k = x.a.cover_frag[w];
-                    if (!x.fp[k] || x.tag[k] == 0) continue;
+                    if (!FA(x, k) || x.tag[k] == 0) continue;
                     const int8_t cell = x.a.cover_cell[w];
                     col_add(x.T, col, x.tag[k], d, cell_p(cell), cell_q(cell));
                 }
@@ -335,7 +345,7 @@ __device__ void init_genotype(Ctx &x) { /* phase.rs:682-691 */
 }
 __device__ void init_assignment(Ctx &x, uint32_t call) { /* phase.rs:673-680 */
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads)
-        if (x.fp[k]) x.tag[k] = uniform(x, LCR_RNG_INIT_SIGMA, call, read_rel(x, k)) < 0.5 ? -1 : 1;
+        if (x.fp[k] & 1) x.tag[k] = uniform(x, LCR_RNG_INIT_SIGMA, call, read_rel(x, k)) < 0.5 ? -1 : 1; /* every fragment used for phasing, sampled or not */
 }
 
 /* phase.rs:1097-1122: all 2^n starting haplotypes */
@@ -381,7 +391,7 @@ __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
         ColFx c0(x), c1(x);
         for (uint32_t w = x.cover_off[i]; w < x.cover_off[i + 1]; ++w) {
             const uint32_t k = x.a.cover_frag[w];
-            if (!x.fp[k] || x.tag[k] == 0) continue;
+            if (!FA(x, k) || x.tag[k] == 0) continue;
             const int8_t cell = x.a.cover_cell[w];
             const int sg = x.tag[k];
             const int sf = flip_read_of(x, k, i, root) ? -sg : sg;
@@ -401,7 +411,7 @@ __device__ long long cross_optimize_by_block(Ctx &x, uint32_t root0) {
        per-block rewrite of tmp_haplotag (phase.rs:1365-1378) */
     if (root0 != NONE32 && x.blk_q[root0] < x.blk_qflip[root0]) {
         for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
-            if (!x.fp[k] || x.tag[k] == 0) continue;
+            if (!FA(x, k) || x.tag[k] == 0) continue;
             uint32_t best_idx = NONE32, best_rank = 0;
             for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
                 const uint32_t s = x.a.elem_snp[e];
@@ -523,7 +533,7 @@ __device__ void phase_ld(Ctx &x) {
         if (prob > best) { best = prob; save_best(x); }
         load_best(x);
         for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
-            if (!x.fp[k] || x.tag[k] == 0) continue;
+            if (!(x.fp[k] & 1) || x.tag[k] == 0) continue; /* phase.rs:1218-1225: no downsampling test here */
             if (uniform(x, LCR_RNG_PERTURB_SIGMA, t, read_rel(x, k)) < 0.1) x.tag[k] = (int8_t)(-x.tag[k]);
         }
         tsync(x);
@@ -536,7 +546,7 @@ __device__ void phase_ld(Ctx &x) {
 /* assign_reads_haplotype (snpfrags.rs:548-625) */
 __device__ void assign_reads(Ctx &x, bool record) {
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
-        if (!x.fp[k]) continue;
+        if (!FA(x, k)) continue;
         const int sg = x.tag[k];
         long long A = 0, B = 0;
         uint32_t cnt = 0;
@@ -596,7 +606,7 @@ __device__ void assign_snps(Ctx &x) {
         int hap1 = 0, hap2 = 0;
         for (uint32_t w = x.cover_off[i] + lane; w < x.cover_off[i + 1]; w += 32) {
             const uint32_t k = x.a.cover_frag[w];
-            if (!x.fp[k] || x.frag_links[k] < x.a.P.min_linkers) continue;
+            if (!FA(x, k) || x.frag_links[k] < x.a.P.min_linkers) continue;
             if (vt0 == 1 && x.assign[k] == 0) continue;
             if (x.assign[k] == 1) hap1++; else if (x.assign[k] == 2) hap2++;
             const int8_t cell = x.a.cover_cell[w];
@@ -641,7 +651,7 @@ __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
         long long Lp = 0, Lm = 0, h1 = 0, h2 = 0, cnt = 0, zz = 0;
         for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += x.nthreads) {
             const uint32_t k = x.a.cover_frag[w];
-            if (!x.fp[k] || x.assign[k] == 0 || x.frag_links[k] < x.a.P.min_linkers) continue;
+            if (!FA(x, k) || x.assign[k] == 0 || x.frag_links[k] < x.a.P.min_linkers) continue;
             if (x.assign[k] == 1) h1++; else if (x.assign[k] == 2) h2++;
             const int8_t cell = x.a.cover_cell[w];
             const int p = cell_p(cell), q = cell_q(cell), sg = x.tag[k];
@@ -686,7 +696,7 @@ __device__ void rescue(Ctx &x, uint16_t list_flag, bool low_frac) {
         if (*(volatile int *)&x.bc->decision) {
             for (uint32_t w = x.cover_off[ti] + x.tid; w < x.cover_off[ti + 1]; w += x.nthreads) {
                 const uint32_t k = x.a.cover_frag[w];
-                x.fp[k] = 1;
+                x.fp[k] |= 1;
                 if (x.tag[k] == 0 || x.assign[k] == 0) x.tag[k] = uniform(x, LCR_RNG_RESCUE_SIGMA, ti, read_rel(x, k)) < 0.5 ? -1 : 1;
             }
         }
@@ -706,7 +716,7 @@ __device__ void phase_sets(Ctx &x) {
     for (;;) {
         int changed = 0;
         for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
-            if (!x.fp[k] || x.assign[k] == 0) continue;
+            if (!(x.fp[k] & 1) || x.assign[k] == 0) continue;
             uint32_t mn[2] = {NONE32, NONE32};
             for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
                 const uint32_t i = x.a.elem_snp[e];
@@ -737,7 +747,7 @@ __device__ void phase_sets(Ctx &x) {
         if (x.label[i] != NONE32) x.c[i].phase_set = (uint32_t)(x.c[x.label[i]].pos + 1);
     /* components are visited in descending order of their first node; a read keeps the first id it meets */
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
-        if (!x.fp[k] || x.assign[k] == 0) continue;
+        if (!(x.fp[k] & 1) || x.assign[k] == 0) continue;
         uint32_t cnt[2] = {0, 0}, root[2] = {0, 0}, nn = 0;
         for (uint32_t e = x.frag_elem_off[k]; e < x.frag_elem_off[k + 1]; ++e) {
             const uint32_t i = x.a.elem_snp[e];
@@ -820,10 +830,14 @@ __device__ void run_region(Ctx &x) {
         x.st[i].z = (x.c[i].flags & LCR_CF_FOR_PHASING) ? 1 : 0;
         x.st[i].w = 0;
     }
+    /* thread.rs:144-151: --downsample applies to a region with at least downsample_depth fragments (k_downsample marked the sampled ones) */
+    const bool apply_ds = (a.P.flags & LCR_FLAG_DOWNSAMPLE) && a.P.downsample_depth > 0 && x.nf >= a.P.downsample_depth && a.ds;
+    x.need = 3;
+    x.apply_ds = apply_ds;
     for (uint32_t k = x.tid; k < x.nf; k += x.nthreads) {
         x.tag[k] = 0;
         x.assign[k] = 0;
-        x.fp[k] = x.frag_links[k] >= a.P.min_linkers ? 1 : 0;
+        x.fp[k] = (uint8_t)((x.frag_links[k] >= a.P.min_linkers ? 1 : 0) | ((!apply_ds || a.ds[x.fb + k]) ? 2 : 0));
     }
     tsync(x);
     uint64_t n_calls;
@@ -842,6 +856,7 @@ __device__ void run_region(Ctx &x) {
     assign_snps(x);
     rescue(x, LCR_CF_EDIT_LIST, false);
     rescue(x, LCR_CF_SOMATIC_LIST, true);
+    x.need = 1; /* thread.rs:181-182: the last round runs over every fragment used for phasing */
     assign_reads(x, true);
     assign_snps(x);
     phase_sets(x);
@@ -905,6 +920,35 @@ __global__ void __launch_bounds__(PBG) k_phase_grid(PhaseArgs a, const uint32_t 
 }
 
 } // namespace
+
+/* downsample_fragments (phase.rs:693-701): one CTA per region that downsamples; thread 0 runs the reference's seeded Fisher-Yates shuffle
+   (sequential by construction: the position in the ChaCha12 stream depends on the rejections before it) over an index array in shared
+   memory (regions of up to DS_SMEM_IDX fragments) or in global scratch, then the CTA marks the first downsample_depth fragments */
+#define DS_SMEM_IDX 51200u
+__global__ void __launch_bounds__(256) k_downsample(PhaseArgs a, uint32_t *scratch) {
+    extern __shared__ uint32_t ds_idx_smem[];
+    const uint32_t reg = blockIdx.x;
+    if (a.ctr->overflow) return;
+    const LcrRegionState rs = a.rstate[reg];
+    const uint32_t depth = a.P.downsample_depth, nf = rs.n_frag;
+    if (rs.status != 0 || depth == 0 || nf < depth) return;
+    uint32_t *idx = nf <= DS_SMEM_IDX ? ds_idx_smem : scratch + rs.frag_begin;
+    for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) idx[i] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        lcr_chacha12 g;
+        lcr_stdrng_seed_from_u64(&g, 2025ull); /* thread.rs:149 */
+        lcr_stdrng_shuffle(&g, idx, nf);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < depth; i += blockDim.x) a.ds[rs.frag_begin + idx[i]] = 1;
+}
+
+void lcr_launch_downsample(const PhaseArgs &a, uint32_t *scratch, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_downsample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DS_SMEM_IDX * 4)); attr_set = true; }
+    if (a.n_regions) k_downsample<<<a.n_regions, 256, DS_SMEM_IDX * 4, st>>>(a, scratch);
+}
 
 void lcr_launch_phase(const PhaseArgs &a, int which, cudaStream_t st) {
     if (a.n_regions) k_phase<<<a.n_regions, PB, 0, st>>>(a, which);

@@ -117,10 +117,13 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 3 : 1) k_enum_search(PhaseA
     const uint32_t *t_snp = reinterpret_cast<const uint32_t *>(tile + S.t_snp);
     const int8_t *t_cell = reinterpret_cast<const int8_t *>(tile + S.t_cell);
     const uint32_t t_e0 = PRE ? t_off[0] : 0u;
-    /* stage the rows: bit 63 = fragment used for phasing, 6 bits per site: (q + 1) | 32 when p < 0 */
+    /* stage the rows: bit 63 = fragment takes part in the sweeps (used for phasing and, when the region downsamples, inside the sampled
+       set), bit 62 = used for phasing at all, 6 bits per site: (q + 1) | 32 when p < 0 */
+    const bool apply_ds = (a.P.flags & LCR_FLAG_DOWNSAMPLE) && a.P.downsample_depth > 0 && nf >= a.P.downsample_depth && a.ds;
     for (uint32_t k = tid; k < nf; k += EW * 32) {
         const uint32_t f = fb + k;
-        unsigned long long row = a.frag_links[f] >= a.P.min_linkers ? (1ull << 63) : 0ull;
+        unsigned long long row = 0ull;
+        if (a.frag_links[f] >= a.P.min_linkers) row = (1ull << 62) | ((!apply_ds || a.ds[f]) ? (1ull << 63) : 0ull);
         uint32_t present = 0;
         if (PRE) {
 #pragma unroll
@@ -372,7 +375,13 @@ __global__ void __launch_bounds__(EW * 32, EW == 8 ? 3 : 1) k_enum_search(PhaseA
         __syncwarp();
         for (uint32_t w = 0; w < nwords; ++w) {
             const uint32_t k = w * 32 + lane;
-            if (k < nf) a.best_tag[fb + k] = (rows[k] >> 63) ? (((sig[w] >> lane) & 1u) ? -1 : 1) : 0;
+            if (k < nf) {
+                int8_t t = 0;
+                if (rows[k] >> 63) t = ((sig[w] >> lane) & 1u) ? -1 : 1;
+                else if ((rows[k] >> 62) & 1u) /* used for phasing but outside the sampled set: it keeps the haplotag init_assignment drew for the winner */
+                    t = lcr_uniform(a.P.seed, region_key, LCR_RNG_INIT_SIGMA, S.win_cfg, rrel[k]) < 0.5 ? -1 : 1;
+                a.best_tag[fb + k] = t;
+            }
         }
         if (lane == 0) a.es_done[reg] = 0x80000000u; /* replayed: k_phase loads the state instead of running the configuration again */
     }

@@ -112,6 +112,7 @@ struct Fragment { /* snp.rs:217-239 */
     double assignment_score = 0;
     uint32_t num_hete_links = 0;
     bool for_phasing = false;
+    bool downsampled = false; /* snp.rs:237 */
 };
 
 struct PairKeyHash {
@@ -845,7 +846,20 @@ struct Worker {
             if (fe.snp_idx == snp) return &fe;
         return nullptr;
     }
-    inline bool frag_active(const Fragment &f) const { return f.for_phasing && f.haplotag != 0; }
+    /* --downsample: while ds_on, a fragment outside the sampled set is skipped wherever the reference tests
+       `apply_downsampling && !downsampled` (phase.rs:262,288,327,369,826,885,983,1021,1326; snpfrags.rs:214,306,414,552) */
+    bool ds_on = false;
+    inline bool ds_ok(const Fragment &f) const { return !ds_on || f.downsampled; }
+    inline bool frag_active(const Fragment &f) const { return f.for_phasing && ds_ok(f) && f.haplotag != 0; }
+    /* downsample_fragments (phase.rs:693-701) with the seed of thread.rs:149 */
+    void downsample_fragments(uint32_t depth, uint64_t seed) {
+        lcr_chacha12 g;
+        lcr_stdrng_seed_from_u64(&g, seed);
+        std::vector<uint32_t> idx(frags.size());
+        for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
+        lcr_stdrng_shuffle(&g, idx.data(), (uint32_t)idx.size());
+        for (uint32_t i = 0; i < depth && i < idx.size(); ++i) frags[idx[i]].downsampled = true;
+    }
 
     /* cal_overall_probability (phase.rs:257-276) */
     double overall_f64() const {
@@ -1304,7 +1318,7 @@ struct Worker {
         if (ra) ra->clear();
         std::vector<int> delta, eta, ps, qs;
         for (Fragment &f : frags) {
-            if (!f.for_phasing) continue;
+            if (!f.for_phasing || !ds_ok(f)) continue;
             const int sigma_k = f.haplotag;
             delta.clear(); eta.clear(); ps.clear(); qs.clear();
             int64_t A = 0, Bs = 0;
@@ -1394,6 +1408,7 @@ struct Worker {
             for (uint32_t k : snp.cover) {
                 const Fragment &f = frags[k];
                 if (!f.for_phasing || f.assignment == 0 || f.num_hete_links < P.min_linkers) continue;
+                if (!ds_ok(f)) continue;
                 for (const FragElem &fe : f.list)
                     if (fe.snp_idx == ti) {
                         if (f.assignment == 1) cd.hap1++; else if (f.assignment == 2) cd.hap2++;
@@ -1437,6 +1452,7 @@ struct Worker {
             for (uint32_t k : snp.cover) {
                 const Fragment &f = frags[k];
                 if (!f.for_phasing || f.num_hete_links < P.min_linkers) continue;
+                if (!ds_ok(f)) continue;
                 if (snp.variant_type == 1 && f.assignment == 0) continue;
                 for (const FragElem &fe : f.list)
                     if (fe.snp_idx == ti) {
@@ -1536,6 +1552,10 @@ struct Worker {
         if (P.flags & LCR_FLAG_SKIP_PHASING) return;
         st = get_fragments();
         if (st) { out.status = st; frags.clear(); for (Cand &c : cands) c.cover.clear(); return; }
+        /* thread.rs:144-151 */
+        const bool apply_downsampling = (P.flags & LCR_FLAG_DOWNSAMPLE) && P.downsample_depth > 0 && frags.size() >= (size_t)P.downsample_depth;
+        if (apply_downsampling) downsample_fragments(P.downsample_depth, 2025);
+        ds_on = apply_downsampling;
         phase();
         if (P.flags & LCR_ORACLE_FLAG_STOP_AFTER_PHASE) { /* test hook: the state phase() leaves (haplotags as HP 1 / 2) */
             for (const Fragment &f : frags) out.hp.emplace_back(f.read, f.haplotag == 1 ? 1 : (f.haplotag == -1 ? 2 : 0));
@@ -1547,6 +1567,7 @@ struct Worker {
         assign_snp_haplotype_genotype();
         eval_rescue(edit_snps, false, P.min_phase_score - 3.0f);
         eval_rescue(somatic_snps, true, P.min_phase_score - 3.0f);
+        ds_on = false; /* thread.rs:181-182: the last round runs over every fragment */
         assign_reads_haplotype(&out.hp);
         assign_snp_haplotype_genotype();
         assign_phase_set(out.ps);
@@ -1722,5 +1743,13 @@ double lcr_oracle_uniform(uint64_t seed, int32_t tid, uint32_t start, uint32_t s
 }
 void lcr_oracle_luts(lcr_luts *t) { lcr_build_luts(t); }
 int lcr_oracle_f64_as_i32(double v) { return lcr_f64_as_i32(v); }
+/* test hooks for the seeded shuffle of --downsample (include/lcr_contract.h) */
+void lcr_oracle_chacha_block(const uint32_t *key, uint64_t counter, int rounds, uint32_t *out) { lcr_chacha_block(key, counter, rounds, out); }
+void lcr_oracle_shuffle(uint64_t seed, uint32_t n, uint32_t *idx) {
+    lcr_chacha12 g;
+    lcr_stdrng_seed_from_u64(&g, seed);
+    for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+    lcr_stdrng_shuffle(&g, idx, n);
+}
 
 } /* extern "C" */

@@ -504,7 +504,7 @@ def cal_delta_eta_sigma_log(delta_i, eta_i, sigma, ps, probs):
 def overall_probability(cands, frags):
     logp = 0.0
     for f in frags:
-        if not f["for_phasing"] or f["haplotag"] == 0:
+        if not f["for_phasing"] or f.get("ds_skip") or f["haplotag"] == 0:  # ds_skip: apply_downsampling && !downsampled (phase.rs:262)
             continue
         for fe in f["list"]:
             if fe["phase_site"]:
@@ -522,7 +522,7 @@ def cross_optimize(cands, frags, with_genotype, counters):
         tmp_tag = {}
         logp = pre_logp = 0.0
         for k, f in enumerate(frags):
-            if not f["for_phasing"] or f["haplotag"] == 0:
+            if not f["for_phasing"] or f.get("ds_skip") or f["haplotag"] == 0:
                 continue
             pl = [fe for fe in f["list"] if fe["phase_site"]]
             if not pl:
@@ -552,7 +552,7 @@ def cross_optimize(cands, frags, with_genotype, counters):
             sigma, ps, probs = [], [], []
             for k in c["cover"]:
                 f = frags[k]
-                if not f["for_phasing"] or f["haplotag"] == 0:
+                if not f["for_phasing"] or f.get("ds_skip") or f["haplotag"] == 0:
                     continue
                 for fe in f["list"]:
                     if fe["snp"] == i and fe["phase_site"]:
@@ -614,6 +614,70 @@ def phase_enum(P, region, cands, frags, reads_in_region_index):
     for f, t in zip(frags, best[2]):
         f["haplotag"] = t
     return counters
+
+
+# ---------------------------------------------------------------- X3 --downsample   phase.rs:693-701, thread.rs:144-151
+def _chacha_block(key, counter, rounds):
+    """One ChaCha block (D. J. Bernstein), 64-bit block counter in words 12-13, zero stream id: what rand_chacha 0.3 generates."""
+    M = 0xFFFFFFFF
+    st = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key) + [counter & M, (counter >> 32) & M, 0, 0]
+    x = list(st)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & M
+        x[d] ^= x[a]
+        x[d] = ((x[d] << 16) | (x[d] >> 16)) & M
+        x[c] = (x[c] + x[d]) & M
+        x[b] ^= x[c]
+        x[b] = ((x[b] << 12) | (x[b] >> 20)) & M
+        x[a] = (x[a] + x[b]) & M
+        x[d] ^= x[a]
+        x[d] = ((x[d] << 8) | (x[d] >> 24)) & M
+        x[c] = (x[c] + x[d]) & M
+        x[b] ^= x[c]
+        x[b] = ((x[b] << 7) | (x[b] >> 25)) & M
+
+    for _ in range(rounds // 2):
+        qr(0, 4, 8, 12), qr(1, 5, 9, 13), qr(2, 6, 10, 14), qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15), qr(1, 6, 11, 12), qr(2, 7, 8, 13), qr(3, 4, 9, 14)
+    return [(a + b) & M for a, b in zip(x, st)]
+
+
+class StdRng:
+    """rand 0.8.5 StdRng (ChaCha12) seeded with SeedableRng::seed_from_u64 (rand_core 0.6: a PCG32 stream fills the key)."""
+
+    def __init__(self, seed):
+        state, key = seed & M64, []
+        for _ in range(8):
+            state = (state * 6364136223846793005 + 11634580027462260723) & M64
+            xorshifted = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+            rot = state >> 59
+            key.append(((xorshifted >> rot) | (xorshifted << ((32 - rot) & 31))) & 0xFFFFFFFF)
+        self.key, self.counter, self.buf = key, 0, []
+
+    def next_u32(self):
+        if not self.buf:
+            self.buf = _chacha_block(self.key, self.counter, 12)
+            self.counter += 1
+        return self.buf.pop(0)
+
+    def below(self, n):
+        """UniformInt<u32>::sample_single(0, n): widening multiply, rejection zone (n << leading_zeros(n)) - 1"""
+        zone = ((n << (32 - n.bit_length())) - 1) & 0xFFFFFFFF
+        while True:
+            m = self.next_u32() * n
+            if (m & 0xFFFFFFFF) <= zone:
+                return m >> 32
+
+
+def downsample_fragments(n_fragments, depth, seed=2025):
+    """Indices of the fragments marked `downsampled`: the first `depth` of SliceRandom::shuffle over 0..n (phase.rs:693-701)."""
+    rng = StdRng(seed)
+    idx = list(range(n_fragments))
+    for i in range(n_fragments - 1, 0, -1):
+        j = rng.below(i + 1)
+        idx[i], idx[j] = idx[j], idx[i]
+    return idx[:depth]
 
 
 # ---------------------------------------------------------------- X2 imported candidates   candidate.rs:530-613

@@ -22,14 +22,14 @@ ENGINES = {}
 def engine(preset, **over):
     key = (preset, tuple(sorted(over.items())))
     if key not in ENGINES:
-        p = host.params_preset(preset, seed=5, min_read_length=30, min_depth=4, flags=FLAGS, **over)
+        p = host.params_preset(preset, seed=5, min_read_length=30, min_depth=4, flags=FLAGS | (abi.LCR_FLAG_DOWNSAMPLE if "downsample_depth" in over else 0), **over)
         ENGINES[key] = (p, host.Engine(p, device=0))
     return ENGINES[key]
 
 
 @settings(max_examples=int(os.environ.get("LCR_GPU_FUZZ_EXAMPLES", "250")), deadline=None, suppress_health_check=list(HealthCheck), derandomize=not os.environ.get("LCR_FUZZ_RANDOM"), database=None)
-@given(xc.regions(), st.booleans(), st.booleans())
-def test_random_regions_match_oracle(case, packed, two_regions):
+@given(xc.regions(), st.booleans(), st.booleans(), st.sampled_from([0, 0, 6, 15]))
+def test_random_regions_match_oracle(case, packed, two_regions, ds_depth):
     preset, ref, recs, start, end = case
     if packed:  # a BAM record cannot hold a lower-case base: what does not pack decodes as N (both sides see the decoded record)
         recs = [dict(r, seq="".join(c if c in "=ACMGRSVTWYHKDBN" else "N" for c in r["seq"])) for r in recs]
@@ -42,7 +42,7 @@ def test_random_regions_match_oracle(case, packed, two_regions):
         regions[1] = (0, mid, end, 0, n)
     else:
         regions = helpers.one_region(start, end, n)
-    p, eng = engine(preset)
+    p, eng = engine(preset, **(dict(downsample_depth=ds_depth) if ds_depth else {}))  # ds_depth > 0: --downsample with that depth
     eng.set_reference(0, ref)
     batch = host.BatchView(reads, regions, seq4=host.pack_seq4(reads) if packed and n else None)
     got = eng.submit(batch)

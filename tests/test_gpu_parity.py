@@ -487,3 +487,41 @@ def test_imported_candidates(monkeypatch, preset, platform, chunk_mb):
     n_expected = sum(1 for recs in external for q, gt, ql in recs if gt in (1, 2, 3) and not ql < 0)
     assert got.n_cand == n_expected > 100 and int((got.hp > 0).sum()) > 100
     assert np.isnan(got.cand["variant_quality"]).any() and np.isnan(got.cand["allele_freqs"]).any() or platform == 1
+
+
+@pytest.mark.parametrize("preset,platform,depth", [("hifi-masseq", 0, 60), ("ont-cdna", 1, 60), ("hifi-masseq", 0, 100000)])
+def test_downsample(preset, platform, depth):
+    """--downsample (thread.rs:144-151, phase.rs:693-701): regions with at least `depth` fragments phase on the subset the reference's seeded
+    shuffle selects (enumeration and LD regions alike); the last assignment round still tags every read."""
+    syn = host.Synthetic(seed=71 + platform, contig_len=200_000, n_contigs=2, platform=platform, depth=30.0, n_het=200, n_edit=30, both_strands=platform, n_threads=4)
+    refs = syn.reference.for_reads(syn.reads)
+    p0 = host.params_preset(preset, seed=8, flags=abi.LCR_FLAG_EMIT_FRAGMENTS)
+    p = host.params_preset(preset, seed=8, flags=abi.LCR_FLAG_EMIT_FRAGMENTS | abi.LCR_FLAG_DOWNSAMPLE, downsample_depth=depth)
+    regions, _ = host.find_regions(syn.reads, p)
+    got, want = run_both(p, syn.reads, refs, regions)
+    helpers.compare_results(got, want, f"{preset}/downsample {depth}")
+    plain, _ = run_both(p0, syn.reads, refs, regions)[0], None
+    n_frag = np.diff(got.fragments["frag_off"])
+    if depth < 1000:
+        assert (n_frag >= depth).sum() >= 2 and (n_frag < depth).sum() >= 2, list(n_frag)
+        assert got.stats["n_sweep_iters"] != plain.stats["n_sweep_iters"] or not np.array_equal(got.hp, plain.hp)
+    else:
+        helpers.compare_results(got, plain, "depth never reached")
+    assert int((got.hp > 0).sum()) > 0.9 * int((plain.hp > 0).sum())
+
+
+def test_downsample_ld_and_grid_paths(monkeypatch):
+    """The same on one deep LD-path region, per-region kernel and cooperative kernel."""
+    syn = host.Synthetic(seed=6, contig_len=40_000, n_contigs=1, platform=0, depth=150.0, n_het=300, n_edit=20, max_intron=500, both_strands=0, single_region=1, n_threads=4)
+    p = host.params_preset("hifi-masseq", seed=12, flags=abi.LCR_FLAG_EMIT_FRAGMENTS | abi.LCR_FLAG_DOWNSAMPLE, downsample_depth=700)
+    regions, _ = host.find_regions(syn.reads, p)
+    refs = syn.reference.for_reads(syn.reads)
+    want = ob.run(p, host.BatchView(syn.reads, regions), refs, mode=0)
+    assert want.stats["n_fragments"] > 1500 and want.cand_off[-1] > 100
+    for big in ("1000000", "64"):
+        monkeypatch.setenv("LCR_BIG_REGION_FRAGS", big)
+        eng = host.Engine(p, device=0)
+        eng.set_references(refs)
+        got = eng.submit(host.BatchView(syn.reads, regions))
+        eng.close()
+        helpers.compare_results(got, want, f"downsample, big region threshold {big}")

@@ -120,12 +120,14 @@ FLAG_OF = dict(rna_editing=abi.CF_RNA_EDITING, dense=abi.CF_DENSE, het_var=abi.C
 
 
 @settings(max_examples=int(os.environ.get("LCR_FUZZ_EXAMPLES", "300")), deadline=None, suppress_health_check=list(HealthCheck), derandomize=not os.environ.get("LCR_FUZZ_RANDOM"), database=None)
-@given(regions())
-def test_pileup_candidates_fragments_agree(case):
+@given(regions(), st.sampled_from([0, 0, 6, 15]))
+def test_pileup_candidates_fragments_agree(case, ds_depth):
     preset, ref, recs, start, end = case
     reads = helpers.make_reads(len(ref), recs)
     region = helpers.one_region(start, end, len(recs))
-    p = host.params_preset(preset, seed=5, min_read_length=30, min_depth=4, flags=abi.LCR_FLAG_EMIT_PLANES | abi.LCR_FLAG_EMIT_FRAGMENTS | STOP_AFTER_PHASE)
+    # ds_depth > 0: --downsample with that depth (regions here hold 10-60 fragments, so the seeded shuffle applies to most of them)
+    p = host.params_preset(preset, seed=5, min_read_length=30, min_depth=4, downsample_depth=max(ds_depth, 1),
+                           flags=abi.LCR_FLAG_EMIT_PLANES | abi.LCR_FLAG_EMIT_FRAGMENTS | STOP_AFTER_PHASE | (abi.LCR_FLAG_DOWNSAMPLE if ds_depth else 0))
     P = params_dict(p)
     batch = host.BatchView(reads, region)
     got = {m: ob.run(p, batch, [ref], mode=m) for m in (0, 1)}
@@ -164,6 +166,10 @@ def test_pileup_candidates_fragments_agree(case):
         np.testing.assert_array_equal(fr["elem_base"], [ord(fe["base"]) for f in frags for fe in f["list"]])
     # phase(): the 2^n enumeration with the contract's random source, when no phase site holds a quality-0 base (none here) and n <= 10
     if len(cands) <= P["max_enum_snps"] and len(cands) <= 6:
+        if ds_depth and len(frags) >= ds_depth:  # thread.rs:144-151
+            chosen = set(py.downsample_fragments(len(frags), ds_depth))
+            for k, f in enumerate(frags):
+                f["ds_skip"] = k not in chosen
         rel = {i: i for i in range(len(pr))}  # the region's read range starts at read 0
         counters = py.phase_enum(P, reg, cands, frags, rel)
         want_hp = np.full(len(pr), -1, dtype=np.int8)

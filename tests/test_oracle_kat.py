@@ -172,3 +172,32 @@ def test_planted_haplotypes_are_recovered():
         agree += max(a, m.sum() - a)
         total += m.sum()
     assert total > 500 and agree / total > 0.97
+
+
+def test_seeded_shuffle_of_downsample():
+    """--downsample draws from StdRng::seed_from_u64(2025) (phase.rs:693-701).  The ChaCha core of the contract's restatement against the
+    published zero-key, zero-nonce keystreams (ChaCha20: RFC 7539 appendix A.1 vector 1; ChaCha12 / ChaCha8: the reduced-round vectors of
+    the same family); the shuffle against the independent Python restatement.  The rand crates themselves are not available here."""
+    import ctypes as C
+    import os
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import py_restatement as py
+
+    L = ob.lib()
+    key = (C.c_uint32 * 8)()
+    out = (C.c_uint32 * 16)()
+    want = {20: "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7", 12: "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f",
+            8: "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e"}
+    for rounds, hexs in want.items():
+        L.lcr_oracle_chacha_block(key, C.c_uint64(0), rounds, out)
+        assert bytes(out)[:32].hex() == hexs, rounds
+        assert b"".join(int(w).to_bytes(4, "little") for w in py._chacha_block([0] * 8, 0, rounds))[:32].hex() == hexs
+    for n, depth in ((1, 1), (2, 2), (10, 10), (1000, 64), (65536, 16), (65537, 16), (100003, 32)):
+        idx = np.zeros(n, dtype="<u4")
+        L.lcr_oracle_shuffle(C.c_uint64(2025), C.c_uint32(n), C.c_void_p(idx.ctypes.data))
+        assert sorted(int(x) for x in idx) == list(range(n)) if n <= 1000 else len(set(int(x) for x in idx)) == n
+        assert [int(x) for x in idx[:depth]] == py.downsample_fragments(n, depth)
