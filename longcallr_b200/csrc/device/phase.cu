@@ -179,6 +179,7 @@ __device__ long long objective(Ctx &x) {
 __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genotype) {
     bool hg_increase = true, ht_increase = true;
     int num_iters = 0;
+    long long obj_iter = 0; /* cooperative grid: this thread's share of the objective of the state the last delta / eta sweep left */
     while (hg_increase | ht_increase) {
         x.n_iters++;
         int better = 0;
@@ -245,8 +246,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
             for (uint32_t p = x.tid >> 5; p < x.n_pieces; p += x.nthreads >> 5) {
                 const uint32_t i = x.piece_col[p];
                 const char4 sti = x.st[i];
-                if (!sti.z) continue;
-                if (keep_conserved && sti.w) continue;
+                if (!sti.z) continue; /* conserved sites are summed too: they are not decided, but they count in the objective */
                 const uint32_t w0 = x.cover_off[i] + (p - x.piece_off[i]) * LCR_COL_PIECE;
                 const uint32_t w1 = min(w0 + LCR_COL_PIECE, x.cover_off[i + 1]);
                 ColFx col(x);
@@ -281,17 +281,24 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
                 }
             }
             tsync(x);
+            obj_iter = 0;
             for (uint32_t i = x.tid; i < x.n; i += x.nthreads) {
                 const char4 sti = x.st[i];
                 if (!sti.z) continue;
-                if (keep_conserved && sti.w) continue;
                 long long *acc = x.col_acc + 5 * (size_t)i;
                 ColFx col(x);
                 col.het_d = __ldcg(acc + 0); col.het_nd = __ldcg(acc + 1); col.homref = __ldcg(acc + 2); col.homvar = __ldcg(acc + 3);
                 col.cov = (uint32_t)__ldcg(acc + 4);
                 if (!col.cov) continue;
                 acc[0] = 0; acc[1] = 0; acc[2] = 0; acc[3] = 0; acc[4] = 0;
-                decide(i, col, sti.x, sti.y);
+                int nd = sti.x, ne = sti.y;
+                if (!(keep_conserved && sti.w)) {
+                    decide(i, col, sti.x, sti.y);
+                    nd = x.st[i].x; ne = x.st[i].y;
+                }
+                /* cal_overall_probability (phase.rs:257-276) column by column: the state this pass leaves is the state the call returns,
+                   and its column sums were taken with the haplotags the last sigma sweep left */
+                obj_iter += ne == 0 ? (nd == sti.x ? col.het_d : col.het_nd) : (ne == 1 ? col.homref : col.homvar);
             }
         } else {
             /* one warp per SNP: lanes stride the column, five shuffled sums */
@@ -321,7 +328,7 @@ __device__ long long cross_optimize(Ctx &x, bool keep_conserved, bool with_genot
         if (++num_iters > 20) break;
     }
     GP_T(g5);
-    const long long obj = objective(x);
+    const long long obj = x.grid ? tsum(x, obj_iter) : objective(x);
     GP_T(g6);
     GP_ADD(14, g5, g6);
     return obj;
@@ -461,18 +468,25 @@ __device__ void phase_ld(Ctx &x) {
             while (qh < qt) {
                 const uint32_t nx = *(volatile uint32_t *)&queue[qh++];
                 const int8_t sx = *(volatile int8_t *)&x.st[nx].x;
-                for (uint32_t w0 = adj_off[nx]; w0 < adj_off[nx + 1]; w0 += 32) {
-                    const uint32_t w = w0 + lane;
-                    const bool valid = w < adj_off[nx + 1];
-                    const uint32_t av = valid ? adj[w] : 0u, v = av & 0x7fffffffu;
-                    const bool fresh = valid && *(volatile uint32_t *)&x.label[v] == NONE32;
-                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                    if (fresh) {
-                        x.label[v] = r;
-                        x.st[v].x = (av & 0x80000000u) ? (int8_t)(-sx) : sx;
-                        queue[qt + __popc(m & lt)] = v;
+                const uint32_t a0 = adj_off[nx], a1 = adj_off[nx + 1];
+                for (uint32_t w0 = a0; w0 < a1; w0 += 128) { /* four 32-wide steps with their loads issued together (each is an L2 round trip) */
+                    uint32_t av[4];
+                    bool fresh[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { const uint32_t w = w0 + 32 * c + lane; av[c] = w < a1 ? adj[w] : NONE32; }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) fresh[c] = av[c] != NONE32 && *(volatile uint32_t *)&x.label[av[c] & 0x7fffffffu] == NONE32; /* no duplicates in one list */
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t m = __ballot_sync(0xffffffffu, fresh[c]);
+                        if (fresh[c]) {
+                            const uint32_t v = av[c] & 0x7fffffffu;
+                            x.label[v] = r;
+                            x.st[v].x = (av[c] & 0x80000000u) ? (int8_t)(-sx) : sx;
+                            queue[qt + __popc(m & lt)] = v;
+                        }
+                        qt += __popc(m);
                     }
-                    qt += __popc(m);
                     __syncwarp();
                 }
             }
@@ -490,14 +504,20 @@ __device__ void phase_ld(Ctx &x) {
                 ++order;
                 if (lane == 0) x.rank[node] = order;
                 __syncwarp();
-                for (uint32_t w0 = adj_off[node]; w0 < adj_off[node + 1]; w0 += 32) {
-                    const uint32_t w = w0 + lane;
-                    const bool valid = w < adj_off[node + 1];
-                    const uint32_t v = valid ? (adj[w] & 0x7fffffffu) : 0u;
-                    const bool push = valid && !*(volatile uint32_t *)&x.rank[v];
-                    const uint32_t m = __ballot_sync(0xffffffffu, push);
-                    if (push) stack[sp + __popc(m & lt)] = v;
-                    sp += __popc(m);
+                const uint32_t a0 = adj_off[node], a1 = adj_off[node + 1];
+                for (uint32_t w0 = a0; w0 < a1; w0 += 128) {
+                    uint32_t av[4];
+                    bool push[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { const uint32_t w = w0 + 32 * c + lane; av[c] = w < a1 ? (adj[w] & 0x7fffffffu) : NONE32; }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) push[c] = av[c] != NONE32 && !*(volatile uint32_t *)&x.rank[av[c]];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t m = __ballot_sync(0xffffffffu, push[c]);
+                        if (push[c]) stack[sp + __popc(m & lt)] = av[c];
+                        sp += __popc(m);
+                    }
                     __syncwarp();
                 }
             }
